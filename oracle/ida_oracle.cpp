@@ -1,0 +1,1043 @@
+// ida_oracle.cpp -- CPU restatement of rust-ida's BDF/Newton hot path.
+//
+// THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, __graft_entry__.smoke()
+// and bench.py's cpu_baseline / --impl reference legs may load it.  The product path
+// (rust_ida_b200/csrc) never links, includes or calls anything in oracle/.
+//
+// What it is: a scalar, single-instance, line-by-line C++17 restatement of the arithmetic
+// of jondo2010/rust-ida (a pure-Rust port of SUNDIALS IDA), written from the reference's
+// behaviour; every function cites the reference file:line it follows.  The Rust reference
+// cannot be built in this environment (no rustc/cargo; the tree is mid-refactor, see
+// SURVEY.md section 8c), so this file is a PORT, pinned against every golden vector the
+// reference's own tests hold (tests/golden/*.json, extracted by tools/extract_golden.py):
+//   bit-exact: LU getrf/getrs known answers, complete_step x3 (incl. rr through pow), norms
+//   16 digits: set_coeffs x2, predict, restore, test_error x2, get_solution
+//   end-to-end: Roberts to t=4e10 (check_ans < 1; 377 step attempts as printed by the
+//   reference author's trace notebook).
+//
+// Arithmetic policy: compile with  g++ -O2 -ffp-contract=off -fno-fast-math  so that no
+// a*b+c is fused (Rust never contracts), evaluation is left-to-right as written in the
+// reference, x.recip() is 1.0/x, powi(2) is x*x, powf is the platform libm pow (glibc here).
+// The pow implementation is injectable (oracle_set_pow) so tests can swap in the
+// bit-reproducible glibc-pow port that the GPU engine uses and measure the difference.
+//
+// Deliberate deviations from the reference (hard part 4), all flagged
+// where they occur:
+//   * Newton "ConvergenceRecover with a current Jacobian": the new-API Newton re-loops
+//     forever (crates/nonlinear/src/newton.rs:146-153) and the old-API handle_n_flag treats it
+//     as fatal (src/lib.rs:1133-1140).  We follow SUNDIALS C / the evident intent of
+//     src/lib.rs:1201-1237: return the recoverable error, ncfn++, rr=0.25, retry <= MXNCF.
+//   * singular Jacobian: the reference panics (src/ida_ls.rs:287 unwrap); we return status
+//     ORC_LSETUP_FAIL for that instance.
+// Bug-compatible on purpose: reset() scales ALL of phi (src/lib.rs:1251); jac gets tt=0
+// (src/ida_ls.rs:260-261).
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+namespace {
+
+// ---- constants: src/constants.rs:4-31,56-112 ; RATEMAX src/ida_nls.rs:15 -------------------
+constexpr int MXORDP1 = 6;
+constexpr int MAXORD_DEFAULT = 5;
+constexpr long MXSTEP_DEFAULT = 500;
+constexpr int MXNCF = 10;
+constexpr int MXNEF = 10;
+constexpr double EPCON = 0.33;
+constexpr double XRATE = 0.25;
+constexpr int MAXNLSIT = 4;
+constexpr double RATEMAX = 0.9;
+constexpr double HMAX_INV_DEFAULT = 0.0;
+constexpr double DBL_EPS = 2.220446049250313e-16;  // f64::EPSILON
+
+typedef double (*pow_fn_t)(double, double);
+pow_fn_t g_pow = static_cast<double (*)(double, double)>(std::pow);
+
+// status codes shared with the engine (include/b200ida.h B200IDA_ST_*)
+enum Status : int {
+    ST_SUCCESS = 0,
+    ST_TOO_MUCH_WORK = -1,   // mxstep steps taken (IdaError::IllegalInput in the reference)
+    ST_TOO_MUCH_ACC = -2,    // IdaError::TooMuchAccuracy
+    ST_ERR_FAIL = -3,        // "IDA_ERR_FAIL"
+    ST_CONV_FAIL = -4,       // IdaError::ConvergenceFail
+    ST_LSETUP_FAIL = -5,     // singular Jacobian (reference: panic)
+    ST_BAD_EWT = -6,         // some ewt component <= 0
+    ST_ILL_INPUT = -7,       // tout too close to t0
+    ST_BAD_T = -8,           // get_solution BadTimeValue (propagated from stop_test1)
+};
+
+enum ProblemKind : int { PK_ROBERTS = 0, PK_LORENZ63 = 1, PK_HEAT2D = 2 };
+
+// ---- problems ------------------------------------------------------------------------------
+struct Problem {
+    int kind;
+    int n;
+    const double* p;  // per-instance parameters
+
+    // Residual::res -- src/traits.rs:28-38
+    void res(double /*tt*/, const double* yy, const double* yp, double* r) const {
+        switch (kind) {
+        case PK_ROBERTS: {
+            // src/sample_problems/roberts.rs:58-61 with (0.04, 1e4, 3e7) -> (k1,k2,k3)
+            const double k1 = p[0], k2 = p[1], k3 = p[2];
+            r[0] = -k1 * yy[0] + k2 * yy[1] * yy[2];
+            r[1] = -r[0] - k3 * yy[1] * yy[1] - yp[1];
+            r[0] -= yp[0];
+            r[2] = yy[0] + yy[1] + yy[2] - 1.0;
+            break;
+        }
+        case PK_LORENZ63: {
+            // tests/lorenz63.rs:47-52 (commented RHS f), posed as F = y' - f(y)
+            const double s = p[0], rr = p[1], b = p[2];
+            r[0] = yp[0] - s * (yy[1] - yy[0]);
+            r[1] = yp[1] - (yy[0] * (rr - yy[2]) - yy[1]);
+            r[2] = yp[2] - (yy[0] * yy[1] - b * yy[2]);
+            break;
+        }
+        case PK_HEAT2D: {
+            // not in the reference; SUNDIALS idaHeat2D: M x M grid, boundary rows algebraic
+            const int M = (int)std::lround(std::sqrt((double)n));
+            const double coeff = p[0];
+            for (int i = 0; i < n; ++i) r[i] = yy[i];
+            for (int j = 1; j < M - 1; ++j)
+                for (int i = 1; i < M - 1; ++i) {
+                    const int loc = j * M + i;
+                    const double dif1 = yy[loc - 1] + yy[loc + 1] - 2.0 * yy[loc];
+                    const double dif2 = yy[loc - M] + yy[loc + M] - 2.0 * yy[loc];
+                    r[loc] = yp[loc] - coeff * (dif1 + dif2);
+                }
+            break;
+        }
+        }
+    }
+
+    // Jacobian::jac -- src/traits.rs:57-69 ; J(i,j) = dF_i/dy_j + cj dF_i/dy'_j, column-major
+    void jac(double /*tt*/, double cj, const double* yy, const double* /*yp*/, const double* /*r*/,
+             double* J) const {
+        auto A = [&](int i, int j) -> double& { return J[j * n + i]; };
+        switch (kind) {
+        case PK_ROBERTS: {
+            // src/sample_problems/roberts.rs:80-90 ; 6.0e7 == 2*k3 exactly
+            const double k1 = p[0], k2 = p[1], k3 = p[2];
+            A(0, 0) = -k1 - cj;
+            A(0, 1) = k2 * yy[2];
+            A(0, 2) = k2 * yy[1];
+            A(1, 0) = k1;
+            A(1, 1) = -k2 * yy[2] - (2.0 * k3) * yy[1] - cj;
+            A(1, 2) = -k2 * yy[1];
+            A(2, 0) = 1.0;
+            A(2, 1) = 1.0;
+            A(2, 2) = 1.0;
+            break;
+        }
+        case PK_LORENZ63: {
+            const double s = p[0], rr = p[1], b = p[2];
+            A(0, 0) = cj + s;
+            A(0, 1) = -s;
+            A(0, 2) = 0.0;
+            A(1, 0) = yy[2] - rr;
+            A(1, 1) = cj + 1.0;
+            A(1, 2) = yy[0];
+            A(2, 0) = -yy[1];
+            A(2, 1) = -yy[0];
+            A(2, 2) = cj + b;
+            break;
+        }
+        case PK_HEAT2D: {
+            const int M = (int)std::lround(std::sqrt((double)n));
+            const double coeff = p[0];
+            for (int i = 0; i < n; ++i) A(i, i) = 1.0;
+            for (int j = 1; j < M - 1; ++j)
+                for (int i = 1; i < M - 1; ++i) {
+                    const int loc = j * M + i;
+                    A(loc, loc) = cj + 4.0 * coeff;
+                    A(loc, loc - 1) = -coeff;
+                    A(loc, loc + 1) = -coeff;
+                    A(loc, loc - M) = -coeff;
+                    A(loc, loc + M) = -coeff;
+                }
+            break;
+        }
+        }
+    }
+};
+
+// ---- dense LU: crates/linear/src/dense.rs -----------------------------------------------------
+// dense_get_rf: dense.rs:86-158.  A column-major n x n, returns 0 or the 1-based column of the
+// zero pivot.  pivot = first row with strictly largest |a_ik| (:111-116); whole-row swap
+// (:126-130); mult = 1/a_kk then multiply (:134-137); column-oriented update skipped when
+// a_kj == 0 (:142-154).
+int dense_get_rf(double* a, int64_t* pivot, int n) {
+    auto A = [&](int i, int j) -> double& { return a[(size_t)j * n + i]; };
+    for (int k = 0; k < n; ++k) {
+        int l = k;
+        for (int i = k + 1; i < n; ++i)
+            if (std::fabs(A(i, k)) > std::fabs(A(l, k))) l = i;
+        pivot[k] = l;
+        if (A(l, k) == 0.0) return k + 1;
+        if (l != k)
+            for (int i = 0; i < n; ++i) std::swap(A(k, i), A(l, i));
+        const double mult = 1.0 / A(k, k);
+        for (int i = k + 1; i < n; ++i) A(i, k) *= mult;
+        for (int j = k + 1; j < n; ++j) {
+            const double a_kj = A(k, j);
+            if (a_kj != 0.0)
+                for (int i = k + 1; i < n; ++i) {
+                    const double a_ik = A(i, k);
+                    A(i, j) -= a_kj * a_ik;
+                }
+        }
+    }
+    return 0;
+}
+
+// dense_get_rs: dense.rs:165-206.
+void dense_get_rs(const double* a, const int64_t* pivot, double* b, int n) {
+    auto A = [&](int i, int j) -> double { return a[(size_t)j * n + i]; };
+    for (int k = 0; k < n; ++k) {
+        const int64_t pk = pivot[k];
+        if (pk != k) std::swap(b[k], b[pk]);
+    }
+    for (int k = 0; k < n - 1; ++k) {
+        const double bk = b[k];
+        for (int i = k + 1; i < n; ++i) b[i] -= A(i, k) * bk;
+    }
+    for (int k = n - 1; k >= 1; --k) {
+        b[k] /= A(k, k);
+        const double bk = b[k];
+        for (int i = 0; i < k; ++i) b[i] -= A(i, k) * bk;
+    }
+    b[0] /= A(0, 0);
+}
+
+// ---- WRMS norm: src/norm_rms.rs:31-38 ; crates/nonlinear/src/norm_wrms.rs:24-33 -------------
+double norm_wrms(const double* x, const double* w, int n) {
+    double acc = 0.0;
+    for (int i = 0; i < n; ++i) {
+        const double p = x[i] * w[i];
+        acc = acc + p * p;
+    }
+    return std::sqrt(acc / (double)n);
+}
+
+// ---- Newton: crates/nonlinear/src/newton.rs:14-32 (state) and :51-167 (solve) -------------------
+// Generic over an NLProblem-like object P providing (crates/nonlinear/src/traits.rs:5-127):
+//   void sys(const double* y, double* f); int setup(const double* y, const double* f, bool jbad)
+//   [0 ok, else fatal]; void lsolve(const double* y, double* b);
+//   int ctest(int curiter, const double* y, const double* del, double tol, const double* w)
+//   [1 converged, 0 continue, -1 ConvergenceRecover].
+// C semantics for the "recover while jcur" arm (see file header).
+struct Newton {
+    std::vector<double> delta;
+    bool jcur = false;
+    int curiter = 0;
+    int maxiters = MAXNLSIT;
+    long niters = 0;
+    long nconvfails = 0;
+
+    // returns 0 ok, 1 recoverable convergence failure, <0 fatal from setup
+    template <class P>
+    int solve(P& problem, int n, const double* y0, double* y, const double* w, double tol, bool call_lsetup) {
+        bool jbad = false;
+        int ret = 0;
+        for (;;) {
+            problem.sys(y0, delta.data());
+            if (call_lsetup) {
+                const int s = problem.setup(y0, delta.data(), jbad);
+                if (s != 0) { ret = s; break; }
+                jcur = true;
+            }
+            curiter = 0;
+            for (int i = 0; i < n; ++i) y[i] = y0[i];
+            for (;;) {
+                niters += 1;
+                for (int i = 0; i < n; ++i) delta[i] = -delta[i];
+                problem.lsolve(y, delta.data());
+                for (int i = 0; i < n; ++i) y[i] += delta[i];
+                const int c = problem.ctest(curiter, y, delta.data(), tol, w);
+                if (c == 1) {
+                    jcur = false;
+                    return 0;
+                }
+                if (c == -1) { ret = 1; break; }
+                curiter += 1;
+                if (curiter >= maxiters) { ret = 1; break; }
+                problem.sys(y, delta.data());
+            }
+            if (ret == 1 && !jcur) {  // newton.rs:146-152
+                nconvfails += 1;
+                call_lsetup = true;
+                jbad = true;
+                continue;
+            }
+            break;
+        }
+        nconvfails += 1;  // newton.rs:162
+        return ret;
+    }
+};
+
+// ---- Ida state: src/lib.rs:89-244, src/ida_nls.rs:20-60, src/ida_ls.rs:15-106,
+//      crates/nonlinear/src/newton.rs:14-32, crates/linear/src/dense.rs:13-20 -----------------
+struct Ida {
+    Problem prob;
+    int n;
+    double rtol;
+    std::vector<double> atol;  // TolControlSV src/tol_control.rs:51-83
+
+    bool setup_done = false;
+    std::vector<double> phi;  // [6][n]
+    double psi[MXORDP1], alpha[MXORDP1], beta[MXORDP1], sigma[MXORDP1], gamma[MXORDP1];
+    std::vector<double> delta, ee, ewt, yy, yp, yypredict, yppredict, savres, x, tmp;
+    std::vector<double> J;
+    std::vector<int64_t> pivots;
+
+    int kk = 0, kused = 0, knew = 0, phase = 0, ns = 0;
+    double hin = 0, h0u = 0, hh = 0, hused = 0, rr = 0, tretlast = 0, cjlast = 0;
+    double eps_newt = 0, epcon = EPCON, hmax_inv = HMAX_INV_DEFAULT, tolsf = 1.0;
+    int maxncf = MXNCF, maxnef = MXNEF, maxord = MAXORD_DEFAULT;
+    long mxstep = MXSTEP_DEFAULT;
+    // IdaNLProblem / IdaLProblem scalars
+    double tn = 0, ss = 0, oldnrm = 0, toldel = 0, cj = 0, cjold = 0, cjratio = 0;
+    Newton nls;
+    // counters: src/lib.rs:70-84 ; src/ida_nls.rs:51,54 ; src/ida_ls.rs:45 ; newton.rs:29-31
+    long nst = 0, nre = 0, nje = 0, nsetups = 0, netf = 0, ncfn = 0;
+    long nattempts = 0;  // one per pass of the step loop (= data_trace frames, src/lib.rs:635-639)
+
+    double* PHI(int j) { return &phi[(size_t)j * n]; }
+
+    // Ida::new -- src/lib.rs:278-405
+    void init(const Problem& p, const double* yy0, const double* yp0, double rtol_, const double* atol_) {
+        prob = p;
+        n = p.n;
+        rtol = rtol_;
+        atol.assign(atol_, atol_ + n);
+        phi.assign((size_t)MXORDP1 * n, 0.0);
+        std::copy(yy0, yy0 + n, PHI(0));
+        std::copy(yp0, yp0 + n, PHI(1));
+        for (int i = 0; i < MXORDP1; ++i) psi[i] = alpha[i] = beta[i] = sigma[i] = gamma[i] = 0.0;
+        for (auto* v : {&delta, &ee, &ewt, &yypredict, &yppredict, &savres, &x, &tmp, &nls.delta})
+            v->assign(n, 0.0);
+        yy.assign(yy0, yy0 + n);  // src/ida_nls.rs:82-83
+        yp.assign(yp0, yp0 + n);
+        J.assign((size_t)n * n, 0.0);
+        pivots.assign(n, 0);
+    }
+
+    // TolControlSV::ewt_set -- src/tol_control.rs:71-82
+    void ewt_set(const double* ycur) {
+        for (int i = 0; i < n; ++i) ewt[i] = 1.0 / (rtol * std::fabs(ycur[i]) + atol[i]);
+    }
+
+    // set_coeffs -- src/lib.rs:722-782
+    double set_coeffs() {
+        if (hh != hused || kk != kused) ns = 0;
+        ns = std::min(ns + 1, kused + 2);
+        if (kk + 1 >= ns) {
+            beta[0] = 1.0;
+            alpha[0] = 1.0;
+            double temp1 = hh;
+            gamma[0] = 0.0;
+            sigma[0] = 1.0;
+            for (int i = 1; i <= kk; ++i) {
+                const double scalar_i = (double)i;
+                const double temp2 = psi[i - 1];
+                psi[i - 1] = temp1;
+                beta[i] = beta[i - 1] * psi[i - 1] / temp2;
+                temp1 = temp2 + hh;
+                alpha[i] = hh / temp1;
+                sigma[i] = scalar_i * sigma[i - 1] * alpha[i];
+                gamma[i] = gamma[i - 1] + alpha[i - 1] / hh;
+            }
+            psi[kk] = temp1;
+        }
+        double alphas = 0.0, alpha0 = 0.0;
+        for (int i = 0; i < kk; ++i) {
+            const double scalar_i = (double)(i + 1);
+            alphas -= 1.0 / scalar_i;
+            alpha0 -= alpha[i];
+        }
+        cjlast = cj;
+        cj = -alphas / hh;
+        double ck = std::fabs(alpha[kk] + alphas - alpha0);
+        ck = std::fmax(ck, alpha[kk]);
+        if (ns <= kk)
+            for (int j = ns; j <= kk; ++j) {
+                double* ph = PHI(j);
+                for (int i = 0; i < n; ++i) ph[i] *= beta[j];
+            }
+        return ck;
+    }
+
+    // predict -- src/lib.rs:894-959
+    void predict() {
+        for (int i = 0; i < n; ++i) yypredict[i] = 0.0;
+        for (int j = 0; j <= kk; ++j) {
+            const double* ph = PHI(j);
+            for (int i = 0; i < n; ++i) yypredict[i] += ph[i];
+        }
+        for (int i = 0; i < n; ++i) yppredict[i] = 0.0;
+        for (int j = 1; j <= kk; ++j) {
+            const double* ph = PHI(j);
+            for (int i = 0; i < n; ++i) yppredict[i] += gamma[j] * ph[i];
+        }
+    }
+
+    // IdaNLProblem::sys -- src/ida_nls.rs:118-153
+    void nls_sys(const double* ycor, double* res) {
+        for (int i = 0; i < n; ++i) yy[i] = yypredict[i] + ycor[i];
+        for (int i = 0; i < n; ++i) yp[i] = yppredict[i];
+        for (int i = 0; i < n; ++i) yp[i] += cj * ycor[i];
+        prob.res(tn, yy.data(), yp.data(), res);
+        nre += 1;
+        for (int i = 0; i < n; ++i) savres[i] = res[i];
+    }
+
+    // IdaNLProblem::setup -- src/ida_nls.rs:156-187 -> IdaLProblem::setup src/ida_ls.rs:232-290
+    // returns 0 or the 1-based singular column
+    int nls_setup(const double* res) {
+        nsetups += 1;
+        nje += 1;
+        std::fill(J.begin(), J.end(), 0.0);
+        prob.jac(0.0, cj, yy.data(), yp.data(), res, J.data());  // tt = 0: src/ida_ls.rs:260-261
+        const int info = dense_get_rf(J.data(), pivots.data(), n);  // Dense::setup dense.rs:38-44
+        if (info != 0) return info;  // reference: unwrap() panic, src/ida_ls.rs:287
+        cjold = cj;
+        cjratio = 1.0;
+        ss = 20.0;
+        return 0;
+    }
+
+    // IdaNLProblem::solve -- src/ida_nls.rs:190-215 -> IdaLProblem::solve src/ida_ls.rs:298-455
+    void nls_lsolve(double* b) {
+        for (int i = 0; i < n; ++i) x[i] = 0.0;
+        for (int i = 0; i < n; ++i) x[i] = b[i];  // Dense::solve copies b into x, dense.rs:58-59
+        dense_get_rs(J.data(), pivots.data(), x.data(), n);
+        for (int i = 0; i < n; ++i) b[i] = x[i];
+        if (cjratio != 1.0) {  // src/ida_ls.rs:406-410
+            const double f = 2.0 / (1.0 + cjratio);
+            for (int i = 0; i < n; ++i) b[i] *= f;
+        }
+    }
+
+    // IdaNLProblem::ctest -- src/ida_nls.rs:218-266 ; 1 converged, 0 continue, -1 recover
+    int nls_ctest(int m, const double* del, double tol, const double* w) {
+        const double delnrm = norm_wrms(del, w, n);
+        if (m == 0) {
+            oldnrm = delnrm;
+            if (delnrm <= 0.0001 * toldel) return 1;
+        } else {
+            const double base = delnrm / oldnrm;
+            const double arg = 1.0 / (double)m;
+            const double rate = g_pow(base, arg);
+            if (rate > RATEMAX) return -1;
+            ss = rate / (1.0 - rate);
+        }
+        if (ss * delnrm <= tol) return 1;
+        return 0;
+    }
+
+    // adapter giving Newton::solve the NLProblem view of this Ida (src/ida_nls.rs:104-266)
+    struct NlpView {
+        Ida& s;
+        void sys(const double* y, double* f) { s.nls_sys(y, f); }
+        int setup(const double*, const double* f, bool) { return s.nls_setup(f) != 0 ? (int)ST_LSETUP_FAIL : 0; }
+        void lsolve(const double*, double* b) { s.nls_lsolve(b); }
+        int ctest(int curiter, const double*, const double* del, double tol, const double* w) {
+            return s.nls_ctest(curiter, del, tol, w);
+        }
+    };
+
+    // nonlinear_solve -- src/lib.rs:787-890
+    int nonlinear_solve() {
+        bool call_lsetup = false;
+        if (nst == 0) {
+            cjold = cj;
+            ss = 20.0;
+            call_lsetup = true;
+        }
+        cjratio = cj / cjold;
+        const double temp1 = (1.0 - XRATE) / (1.0 + XRATE);
+        const double temp2 = 1.0 / temp1;
+        if (cjratio < temp1 || cjratio > temp2) call_lsetup = true;
+        if (cj != cjlast) ss = 100.0;
+        for (int i = 0; i < n; ++i) delta[i] = 0.0;
+        // w = ewt.clone()
+        NlpView view{*this};
+        const int ret = nls.solve(view, n, delta.data(), ee.data(), ewt.data(), eps_newt, call_lsetup);
+        for (int i = 0; i < n; ++i) yy[i] = yypredict[i] + ee[i];
+        for (int i = 0; i < n; ++i) yp[i] = yppredict[i];
+        for (int i = 0; i < n; ++i) yp[i] += cj * ee[i];
+        return ret;
+    }
+
+    // test_error -- src/lib.rs:967-1039 ; returns converged
+    bool test_error(double ck, double& err_k, double& err_km1) {
+        const double scalar_kk = (double)kk;
+        const double enorm_k = norm_wrms(ee.data(), ewt.data(), n);
+        err_k = sigma[kk] * enorm_k;
+        const double terr_k = err_k * (scalar_kk + 1.0);
+        err_km1 = 0.0;
+        int knew_ = kk;
+        if (kk > 1) {
+            const double* phk = PHI(kk);
+            for (int i = 0; i < n; ++i) delta[i] = phk[i] + ee[i];
+            const double enorm_km1 = norm_wrms(delta.data(), ewt.data(), n);
+            err_km1 = sigma[kk - 1] * enorm_km1;
+            const double terr_km1 = scalar_kk * err_km1;
+            if (kk > 2) {
+                const double* phkm1 = PHI(kk - 1);
+                for (int i = 0; i < n; ++i) delta[i] += phkm1[i];
+                const double enorm_km2 = norm_wrms(delta.data(), ewt.data(), n);
+                const double err_km2 = sigma[kk - 2] * enorm_km2;
+                const double terr_km2 = (scalar_kk - 1.0) * err_km2;
+                if (std::fmax(terr_km1, terr_km2) <= terr_k) knew_ = kk - 1;
+            } else {
+                if (terr_km1 <= terr_k * 0.5) knew_ = kk - 1;
+            }
+        }
+        knew = knew_;
+        return (ck * enorm_k) <= 1.0;
+    }
+
+    // restore -- src/lib.rs:1044-1083
+    void restore(double saved_t) {
+        tn = saved_t;
+        for (int j = 1; j <= kk; ++j) psi[j - 1] = psi[j] - hh;
+        if (ns <= kk)
+            for (int j = ns; j <= kk; ++j) {
+                const double c = 1.0 / beta[j];
+                double* ph = PHI(j);
+                for (int i = 0; i < n; ++i) ph[i] *= c;
+            }
+    }
+
+    // handle_n_flag -- src/lib.rs:1120-1244 ; nflag: 2 = error test fail, 1 = recoverable conv
+    // fail.  returns 0 (predict again) or a fatal Status.
+    int handle_n_flag(int nflag, double err_k, double err_km1, long& ncf, long& nef) {
+        phase = 1;
+        if (nflag == 2) {
+            nef += 1;
+            netf += 1;
+            if (nef == 1) {
+                const double err_knew = (kk == knew) ? err_k : err_km1;
+                kk = knew;
+                const double base = 2.0 * err_knew + 0.0001;
+                const double arg = 1.0 / (double)(kk + 1);
+                rr = 0.9 * g_pow(base, -arg);
+                rr = std::fmax(0.25, std::fmin(0.9, rr));
+                hh *= rr;
+                return 0;
+            } else if (nef == 2) {
+                kk = knew;
+                rr = 0.25;
+                hh *= rr;
+                return 0;
+            } else if (nef < maxnef) {
+                kk = 1;
+                rr = 0.25;
+                hh *= rr;
+                return 0;
+            }
+            return ST_ERR_FAIL;
+        }
+        // recoverable convergence failure (C semantics; src/lib.rs:1201-1237)
+        ncf += 1;
+        ncfn += 1;
+        rr = 0.25;
+        hh *= rr;
+        if (ncf < maxncf) return 0;
+        return ST_CONV_FAIL;
+    }
+
+    // reset -- src/lib.rs:1249-1252 (scales ALL of phi: bug-compatible)
+    void reset() {
+        psi[0] = hh;
+        for (auto& v : phi) v *= rr;
+    }
+
+    // complete_step -- src/impl_complete_step.rs:22-177
+    void complete_step(double err_k, double err_km1) {
+        nst += 1;
+        const int kdiff = kk - kused;
+        kused = kk;
+        hused = hh;
+        if (knew == kk - 1 || kk == maxord) phase = 1;
+        if (phase == 0) {
+            if (nst > 1) {
+                kk += 1;
+                double hnew = 2.0 * hh;
+                const double t = std::fabs(hnew) * hmax_inv;
+                if (t > 1.0) hnew /= t;
+                hh = hnew;
+            }
+        } else {
+            enum { LOWER, MAINTAIN, RAISE } action;
+            double err_kp1 = 0.0;
+            if (knew == kk - 1) {
+                action = LOWER;
+            } else if (kk == maxord) {
+                action = MAINTAIN;
+            } else if (kk + 1 >= ns || kdiff == 1) {
+                action = MAINTAIN;
+            } else {
+                const double* php1 = PHI(kk + 1);
+                for (int i = 0; i < n; ++i) tmp[i] = ee[i] - php1[i];
+                const double enorm = norm_wrms(tmp.data(), ewt.data(), n);
+                err_kp1 = enorm / (double)(kk + 2);
+                const double terr_k = (double)(kk + 1) * err_k;
+                const double terr_kp1 = (double)(kk + 2) * err_kp1;
+                if (kk == 1) {
+                    action = (terr_kp1 >= 0.5 * terr_k) ? MAINTAIN : RAISE;
+                } else {
+                    const double terr_km1 = (double)kk * err_km1;
+                    if (terr_km1 <= std::fmin(terr_k, terr_kp1)) action = LOWER;
+                    else if (terr_kp1 >= terr_k) action = MAINTAIN;
+                    else action = RAISE;
+                }
+            }
+            double err_knew;
+            if (action == RAISE) { kk += 1; err_knew = err_kp1; }
+            else if (action == LOWER) { kk -= 1; err_knew = err_km1; }
+            else err_knew = err_k;
+
+            double hnew = hh;
+            {
+                const double base = 2.0 * err_knew + 0.0001;
+                const double arg = -(1.0 / (double)(kk + 1));
+                rr = g_pow(base, arg);
+            }
+            if (rr >= 2.0) {
+                hnew = 2.0 * hh;
+                const double t = std::fabs(hnew) * hmax_inv;
+                if (t > 1.0) hnew /= t;
+            } else if (rr <= 1.0) {
+                rr = std::fmax(0.5, std::fmin(rr, 0.9));
+                hnew = hh * rr;
+            }
+            hh = hnew;
+        }
+        if (kused < maxord) std::copy(ee.begin(), ee.end(), PHI(kused + 1));
+        for (int i = 0; i < n; ++i) tmp[i] = ee[i];
+        for (int j = kused; j >= 0; --j) {
+            double* ph = PHI(j);
+            for (int i = 0; i < n; ++i) {
+                tmp[i] += ph[i];
+                ph[i] = tmp[i];
+            }
+        }
+    }
+
+    // step -- src/lib.rs:613-711 ; returns 0 or fatal Status
+    int step() {
+        const double saved_t = tn;
+        if (nst == 0) {
+            kk = 1;
+            kused = 0;
+            hused = 0.0;
+            psi[0] = hh;
+            cj = 1.0 / hh;
+            phase = 0;
+            ns = 0;
+        }
+        long ncf = 0, nef = 0;
+        double ck, err_k = 0.0, err_km1 = 0.0;
+        for (;;) {
+            nattempts += 1;
+            ck = set_coeffs();
+            tn += hh;
+            predict();
+            int nflag = nonlinear_solve();
+            bool converged = false;
+            err_k = 0.0;
+            err_km1 = 0.0;
+            if (nflag == 0) {
+                converged = test_error(ck, err_k, err_km1);
+                if (!converged) nflag = 2;
+            }
+            if (converged) break;
+            restore(saved_t);
+            if (nflag < 0) {  // singular Jacobian: fatal (reference panics)
+                ncfn += 1;
+                return nflag;
+            }
+            const int kflag = handle_n_flag(nflag, err_k, err_km1, ncf, nef);
+            if (kflag != 0) return kflag;
+            if (nst == 0) reset();
+        }
+        complete_step(err_k, err_km1);
+        for (int i = 0; i < n; ++i) ee[i] *= ck;
+        return 0;
+    }
+
+    // get_solution -- src/lib.rs:1274-1343 ; returns 0 or ST_BAD_T
+    int get_solution(double t) {
+        const double sgn = (hh > 0.0 || (hh == 0.0 && !std::signbit(hh))) ? 1.0 : -1.0;  // f64::signum
+        const double tfuzz = 100.0 * DBL_EPS * (std::fabs(tn) + std::fabs(hh)) * sgn;
+        const double tp = tn - hused - tfuzz;
+        if ((t - tp) * hh < 0.0) return ST_BAD_T;
+        const int kord = (kused == 0) ? 1 : kused;
+        const double delt = t - tn;
+        double c = 1.0, d = 0.0;
+        double gam = delt / psi[0];
+        double cvals[MXORDP1], dvals[MXORDP1];
+        cvals[0] = c;
+        for (int j = 1; j <= kord; ++j) {
+            d = d * gam + c / psi[j - 1];
+            c = c * gam;
+            gam = (delt + psi[j - 1]) / psi[j];
+            cvals[j] = c;
+            dvals[j - 1] = d;
+        }
+        for (int i = 0; i < n; ++i) yy[i] = 0.0;
+        for (int j = 0; j <= kord; ++j) {
+            const double* ph = PHI(j);
+            for (int i = 0; i < n; ++i) yy[i] += cvals[j] * ph[i];
+        }
+        for (int i = 0; i < n; ++i) yp[i] = 0.0;
+        for (int j = 1; j <= kord; ++j) {
+            const double* ph = PHI(j);
+            for (int i = 0; i < n; ++i) yp[i] += dvals[j - 1] * ph[i];
+        }
+        return 0;
+    }
+
+    // solve (IdaTask::Normal, no roots, no tstop) -- src/impl_solve.rs:69-376 with
+    // stop_test1/2 NORMAL branches src/impl_stop_test.rs:53-65,152-161
+    int solve(double tout, double& tret) {
+        if (nst == 0) {
+            if (!setup_done) {
+                ewt_set(PHI(0));  // initial_setup src/lib.rs:537-545
+                setup_done = true;
+            }
+            const double tdist = std::fabs(tout - tn);
+            if (tdist == 0.0) return ST_ILL_INPUT;
+            const double troundoff = 2.0 * DBL_EPS * (std::fabs(tn) + std::fabs(tout));
+            if (tdist < troundoff) return ST_ILL_INPUT;
+            hh = hin;
+            if (hh != 0.0 && (tout - tn) * hh < 0.0) return ST_ILL_INPUT;
+            if (hh == 0.0) {
+                hh = 0.001 * tdist;
+                const double ypnorm = norm_wrms(PHI(1), ewt.data(), n);
+                if (ypnorm > 2.0 / hh) hh = 0.5 / ypnorm;
+                if (tout < tn) hh = -hh;
+            }
+            const double rh = std::fabs(hh) * hmax_inv;
+            if (rh > 1.0) hh /= rh;
+            h0u = hh;
+            kk = 0;
+            kused = 0;
+            {
+                double* p1 = PHI(1);
+                for (int i = 0; i < n; ++i) p1[i] *= hh;
+            }
+            eps_newt = epcon;
+            toldel = 0.0001 * eps_newt;
+        }
+        long nstloc = 0;
+        if (nst > 0) {
+            // stop_test1, NORMAL
+            if (tout == tretlast) {
+                tretlast = tout;
+                tret = tout;
+                return ST_SUCCESS;
+            }
+            if ((tn - tout) * hh >= 0.0) {
+                const int ier = get_solution(tout);
+                if (ier != 0) return ier;
+                tretlast = tout;
+                tret = tout;
+                return ST_SUCCESS;
+            }
+        }
+        for (;;) {
+            if (mxstep > 0 && nstloc >= mxstep) {
+                tret = tn;
+                tretlast = tn;
+                return ST_TOO_MUCH_WORK;
+            }
+            if (nst > 0) {
+                ewt_set(PHI(0));
+                bool bad = false;
+                for (int i = 0; i < n; ++i) bad = bad || (ewt[i] <= 0.0);
+                if (bad) {
+                    get_solution(tn);
+                    tret = tn;
+                    tretlast = tn;
+                    return ST_BAD_EWT;
+                }
+            }
+            const double nrm = norm_wrms(PHI(0), ewt.data(), n);
+            tolsf = DBL_EPS * nrm;
+            if (tolsf > 1.0) {
+                tolsf *= 10.0;
+                tret = tn;
+                tretlast = tn;
+                if (nst > 0) get_solution(tn);
+                return ST_TOO_MUCH_ACC;
+            }
+            const int sflag = step();
+            if (sflag != 0) {
+                if (get_solution(tn) == 0) {
+                    tret = tn;
+                    tretlast = tn;
+                }
+                return sflag;
+            }
+            nstloc += 1;
+            // stop_test2, NORMAL
+            if ((tn - tout) * hh >= 0.0) {
+                tret = tout;
+                tretlast = tout;
+                get_solution(tout);
+                return ST_SUCCESS;
+            }
+        }
+    }
+};
+
+}  // namespace
+
+// =================================================================================================
+// C interface for ctypes (tests, bench cpu_baseline).  Everything here is test infrastructure.
+// =================================================================================================
+extern "C" {
+
+void oracle_set_pow(pow_fn_t f) { g_pow = f ? f : static_cast<double (*)(double, double)>(std::pow); }
+double oracle_pow(double x, double y) { return g_pow(x, y); }
+
+int oracle_getrf(double* a_colmajor, int64_t* pivot, int n) { return dense_get_rf(a_colmajor, pivot, n); }
+void oracle_getrs(const double* a_colmajor, const int64_t* pivot, double* b, int n) {
+    dense_get_rs(a_colmajor, pivot, b, n);
+}
+double oracle_wrms(const double* x, const double* w, int n) { return norm_wrms(x, w, n); }
+
+void oracle_res(int kind, int n, const double* params, double t, const double* yy, const double* yp, double* r) {
+    Problem p{kind, n, params};
+    p.res(t, yy, yp, r);
+}
+void oracle_jac(int kind, int n, const double* params, double cj, const double* yy, const double* yp,
+                double* J_colmajor) {
+    Problem p{kind, n, params};
+    std::fill(J_colmajor, J_colmajor + (size_t)n * n, 0.0);
+    p.jac(0.0, cj, yy, yp, nullptr, J_colmajor);
+}
+
+// ---- unit hooks used by the golden-vector tests (state poked like src/tests/*.rs do) ----------
+struct OracleUnit {
+    Ida ida;
+};
+
+static double kZeros[512];
+void* oracle_unit_new(int n) {
+    auto* u = new OracleUnit();
+    static const double par[3] = {0.04, 1.0e4, 3.0e7};
+    Problem p{PK_ROBERTS, n, par};
+    std::vector<double> atol(n, 1e-4);
+    u->ida.init(p, kZeros, kZeros, 1e-4, atol.data());
+    return u;
+}
+void oracle_unit_free(void* h) { delete static_cast<OracleUnit*>(h); }
+
+// field access by name: doubles
+static double* unit_dptr(Ida& s, const char* f, int* len) {
+    const int n = s.n;
+#define FV(name, vec) if (!std::strcmp(f, name)) { *len = (int)(vec).size(); return (vec).data(); }
+#define FA(name, arr) if (!std::strcmp(f, name)) { *len = MXORDP1; return (arr); }
+#define FS(name, sc) if (!std::strcmp(f, name)) { *len = 1; return &(sc); }
+    FV("phi", s.phi) FA("psi", s.psi) FA("alpha", s.alpha) FA("beta", s.beta) FA("sigma", s.sigma)
+    FA("gamma", s.gamma) FV("ee", s.ee) FV("ewt", s.ewt) FV("delta", s.delta) FV("yy", s.yy) FV("yp", s.yp)
+    FV("yypredict", s.yypredict) FV("yppredict", s.yppredict)
+    FS("hh", s.hh) FS("hused", s.hused) FS("rr", s.rr) FS("hmax_inv", s.hmax_inv) FS("cj", s.cj)
+    FS("cjlast", s.cjlast) FS("cjold", s.cjold) FS("cjratio", s.cjratio) FS("ss", s.ss) FS("tn", s.tn)
+    FS("eps_newt", s.eps_newt) FS("toldel", s.toldel)
+#undef FV
+#undef FA
+#undef FS
+    (void)n;
+    return nullptr;
+}
+int oracle_unit_set_d(void* h, const char* field, const double* v, int len) {
+    int l = 0;
+    double* p = unit_dptr(static_cast<OracleUnit*>(h)->ida, field, &l);
+    if (!p || l != len) return -1;
+    std::copy(v, v + len, p);
+    return 0;
+}
+int oracle_unit_get_d(void* h, const char* field, double* v, int len) {
+    int l = 0;
+    double* p = unit_dptr(static_cast<OracleUnit*>(h)->ida, field, &l);
+    if (!p || l != len) return -1;
+    std::copy(p, p + len, v);
+    return 0;
+}
+static long* unit_iptr(Ida& s, const char* f, int* which) {
+    *which = 0;
+#define FI(name, v) if (!std::strcmp(f, name)) { *which = 1; static long t; t = (long)(v); return &t; }
+    FI("kk", s.kk) FI("kused", s.kused) FI("knew", s.knew) FI("phase", s.phase) FI("ns", s.ns)
+    FI("nst", s.nst) FI("maxord", s.maxord)
+#undef FI
+    return nullptr;
+}
+int oracle_unit_set_i(void* h, const char* f, long v) {
+    Ida& s = static_cast<OracleUnit*>(h)->ida;
+    if (!std::strcmp(f, "kk")) s.kk = (int)v;
+    else if (!std::strcmp(f, "kused")) s.kused = (int)v;
+    else if (!std::strcmp(f, "knew")) s.knew = (int)v;
+    else if (!std::strcmp(f, "phase")) s.phase = (int)v;
+    else if (!std::strcmp(f, "ns")) s.ns = (int)v;
+    else if (!std::strcmp(f, "nst")) s.nst = v;
+    else if (!std::strcmp(f, "maxord")) s.maxord = (int)v;
+    else return -1;
+    return 0;
+}
+long oracle_unit_get_i(void* h, const char* f) {
+    int w;
+    long* p = unit_iptr(static_cast<OracleUnit*>(h)->ida, f, &w);
+    return p ? *p : -999999;
+}
+double oracle_unit_set_coeffs(void* h) { return static_cast<OracleUnit*>(h)->ida.set_coeffs(); }
+void oracle_unit_predict(void* h) { static_cast<OracleUnit*>(h)->ida.predict(); }
+void oracle_unit_restore(void* h, double saved_t) { static_cast<OracleUnit*>(h)->ida.restore(saved_t); }
+int oracle_unit_test_error(void* h, double ck, double* err_k, double* err_km1) {
+    return static_cast<OracleUnit*>(h)->ida.test_error(ck, *err_k, *err_km1) ? 1 : 0;
+}
+void oracle_unit_complete_step(void* h, double err_k, double err_km1) {
+    static_cast<OracleUnit*>(h)->ida.complete_step(err_k, err_km1);
+}
+int oracle_unit_get_solution(void* h, double t) { return static_cast<OracleUnit*>(h)->ida.get_solution(t); }
+
+// ---- Newton known-answer problem: the data of crates/nonlinear/src/newton.rs:192-343 -----------
+// f1 = x^2+y^2+z^2-1, f2 = 2x^2+y^2-4z, f3 = 3x^2-4y+z^2 ; J analytic; ctest = (wrms(del) <= tol)
+struct Quad3 {
+    double a[9];
+    int64_t piv[3];
+    void sys(const double* v, double* f) {
+        const double x = v[0], y = v[1], z = v[2];
+        f[0] = x * x + y * y + z * z - 1.0;
+        f[1] = 2.0 * (x * x) + y * y - 4.0 * z;
+        f[2] = 3.0 * (x * x) - 4.0 * y + z * z;
+    }
+    int setup(const double* v, const double*, bool) {
+        const double x = v[0], y = v[1], z = v[2];
+        const double col0[3] = {2.0 * x, 4.0 * x, 6.0 * x}, col1[3] = {2.0 * y, 2.0 * y, -4.0},
+                     col2[3] = {2.0 * z, -4.0, 2.0 * z};
+        for (int i = 0; i < 3; ++i) { a[i] = col0[i]; a[3 + i] = col1[i]; a[6 + i] = col2[i]; }
+        return dense_get_rf(a, piv, 3);
+    }
+    void lsolve(const double*, double* b) { dense_get_rs(a, piv, b, 3); }
+    int ctest(int, const double*, const double* del, double tol, const double* w) {
+        return norm_wrms(del, w, 3) <= tol ? 1 : 0;
+    }
+};
+int oracle_newton_quad3(const double* y0, const double* w, double tol, int maxiters, double* y, long* niters,
+                        long* nconvfails) {
+    Newton nls;
+    nls.maxiters = maxiters;
+    nls.delta.assign(3, 0.0);
+    Quad3 p;
+    const int r = nls.solve(p, 3, y0, y, w, tol, true);
+    *niters = nls.niters;
+    *nconvfails = nls.nconvfails;
+    return r;
+}
+
+// ---- ensemble driver: one Ida per instance, instances spread over nthreads --------------------
+// Layouts are SoA: params [P][B], yy0/yp0/yy/yp [n][B].  touts: the ladder of output times, each
+// one a separate solve() call (h0 depends on the first tout; mxstep is per call).
+// yy_out/yp_out: final state [n][B] (may be null); yy_traj: [ntout][n][B] (may be null).
+// counters [9][B]: nst, nre, nje, nni, netf, ncfn, nsetups, nls_nconvfails, nattempts.
+// stepinfo_i [2][B]: kused, kk ; stepinfo_d [4][B]: hused, hh, tn, tret.
+// status [ntout][B] per-call status (may be null); returns 0.
+int oracle_ensemble_solve(int kind, int n, int64_t B, int nparams, const double* params, const double* yy0,
+                          const double* yp0, double rtol, const double* atol, const double* touts, int ntout,
+                          int nthreads, double* yy_out, double* yp_out, double* yy_traj, int64_t* counters,
+                          int64_t* stepinfo_i, double* stepinfo_d, int32_t* status) {
+    if (nthreads < 1) nthreads = 1;
+    std::atomic<int64_t> next(0);
+    auto worker = [&]() {
+        std::vector<double> par(nparams), y0(n), yp0v(n);
+        for (;;) {
+            const int64_t chunk = 16;
+            const int64_t b0 = next.fetch_add(chunk);
+            if (b0 >= B) break;
+            const int64_t b1 = std::min(B, b0 + chunk);
+            for (int64_t b = b0; b < b1; ++b) {
+                for (int k = 0; k < nparams; ++k) par[k] = params[(size_t)k * B + b];
+                for (int i = 0; i < n; ++i) {
+                    y0[i] = yy0[(size_t)i * B + b];
+                    yp0v[i] = yp0[(size_t)i * B + b];
+                }
+                Ida ida;
+                Problem p{kind, n, par.data()};
+                ida.init(p, y0.data(), yp0v.data(), rtol, atol);
+                double tret = 0.0;
+                for (int it = 0; it < ntout; ++it) {
+                    const int st = ida.solve(touts[it], tret);
+                    if (status) status[(size_t)it * B + b] = st;
+                    if (yy_traj)
+                        for (int i = 0; i < n; ++i) yy_traj[((size_t)it * n + i) * B + b] = ida.yy[i];
+                }
+                for (int i = 0; i < n; ++i) {
+                    if (yy_out) yy_out[(size_t)i * B + b] = ida.yy[i];
+                    if (yp_out) yp_out[(size_t)i * B + b] = ida.yp[i];
+                }
+                if (counters) {
+                    const long c[9] = {ida.nst, ida.nre, ida.nje, ida.nls.niters, ida.netf,
+                                       ida.ncfn, ida.nsetups, ida.nls.nconvfails, ida.nattempts};
+                    for (int k = 0; k < 9; ++k) counters[(size_t)k * B + b] = c[k];
+                }
+                if (stepinfo_i) {
+                    stepinfo_i[b] = ida.kused;
+                    stepinfo_i[(size_t)B + b] = ida.kk;
+                }
+                if (stepinfo_d) {
+                    stepinfo_d[b] = ida.hused;
+                    stepinfo_d[(size_t)B + b] = ida.hh;
+                    stepinfo_d[(size_t)2 * B + b] = ida.tn;
+                    stepinfo_d[(size_t)3 * B + b] = tret;
+                }
+            }
+        }
+    };
+    if (nthreads == 1) {
+        worker();
+    } else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nthreads; ++t) th.emplace_back(worker);
+        for (auto& t : th) t.join();
+    }
+    return 0;
+}
+
+// single-instance trace: records (nst, kused, hused, y[0..n)) after every solve() call, used to
+// reproduce the table of examples/roberts.rs:87-113
+int oracle_single_trace(int kind, int n, const double* params, const double* yy0, const double* yp0, double rtol,
+                        const double* atol, const double* touts, int ntout, double* rows /*[ntout][3+n]*/,
+                        int64_t* counters /*[9]*/) {
+    Ida ida;
+    Problem p{kind, n, params};
+    ida.init(p, yy0, yp0, rtol, atol);
+    double tret = 0.0;
+    int last = 0;
+    for (int it = 0; it < ntout; ++it) {
+        last = ida.solve(touts[it], tret);
+        double* r = rows + (size_t)it * (3 + n);
+        r[0] = (double)ida.nst;
+        r[1] = (double)ida.kused;
+        r[2] = ida.hused;
+        for (int i = 0; i < n; ++i) r[3 + i] = ida.yy[i];
+        if (last != 0) break;
+    }
+    const long c[9] = {ida.nst, ida.nre, ida.nje, ida.nls.niters, ida.netf, ida.ncfn, ida.nsetups,
+                       ida.nls.nconvfails, ida.nattempts};
+    for (int k = 0; k < 9; ++k) counters[k] = c[k];
+    return last;
+}
+
+}  // extern "C"
