@@ -1,0 +1,178 @@
+/* b200ida.h -- C ABI of the B200-native batched IDA engine (libb200ida.so).
+ *
+ * Drop-in boundary for ONE hot path of jondo2010/rust-ida: the per-step BDF/Newton inner loop run over
+ * large ensembles of independent DAE instances.  Every entry point names the reference interface it
+ * replaces (file:line under the reference tree).  Plain pointers and sizes only; no C++/torch types.
+ * There is no CPU fallback and no backend dispatch: every compute entry point launches hand-written
+ * sm_100a CUDA kernels and fails with B200IDA_ERR_CUDA / B200IDA_ERR_NO_DEVICE when it cannot.
+ *
+ * Conventions
+ *   - "SoA" arrays are component-major: element (i, b) of an [n][batch] array is at  i*batch + b ,
+ *     so that consecutive instances are consecutive in memory (coalesced, vectorisable FP64 access).
+ *   - "AoS" matrices are one column-major n x n matrix per instance (nalgebra's owned storage, the
+ *     layout `LSolver::setup` receives, crates/linear/src/traits.rs:52-54): element (i, j) of
+ *     instance b is at  b*n*n + j*n + i ; AoS vectors are  b*n + i .
+ *   - `mem` says where caller buffers live: B200IDA_MEM_DEVICE (device pointers, no copies, work is
+ *     enqueued on `stream` and the call returns without synchronising) or B200IDA_MEM_HOST (host
+ *     pointers; the call copies in, runs, copies out and synchronises -- the end-to-end path).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *   - Return value: 0 on success, negative B200IDA_ERR_* otherwise.  Per-instance outcomes are
+ *     reported in status / info arrays, never through the return value.
+ *   - Arithmetic policy: IEEE-754 binary64, round-to-nearest, NO fused multiply-add contraction
+ *     (kernels are built with -fmad=false) so results are bit-identical to the reference's
+ *     un-fused Rust arithmetic; pow is glibc-2.39-compatible (csrc/detpow.h).
+ */
+#ifndef B200IDA_H
+#define B200IDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200IDA_VERSION 100
+
+/* ---- return codes -------------------------------------------------------------------------------- */
+#define B200IDA_OK 0
+#define B200IDA_ERR_ARG (-1)       /* bad argument (null pointer, n out of range, unknown enum ...) */
+#define B200IDA_ERR_CUDA (-2)      /* a CUDA runtime call or kernel launch failed; see b200ida_last_error */
+#define B200IDA_ERR_NO_DEVICE (-3) /* no sm_100-class CUDA device is available */
+#define B200IDA_ERR_UNSUPPORTED (-4) /* (problem, n) combination has no kernel */
+
+/* ---- memory space / layout ------------------------------------------------------------------------ */
+#define B200IDA_MEM_DEVICE 0
+#define B200IDA_MEM_HOST 1
+#define B200IDA_LAYOUT_SOA 0
+#define B200IDA_LAYOUT_AOS 1
+
+const char* b200ida_last_error(void); /* thread-local text of the last failure */
+int b200ida_version(void);
+int b200ida_device_count(void);
+
+/* =====================================================================================================
+ * Level 1 -- batched dense linear algebra and norms.
+ * Replaces, for `batch` independent systems at once:
+ *   LSolver::setup   crates/linear/src/traits.rs:52-54  -> Dense::setup / dense_get_rf  crates/linear/src/dense.rs:38-44, 86-158
+ *   LSolver::solve   crates/linear/src/traits.rs:70-80  -> Dense::solve / dense_get_rs  crates/linear/src/dense.rs:46-63, 165-206
+ *   NormWRMS::norm_wrms  crates/nonlinear/src/norm_wrms.rs:24-33 ; NormRms::norm_wrms  src/norm_rms.rs:31-38
+ * ===================================================================================================== */
+
+/* In-place LU with partial (row) pivoting of `batch` n x n matrices.
+ *   A     [in,out]  matrices, `layout` SoA ([n][n][batch]: element (i, j) of system b at (i*n+j)*batch + b)
+ *                   or AoS (one column-major matrix per system, see Conventions)
+ *   piv   [out]     0-based pivot rows, int64 like the reference's `usize` pivots; SoA [n][batch] or AoS [batch][n]
+ *   info  [out]     [batch]; 0, or the 1-based column of the first zero pivot exactly as
+ *                   linear::Error::LUFactFail{col} (crates/linear/src/lib.rs:9-13, dense.rs:120-122);
+ *                   the factorisation of that matrix stops there, like the reference's early return.
+ * Semantics are bit-exact dense_get_rf: pivot = first row with strictly largest |a_ik|; whole-row swap;
+ * multipliers a_ik * (1/a_kk); column-oriented update skipped when a_kj == 0.  1 <= n <= 256. */
+int b200ida_getrf_batched(double* A, int64_t* piv, int32_t* info, int n, int64_t batch, int layout, int mem,
+                          void* stream);
+
+/* Solve A x = b for `batch` systems from the factors and pivots of b200ida_getrf_batched.
+ *   bx [in,out]  right-hand sides on entry, solutions on return (the reference copies b into x first,
+ *                dense.rs:58-61); SoA [n][batch] or AoS [batch][n]. */
+int b200ida_getrs_batched(const double* LU, const int64_t* piv, double* bx, int n, int64_t batch, int layout,
+                          int mem, void* stream);
+
+/* out[b] = sqrt( (sum_i (x_i w_i)^2) / n ), summed in index order from 0 (bit-exact with the fold in
+ * src/norm_rms.rs:32-37).  x, w: SoA [n][batch] or AoS [batch][n]; out: [batch]. */
+int b200ida_wrms_batched(const double* x, const double* w, double* out, int n, int64_t batch, int layout,
+                         int mem, void* stream);
+
+/* =====================================================================================================
+ * Level 2 -- ensemble IDA.  One handle = `batch` independent instances of
+ *   Ida<P, Dense, Newton, TolControlSV>   (src/lib.rs:89-95)
+ * whose whole solve() loop -- ewt_set, set_coeffs, predict, Newton with res/jac/getrf/getrs, ctest,
+ * test_error, restore/handle_n_flag, complete_step, stop tests, get_solution -- runs on the device
+ * with per-instance step size, order and retry state; the host never sees a step.
+ * ===================================================================================================== */
+
+/* Problems = device-side implementations of the Residual/Jacobian traits (src/traits.rs:28-38, 57-69). */
+#define B200IDA_PROBLEM_ROBERTS 0  /* src/sample_problems/roberts.rs, params (k1,k2,k3) = (0.04,1e4,3e7), n=3 */
+#define B200IDA_PROBLEM_LORENZ63 1 /* tests/lorenz63.rs posed as F = y' - f(y), params (p,r,b), n=3 */
+#define B200IDA_PROBLEM_HEAT2D 2   /* SUNDIALS idaHeat2D-style M x M grid, params (coeff), n=M*M */
+
+/* IdaTask (src/lib.rs:51-55).  Only Normal is on the hot path. */
+#define B200IDA_TASK_NORMAL 0
+
+/* Per-instance status of one solve call.  0 = IdaSolveStatus::Success (src/lib.rs:57-63); negative =
+ * the IdaError the reference would have returned (src/error.rs:18-126). */
+#define B200IDA_ST_SUCCESS 0
+#define B200IDA_ST_TOO_MUCH_WORK (-1) /* mxstep (500) steps in this call, src/impl_solve.rs:249-260 */
+#define B200IDA_ST_TOO_MUCH_ACC (-2)  /* IdaError::TooMuchAccuracy, src/impl_solve.rs:296-308 */
+#define B200IDA_ST_ERR_FAIL (-3)      /* IDA_ERR_FAIL: MXNEF error-test failures, src/lib.rs:1194-1198 */
+#define B200IDA_ST_CONV_FAIL (-4)     /* IdaError::ConvergenceFail: MXNCF failures, src/lib.rs:1232-1234 */
+#define B200IDA_ST_LSETUP_FAIL (-5)   /* singular Jacobian; the reference panics (src/ida_ls.rs:287) */
+#define B200IDA_ST_BAD_EWT (-6)       /* an ewt component <= 0, src/impl_solve.rs:272-285 */
+#define B200IDA_ST_ILL_INPUT (-7)     /* tout too close to t0, src/impl_solve.rs:97-109 */
+#define B200IDA_ST_BAD_T (-8)         /* IdaError::BadTimeValue from get_solution, src/lib.rs:1286-1292 */
+
+typedef struct b200ida_ensemble b200ida_ensemble; /* opaque */
+
+/* Ida::new(problem, yy0, yp0, TolControlSV::new(rtol, atol))  -- src/lib.rs:278-283, src/tol_control.rs:59-66.
+ *   problem  B200IDA_PROBLEM_*            n       system size (3 for Roberts/Lorenz, M*M for heat)
+ *   batch    number of instances          nparams rows of `params`
+ *   params   SoA [nparams][batch]         yy0,yp0 SoA [n][batch]       atol host array [n]
+ *   mem      where params/yy0/yp0 live    device  CUDA device ordinal
+ * tn starts at 0 as in the reference (src/ida_nls.rs:90); there is no t0 argument. */
+int b200ida_create(b200ida_ensemble** out, int problem, int n, int64_t batch, int nparams, const double* params,
+                   const double* yy0, const double* yp0, double rtol, const double* atol, int mem, int device,
+                   void* stream);
+int b200ida_destroy(b200ida_ensemble* e);
+
+/* Re-initialise every instance to t = 0 with new initial conditions (and new parameters when `params`
+ * is non-NULL), keeping the allocation: the ensemble analogue of constructing a fresh Ida::new
+ * (src/lib.rs:278-405) -- all counters, phi, psi.. are reset. */
+int b200ida_reinit(b200ida_ensemble* e, const double* params, const double* yy0, const double* yp0, int mem);
+
+/* Ida::solve(tout, &mut tret, IdaTask::Normal) for every instance -- src/impl_solve.rs:69-376.
+ * One kernel launch; returns after enqueueing (device outputs) or after copying `status` back (host).
+ *   status [out, may be NULL]  [batch] B200IDA_ST_*, in memory space `mem`. */
+int b200ida_solve(b200ida_ensemble* e, double tout, int itask, int32_t* status, int mem);
+
+/* The same, for a whole ladder of output times in ONE launch: equivalent to calling b200ida_solve for
+ * touts[0], touts[1], ... in order (h0 depends on the first tout, mxstep is per call), but each instance
+ * moves on to its next tout as soon as it reaches the previous one, which removes the per-call
+ * reconvergence of slow and fast instances.
+ *   yy_traj [out, may be NULL]  SoA [ntout][n][batch] interpolated y(tout_k)  (get_solution, src/lib.rs:1274-1343)
+ *   status  [out, may be NULL]  [ntout][batch] */
+int b200ida_solve_ladder(b200ida_ensemble* e, const double* touts /* host */, int ntout, int itask, double* yy_traj,
+                         int32_t* status, int mem);
+
+/* get_yy / get_yp (src/ida_io.rs:11-19) and the tret of the last solve; SoA [n][batch] / [batch]; NULL skips. */
+int b200ida_get_state(b200ida_ensemble* e, double* yy, double* yp, double* tret, int mem);
+
+/* Statistics, [batch] each, NULL skips.  Names follow src/ida_io.rs:
+ *   nst get_num_steps :58   nre get_num_res_evals :64   nje get_num_jac_evals :79
+ *   nni get_num_nonlin_solv_iters :84   netf get_num_err_test_fails :74
+ *   ncfn get_num_nonlin_solv_conv_fails :104   nsetups get_num_lin_solv_setups :69
+ *   nattempts = step attempts (one data_trace frame each, src/lib.rs:635-639). */
+int b200ida_get_counters(b200ida_ensemble* e, int64_t* nst, int64_t* nre, int64_t* nje, int64_t* nni, int64_t* netf,
+                         int64_t* ncfn, int64_t* nsetups, int64_t* nattempts, int mem);
+
+/* get_last_order :22, get_current_order :27, get_last_step :38, get_current_step :43,
+ * get_current_time :48, get_actual_init_step :32 (src/ida_io.rs); [batch] each, NULL skips. */
+int b200ida_get_step_info(b200ida_ensemble* e, int32_t* kused, int32_t* kcur, double* hused, double* hcur,
+                          double* tcur, double* h0u, int mem);
+
+/* wait for everything enqueued on the ensemble's stream */
+int b200ida_sync(b200ida_ensemble* e);
+
+/* =====================================================================================================
+ * Measurement helpers (used by bench.py for the FP64 roofline denominator; not part of the drop-in).
+ * ===================================================================================================== */
+/* Runs a register-resident FP64 loop (kind 0 = DFMA, 1 = DADD, 2 = DMUL) and returns its rate in
+ * G instructions/s per GPU (thread-level operations: one DFMA counts 1). */
+int b200ida_fp64_issue_rate(int kind, int device, double* ginstr_per_s);
+
+/* out[i] = det_pow(x[i], y[i]) on the device: the glibc-2.39-compatible pow the engine uses wherever the
+ * reference calls f64::powf (src/impl_complete_step.rs:128-132, src/lib.rs:1163-1169, src/ida_nls.rs:249-253).
+ * Exposed so tests can prove device pow == host libm pow bit-for-bit. */
+int b200ida_detpow_batched(const double* x, const double* y, double* out, int64_t n, int mem, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200IDA_H */

@@ -1,0 +1,21 @@
+"""rust_ida_b200 -- B200-native batched IDA engine: the data-parallel hot path of jondo2010/rust-ida
+(per-step BDF/Newton loop over ensembles of independent DAE instances) as hand-written sm_100a CUDA
+behind a C ABI (include/b200ida.h), with a host-side mirror of the reference's interfaces:
+
+    linear.Dense / LSolverType / LUFactFail   <- crates/linear (LSolver trait, Dense LU)
+    linear.norm_wrms                          <- src/norm_rms.rs, crates/nonlinear/src/norm_wrms.rs
+    tol_control.TolControlSV / TolControlSS   <- src/tol_control.rs
+    problems.Roberts / Lorenz63               <- src/sample_problems, tests/lorenz63.rs
+    Ida / IdaTask / IdaSolveStatus            <- src/lib.rs, src/impl_solve.rs, src/ida_io.rs
+
+No CPU fallback: compute calls raise if libb200ida.so or a CUDA device is missing.
+"""
+from . import _lib
+from ._lib import B200IdaError, build, device_count
+from .ida import Ida, IdaSolveStatus, IdaTask
+from .linear import Dense, LSolverType, LUFactFail, norm_wrms
+from .problems import Lorenz63, Roberts
+from .tol_control import TolControlSS, TolControlSV
+
+__all__ = ["Ida", "IdaTask", "IdaSolveStatus", "Dense", "LSolverType", "LUFactFail", "norm_wrms", "Roberts",
+           "Lorenz63", "TolControlSV", "TolControlSS", "B200IdaError", "build", "device_count"]

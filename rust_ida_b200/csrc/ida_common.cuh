@@ -1,0 +1,71 @@
+// ida_common.cuh -- constants, state layout and small helpers shared by the ensemble-IDA kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/b200ida.h"
+
+namespace b200ida {
+
+// ---- algorithm constants: src/constants.rs:4-31 ; RATEMAX src/ida_nls.rs:15 ---------------------------
+constexpr int MXORDP1 = 6;
+constexpr int MAXORD = 5;
+constexpr int MXSTEP = 500;
+constexpr int MXNCF = 10;
+constexpr int MXNEF = 10;
+constexpr int MAXNLSIT = 4;
+constexpr double EPCON = 0.33;
+constexpr double XRATE = 0.25;
+constexpr double RATEMAX = 0.9;
+constexpr double HMAX_INV = 0.0;
+constexpr double DBL_EPS = 2.220446049250313e-16;
+
+constexpr int MAX_ATOL = 256;   // largest n any kernel supports
+constexpr int MAX_TOUTS = 64;   // ladder length per launch
+
+// ---- per-instance persistent state in HBM, structure-of-arrays over the ensemble -----------------------
+// doubles: dstate[field][batch], ints: istate[field][batch].  Field offsets for system size n:
+struct Layout {
+    int n;
+    __host__ __device__ constexpr explicit Layout(int n_) : n(n_) {}
+    // doubles
+    __host__ __device__ constexpr int phi(int j, int i) const { return j * n + i; }  // [6][n]
+    __host__ __device__ constexpr int psi(int j) const { return 6 * n + j; }
+    __host__ __device__ constexpr int alpha(int j) const { return 6 * n + 6 + j; }
+    __host__ __device__ constexpr int beta(int j) const { return 6 * n + 12 + j; }
+    __host__ __device__ constexpr int sigma(int j) const { return 6 * n + 18 + j; }
+    __host__ __device__ constexpr int gamma(int j) const { return 6 * n + 24 + j; }
+    __host__ __device__ constexpr int ee(int i) const { return 6 * n + 30 + i; }
+    __host__ __device__ constexpr int ewt(int i) const { return 7 * n + 30 + i; }
+    __host__ __device__ constexpr int yy(int i) const { return 8 * n + 30 + i; }
+    __host__ __device__ constexpr int yp(int i) const { return 9 * n + 30 + i; }
+    __host__ __device__ constexpr int scal(int s) const { return 10 * n + 30 + s; }
+    __host__ __device__ constexpr int J(int i, int j) const { return 10 * n + 30 + NSCAL + j * n + i; }  // col-major
+    __host__ __device__ constexpr int ndouble() const { return 10 * n + 30 + NSCAL + n * n; }
+    // ints
+    __host__ __device__ constexpr int piv(int i) const { return NINT + i; }
+    __host__ __device__ constexpr int nint() const { return NINT + n; }
+
+    enum Scal { HH, HUSED, RR, CJ, CJOLD, CJLAST, CJRATIO, SS, TOLDEL, EPS_NEWT, TN, TRETLAST, H0U, TOLSF, TRET, NSCAL };
+    enum Int { KK, KUSED, KNEW, PHASE, NS, SETUP_DONE, JCUR, NST, NRE, NJE, NNI, NETF, NCFN, NSETUPS, NLSCF, NATT, NINT };
+};
+
+struct TolParams {   // TolControlSV (src/tol_control.rs:51-83), passed by value to kernels
+    double rtol;
+    double atol[MAX_ATOL];
+};
+
+struct LadderParams {
+    int ntout;
+    double touts[MAX_TOUTS];
+};
+
+// select a[k] from a 6-entry register array without dynamic indexing
+__device__ __forceinline__ double pick6(const double (&a)[MXORDP1], int k) {
+    double v = a[0];
+#pragma unroll
+    for (int j = 1; j < MXORDP1; ++j) v = (k == j) ? a[j] : v;
+    return v;
+}
+
+}  // namespace b200ida

@@ -1,0 +1,398 @@
+// ida_engine.cu -- C ABI (include/b200ida.h, "Level 2") of the ensemble IDA engine and its kernels.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false  (no FMA contraction:
+// the reference's Rust arithmetic is un-fused; see DESIGN.md "Arithmetic policy").
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+
+#include "host_util.h"
+#include "ida_common.cuh"
+#include "ida_thread.cuh"
+#include "problems.cuh"
+
+namespace b200ida {
+
+char* last_error_buf() {
+    static thread_local char buf[512] = "";
+    return buf;
+}
+
+// ---- kernels -----------------------------------------------------------------------------------------
+
+// Thread-per-instance solve over a ladder of output times (ida_thread.cuh).
+template <class P>
+__global__ void __launch_bounds__(128)
+ida_solve_thread_kernel(double* __restrict__ ds, int* __restrict__ is, const double* __restrict__ params, int64_t B,
+                        TolN<P::N> tol, LadderParams lad, double* __restrict__ yy_traj, int32_t* __restrict__ status) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    IdaThread<P> s;
+    s.prob.load(params, B, b);
+    s.load(ds, is, B, b);
+    s.solve_ladder(lad, tol, yy_traj, status, B, b);
+    s.store(ds, is, B, b);
+}
+
+// Ida::new (src/lib.rs:278-405): phi[0] = yy0, phi[1] = yp0, yy = yy0, yp = yp0 (src/ida_nls.rs:82-83),
+// tolsf = 1, everything else 0 (the state buffers are zeroed before this kernel).
+__global__ void ida_init_kernel(double* __restrict__ ds, const double* __restrict__ yy0, const double* __restrict__ yp0,
+                                int n, int64_t B) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const Layout lay(n);
+    for (int i = 0; i < n; ++i) {
+        const double y = yy0[(int64_t)i * B + b], yp = yp0[(int64_t)i * B + b];
+        ds[(int64_t)lay.phi(0, i) * B + b] = y;
+        ds[(int64_t)lay.phi(1, i) * B + b] = yp;
+        ds[(int64_t)lay.yy(i) * B + b] = y;
+        ds[(int64_t)lay.yp(i) * B + b] = yp;
+    }
+    ds[(int64_t)lay.scal(Layout::TOLSF) * B + b] = 1.0;
+}
+
+__global__ void widen_i32_kernel(const int* __restrict__ src, int64_t* __restrict__ dst, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = (int64_t)src[i];
+}
+
+__global__ void detpow_kernel(const double* __restrict__ x, const double* __restrict__ y, double* __restrict__ out,
+                              int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = detpow::det_pow(x[i], y[i]);
+}
+
+// FP64 issue-rate microbenchmark: 8 independent dependency chains per thread, register resident.
+template <int KIND>
+__global__ void __launch_bounds__(256) fp64_rate_kernel(double* out, int iters, double seed) {
+    double a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = seed + (double)(threadIdx.x + i) * 1e-9;
+    const double m = 1.0000000001, c = 1e-12;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (KIND == 0) a[i] = __fma_rn(a[i], m, c);
+            else if (KIND == 1) a[i] = __dadd_rn(a[i], c);
+            else a[i] = __dmul_rn(a[i], m);
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += a[i];
+    if (s == 123.456) out[0] = s;  // keep the loop alive
+}
+
+}  // namespace b200ida
+
+using namespace b200ida;
+
+// ---- the opaque handle ---------------------------------------------------------------------------------
+struct b200ida_ensemble {
+    int problem = 0, n = 0, nparams = 0, device = 0;
+    int64_t B = 0;
+    double rtol = 0.0;
+    double atol[MAX_ATOL];
+    cudaStream_t stream = nullptr;
+    double* dstate = nullptr;  // [ndouble][B]
+    int* istate = nullptr;     // [nint][B]
+    double* params = nullptr;  // [nparams][B]
+};
+
+static int check_mem(int mem) { return (mem == B200IDA_MEM_DEVICE || mem == B200IDA_MEM_HOST) ? 0 : -1; }
+
+extern "C" {
+
+const char* b200ida_last_error(void) { return last_error_buf(); }
+int b200ida_version(void) { return B200IDA_VERSION; }
+int b200ida_device_count(void) {
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return c;
+}
+
+int b200ida_reinit(b200ida_ensemble* e, const double* params, const double* yy0, const double* yp0, int mem) {
+    if (!e || !yy0 || !yp0 || check_mem(mem)) return set_error(B200IDA_ERR_ARG, "b200ida_reinit: bad argument");
+    B200_CUDA_TRY(cudaSetDevice(e->device));
+    const Layout lay(e->n);
+    const int64_t batch = e->B;
+    const int n = e->n;
+    const size_t nd = (size_t)lay.ndouble() * batch, ni = (size_t)lay.nint() * batch;
+    cudaStream_t st = e->stream;
+    const cudaMemcpyKind kind = (mem == B200IDA_MEM_HOST) ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    DevBuf y0b, yp0b;
+    const double *dy0 = yy0, *dyp0 = yp0;
+    const size_t vbytes = (size_t)n * batch * sizeof(double);
+    B200_CUDA_TRY(cudaMemsetAsync(e->dstate, 0, nd * sizeof(double), st));
+    B200_CUDA_TRY(cudaMemsetAsync(e->istate, 0, ni * sizeof(int), st));
+    if (params) B200_CUDA_TRY(cudaMemcpyAsync(e->params, params, (size_t)e->nparams * batch * sizeof(double), kind, st));
+    if (mem == B200IDA_MEM_HOST) {
+        B200_CUDA_TRY(y0b.alloc(vbytes));
+        B200_CUDA_TRY(yp0b.alloc(vbytes));
+        B200_CUDA_TRY(cudaMemcpyAsync(y0b.p, yy0, vbytes, kind, st));
+        B200_CUDA_TRY(cudaMemcpyAsync(yp0b.p, yp0, vbytes, kind, st));
+        dy0 = y0b.as<double>();
+        dyp0 = yp0b.as<double>();
+    }
+    const int tb = 256;
+    ida_init_kernel<<<(unsigned)((batch + tb - 1) / tb), tb, 0, st>>>(e->dstate, dy0, dyp0, n, batch);
+    B200_CUDA_TRY(cudaGetLastError());
+    if (mem == B200IDA_MEM_HOST) B200_CUDA_TRY(cudaStreamSynchronize(st));  // scratch is freed on return
+    return B200IDA_OK;
+}
+
+int b200ida_create(b200ida_ensemble** out, int problem, int n, int64_t batch, int nparams, const double* params,
+                   const double* yy0, const double* yp0, double rtol, const double* atol, int mem, int device,
+                   void* stream) {
+    if (!out || !params || !yy0 || !yp0 || !atol || batch <= 0 || check_mem(mem))
+        return set_error(B200IDA_ERR_ARG, "b200ida_create: null pointer, batch <= 0 or bad mem");
+    int need_n = 0, need_p = 0;
+    switch (problem) {
+    case B200IDA_PROBLEM_ROBERTS: need_n = Roberts::N; need_p = Roberts::NP; break;
+    case B200IDA_PROBLEM_LORENZ63: need_n = Lorenz63::N; need_p = Lorenz63::NP; break;
+    default: return set_error(B200IDA_ERR_UNSUPPORTED, "b200ida_create: problem %d has no kernel", problem);
+    }
+    if (n != need_n || nparams != need_p)
+        return set_error(B200IDA_ERR_ARG, "b200ida_create: problem %d needs n=%d nparams=%d (got %d, %d)", problem,
+                         need_n, need_p, n, nparams);
+    if (b200ida_device_count() <= device || device < 0)
+        return set_error(B200IDA_ERR_NO_DEVICE, "b200ida_create: CUDA device %d not available", device);
+    B200_CUDA_TRY(cudaSetDevice(device));
+
+    b200ida_ensemble* e = new (std::nothrow) b200ida_ensemble();
+    if (!e) return set_error(B200IDA_ERR_ARG, "out of host memory");
+    e->problem = problem;
+    e->n = n;
+    e->nparams = nparams;
+    e->device = device;
+    e->B = batch;
+    e->rtol = rtol;
+    memset(e->atol, 0, sizeof(e->atol));
+    memcpy(e->atol, atol, sizeof(double) * n);
+    e->stream = static_cast<cudaStream_t>(stream);
+    const Layout lay(n);
+    const size_t nd = (size_t)lay.ndouble() * batch, ni = (size_t)lay.nint() * batch;
+    cudaError_t err;
+    if ((err = cudaMalloc(&e->dstate, nd * sizeof(double))) != cudaSuccess ||
+        (err = cudaMalloc(&e->istate, ni * sizeof(int))) != cudaSuccess ||
+        (err = cudaMalloc(&e->params, (size_t)nparams * batch * sizeof(double))) != cudaSuccess) {
+        b200ida_destroy(e);
+        return set_error(B200IDA_ERR_CUDA, "b200ida_create: cudaMalloc -> %s", cudaGetErrorString(err));
+    }
+    int rc = b200ida_reinit(e, params, yy0, yp0, mem);
+    if (rc != B200IDA_OK) {
+        b200ida_destroy(e);
+        return rc;
+    }
+    *out = e;
+    return B200IDA_OK;
+}
+
+int b200ida_destroy(b200ida_ensemble* e) {
+    if (!e) return B200IDA_OK;
+    cudaSetDevice(e->device);
+    if (e->dstate) cudaFree(e->dstate);
+    if (e->istate) cudaFree(e->istate);
+    if (e->params) cudaFree(e->params);
+    delete e;
+    return B200IDA_OK;
+}
+
+int b200ida_solve_ladder(b200ida_ensemble* e, const double* touts, int ntout, int itask, double* yy_traj,
+                         int32_t* status, int mem) {
+    if (!e || !touts || ntout < 1 || ntout > MAX_TOUTS || check_mem(mem))
+        return set_error(B200IDA_ERR_ARG, "b200ida_solve_ladder: bad argument (1 <= ntout <= %d)", MAX_TOUTS);
+    if (itask != B200IDA_TASK_NORMAL)
+        return set_error(B200IDA_ERR_UNSUPPORTED, "b200ida_solve: only IdaTask::Normal is on the device path");
+    B200_CUDA_TRY(cudaSetDevice(e->device));
+    LadderParams lad;
+    lad.ntout = ntout;
+    for (int i = 0; i < MAX_TOUTS; ++i) lad.touts[i] = i < ntout ? touts[i] : 0.0;
+
+    DevBuf trajb, statb;
+    double* d_traj = yy_traj;
+    int32_t* d_stat = status;
+    const size_t traj_bytes = (size_t)ntout * e->n * e->B * sizeof(double);
+    const size_t stat_bytes = (size_t)ntout * e->B * sizeof(int32_t);
+    if (mem == B200IDA_MEM_HOST) {
+        if (yy_traj) {
+            B200_CUDA_TRY(trajb.alloc(traj_bytes));
+            d_traj = trajb.as<double>();
+        }
+        if (status) {
+            B200_CUDA_TRY(statb.alloc(stat_bytes));
+            d_stat = statb.as<int32_t>();
+        }
+    }
+    const int tb = 128;
+    const unsigned grid = (unsigned)((e->B + tb - 1) / tb);
+    switch (e->problem) {
+    case B200IDA_PROBLEM_ROBERTS: {
+        TolN<3> tol;
+        tol.rtol = e->rtol;
+        for (int i = 0; i < 3; ++i) tol.atol[i] = e->atol[i];
+        ida_solve_thread_kernel<Roberts><<<grid, tb, 0, e->stream>>>(e->dstate, e->istate, e->params, e->B, tol, lad,
+                                                                     d_traj, d_stat);
+        break;
+    }
+    case B200IDA_PROBLEM_LORENZ63: {
+        TolN<3> tol;
+        tol.rtol = e->rtol;
+        for (int i = 0; i < 3; ++i) tol.atol[i] = e->atol[i];
+        ida_solve_thread_kernel<Lorenz63><<<grid, tb, 0, e->stream>>>(e->dstate, e->istate, e->params, e->B, tol, lad,
+                                                                      d_traj, d_stat);
+        break;
+    }
+    default: return set_error(B200IDA_ERR_UNSUPPORTED, "no kernel for problem %d", e->problem);
+    }
+    B200_CUDA_TRY(cudaGetLastError());
+    if (mem == B200IDA_MEM_HOST) {
+        if (yy_traj) B200_CUDA_TRY(cudaMemcpyAsync(yy_traj, d_traj, traj_bytes, cudaMemcpyDeviceToHost, e->stream));
+        if (status) B200_CUDA_TRY(cudaMemcpyAsync(status, d_stat, stat_bytes, cudaMemcpyDeviceToHost, e->stream));
+        B200_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    }
+    return B200IDA_OK;
+}
+
+int b200ida_solve(b200ida_ensemble* e, double tout, int itask, int32_t* status, int mem) {
+    return b200ida_solve_ladder(e, &tout, 1, itask, nullptr, status, mem);
+}
+
+static int copy_out(b200ida_ensemble* e, void* dst, const void* src, size_t bytes, int mem) {
+    if (!dst) return B200IDA_OK;
+    B200_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, mem == B200IDA_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice,
+                                  e->stream));
+    return B200IDA_OK;
+}
+
+int b200ida_get_state(b200ida_ensemble* e, double* yy, double* yp, double* tret, int mem) {
+    if (!e || check_mem(mem)) return set_error(B200IDA_ERR_ARG, "b200ida_get_state: bad argument");
+    B200_CUDA_TRY(cudaSetDevice(e->device));
+    const Layout lay(e->n);
+    int rc;
+    if ((rc = copy_out(e, yy, e->dstate + (size_t)lay.yy(0) * e->B, (size_t)e->n * e->B * sizeof(double), mem))) return rc;
+    if ((rc = copy_out(e, yp, e->dstate + (size_t)lay.yp(0) * e->B, (size_t)e->n * e->B * sizeof(double), mem))) return rc;
+    if ((rc = copy_out(e, tret, e->dstate + (size_t)lay.scal(Layout::TRET) * e->B, (size_t)e->B * sizeof(double), mem))) return rc;
+    if (mem == B200IDA_MEM_HOST) B200_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return B200IDA_OK;
+}
+
+static int widen_out(b200ida_ensemble* e, int64_t* dst, int field, int mem) {
+    if (!dst) return B200IDA_OK;
+    const int* src = e->istate + (size_t)field * e->B;
+    const int tb = 256;
+    const unsigned grid = (unsigned)((e->B + tb - 1) / tb);
+    if (mem == B200IDA_MEM_DEVICE) {
+        widen_i32_kernel<<<grid, tb, 0, e->stream>>>(src, dst, e->B);
+        B200_CUDA_TRY(cudaGetLastError());
+        return B200IDA_OK;
+    }
+    DevBuf tmp;
+    B200_CUDA_TRY(tmp.alloc((size_t)e->B * sizeof(int64_t)));
+    widen_i32_kernel<<<grid, tb, 0, e->stream>>>(src, tmp.as<int64_t>(), e->B);
+    B200_CUDA_TRY(cudaGetLastError());
+    B200_CUDA_TRY(cudaMemcpyAsync(dst, tmp.p, (size_t)e->B * sizeof(int64_t), cudaMemcpyDeviceToHost, e->stream));
+    B200_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return B200IDA_OK;
+}
+
+int b200ida_get_counters(b200ida_ensemble* e, int64_t* nst, int64_t* nre, int64_t* nje, int64_t* nni, int64_t* netf,
+                         int64_t* ncfn, int64_t* nsetups, int64_t* nattempts, int mem) {
+    if (!e || check_mem(mem)) return set_error(B200IDA_ERR_ARG, "b200ida_get_counters: bad argument");
+    B200_CUDA_TRY(cudaSetDevice(e->device));
+    int rc;
+    if ((rc = widen_out(e, nst, Layout::NST, mem))) return rc;
+    if ((rc = widen_out(e, nre, Layout::NRE, mem))) return rc;
+    if ((rc = widen_out(e, nje, Layout::NJE, mem))) return rc;
+    if ((rc = widen_out(e, nni, Layout::NNI, mem))) return rc;
+    if ((rc = widen_out(e, netf, Layout::NETF, mem))) return rc;
+    if ((rc = widen_out(e, ncfn, Layout::NCFN, mem))) return rc;
+    if ((rc = widen_out(e, nsetups, Layout::NSETUPS, mem))) return rc;
+    if ((rc = widen_out(e, nattempts, Layout::NATT, mem))) return rc;
+    return B200IDA_OK;
+}
+
+int b200ida_get_step_info(b200ida_ensemble* e, int32_t* kused, int32_t* kcur, double* hused, double* hcur,
+                          double* tcur, double* h0u, int mem) {
+    if (!e || check_mem(mem)) return set_error(B200IDA_ERR_ARG, "b200ida_get_step_info: bad argument");
+    B200_CUDA_TRY(cudaSetDevice(e->device));
+    const Layout lay(e->n);
+    const size_t B = (size_t)e->B;
+    int rc;
+    if ((rc = copy_out(e, kused, e->istate + (size_t)Layout::KUSED * B, B * sizeof(int32_t), mem))) return rc;
+    if ((rc = copy_out(e, kcur, e->istate + (size_t)Layout::KK * B, B * sizeof(int32_t), mem))) return rc;
+    if ((rc = copy_out(e, hused, e->dstate + (size_t)lay.scal(Layout::HUSED) * B, B * sizeof(double), mem))) return rc;
+    if ((rc = copy_out(e, hcur, e->dstate + (size_t)lay.scal(Layout::HH) * B, B * sizeof(double), mem))) return rc;
+    if ((rc = copy_out(e, tcur, e->dstate + (size_t)lay.scal(Layout::TN) * B, B * sizeof(double), mem))) return rc;
+    if ((rc = copy_out(e, h0u, e->dstate + (size_t)lay.scal(Layout::H0U) * B, B * sizeof(double), mem))) return rc;
+    if (mem == B200IDA_MEM_HOST) B200_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return B200IDA_OK;
+}
+
+int b200ida_sync(b200ida_ensemble* e) {
+    if (!e) return set_error(B200IDA_ERR_ARG, "b200ida_sync: null handle");
+    B200_CUDA_TRY(cudaSetDevice(e->device));
+    B200_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return B200IDA_OK;
+}
+
+int b200ida_detpow_batched(const double* x, const double* y, double* out, int64_t n, int mem, void* stream) {
+    if (!x || !y || !out || n < 1 || check_mem(mem)) return set_error(B200IDA_ERR_ARG, "b200ida_detpow_batched: bad argument");
+    if (b200ida_device_count() < 1) return set_error(B200IDA_ERR_NO_DEVICE, "b200ida_detpow_batched: no CUDA device");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    if (mem == B200IDA_MEM_DEVICE) {
+        detpow_kernel<<<grid, 256, 0, st>>>(x, y, out, n);
+        B200_CUDA_TRY(cudaGetLastError());
+        return B200IDA_OK;
+    }
+    DevBuf dx, dy, dout;
+    const size_t bytes = (size_t)n * sizeof(double);
+    B200_CUDA_TRY(dx.alloc(bytes));
+    B200_CUDA_TRY(dy.alloc(bytes));
+    B200_CUDA_TRY(dout.alloc(bytes));
+    B200_CUDA_TRY(cudaMemcpyAsync(dx.p, x, bytes, cudaMemcpyHostToDevice, st));
+    B200_CUDA_TRY(cudaMemcpyAsync(dy.p, y, bytes, cudaMemcpyHostToDevice, st));
+    detpow_kernel<<<grid, 256, 0, st>>>(dx.as<double>(), dy.as<double>(), dout.as<double>(), n);
+    B200_CUDA_TRY(cudaGetLastError());
+    B200_CUDA_TRY(cudaMemcpyAsync(out, dout.p, bytes, cudaMemcpyDeviceToHost, st));
+    B200_CUDA_TRY(cudaStreamSynchronize(st));
+    return B200IDA_OK;
+}
+
+int b200ida_fp64_issue_rate(int kind, int device, double* ginstr_per_s) {
+    if (!ginstr_per_s || kind < 0 || kind > 2) return set_error(B200IDA_ERR_ARG, "b200ida_fp64_issue_rate: bad argument");
+    if (b200ida_device_count() <= device) return set_error(B200IDA_ERR_NO_DEVICE, "no CUDA device %d", device);
+    B200_CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    B200_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, tb = 256, iters = 20000;
+    DevBuf out;
+    B200_CUDA_TRY(out.alloc(8));
+    cudaEvent_t e0, e1;
+    B200_CUDA_TRY(cudaEventCreate(&e0));
+    B200_CUDA_TRY(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        B200_CUDA_TRY(cudaEventRecord(e0));
+        if (kind == 0) fp64_rate_kernel<0><<<blocks, tb>>>(out.as<double>(), iters, 1.0);
+        else if (kind == 1) fp64_rate_kernel<1><<<blocks, tb>>>(out.as<double>(), iters, 1.0);
+        else fp64_rate_kernel<2><<<blocks, tb>>>(out.as<double>(), iters, 1.0);
+        B200_CUDA_TRY(cudaEventRecord(e1));
+        B200_CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        B200_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    const double ops = (double)blocks * tb * (double)iters * 8.0;
+    *ginstr_per_s = ops / ((double)best * 1e-3) * 1e-9;
+    return B200IDA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,839 @@
+// ida_thread.cuh -- thread-per-instance ensemble IDA for small compile-time n (Roberts, Lorenz: n = 3).
+//
+// One CUDA thread integrates one DAE instance; the whole `Ida::solve` loop of the reference
+// (src/impl_solve.rs:69-376) runs on the device.  All per-instance state (phi, psi..gamma, ee, ewt,
+// yy, yp, the LU factors and pivots, ~20 scalars, counters) is loaded once from the SoA arrays in
+// HBM into registers, integrated, and stored back once: HBM traffic is ~1.5 KB per instance per
+// launch, three orders of magnitude below what the FP64 pipe needs, so the kernel is FP64-issue-bound
+// by design ("Kernels").  Every small array is indexed with compile-time indices under
+// predicates (`if (j <= kk)`) so nothing lands in local memory.
+//
+// Divergence: lanes differ in step count, retries and Newton iterations.  The solve loop is
+// FLATTENED: one trip of the single `while` = one step ATTEMPT of every live lane, whatever output
+// time (ladder rung) or retry that lane is on, so a warp's time is max-over-lanes of total attempts,
+// not a sum of per-step or per-rung maxima.
+//
+// Arithmetic is written operation-for-operation like the reference (file:line on each routine), built
+// with -fmad=false: + - * / sqrt are IEEE correctly rounded and un-fused, pow is detpow.h.
+#pragma once
+#include "detpow.h"
+#include "ida_common.cuh"
+
+namespace b200ida {
+
+template <int N>
+struct TolN {
+    double rtol;
+    double atol[N];
+};
+
+template <class P>
+struct IdaThread {
+    static constexpr int N = P::N;
+    using L = Layout;
+
+    // ---- persistent state (src/lib.rs:89-244, src/ida_nls.rs:20-60, src/ida_ls.rs:15-106,
+    //      newton.rs:14-32, dense.rs:13-20) ------------------------------------------------------------
+    double phi[MXORDP1][N];
+    double psi[MXORDP1], alpha[MXORDP1], beta[MXORDP1], sigma[MXORDP1], gamma[MXORDP1];
+    double ee[N], ewt[N], yy[N], yp[N];
+    double J[N][N];
+    int piv[N];
+    double hh, hused, rr, cj, cjold, cjlast, cjratio, ss, toldel, eps_newt, tn, tretlast, h0u, tolsf, tret;
+    int kk, kused, knew, phase, ns, setup_done, jcur;
+    int nst, nre, nje, nni, netf, ncfn, nsetups, nlscf, natt;
+    // ---- scratch ------------------------------------------------------------------------------------
+    double yypredict[N], yppredict[N], delta[N], oldnrm;
+    P prob;
+
+    // ---- HBM <-> registers ---------------------------------------------------------------------------
+    __device__ __forceinline__ void load(const double* __restrict__ ds, const int* __restrict__ is, int64_t B, int64_t b) {
+        constexpr Layout lay(N);
+#pragma unroll
+        for (int j = 0; j < MXORDP1; ++j) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) phi[j][i] = ds[(int64_t)lay.phi(j, i) * B + b];
+            psi[j] = ds[(int64_t)lay.psi(j) * B + b];
+            alpha[j] = ds[(int64_t)lay.alpha(j) * B + b];
+            beta[j] = ds[(int64_t)lay.beta(j) * B + b];
+            sigma[j] = ds[(int64_t)lay.sigma(j) * B + b];
+            gamma[j] = ds[(int64_t)lay.gamma(j) * B + b];
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            ee[i] = ds[(int64_t)lay.ee(i) * B + b];
+            ewt[i] = ds[(int64_t)lay.ewt(i) * B + b];
+            yy[i] = ds[(int64_t)lay.yy(i) * B + b];
+            yp[i] = ds[(int64_t)lay.yp(i) * B + b];
+            piv[i] = is[(int64_t)lay.piv(i) * B + b];
+#pragma unroll
+            for (int j = 0; j < N; ++j) J[i][j] = ds[(int64_t)lay.J(i, j) * B + b];
+        }
+#define LD_S(f, F) f = ds[(int64_t)lay.scal(L::F) * B + b];
+        LD_S(hh, HH) LD_S(hused, HUSED) LD_S(rr, RR) LD_S(cj, CJ) LD_S(cjold, CJOLD) LD_S(cjlast, CJLAST)
+        LD_S(cjratio, CJRATIO) LD_S(ss, SS) LD_S(toldel, TOLDEL) LD_S(eps_newt, EPS_NEWT) LD_S(tn, TN)
+        LD_S(tretlast, TRETLAST) LD_S(h0u, H0U) LD_S(tolsf, TOLSF) LD_S(tret, TRET)
+#undef LD_S
+#define LD_I(f, F) f = is[(int64_t)L::F * B + b];
+        LD_I(kk, KK) LD_I(kused, KUSED) LD_I(knew, KNEW) LD_I(phase, PHASE) LD_I(ns, NS) LD_I(setup_done, SETUP_DONE)
+        LD_I(jcur, JCUR) LD_I(nst, NST) LD_I(nre, NRE) LD_I(nje, NJE) LD_I(nni, NNI) LD_I(netf, NETF)
+        LD_I(ncfn, NCFN) LD_I(nsetups, NSETUPS) LD_I(nlscf, NLSCF) LD_I(natt, NATT)
+#undef LD_I
+    }
+
+    __device__ __forceinline__ void store(double* __restrict__ ds, int* __restrict__ is, int64_t B, int64_t b) const {
+        constexpr Layout lay(N);
+#pragma unroll
+        for (int j = 0; j < MXORDP1; ++j) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) ds[(int64_t)lay.phi(j, i) * B + b] = phi[j][i];
+            ds[(int64_t)lay.psi(j) * B + b] = psi[j];
+            ds[(int64_t)lay.alpha(j) * B + b] = alpha[j];
+            ds[(int64_t)lay.beta(j) * B + b] = beta[j];
+            ds[(int64_t)lay.sigma(j) * B + b] = sigma[j];
+            ds[(int64_t)lay.gamma(j) * B + b] = gamma[j];
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            ds[(int64_t)lay.ee(i) * B + b] = ee[i];
+            ds[(int64_t)lay.ewt(i) * B + b] = ewt[i];
+            ds[(int64_t)lay.yy(i) * B + b] = yy[i];
+            ds[(int64_t)lay.yp(i) * B + b] = yp[i];
+            is[(int64_t)lay.piv(i) * B + b] = piv[i];
+#pragma unroll
+            for (int j = 0; j < N; ++j) ds[(int64_t)lay.J(i, j) * B + b] = J[i][j];
+        }
+#define ST_S(f, F) ds[(int64_t)lay.scal(L::F) * B + b] = f;
+        ST_S(hh, HH) ST_S(hused, HUSED) ST_S(rr, RR) ST_S(cj, CJ) ST_S(cjold, CJOLD) ST_S(cjlast, CJLAST)
+        ST_S(cjratio, CJRATIO) ST_S(ss, SS) ST_S(toldel, TOLDEL) ST_S(eps_newt, EPS_NEWT) ST_S(tn, TN)
+        ST_S(tretlast, TRETLAST) ST_S(h0u, H0U) ST_S(tolsf, TOLSF) ST_S(tret, TRET)
+#undef ST_S
+#define ST_I(f, F) is[(int64_t)L::F * B + b] = f;
+        ST_I(kk, KK) ST_I(kused, KUSED) ST_I(knew, KNEW) ST_I(phase, PHASE) ST_I(ns, NS) ST_I(setup_done, SETUP_DONE)
+        ST_I(jcur, JCUR) ST_I(nst, NST) ST_I(nre, NRE) ST_I(nje, NJE) ST_I(nni, NNI) ST_I(netf, NETF)
+        ST_I(ncfn, NCFN) ST_I(nsetups, NSETUPS) ST_I(nlscf, NLSCF) ST_I(natt, NATT)
+#undef ST_I
+    }
+
+    // ---- WRMS norm: src/norm_rms.rs:31-38 (ordered fold from 0) -----------------------------------------
+    __device__ __forceinline__ static double wrms(const double (&x)[N], const double (&w)[N]) {
+        double acc = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const double p = x[i] * w[i];
+            acc = acc + p * p;
+        }
+        return sqrt(acc / (double)N);
+    }
+
+    // ---- TolControlSV::ewt_set: src/tol_control.rs:71-82 -------------------------------------------------
+    __device__ __forceinline__ void ewt_set(const TolN<N>& tol) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) ewt[i] = 1.0 / (tol.rtol * fabs(phi[0][i]) + tol.atol[i]);
+    }
+
+    // ---- set_coeffs: src/lib.rs:722-782 ----------------------------------------------------------------
+    __device__ __forceinline__ double set_coeffs() {
+        if (hh != hused || kk != kused) ns = 0;
+        ns = min(ns + 1, kused + 2);
+        if (kk + 1 >= ns) {
+            beta[0] = 1.0;
+            alpha[0] = 1.0;
+            double temp1 = hh;
+            gamma[0] = 0.0;
+            sigma[0] = 1.0;
+#pragma unroll
+            for (int i = 1; i <= MAXORD; ++i) {
+                if (i <= kk) {
+                    const double temp2 = psi[i - 1];
+                    psi[i - 1] = temp1;
+                    beta[i] = beta[i - 1] * psi[i - 1] / temp2;
+                    temp1 = temp2 + hh;
+                    alpha[i] = hh / temp1;
+                    sigma[i] = (double)i * sigma[i - 1] * alpha[i];
+                    gamma[i] = gamma[i - 1] + alpha[i - 1] / hh;
+                }
+            }
+#pragma unroll
+            for (int i = 1; i <= MAXORD; ++i)
+                if (i == kk) psi[i] = temp1;
+        }
+        double alphas = 0.0, alpha0 = 0.0;
+#pragma unroll
+        for (int i = 0; i < MAXORD; ++i) {
+            if (i < kk) {
+                alphas -= 1.0 / (double)(i + 1);
+                alpha0 -= alpha[i];
+            }
+        }
+        cjlast = cj;
+        cj = -alphas / hh;
+        const double akk = pick6(alpha, kk);
+        double ck = fabs(akk + alphas - alpha0);
+        ck = fmax(ck, akk);
+#pragma unroll
+        for (int j = 1; j <= MAXORD; ++j) {
+            if (j >= ns && j <= kk) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) phi[j][i] *= beta[j];
+            }
+        }
+        // j = 0 is only reachable with ns == 0, which set_coeffs never leaves (ns >= 1)
+        return ck;
+    }
+
+    // ---- predict: src/lib.rs:894-959 -------------------------------------------------------------------
+    __device__ __forceinline__ void predict() {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            yypredict[i] = 0.0;
+            yppredict[i] = 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j <= MAXORD; ++j) {
+            if (j <= kk) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) yypredict[i] += phi[j][i];
+            }
+        }
+#pragma unroll
+        for (int j = 1; j <= MAXORD; ++j) {
+            if (j <= kk) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) yppredict[i] += gamma[j] * phi[j][i];
+            }
+        }
+    }
+
+    // ---- dense_get_rf: crates/linear/src/dense.rs:86-158 ; returns 0 or 1-based zero-pivot column -------
+    __device__ __forceinline__ int getrf() {
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            int l = k;
+            double best = fabs(J[k][k]);
+#pragma unroll
+            for (int i = k + 1; i < N; ++i) {
+                const double v = fabs(J[i][k]);
+                if (v > best) {
+                    best = v;
+                    l = i;
+                }
+            }
+            piv[k] = l;
+            if (best == 0.0) return k + 1;  // |a_lk| == 0  <=>  a_lk == 0 (NaN never wins the > test)
+#pragma unroll
+            for (int i = k + 1; i < N; ++i) {
+                if (l == i) {
+#pragma unroll
+                    for (int c = 0; c < N; ++c) {
+                        const double t = J[k][c];
+                        J[k][c] = J[i][c];
+                        J[i][c] = t;
+                    }
+                }
+            }
+            const double mult = 1.0 / J[k][k];
+#pragma unroll
+            for (int i = k + 1; i < N; ++i) J[i][k] *= mult;
+#pragma unroll
+            for (int j = k + 1; j < N; ++j) {
+                const double a_kj = J[k][j];
+                if (a_kj != 0.0) {
+#pragma unroll
+                    for (int i = k + 1; i < N; ++i) J[i][j] -= a_kj * J[i][k];
+                }
+            }
+        }
+        return 0;
+    }
+
+    // ---- dense_get_rs: crates/linear/src/dense.rs:165-206 ---------------------------------------------
+    __device__ __forceinline__ void getrs(double (&b)[N]) const {
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+#pragma unroll
+            for (int i = k + 1; i < N; ++i) {
+                if (piv[k] == i) {
+                    const double t = b[k];
+                    b[k] = b[i];
+                    b[i] = t;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < N - 1; ++k) {
+            const double bk = b[k];
+#pragma unroll
+            for (int i = k + 1; i < N; ++i) b[i] -= J[i][k] * bk;
+        }
+#pragma unroll
+        for (int k = N - 1; k >= 1; --k) {
+            b[k] /= J[k][k];
+            const double bk = b[k];
+#pragma unroll
+            for (int i = 0; i < k; ++i) b[i] -= J[i][k] * bk;
+        }
+        b[0] /= J[0][0];
+    }
+
+    // ---- IdaNLProblem::sys: src/ida_nls.rs:118-153 ------------------------------------------------------
+    __device__ __forceinline__ void nls_sys(const double (&ycor)[N], double (&res)[N]) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            yy[i] = yypredict[i] + ycor[i];
+            yp[i] = yppredict[i] + cj * ycor[i];
+        }
+        prob.res(tn, yy, yp, res);
+        nre += 1;
+    }
+
+    // ---- IdaNLProblem::setup -> IdaLProblem::setup: src/ida_nls.rs:156-187, src/ida_ls.rs:232-290 --------
+    __device__ __forceinline__ int nls_setup(const double (&res)[N]) {
+        nsetups += 1;
+        nje += 1;
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+#pragma unroll
+            for (int j = 0; j < N; ++j) J[i][j] = 0.0;
+        prob.jac(0.0, cj, yy, yp, res, J);  // tt = 0 as in src/ida_ls.rs:260-261
+        const int info = getrf();
+        if (info != 0) return info;
+        cjold = cj;
+        cjratio = 1.0;
+        ss = 20.0;
+        return 0;
+    }
+
+    // ---- IdaNLProblem::solve -> IdaLProblem::solve: src/ida_nls.rs:190-215, src/ida_ls.rs:298-455 --------
+    __device__ __forceinline__ void nls_lsolve(double (&b)[N]) const {
+        getrs(b);
+        if (cjratio != 1.0) {
+            const double f = 2.0 / (1.0 + cjratio);
+#pragma unroll
+            for (int i = 0; i < N; ++i) b[i] *= f;
+        }
+    }
+
+    // ---- IdaNLProblem::ctest: src/ida_nls.rs:218-266 ; 1 converged, 0 continue, -1 recover ----------------
+    __device__ __forceinline__ int nls_ctest(int m, const double (&del)[N], double tol) {
+        const double delnrm = wrms(del, ewt);
+        if (m == 0) {
+            oldnrm = delnrm;
+            if (delnrm <= 0.0001 * toldel) return 1;
+        } else {
+            const double base = delnrm / oldnrm;
+            const double arg = 1.0 / (double)m;
+            const double rate = detpow::det_pow(base, arg);
+            if (rate > RATEMAX) return -1;
+            ss = rate / (1.0 - rate);
+        }
+        if (ss * delnrm <= tol) return 1;
+        return 0;
+    }
+
+    // ---- nonlinear_solve + Newton::solve: src/lib.rs:787-890, crates/nonlinear/src/newton.rs:51-167 -------
+    // returns 0 ok, 1 recoverable convergence failure, B200IDA_ST_LSETUP_FAIL on a singular Jacobian.
+    // (C semantics for "recover while the Jacobian is current": fail the attempt; DESIGN.md "Deviations".)
+    __device__ __forceinline__ int nonlinear_solve() {
+        bool call_lsetup = false;
+        if (nst == 0) {
+            cjold = cj;
+            ss = 20.0;
+            call_lsetup = true;
+        }
+        cjratio = cj / cjold;
+        const double temp1 = (1.0 - XRATE) / (1.0 + XRATE);
+        const double temp2 = 1.0 / temp1;
+        if (cjratio < temp1 || cjratio > temp2) call_lsetup = true;
+        if (cj != cjlast) ss = 100.0;
+
+        double nd[N];  // Newton.delta
+        int ret = 0;
+        for (;;) {  // at most two passes: the second with a fresh Jacobian
+#pragma unroll
+            for (int i = 0; i < N; ++i) delta[i] = 0.0;
+            nls_sys(delta, nd);
+            if (call_lsetup) {
+                if (nls_setup(nd) != 0) {
+                    ret = B200IDA_ST_LSETUP_FAIL;
+                    break;
+                }
+                jcur = 1;
+            }
+            int curiter = 0;
+#pragma unroll
+            for (int i = 0; i < N; ++i) ee[i] = 0.0;  // y = y0 = 0
+            for (;;) {
+                nni += 1;
+#pragma unroll
+                for (int i = 0; i < N; ++i) nd[i] = -nd[i];
+                nls_lsolve(nd);
+#pragma unroll
+                for (int i = 0; i < N; ++i) ee[i] += nd[i];
+                const int c = nls_ctest(curiter, nd, eps_newt);
+                if (c == 1) {
+                    jcur = 0;
+                    ret = 0;
+                    break;
+                }
+                if (c == -1) {
+                    ret = 1;
+                    break;
+                }
+                curiter += 1;
+                if (curiter >= MAXNLSIT) {
+                    ret = 1;
+                    break;
+                }
+                nls_sys(ee, nd);
+            }
+            if (ret == 1 && !jcur) {
+                nlscf += 1;
+                call_lsetup = true;
+                continue;
+            }
+            break;
+        }
+        if (ret != 0) nlscf += 1;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            yy[i] = yypredict[i] + ee[i];
+            yp[i] = yppredict[i] + cj * ee[i];
+        }
+        return ret;
+    }
+
+    // ---- test_error: src/lib.rs:967-1039 -------------------------------------------------------------------
+    __device__ __forceinline__ bool test_error(double ck, double& err_k, double& err_km1) {
+        const double scalar_kk = (double)kk;
+        const double enorm_k = wrms(ee, ewt);
+        err_k = pick6(sigma, kk) * enorm_k;
+        const double terr_k = err_k * (scalar_kk + 1.0);
+        err_km1 = 0.0;
+        int knew_ = kk;
+        if (kk > 1) {
+            double phk[N], phkm1[N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                double a = phi[1][i], c = phi[0][i];
+#pragma unroll
+                for (int j = 2; j <= MAXORD; ++j) {
+                    if (kk == j) {
+                        a = phi[j][i];
+                        c = phi[j - 1][i];
+                    }
+                }
+                phk[i] = a;
+                phkm1[i] = c;
+            }
+#pragma unroll
+            for (int i = 0; i < N; ++i) delta[i] = phk[i] + ee[i];
+            const double enorm_km1 = wrms(delta, ewt);
+            err_km1 = pick6(sigma, kk - 1) * enorm_km1;
+            const double terr_km1 = scalar_kk * err_km1;
+            if (kk > 2) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) delta[i] += phkm1[i];
+                const double enorm_km2 = wrms(delta, ewt);
+                const double err_km2 = pick6(sigma, kk - 2) * enorm_km2;
+                const double terr_km2 = (scalar_kk - 1.0) * err_km2;
+                if (fmax(terr_km1, terr_km2) <= terr_k) knew_ = kk - 1;
+            } else {
+                if (terr_km1 <= terr_k * 0.5) knew_ = kk - 1;
+            }
+        }
+        knew = knew_;
+        return (ck * enorm_k) <= 1.0;
+    }
+
+    // ---- restore: src/lib.rs:1044-1083 -----------------------------------------------------------------------
+    __device__ __forceinline__ void restore(double saved_t) {
+        tn = saved_t;
+#pragma unroll
+        for (int j = 1; j <= MAXORD; ++j)
+            if (j <= kk) psi[j - 1] = psi[j] - hh;
+#pragma unroll
+        for (int j = 1; j <= MAXORD; ++j) {
+            if (j >= ns && j <= kk) {
+                const double c = 1.0 / beta[j];
+#pragma unroll
+                for (int i = 0; i < N; ++i) phi[j][i] *= c;
+            }
+        }
+    }
+
+    // ---- handle_n_flag: src/lib.rs:1120-1244 ; nflag 2 = error-test failure, 1 = convergence failure ----------
+    __device__ __forceinline__ int handle_n_flag(int nflag, double err_k, double err_km1, int& ncf, int& nef) {
+        phase = 1;
+        if (nflag == 2) {
+            nef += 1;
+            netf += 1;
+            if (nef == 1) {
+                const double err_knew = (kk == knew) ? err_k : err_km1;
+                kk = knew;
+                const double base = 2.0 * err_knew + 0.0001;
+                const double arg = 1.0 / (double)(kk + 1);
+                rr = 0.9 * detpow::det_pow(base, -arg);
+                rr = fmax(0.25, fmin(0.9, rr));
+                hh *= rr;
+                return 0;
+            } else if (nef == 2) {
+                kk = knew;
+                rr = 0.25;
+                hh *= rr;
+                return 0;
+            } else if (nef < MXNEF) {
+                kk = 1;
+                rr = 0.25;
+                hh *= rr;
+                return 0;
+            }
+            return B200IDA_ST_ERR_FAIL;
+        }
+        ncf += 1;
+        ncfn += 1;
+        rr = 0.25;
+        hh *= rr;
+        if (ncf < MXNCF) return 0;
+        return B200IDA_ST_CONV_FAIL;
+    }
+
+    // ---- reset: src/lib.rs:1249-1252 (scales ALL of phi, like the reference) ---------------------------------
+    __device__ __forceinline__ void reset() {
+        psi[0] = hh;
+#pragma unroll
+        for (int j = 0; j < MXORDP1; ++j)
+#pragma unroll
+            for (int i = 0; i < N; ++i) phi[j][i] *= rr;
+    }
+
+    // ---- complete_step: src/impl_complete_step.rs:22-177 -------------------------------------------------------
+    __device__ __forceinline__ void complete_step(double err_k, double err_km1) {
+        nst += 1;
+        const int kdiff = kk - kused;
+        kused = kk;
+        hused = hh;
+        if (knew == kk - 1 || kk == MAXORD) phase = 1;
+        if (phase == 0) {
+            if (nst > 1) {
+                kk += 1;
+                double hnew = 2.0 * hh;
+                const double t = fabs(hnew) * HMAX_INV;
+                if (t > 1.0) hnew /= t;
+                hh = hnew;
+            }
+        } else {
+            int action;  // 0 lower, 1 maintain, 2 raise
+            double err_kp1 = 0.0;
+            if (knew == kk - 1) {
+                action = 0;
+            } else if (kk == MAXORD) {
+                action = 1;
+            } else if (kk + 1 >= ns || kdiff == 1) {
+                action = 1;
+            } else {
+                double t[N];
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    double p = phi[2][i];  // kk + 1 in 2..5 here (1 <= kk <= 4)
+#pragma unroll
+                    for (int j = 3; j <= MAXORD; ++j) p = (kk + 1 == j) ? phi[j][i] : p;
+                    t[i] = ee[i] - p;
+                }
+                const double enorm = wrms(t, ewt);
+                err_kp1 = enorm / (double)(kk + 2);
+                const double terr_k = (double)(kk + 1) * err_k;
+                const double terr_kp1 = (double)(kk + 2) * err_kp1;
+                if (kk == 1) {
+                    action = (terr_kp1 >= 0.5 * terr_k) ? 1 : 2;
+                } else {
+                    const double terr_km1 = (double)kk * err_km1;
+                    if (terr_km1 <= fmin(terr_k, terr_kp1)) action = 0;
+                    else if (terr_kp1 >= terr_k) action = 1;
+                    else action = 2;
+                }
+            }
+            double err_knew;
+            if (action == 2) {
+                kk += 1;
+                err_knew = err_kp1;
+            } else if (action == 0) {
+                kk -= 1;
+                err_knew = err_km1;
+            } else {
+                err_knew = err_k;
+            }
+            double hnew = hh;
+            {
+                const double base = 2.0 * err_knew + 0.0001;
+                const double arg = -(1.0 / (double)(kk + 1));
+                rr = detpow::det_pow(base, arg);
+            }
+            if (rr >= 2.0) {
+                hnew = 2.0 * hh;
+                const double t = fabs(hnew) * HMAX_INV;
+                if (t > 1.0) hnew /= t;
+            } else if (rr <= 1.0) {
+                rr = fmax(0.5, fmin(rr, 0.9));
+                hnew = hh * rr;
+            }
+            hh = hnew;
+        }
+        if (kused < MAXORD) {
+#pragma unroll
+            for (int j = 1; j <= MAXORD; ++j) {
+                if (j == kused + 1) {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) phi[j][i] = ee[i];
+                }
+            }
+        }
+        double tmp[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) tmp[i] = ee[i];
+#pragma unroll
+        for (int j = MAXORD; j >= 0; --j) {
+            if (j <= kused) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    tmp[i] += phi[j][i];
+                    phi[j][i] = tmp[i];
+                }
+            }
+        }
+    }
+
+    // ---- get_solution: src/lib.rs:1274-1343 ; returns 0 or B200IDA_ST_BAD_T ------------------------------------
+    __device__ __forceinline__ int get_solution(double t) {
+        const double sgn = (hh > 0.0 || (hh == 0.0 && !signbit(hh))) ? 1.0 : -1.0;
+        const double tfuzz = 100.0 * DBL_EPS * (fabs(tn) + fabs(hh)) * sgn;
+        const double tp = tn - hused - tfuzz;
+        if ((t - tp) * hh < 0.0) return B200IDA_ST_BAD_T;
+        const int kord = (kused == 0) ? 1 : kused;
+        const double delt = t - tn;
+        double c = 1.0, d = 0.0;
+        double gam = delt / psi[0];
+        double cvals[MXORDP1], dvals[MXORDP1];
+        cvals[0] = c;
+#pragma unroll
+        for (int j = 1; j <= MAXORD; ++j) {
+            cvals[j] = 0.0;
+            dvals[j - 1] = 0.0;
+            if (j <= kord) {
+                d = d * gam + c / psi[j - 1];
+                c = c * gam;
+                gam = (delt + psi[j - 1]) / psi[j];
+                cvals[j] = c;
+                dvals[j - 1] = d;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            yy[i] = 0.0;
+            yp[i] = 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j <= MAXORD; ++j) {
+            if (j <= kord) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) yy[i] += cvals[j] * phi[j][i];
+            }
+        }
+#pragma unroll
+        for (int j = 1; j <= MAXORD; ++j) {
+            if (j <= kord) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) yp[i] += dvals[j - 1] * phi[j][i];
+            }
+        }
+        return 0;
+    }
+
+    // ---- first-call block of solve(): src/impl_solve.rs:84-173 ; returns 0 or B200IDA_ST_ILL_INPUT ---------------
+    __device__ __forceinline__ int first_call(double tout, const TolN<N>& tol) {
+        if (!setup_done) {
+            ewt_set(tol);  // initial_setup, src/lib.rs:537-545
+            setup_done = 1;
+        }
+        const double tdist = fabs(tout - tn);
+        if (tdist == 0.0) return B200IDA_ST_ILL_INPUT;
+        const double troundoff = 2.0 * DBL_EPS * (fabs(tn) + fabs(tout));
+        if (tdist < troundoff) return B200IDA_ST_ILL_INPUT;
+        hh = 0.0;  // hin: no setter exists in the reference
+        {
+            hh = 0.001 * tdist;
+            const double ypnorm = wrms(phi[1], ewt);
+            if (ypnorm > 2.0 / hh) hh = 0.5 / ypnorm;
+            if (tout < tn) hh = -hh;
+        }
+        const double rh = fabs(hh) * HMAX_INV;
+        if (rh > 1.0) hh /= rh;
+        h0u = hh;
+        kk = 0;
+        kused = 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) phi[1][i] *= hh;
+        eps_newt = EPCON;
+        toldel = 0.0001 * eps_newt;
+        return 0;
+    }
+
+    // ---- the flattened solve loop over a ladder of output times ---------------------------------------------------
+    // Equivalent to calling Ida::solve(touts[k], .., Normal) for k = 0..ntout-1 (src/impl_solve.rs:69-376 with the
+    // NORMAL branches of stop_test1/2, src/impl_stop_test.rs:53-65,152-161).  After call k, yy is written to
+    // yy_traj[k][.][b] and the call's status to status[k][b] when those pointers are non-null.
+    __device__ __forceinline__ void solve_ladder(const LadderParams& lad, const TolN<N>& tol, double* __restrict__ yy_traj,
+                                                 int32_t* __restrict__ status, int64_t B, int64_t b) {
+        int it = 0;
+        bool need_prologue = true;
+        bool in_step = false;
+        bool call_done = false;
+        int call_status = 0;
+        int nstloc = 0;
+        double saved_t = 0.0, tout = 0.0;
+        int ncf = 0, nef = 0;
+
+        while (it < lad.ntout) {
+            if (need_prologue) {
+                need_prologue = false;
+                tout = lad.touts[it];
+                nstloc = 0;
+                in_step = false;
+                call_done = false;
+                call_status = 0;
+                if (nst == 0) {
+                    const int r = first_call(tout, tol);
+                    if (r != 0) {
+                        call_done = true;
+                        call_status = r;
+                    }
+                } else {
+                    // stop_test1, NORMAL: src/impl_stop_test.rs:53-65
+                    if (tout == tretlast) {
+                        tretlast = tout;
+                        tret = tout;
+                        call_done = true;
+                    } else if ((tn - tout) * hh >= 0.0) {
+                        const int ier = get_solution(tout);
+                        if (ier == 0) {
+                            tretlast = tout;
+                            tret = tout;
+                        }
+                        call_status = ier;
+                        call_done = true;
+                    }
+                }
+            }
+            if (!call_done && !in_step) {
+                // top of the step loop: src/impl_solve.rs:246-311
+                if (nstloc >= MXSTEP) {
+                    tret = tn;
+                    tretlast = tn;
+                    call_status = B200IDA_ST_TOO_MUCH_WORK;
+                    call_done = true;
+                } else {
+                    bool bad = false;
+                    if (nst > 0) {
+                        ewt_set(tol);
+#pragma unroll
+                        for (int i = 0; i < N; ++i) bad = bad || (ewt[i] <= 0.0);
+                    }
+                    if (bad) {
+                        get_solution(tn);
+                        tret = tn;
+                        tretlast = tn;
+                        call_status = B200IDA_ST_BAD_EWT;
+                        call_done = true;
+                    } else {
+                        const double nrm = wrms(phi[0], ewt);
+                        tolsf = DBL_EPS * nrm;
+                        if (tolsf > 1.0) {
+                            tolsf *= 10.0;
+                            tret = tn;
+                            tretlast = tn;
+                            if (nst > 0) get_solution(tn);
+                            call_status = B200IDA_ST_TOO_MUCH_ACC;
+                            call_done = true;
+                        } else {
+                            // step() entry: src/lib.rs:617-631
+                            saved_t = tn;
+                            if (nst == 0) {
+                                kk = 1;
+                                kused = 0;
+                                hused = 0.0;
+                                psi[0] = hh;
+                                cj = 1.0 / hh;
+                                phase = 0;
+                                ns = 0;
+                            }
+                            ncf = 0;
+                            nef = 0;
+                            in_step = true;
+                        }
+                    }
+                }
+            }
+            if (!call_done) {
+                // one step attempt: src/lib.rs:634-694
+                natt += 1;
+                const double ck = set_coeffs();
+                tn += hh;
+                predict();
+                int nflag = nonlinear_solve();
+                double err_k = 0.0, err_km1 = 0.0;
+                bool converged = false;
+                if (nflag == 0) {
+                    converged = test_error(ck, err_k, err_km1);
+                    if (!converged) nflag = 2;
+                }
+                if (converged) {
+                    complete_step(err_k, err_km1);
+#pragma unroll
+                    for (int i = 0; i < N; ++i) ee[i] *= ck;  // src/lib.rs:708
+                    in_step = false;
+                    nstloc += 1;
+                    // stop_test2, NORMAL: src/impl_stop_test.rs:152-161
+                    if ((tn - tout) * hh >= 0.0) {
+                        tret = tout;
+                        tretlast = tout;
+                        get_solution(tout);
+                        call_status = B200IDA_ST_SUCCESS;
+                        call_done = true;
+                    }
+                } else {
+                    restore(saved_t);
+                    int kflag;
+                    if (nflag < 0) {
+                        ncfn += 1;
+                        kflag = nflag;
+                    } else {
+                        kflag = handle_n_flag(nflag, err_k, err_km1, ncf, nef);
+                    }
+                    if (kflag != 0) {
+                        // failed step: src/impl_solve.rs:314-327
+                        if (get_solution(tn) == 0) {
+                            tret = tn;
+                            tretlast = tn;
+                        }
+                        call_status = kflag;
+                        call_done = true;
+                        in_step = false;
+                    } else if (nst == 0) {
+                        reset();
+                    }
+                }
+            }
+            if (call_done) {
+                if (yy_traj) {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) yy_traj[((int64_t)it * N + i) * B + b] = yy[i];
+                }
+                if (status) status[(int64_t)it * B + b] = call_status;
+                it += 1;
+                need_prologue = true;
+            }
+        }
+    }
+};
+
+}  // namespace b200ida

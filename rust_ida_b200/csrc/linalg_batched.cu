@@ -1,0 +1,489 @@
+// linalg_batched.cu -- C ABI "Level 1" (include/b200ida.h): batched dense LU (getrf), triangular solves
+// (getrs) and WRMS norms for ensembles of small and medium systems.
+//
+// Reference semantics, reproduced bit-for-bit (crates/linear/src/dense.rs:86-206, src/norm_rms.rs:31-38):
+//   getrf: pivot = first row with strictly largest |a_ik|; whole-row swap; l_ik = a_ik * (1/a_kk);
+//          a_ij -= a_kj * l_ik, column j skipped when a_kj == 0; zero pivot -> info = k+1 and stop.
+//   getrs: apply pivots to b; unit-lower forward sweep; backward sweep dividing by u_kk.
+//   wrms : sqrt( fold_{i=0..n-1}(acc + (x_i w_i)^2) / n ).
+// Every a_ij update of elimination step k is a single mul + sub that depends only on step k-1, so any
+// parallelisation over (i, j) inside one step is bit-exact; only the k loop is sequential.  No FMA
+// (-fmad=false).
+//
+// Kernels
+//   *_thread_soa<N>   n <= 8, SoA: one thread per system, matrix in registers, perfectly coalesced
+//                     [n][n][batch] loads/stores -> HBM-bound (16 n^2 + 8n B/system for getrf).
+//   *_cta             any n <= 256, either layout: one CTA per system; the matrix is staged in shared
+//                     memory when it fits (n <= 160), else factored in place in global memory / L2.
+#include "host_util.h"
+#include "ida_common.cuh"
+
+namespace b200ida {
+
+// element (i, j) of system b
+template <bool SOA>
+__device__ __forceinline__ size_t mat_idx(int i, int j, int n, int64_t b, int64_t B) {
+    return SOA ? ((size_t)(i * n + j) * B + b) : ((size_t)b * n * n + (size_t)j * n + i);
+}
+template <bool SOA>
+__device__ __forceinline__ size_t vec_idx(int i, int n, int64_t b, int64_t B) {
+    return SOA ? ((size_t)i * B + b) : ((size_t)b * n + i);
+}
+
+// ---- thread-per-system, registers, SoA --------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(128) getrf_thread_soa(double* __restrict__ A, int64_t* __restrict__ piv,
+                                                        int32_t* __restrict__ info, int64_t B) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double a[N][N];
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int i = 0; i < N; ++i) a[i][j] = A[(size_t)(i * N + j) * B + b];
+    int p[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) p[k] = 0;
+    int inf = 0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        if (inf == 0) {
+            int l = k;
+            double best = fabs(a[k][k]);
+#pragma unroll
+            for (int i = k + 1; i < N; ++i) {
+                const double v = fabs(a[i][k]);
+                if (v > best) {
+                    best = v;
+                    l = i;
+                }
+            }
+            p[k] = l;
+            if (best == 0.0) {
+                inf = k + 1;
+            } else {
+#pragma unroll
+                for (int i = k + 1; i < N; ++i) {
+                    if (l == i) {
+#pragma unroll
+                        for (int c = 0; c < N; ++c) {
+                            const double t = a[k][c];
+                            a[k][c] = a[i][c];
+                            a[i][c] = t;
+                        }
+                    }
+                }
+                const double mult = 1.0 / a[k][k];
+#pragma unroll
+                for (int i = k + 1; i < N; ++i) a[i][k] *= mult;
+#pragma unroll
+                for (int j = k + 1; j < N; ++j) {
+                    const double a_kj = a[k][j];
+                    if (a_kj != 0.0) {
+#pragma unroll
+                        for (int i = k + 1; i < N; ++i) a[i][j] -= a_kj * a[i][k];
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int i = 0; i < N; ++i) A[(size_t)(i * N + j) * B + b] = a[i][j];
+#pragma unroll
+    for (int k = 0; k < N; ++k) piv[(size_t)k * B + b] = p[k];
+    info[b] = inf;
+}
+
+template <int N>
+__global__ void __launch_bounds__(128) getrs_thread_soa(const double* __restrict__ A, const int64_t* __restrict__ piv,
+                                                        double* __restrict__ bx, int64_t B) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double a[N][N], x[N];
+    int p[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int i = 0; i < N; ++i) a[i][j] = A[(size_t)(i * N + j) * B + b];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        x[i] = bx[(size_t)i * B + b];
+        p[i] = (int)piv[(size_t)i * B + b];
+    }
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+#pragma unroll
+        for (int i = k + 1; i < N; ++i) {
+            if (p[k] == i) {
+                const double t = x[k];
+                x[k] = x[i];
+                x[i] = t;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < N - 1; ++k) {
+        const double bk = x[k];
+#pragma unroll
+        for (int i = k + 1; i < N; ++i) x[i] -= a[i][k] * bk;
+    }
+#pragma unroll
+    for (int k = N - 1; k >= 1; --k) {
+        x[k] /= a[k][k];
+        const double bk = x[k];
+#pragma unroll
+        for (int i = 0; i < k; ++i) x[i] -= a[i][k] * bk;
+    }
+    x[0] /= a[0][0];
+#pragma unroll
+    for (int i = 0; i < N; ++i) bx[(size_t)i * B + b] = x[i];
+}
+
+// ---- CTA-per-system, shared memory (or in-place global when the matrix does not fit) ----------------
+constexpr int CTA_THREADS = 256;
+constexpr int SMEM_MAX_N = 160;  // 160*160*8 = 204,800 B <= 227 KB
+
+template <bool SOA, bool SMEM>
+__global__ void __launch_bounds__(CTA_THREADS) getrf_cta(double* __restrict__ A, int64_t* __restrict__ piv,
+                                                         int32_t* __restrict__ info, int n, int64_t B) {
+    extern __shared__ double sm[];
+    __shared__ int s_l;
+    __shared__ double s_red_v[CTA_THREADS / 32];
+    __shared__ int s_red_i[CTA_THREADS / 32];
+    const int tid = threadIdx.x;
+    for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+        double* M;    // column-major view, leading dimension n
+        if (SMEM) {
+            for (int e = tid; e < n * n; e += CTA_THREADS) sm[e] = A[mat_idx<SOA>(e % n, e / n, n, b, B)];
+            M = sm;
+            __syncthreads();
+        } else {
+            M = A + (size_t)b * n * n;  // AoS only (dispatch guarantees it)
+        }
+        int inf = 0;
+        for (int k = 0; k < n; ++k) {
+            // pivot search: l = k; for i > k: if |a_ik| > |a_lk| then l = i   (dense.rs:109-116).
+            // i.e. the lowest-index maximum over rows k..n-1, where a NaN never wins and a NaN in row k
+            // keeps l = k.
+            const double vk = fabs(M[(size_t)k * n + k]);
+            double best = -1.0;
+            int bi = 0x7fffffff;
+            for (int i = k + tid; i < n; i += CTA_THREADS) {
+                const double v = fabs(M[(size_t)k * n + i]);
+                if (v > best) {
+                    best = v;
+                    bi = i;
+                }
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const double ov = __shfl_down_sync(0xffffffffu, best, off);
+                const int oi = __shfl_down_sync(0xffffffffu, bi, off);
+                if (ov > best || (ov == best && oi < bi)) {
+                    best = ov;
+                    bi = oi;
+                }
+            }
+            if ((tid & 31) == 0) {
+                s_red_v[tid >> 5] = best;
+                s_red_i[tid >> 5] = bi;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                double bv = s_red_v[0];
+                int bidx = s_red_i[0];
+                for (int w = 1; w < CTA_THREADS / 32; ++w) {
+                    if (s_red_v[w] > bv || (s_red_v[w] == bv && s_red_i[w] < bidx)) {
+                        bv = s_red_v[w];
+                        bidx = s_red_i[w];
+                    }
+                }
+                if (vk != vk) bidx = k;  // NaN in row k: nothing compares greater
+                s_l = bidx;
+                piv[SOA ? ((size_t)k * B + b) : ((size_t)b * n + k)] = bidx;
+            }
+            __syncthreads();
+            const int l = s_l;
+            if (M[(size_t)k * n + l] == 0.0) {
+                inf = k + 1;
+                break;
+            }
+            if (l != k) {
+                for (int c = tid; c < n; c += CTA_THREADS) {
+                    const double t = M[(size_t)c * n + k];
+                    M[(size_t)c * n + k] = M[(size_t)c * n + l];
+                    M[(size_t)c * n + l] = t;
+                }
+                __syncthreads();
+            }
+            const double mult = 1.0 / M[(size_t)k * n + k];
+            __syncthreads();
+            for (int i = k + 1 + tid; i < n; i += CTA_THREADS) M[(size_t)k * n + i] *= mult;
+            __syncthreads();
+            const int m = n - k - 1;
+            for (int e = tid; e < m * m; e += CTA_THREADS) {
+                const int i = k + 1 + e % m, j = k + 1 + e / m;
+                const double a_kj = M[(size_t)j * n + k];
+                if (a_kj != 0.0) M[(size_t)j * n + i] -= a_kj * M[(size_t)k * n + i];
+            }
+            __syncthreads();
+        }
+        if (SMEM) {
+            __syncthreads();
+            for (int e = tid; e < n * n; e += CTA_THREADS) A[mat_idx<SOA>(e % n, e / n, n, b, B)] = sm[e];
+        }
+        if (tid == 0) info[b] = inf;
+        __syncthreads();
+    }
+}
+
+template <bool SOA>
+__global__ void __launch_bounds__(CTA_THREADS) getrs_cta(const double* __restrict__ A, const int64_t* __restrict__ piv,
+                                                         double* __restrict__ bx, int n, int64_t B) {
+    __shared__ double x[256];
+    const int tid = threadIdx.x;
+    for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+        for (int i = tid; i < n; i += CTA_THREADS) x[i] = bx[vec_idx<SOA>(i, n, b, B)];
+        __syncthreads();
+        if (tid == 0) {
+            for (int k = 0; k < n; ++k) {
+                const int pk = (int)piv[SOA ? ((size_t)k * B + b) : ((size_t)b * n + k)];
+                if (pk != k) {
+                    const double t = x[k];
+                    x[k] = x[pk];
+                    x[pk] = t;
+                }
+            }
+        }
+        __syncthreads();
+        for (int k = 0; k < n - 1; ++k) {
+            const double bk = x[k];
+            __syncthreads();
+            for (int i = k + 1 + tid; i < n; i += CTA_THREADS) x[i] -= A[mat_idx<SOA>(i, k, n, b, B)] * bk;
+            __syncthreads();
+        }
+        for (int k = n - 1; k >= 1; --k) {
+            if (tid == 0) x[k] /= A[mat_idx<SOA>(k, k, n, b, B)];
+            __syncthreads();
+            const double bk = x[k];
+            for (int i = tid; i < k; i += CTA_THREADS) x[i] -= A[mat_idx<SOA>(i, k, n, b, B)] * bk;
+            __syncthreads();
+        }
+        if (tid == 0) x[0] /= A[mat_idx<SOA>(0, 0, n, b, B)];
+        __syncthreads();
+        for (int i = tid; i < n; i += CTA_THREADS) bx[vec_idx<SOA>(i, n, b, B)] = x[i];
+        __syncthreads();
+    }
+}
+
+template <bool SOA>
+__global__ void __launch_bounds__(256) wrms_thread(const double* __restrict__ x, const double* __restrict__ w,
+                                                   double* __restrict__ out, int n, int64_t B) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double acc = 0.0;
+    for (int i = 0; i < n; ++i) {
+        const double p = x[vec_idx<SOA>(i, n, b, B)] * w[vec_idx<SOA>(i, n, b, B)];
+        acc = acc + p * p;
+    }
+    out[b] = sqrt(acc / (double)n);
+}
+
+// AoS <-> SoA transposes used when a large-n SoA batch has to go through the AoS in-place kernel
+__global__ void transpose_to_aos(const double* __restrict__ soa, double* __restrict__ aos, int64_t rows, int64_t B) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= rows * B) return;
+    const int64_t r = e / B, b = e % B;
+    aos[b * rows + r] = soa[e];
+}
+__global__ void transpose_to_soa(const double* __restrict__ aos, double* __restrict__ soa, int64_t rows, int64_t B) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= rows * B) return;
+    const int64_t r = e / B, b = e % B;
+    soa[e] = aos[b * rows + r];
+}
+
+template <int N>
+static void launch_getrf_thread(double* A, int64_t* piv, int32_t* info, int64_t B, cudaStream_t st) {
+    getrf_thread_soa<N><<<(unsigned)((B + 127) / 128), 128, 0, st>>>(A, piv, info, B);
+}
+template <int N>
+static void launch_getrs_thread(const double* A, const int64_t* piv, double* bx, int64_t B, cudaStream_t st) {
+    getrs_thread_soa<N><<<(unsigned)((B + 127) / 128), 128, 0, st>>>(A, piv, bx, B);
+}
+
+static int sm_count() {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms;
+}
+
+// device-pointer implementations -------------------------------------------------------------------------
+static int getrf_dev(double* A, int64_t* piv, int32_t* info, int n, int64_t B, int layout, cudaStream_t st) {
+    const bool soa = layout == B200IDA_LAYOUT_SOA;
+    if (soa && n <= 8) {
+        switch (n) {
+        case 1: launch_getrf_thread<1>(A, piv, info, B, st); break;
+        case 2: launch_getrf_thread<2>(A, piv, info, B, st); break;
+        case 3: launch_getrf_thread<3>(A, piv, info, B, st); break;
+        case 4: launch_getrf_thread<4>(A, piv, info, B, st); break;
+        case 5: launch_getrf_thread<5>(A, piv, info, B, st); break;
+        case 6: launch_getrf_thread<6>(A, piv, info, B, st); break;
+        case 7: launch_getrf_thread<7>(A, piv, info, B, st); break;
+        default: launch_getrf_thread<8>(A, piv, info, B, st); break;
+        }
+        B200_CUDA_TRY(cudaGetLastError());
+        return B200IDA_OK;
+    }
+    const unsigned grid = (unsigned)(B < (int64_t)sm_count() * 8 ? B : (int64_t)sm_count() * 8);
+    if (n <= SMEM_MAX_N) {
+        const size_t smem = (size_t)n * n * sizeof(double);
+        if (soa) {
+            B200_CUDA_TRY(cudaFuncSetAttribute(getrf_cta<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            getrf_cta<true, true><<<grid, CTA_THREADS, smem, st>>>(A, piv, info, n, B);
+        } else {
+            B200_CUDA_TRY(cudaFuncSetAttribute(getrf_cta<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            getrf_cta<false, true><<<grid, CTA_THREADS, smem, st>>>(A, piv, info, n, B);
+        }
+        B200_CUDA_TRY(cudaGetLastError());
+        return B200IDA_OK;
+    }
+    // n > SMEM_MAX_N: in-place in global memory on an AoS copy
+    if (!soa) {
+        getrf_cta<false, false><<<grid, CTA_THREADS, 0, st>>>(A, piv, info, n, B);
+        B200_CUDA_TRY(cudaGetLastError());
+        return B200IDA_OK;
+    }
+    DevBuf tmp, ptmp;
+    const int64_t rows = (int64_t)n * n;
+    B200_CUDA_TRY(tmp.alloc((size_t)rows * B * sizeof(double)));
+    const unsigned tg = (unsigned)((rows * B + 255) / 256);
+    transpose_to_aos<<<tg, 256, 0, st>>>(A, tmp.as<double>(), rows, B);
+    B200_CUDA_TRY(ptmp.alloc((size_t)n * B * sizeof(int64_t)));
+    getrf_cta<false, false><<<grid, CTA_THREADS, 0, st>>>(tmp.as<double>(), ptmp.as<int64_t>(), info, n, B);
+    transpose_to_soa<<<tg, 256, 0, st>>>(tmp.as<double>(), A, rows, B);
+    // pivots: int64 has the same width as double, reuse the transpose kernel bit-for-bit
+    transpose_to_soa<<<(unsigned)(((int64_t)n * B + 255) / 256), 256, 0, st>>>(
+        reinterpret_cast<const double*>(ptmp.as<int64_t>()), reinterpret_cast<double*>(piv), n, B);
+    B200_CUDA_TRY(cudaGetLastError());
+    B200_CUDA_TRY(cudaStreamSynchronize(st));  // scratch freed on return
+    return B200IDA_OK;
+}
+
+static int getrs_dev(const double* LU, const int64_t* piv, double* bx, int n, int64_t B, int layout, cudaStream_t st) {
+    const bool soa = layout == B200IDA_LAYOUT_SOA;
+    if (soa && n <= 8) {
+        switch (n) {
+        case 1: launch_getrs_thread<1>(LU, piv, bx, B, st); break;
+        case 2: launch_getrs_thread<2>(LU, piv, bx, B, st); break;
+        case 3: launch_getrs_thread<3>(LU, piv, bx, B, st); break;
+        case 4: launch_getrs_thread<4>(LU, piv, bx, B, st); break;
+        case 5: launch_getrs_thread<5>(LU, piv, bx, B, st); break;
+        case 6: launch_getrs_thread<6>(LU, piv, bx, B, st); break;
+        case 7: launch_getrs_thread<7>(LU, piv, bx, B, st); break;
+        default: launch_getrs_thread<8>(LU, piv, bx, B, st); break;
+        }
+        B200_CUDA_TRY(cudaGetLastError());
+        return B200IDA_OK;
+    }
+    const unsigned grid = (unsigned)(B < (int64_t)sm_count() * 8 ? B : (int64_t)sm_count() * 8);
+    if (soa) getrs_cta<true><<<grid, CTA_THREADS, 0, st>>>(LU, piv, bx, n, B);
+    else getrs_cta<false><<<grid, CTA_THREADS, 0, st>>>(LU, piv, bx, n, B);
+    B200_CUDA_TRY(cudaGetLastError());
+    return B200IDA_OK;
+}
+
+static int wrms_dev(const double* x, const double* w, double* out, int n, int64_t B, int layout, cudaStream_t st) {
+    const unsigned grid = (unsigned)((B + 255) / 256);
+    if (layout == B200IDA_LAYOUT_SOA) wrms_thread<true><<<grid, 256, 0, st>>>(x, w, out, n, B);
+    else wrms_thread<false><<<grid, 256, 0, st>>>(x, w, out, n, B);
+    B200_CUDA_TRY(cudaGetLastError());
+    return B200IDA_OK;
+}
+
+static int check_common(const void* a, const void* b, int n, int64_t batch, int layout, int mem, const char* who) {
+    if (!a || !b || n < 1 || n > 256 || batch < 1 || (layout != B200IDA_LAYOUT_SOA && layout != B200IDA_LAYOUT_AOS) ||
+        (mem != B200IDA_MEM_DEVICE && mem != B200IDA_MEM_HOST))
+        return set_error(B200IDA_ERR_ARG, "%s: bad argument (1 <= n <= 256, batch >= 1, valid layout/mem, non-null)", who);
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess || c == 0) {
+        cudaGetLastError();
+        return set_error(B200IDA_ERR_NO_DEVICE, "%s: no CUDA device", who);
+    }
+    return B200IDA_OK;
+}
+
+}  // namespace b200ida
+
+using namespace b200ida;
+
+extern "C" {
+
+int b200ida_getrf_batched(double* A, int64_t* piv, int32_t* info, int n, int64_t batch, int layout, int mem,
+                          void* stream) {
+    int rc = check_common(A, piv, n, batch, layout, mem, "b200ida_getrf_batched");
+    if (rc) return rc;
+    if (!info) return set_error(B200IDA_ERR_ARG, "b200ida_getrf_batched: info is null");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (mem == B200IDA_MEM_DEVICE) return getrf_dev(A, piv, info, n, batch, layout, st);
+    DevBuf dA, dP, dI;
+    const size_t ab = (size_t)n * n * batch * sizeof(double), pb = (size_t)n * batch * sizeof(int64_t),
+                 ib = (size_t)batch * sizeof(int32_t);
+    B200_CUDA_TRY(dA.alloc(ab));
+    B200_CUDA_TRY(dP.alloc(pb));
+    B200_CUDA_TRY(dI.alloc(ib));
+    B200_CUDA_TRY(cudaMemcpyAsync(dA.p, A, ab, cudaMemcpyHostToDevice, st));
+    B200_CUDA_TRY(cudaMemsetAsync(dP.p, 0, pb, st));
+    if ((rc = getrf_dev(dA.as<double>(), dP.as<int64_t>(), dI.as<int32_t>(), n, batch, layout, st))) return rc;
+    B200_CUDA_TRY(cudaMemcpyAsync(A, dA.p, ab, cudaMemcpyDeviceToHost, st));
+    B200_CUDA_TRY(cudaMemcpyAsync(piv, dP.p, pb, cudaMemcpyDeviceToHost, st));
+    B200_CUDA_TRY(cudaMemcpyAsync(info, dI.p, ib, cudaMemcpyDeviceToHost, st));
+    B200_CUDA_TRY(cudaStreamSynchronize(st));
+    return B200IDA_OK;
+}
+
+int b200ida_getrs_batched(const double* LU, const int64_t* piv, double* bx, int n, int64_t batch, int layout,
+                          int mem, void* stream) {
+    int rc = check_common(LU, piv, n, batch, layout, mem, "b200ida_getrs_batched");
+    if (rc) return rc;
+    if (!bx) return set_error(B200IDA_ERR_ARG, "b200ida_getrs_batched: bx is null");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (mem == B200IDA_MEM_DEVICE) return getrs_dev(LU, piv, bx, n, batch, layout, st);
+    DevBuf dA, dP, dX;
+    const size_t ab = (size_t)n * n * batch * sizeof(double), pb = (size_t)n * batch * sizeof(int64_t),
+                 xb = (size_t)n * batch * sizeof(double);
+    B200_CUDA_TRY(dA.alloc(ab));
+    B200_CUDA_TRY(dP.alloc(pb));
+    B200_CUDA_TRY(dX.alloc(xb));
+    B200_CUDA_TRY(cudaMemcpyAsync(dA.p, LU, ab, cudaMemcpyHostToDevice, st));
+    B200_CUDA_TRY(cudaMemcpyAsync(dP.p, piv, pb, cudaMemcpyHostToDevice, st));
+    B200_CUDA_TRY(cudaMemcpyAsync(dX.p, bx, xb, cudaMemcpyHostToDevice, st));
+    if ((rc = getrs_dev(dA.as<double>(), dP.as<int64_t>(), dX.as<double>(), n, batch, layout, st))) return rc;
+    B200_CUDA_TRY(cudaMemcpyAsync(bx, dX.p, xb, cudaMemcpyDeviceToHost, st));
+    B200_CUDA_TRY(cudaStreamSynchronize(st));
+    return B200IDA_OK;
+}
+
+int b200ida_wrms_batched(const double* x, const double* w, double* out, int n, int64_t batch, int layout, int mem,
+                         void* stream) {
+    int rc = check_common(x, w, n, batch, layout, mem, "b200ida_wrms_batched");
+    if (rc) return rc;
+    if (!out) return set_error(B200IDA_ERR_ARG, "b200ida_wrms_batched: out is null");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (mem == B200IDA_MEM_DEVICE) return wrms_dev(x, w, out, n, batch, layout, st);
+    DevBuf dX, dW, dO;
+    const size_t vb = (size_t)n * batch * sizeof(double), ob = (size_t)batch * sizeof(double);
+    B200_CUDA_TRY(dX.alloc(vb));
+    B200_CUDA_TRY(dW.alloc(vb));
+    B200_CUDA_TRY(dO.alloc(ob));
+    B200_CUDA_TRY(cudaMemcpyAsync(dX.p, x, vb, cudaMemcpyHostToDevice, st));
+    B200_CUDA_TRY(cudaMemcpyAsync(dW.p, w, vb, cudaMemcpyHostToDevice, st));
+    if ((rc = wrms_dev(dX.as<double>(), dW.as<double>(), dO.as<double>(), n, batch, layout, st))) return rc;
+    B200_CUDA_TRY(cudaMemcpyAsync(out, dO.p, ob, cudaMemcpyDeviceToHost, st));
+    B200_CUDA_TRY(cudaStreamSynchronize(st));
+    return B200IDA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,189 @@
+"""`Ida` -- the reference's stepping API (Ida::new / Ida::solve / getters) over an ensemble.
+
+Mirrors src/lib.rs:278-283 (new), src/impl_solve.rs:69-74 (solve) and src/ida_io.rs (getters): same
+names, argument meaning and statuses, but every call acts on `batch` independent instances at once and
+all per-step work happens inside one CUDA kernel launch (C ABI "Level 2", include/b200ida.h).
+"""
+import ctypes as C
+import enum
+
+import numpy as np
+
+from . import _buffers as B
+from . import _lib
+from .tol_control import TolControlSV
+
+
+class IdaTask(enum.Enum):  # src/lib.rs:51-55
+    Normal = 0
+    OneStep = 1
+
+
+class IdaSolveStatus(enum.IntEnum):
+    """0 = IdaSolveStatus::Success (src/lib.rs:57-63); negatives = the IdaError the reference returns."""
+    Success = 0
+    TooMuchWork = -1      # mxstep steps in one call (IdaError::IllegalInput, src/impl_solve.rs:249-260)
+    TooMuchAccuracy = -2  # src/impl_solve.rs:296-308
+    ErrFail = -3          # src/lib.rs:1194-1198
+    ConvergenceFail = -4  # src/lib.rs:1232-1234
+    LinearSetupFail = -5  # singular Jacobian (reference: panic, src/ida_ls.rs:287)
+    BadErrorWeight = -6   # src/impl_solve.rs:272-285
+    IllegalInput = -7     # src/impl_solve.rs:97-109
+    BadTimeValue = -8     # src/lib.rs:1286-1292
+
+
+class Ida:
+    """Ida<P, Dense, Newton, TolControlSV> for a whole ensemble."""
+
+    def __init__(self, problem, yy0, yp0, tol_control, device=0):
+        """Ida::new(problem, yy0, yp0, tol_control) (src/lib.rs:278-283).  yy0, yp0: (n, batch) SoA,
+        numpy (host; copied in) or torch CUDA tensors (device), same space as problem.params."""
+        _lib.require_device()
+        n, batch = problem.model_size(), problem.batch
+        if tuple(yy0.shape) != (n, batch) or tuple(yp0.shape) != (n, batch):
+            raise ValueError("yy0 / yp0 must have shape (%d, %d)" % (n, batch))  # assert_eq!, src/lib.rs:284
+        if not isinstance(tol_control, TolControlSV):
+            raise TypeError("tol_control must be TolControlSV or TolControlSS")
+        self.problem, self.n, self.batch, self.device = problem, n, batch, device
+        self._atol = np.ascontiguousarray(tol_control.atol_vector(n))
+        pp, m1 = B.describe(problem.params, np.float64, "params")
+        py, m2 = B.describe(yy0, np.float64, "yy0")
+        pyp, m3 = B.describe(yp0, np.float64, "yp0")
+        self._mem = B.common_mem(m1, m2, m3)
+        self._ref = yy0  # which space outputs are allocated in
+        h = C.c_void_p()
+        _lib.check(_lib.lib().b200ida_create(C.byref(h), problem.kind, n, batch, problem.nparams, pp, py, pyp,
+                                             tol_control.ida_rtol, self._atol.ctypes.data, self._mem, device,
+                                             B.current_stream(self._mem)))
+        self._h = h
+
+    new = classmethod(lambda cls, *a, **k: cls(*a, **k))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().b200ida_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def reinit(self, yy0, yp0, params=None):
+        """fresh Ida::new state for every instance (t = 0, counters 0), keeping the device allocation"""
+        py, m1 = B.describe(yy0, np.float64, "yy0")
+        pyp, m2 = B.describe(yp0, np.float64, "yp0")
+        pp, m3 = B.describe(params, np.float64, "params")
+        mem = B.common_mem(m1, m2, m3)
+        _lib.check(_lib.lib().b200ida_reinit(self._h, pp, py, pyp, mem))
+
+    # ---- stepping ---------------------------------------------------------------------------------------
+    def solve(self, tout, itask=IdaTask.Normal):
+        """Ida::solve(tout, &mut tret, itask) (src/impl_solve.rs:69-74) for every instance.
+        Returns (status, tret): int32 (batch,) of IdaSolveStatus values and float64 (batch,)."""
+        if itask != IdaTask.Normal:
+            raise NotImplementedError("only IdaTask::Normal is on the device path")
+        status = B.empty_like_space(self._ref, (self.batch,), np.int32)
+        ps, _ = B.describe(status, np.int32, "status")
+        _lib.check(_lib.lib().b200ida_solve(self._h, float(tout), 0, ps, self._mem))
+        tret = B.empty_like_space(self._ref, (self.batch,), np.float64)
+        pt, _ = B.describe(tret, np.float64, "tret")
+        _lib.check(_lib.lib().b200ida_get_state(self._h, None, None, pt, self._mem))
+        return status, tret
+
+    def solve_ladder(self, touts, itask=IdaTask.Normal, want_traj=True):
+        """solve() for touts[0], touts[1], ... in ONE launch.  Returns (status (ntout, batch),
+        yy_traj (ntout, n, batch) or None)."""
+        if itask != IdaTask.Normal:
+            raise NotImplementedError("only IdaTask::Normal is on the device path")
+        touts = np.ascontiguousarray(touts, dtype=np.float64)
+        nt = touts.size
+        status = B.empty_like_space(self._ref, (nt, self.batch), np.int32)
+        traj = B.empty_like_space(self._ref, (nt, self.n, self.batch), np.float64) if want_traj else None
+        ps, _ = B.describe(status, np.int32, "status")
+        pj, _ = B.describe(traj, np.float64, "yy_traj")
+        _lib.check(_lib.lib().b200ida_solve_ladder(self._h, touts.ctypes.data, nt, 0, pj, ps, self._mem))
+        return status, traj
+
+    def sync(self):
+        _lib.check(_lib.lib().b200ida_sync(self._h))
+
+    # ---- getters: src/ida_io.rs -----------------------------------------------------------------------------
+    def _state(self, which):
+        out = B.empty_like_space(self._ref, (self.n, self.batch) if which < 2 else (self.batch,), np.float64)
+        p, _ = B.describe(out, np.float64, "out")
+        args = [None, None, None]
+        args[which] = p
+        _lib.check(_lib.lib().b200ida_get_state(self._h, args[0], args[1], args[2], self._mem))
+        return out
+
+    def get_yy(self):  # ida_io.rs:11
+        return self._state(0)
+
+    def get_yp(self):  # ida_io.rs:16
+        return self._state(1)
+
+    def _counter(self, idx):
+        out = B.empty_like_space(self._ref, (self.batch,), np.int64)
+        p, _ = B.describe(out, np.int64, "out")
+        args = [None] * 8
+        args[idx] = p
+        _lib.check(_lib.lib().b200ida_get_counters(self._h, *args, self._mem))
+        return out
+
+    def get_num_steps(self):  # :58
+        return self._counter(0)
+
+    def get_num_res_evals(self):  # :64
+        return self._counter(1)
+
+    def get_num_jac_evals(self):  # :79
+        return self._counter(2)
+
+    def get_num_nonlin_solv_iters(self):  # :84
+        return self._counter(3)
+
+    def get_num_err_test_fails(self):  # :74
+        return self._counter(4)
+
+    def get_num_nonlin_solv_conv_fails(self):  # :104
+        return self._counter(5)
+
+    def get_num_lin_solv_setups(self):  # :69
+        return self._counter(6)
+
+    def get_num_step_attempts(self):  # data_trace frames, src/lib.rs:635-639
+        return self._counter(7)
+
+    def get_num_lin_res_evals(self):  # :92 (always 0: no DQ Jacobian)
+        return B.empty_like_space(self._ref, (self.batch,), np.int64) * 0
+
+    def _stepinfo(self, idx):
+        dt = np.int32 if idx < 2 else np.float64
+        out = B.empty_like_space(self._ref, (self.batch,), dt)
+        p, _ = B.describe(out, dt, "out")
+        args = [None] * 6
+        args[idx] = p
+        _lib.check(_lib.lib().b200ida_get_step_info(self._h, *args, self._mem))
+        return out
+
+    def get_last_order(self):  # :22
+        return self._stepinfo(0)
+
+    def get_current_order(self):  # :27
+        return self._stepinfo(1)
+
+    def get_last_step(self):  # :38
+        return self._stepinfo(2)
+
+    def get_current_setp(self):  # :43 (sic, the reference's spelling)
+        return self._stepinfo(3)
+
+    get_current_step = get_current_setp
+
+    def get_current_time(self):  # :48
+        return self._stepinfo(4)
+
+    def get_actual_init_step(self):  # :32
+        return self._stepinfo(5)
+
+    def counters(self):
+        names = ("nst", "nre", "nje", "nni", "netf", "ncfn", "nsetups", "nattempts")
+        return {k: self._counter(i) for i, k in enumerate(names)}

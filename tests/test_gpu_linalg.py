@@ -1,0 +1,138 @@
+"""GPU parity: batched getrf / getrs / wrms through the C ABI vs the CPU oracle -- bit-exact factors,
+pivots (LU pivot sequences must be bit-exact), solutions and norms."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from helpers import assert_bit_equal
+
+pytestmark = pytest.mark.gpu
+
+
+def gen_matrices(n, batch, seed=1234):
+    """the reference's own (commented-out) generator: U(0, 1/n) + anti-identity (benches/dense.rs:236-255)"""
+    rng = np.random.default_rng(seed + n)
+    a = rng.uniform(0.0, 1.0 / n, size=(batch, n, n))
+    a += np.eye(n)[::-1][None]
+    b = rng.uniform(0.0, 1.0, size=(batch, n))
+    return a, b
+
+
+def oracle_lu(a, b):
+    from oracle import binding as ob
+    lus, pivs, xs, infos = [], [], [], []
+    for k in range(a.shape[0]):
+        lu, piv, info = ob.getrf(a[k])
+        lus.append(lu)
+        pivs.append(piv)
+        infos.append(info)
+        xs.append(ob.getrs(lu, piv, b[k]) if info == 0 else b[k])
+    return np.array(lus), np.array(pivs), np.array(xs), np.array(infos)
+
+
+def run_gpu(a, b, layout, device_buffers):
+    """a: (batch, n, n) mathematical matrices, b: (batch, n)"""
+    import torch
+    import rust_ida_b200 as r
+    batch, n, _ = a.shape
+    if layout == "soa":
+        A = np.ascontiguousarray(a.transpose(1, 2, 0))  # [i, j, b]
+        X = np.ascontiguousarray(b.T)
+    else:
+        A = np.ascontiguousarray(a.transpose(0, 2, 1))  # column-major per matrix: [b, j, i]
+        X = b.copy()
+    Bv = X.copy()
+    ls = r.Dense.new(n, batch, layout=layout, raise_on_singular=False)
+    if device_buffers:
+        A, X, Bv = (torch.from_numpy(v).cuda() for v in (A, X, Bv))
+    ls.setup(A)
+    ls.solve(A, X, Bv, 0.0)
+    if device_buffers:
+        torch.cuda.synchronize()
+        A, X = A.cpu().numpy(), X.cpu().numpy()
+        piv, info = ls.pivots.cpu().numpy(), ls.info.cpu().numpy()
+    else:
+        piv, info = ls.pivots, ls.info
+    if layout == "soa":
+        return A.transpose(2, 0, 1), piv.T, X.T, info
+    return A.transpose(0, 2, 1), piv, X, info
+
+
+@pytest.mark.parametrize("layout", ["soa", "aos"])
+@pytest.mark.parametrize("n,batch", [(3, 4099), (4, 1000), (8, 517), (16, 130), (32, 67), (64, 19), (100, 9),
+                                     (128, 5), (200, 3), (256, 2)])
+def test_getrf_getrs_bit_exact(n, batch, layout):
+    a, b = gen_matrices(n, batch)
+    lu_ref, piv_ref, x_ref, info_ref = oracle_lu(a, b)
+    lu, piv, x, info = run_gpu(a, b, layout, device_buffers=(n % 2 == 0))
+    assert np.array_equal(info, info_ref)
+    assert np.array_equal(piv, piv_ref), "pivot sequences differ"
+    assert_bit_equal(lu, lu_ref, "LU factors n=%d" % n)
+    assert_bit_equal(x, x_ref, "solutions n=%d" % n)
+    assert (piv[:, 0] != 0).any()  # the anti-identity forces row swaps
+
+
+def test_golden_matrices_on_gpu(golden_dir):
+    """the reference's own known answers (crates/linear/src/dense.rs:267-311), bit-exact incl. pivots [2,1,2]"""
+    with open(os.path.join(golden_dir, "dense.json")) as f:
+        t = json.load(f)["tests"]
+    mats, expects = [], []
+    for name in ("test_get_rf1", "test_get_rf2"):
+        it = {i["name"]: i for i in t[name]}
+        mats.append(np.array(it["mat_a"]["value"]).T)
+        expects.append(np.array(it["expect"]["value"]).T)
+    a = np.array(mats)
+    for layout in ("soa", "aos"):
+        lu, piv, _, info = run_gpu(a, np.ones((2, 3)), layout, device_buffers=False)
+        assert info.tolist() == [0, 0]
+        assert piv.tolist() == [[2, 1, 2], [2, 1, 2]]
+        assert_bit_equal(lu, np.array(expects), "golden LU")
+    # getrs known answers (dense.rs:215-265)
+    import rust_ida_b200 as r
+    for name in ("test_get_rs1", "test_get_rs2"):
+        it = {i["name"]: i for i in t[name]}
+        lu = np.array(it["mat_a"]["value"]).T
+        ls = r.Dense.new(3, 1, layout="soa")
+        ls.pivots = np.array(it["pivot"]["value"], dtype=np.int64).reshape(3, 1).copy()
+        x = np.zeros((3, 1))
+        ls.solve(np.ascontiguousarray(lu.reshape(3, 3, 1)), x, np.array(it["b"]["value"]).reshape(3, 1).copy(), 0.0)
+        assert_bit_equal(x[:, 0], np.array(it["expect"]["value"]), name)
+
+
+@pytest.mark.parametrize("layout,n", [("soa", 3), ("aos", 3), ("soa", 20), ("aos", 40)])
+def test_singular_reports_one_based_column(layout, n):
+    import rust_ida_b200 as r
+    rng = np.random.default_rng(7)
+    a = rng.uniform(0.5, 1.5, size=(4, n, n)) + np.eye(n)[None] * n
+    a[1, :, 0] = 0.0            # first column zero -> col 1
+    a[2, :, n - 1] = a[2, :, 0]  # last column duplicates the first -> zero pivot at the last step (col n)
+    a[3] = 0.0
+    _, _, _, info_ref = oracle_lu(a, np.ones((4, n)))
+    _, _, _, info = run_gpu(a, np.ones((4, n)), layout, device_buffers=False)
+    assert info.tolist() == info_ref.tolist()
+    assert info[0] == 0 and info[1] == 1 and info[3] == 1
+    ls = r.Dense.new(n, 4, layout=layout)
+    A = np.ascontiguousarray(a.transpose(1, 2, 0) if layout == "soa" else a.transpose(0, 2, 1))
+    with pytest.raises(r.LUFactFail) as ei:
+        ls.setup(A)
+    assert ei.value.col == 1 and ei.value.index == 1  # 1-based column, like linear::Error::LUFactFail
+
+
+@pytest.mark.parametrize("layout", ["soa", "aos"])
+@pytest.mark.parametrize("n,batch", [(3, 1000), (32, 257), (100, 33)])
+def test_wrms_bit_exact(n, batch, layout):
+    import rust_ida_b200 as r
+    from oracle import binding as ob
+    rng = np.random.default_rng(n)
+    x = rng.normal(size=(batch, n)) * 10.0 ** rng.integers(-8, 8, size=(batch, 1))
+    w = 1.0 / (1e-4 * np.abs(x) + 1e-8)
+    ref = np.array([ob.wrms(x[k], w[k]) for k in range(batch)])
+    if layout == "soa":
+        out = r.norm_wrms(np.ascontiguousarray(x.T), np.ascontiguousarray(w.T), layout="soa")
+    else:
+        out = r.norm_wrms(x, w, layout="aos")
+    assert_bit_equal(out, ref, "wrms")
+    # the reference's own pin: wrms(-0.5, 0.5, n=32) == 0.25
+    assert r.norm_wrms(np.full((32, 1), -0.5), np.full((32, 1), 0.5))[0] == 0.25
