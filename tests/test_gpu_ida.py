@@ -108,17 +108,21 @@ def test_lorenz_ensemble_parity():
 
 
 def test_mxstep_is_per_call_and_resumable():
-    """mxstep = 500 per solve() call (src/impl_solve.rs:249-260): one huge tout returns TooMuchWork after
-    exactly 500 steps, and calling again continues from there -- same as the oracle."""
-    from rust_ida_b200 import IdaSolveStatus, Roberts
+    """mxstep = 500 per solve() call (src/impl_solve.rs:249-260): Lorenz needs 613 steps to t = 5, so a single
+    solve(5.0) returns TooMuchWork after exactly 500 steps, and calling again continues from there -- same as
+    the oracle."""
+    from rust_ida_b200 import IdaSolveStatus, Lorenz63
     ob, _ = oracle_with_detpow()
-    p = np.array(Roberts.DEFAULT).reshape(3, 1).repeat(3, axis=1).copy()
-    yy0, yp0 = Roberts.consistent_ic(p)
-    touts = np.array([4e30, 4e30, 8e30])
-    ref = ob.ensemble_solve(ob.PK_ROBERTS, 3, p, yy0, yp0, ROBERTS_RTOL, ROBERTS_ATOL, touts, want_traj=True)
-    g = run_engine(Roberts, p, yy0, yp0, ROBERTS_RTOL, ROBERTS_ATOL, touts, ladder=True)
-    assert g["status"][0, 0] == IdaSolveStatus.TooMuchWork and ref["status"][0, 0] == -1
+    p = np.array(Lorenz63.DEFAULT).reshape(3, 1).repeat(3, axis=1).copy()
+    yy0, yp0 = Lorenz63.consistent_ic(p)
+    touts = np.array([5.0, 5.0, 6.0])
+    ref = ob.ensemble_solve(ob.PK_LORENZ63, 3, p, yy0, yp0, LORENZ_RTOL, LORENZ_ATOL, touts, want_traj=True)
+    g = run_engine(Lorenz63, p, yy0, yp0, LORENZ_RTOL, LORENZ_ATOL, touts, ladder=True)
+    assert g["status"][:, 0].tolist() == [IdaSolveStatus.TooMuchWork, 0, 0] and ref["status"][:, 0].tolist() == [-1, 0, 0]
     compare(g, ref)
+    # the same through separate solve() calls
+    g2 = run_engine(Lorenz63, p, yy0, yp0, LORENZ_RTOL, LORENZ_ATOL, touts, ladder=False)
+    compare(g2, ref)
 
 
 def test_error_statuses_match_oracle():
