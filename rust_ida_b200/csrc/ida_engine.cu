@@ -23,12 +23,14 @@ char* last_error_buf() {
 
 // Thread-per-instance solve over a ladder of output times (ida_thread.cuh).
 template <class P>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(THREAD_BLOCK, 4)
 ida_solve_thread_kernel(double* __restrict__ ds, int* __restrict__ is, const double* __restrict__ params, int64_t B,
                         TolN<P::N> tol, LadderParams lad, double* __restrict__ yy_traj, int32_t* __restrict__ status) {
+    extern __shared__ double smem[];
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     IdaThread<P> s;
+    s.sm = smem + threadIdx.x;
     s.prob.load(params, B, b);
     s.load(ds, is, B, b);
     s.solve_ladder(lad, tol, yy_traj, status, B, b);
@@ -228,14 +230,15 @@ int b200ida_solve_ladder(b200ida_ensemble* e, const double* touts, int ntout, in
             d_stat = statb.as<int32_t>();
         }
     }
-    const int tb = 128;
+    const int tb = THREAD_BLOCK;
     const unsigned grid = (unsigned)((e->B + tb - 1) / tb);
+    const size_t smem = (size_t)IdaThread<Roberts>::SMEM_DOUBLES * tb * sizeof(double);  // n = 3 for both problems
     switch (e->problem) {
     case B200IDA_PROBLEM_ROBERTS: {
         TolN<3> tol;
         tol.rtol = e->rtol;
         for (int i = 0; i < 3; ++i) tol.atol[i] = e->atol[i];
-        ida_solve_thread_kernel<Roberts><<<grid, tb, 0, e->stream>>>(e->dstate, e->istate, e->params, e->B, tol, lad,
+        ida_solve_thread_kernel<Roberts><<<grid, tb, smem, e->stream>>>(e->dstate, e->istate, e->params, e->B, tol, lad,
                                                                      d_traj, d_stat);
         break;
     }
@@ -243,7 +246,7 @@ int b200ida_solve_ladder(b200ida_ensemble* e, const double* touts, int ntout, in
         TolN<3> tol;
         tol.rtol = e->rtol;
         for (int i = 0; i < 3; ++i) tol.atol[i] = e->atol[i];
-        ida_solve_thread_kernel<Lorenz63><<<grid, tb, 0, e->stream>>>(e->dstate, e->istate, e->params, e->B, tol, lad,
+        ida_solve_thread_kernel<Lorenz63><<<grid, tb, smem, e->stream>>>(e->dstate, e->istate, e->params, e->B, tol, lad,
                                                                       d_traj, d_stat);
         break;
     }

@@ -1,17 +1,24 @@
 // ida_thread.cuh -- thread-per-instance ensemble IDA for small compile-time n (Roberts, Lorenz: n = 3).
 //
 // One CUDA thread integrates one DAE instance; the whole `Ida::solve` loop of the reference
-// (src/impl_solve.rs:69-376) runs on the device.  All per-instance state (phi, psi..gamma, ee, ewt,
-// yy, yp, the LU factors and pivots, ~20 scalars, counters) is loaded once from the SoA arrays in
-// HBM into registers, integrated, and stored back once: HBM traffic is ~1.5 KB per instance per
-// launch, three orders of magnitude below what the FP64 pipe needs, so the kernel is FP64-issue-bound
-// by design ("Kernels").  Every small array is indexed with compile-time indices under
-// predicates (`if (j <= kk)`) so nothing lands in local memory.
+// (src/impl_solve.rs:69-376) runs on the device.  Per-instance state is loaded once from the SoA arrays
+// in HBM, integrated, and stored back once: HBM traffic is ~1.5 KB per instance per launch, three orders
+// of magnitude below what the FP64 pipe needs, so the kernel is FP64-issue-bound by design.
 //
-// Divergence: lanes differ in step count, retries and Newton iterations.  The solve loop is
-// FLATTENED: one trip of the single `while` = one step ATTEMPT of every live lane, whatever output
-// time (ladder rung) or retry that lane is on, so a warp's time is max-over-lanes of total attempts,
-// not a sum of per-step or per-rung maxima.
+// Where the state lives while integrating (v2; profiles/r1a_* show why v1's all-in-registers layout with
+// fully unrolled predicated loops lost: 248 registers -> 12 % occupancy, a 267 KB kernel body -> the
+// dominant stall was instruction fetch):
+//   * the divided-difference array phi[6][n] and the five 6-entry coefficient arrays psi/alpha/beta/
+//     sigma/gamma are indexed by the (per-instance, run-time) order kk, so they sit in SHARED memory,
+//     one column per thread ([field][thread], 8-byte words -> conflict-free), and the loops over the
+//     order are real loops (small code, divergence only in trip count);
+//   * n-vectors (ee, ewt, yy, yp, predictors), the LU factors, pivots and ~20 scalars are registers;
+//   * pow, the WRMS norm and the interpolation are out-of-line functions shared by all call sites.
+//
+// Divergence: lanes differ in step count, retries and Newton iterations.  The solve loop is FLATTENED:
+// one trip of the single `while` = one step ATTEMPT of every live lane, whatever output time (ladder
+// rung) or retry that lane is on, so a warp's time is max-over-lanes of total attempts, not a sum of
+// per-step or per-rung maxima.
 //
 // Arithmetic is written operation-for-operation like the reference (file:line on each routine), built
 // with -fmad=false: + - * / sqrt are IEEE correctly rounded and un-fused, pow is detpow.h.
@@ -21,21 +28,95 @@
 
 namespace b200ida {
 
+constexpr int THREAD_BLOCK = 128;  // threads per CTA of the thread-per-instance kernels
+
 template <int N>
 struct TolN {
     double rtol;
     double atol[N];
 };
 
+__device__ __noinline__ double pow_noinline(double x, double y) { return detpow::det_pow(x, y); }
+
+// ---- WRMS norm: src/norm_rms.rs:31-38 (ordered fold from 0) -------------------------------------------
+template <int N>
+__device__ __forceinline__ double wrms_inline(const double (&x)[N], const double (&w)[N]) {
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const double p = x[i] * w[i];
+        acc = acc + p * p;
+    }
+    return sqrt(acc / (double)N);
+}
+__device__ __noinline__ double wrms3(double x0, double x1, double x2, double w0, double w1, double w2) {
+    const double x[3] = {x0, x1, x2}, w[3] = {w0, w1, w2};
+    return wrms_inline<3>(x, w);
+}
+template <int N>
+__device__ __forceinline__ double wrms(const double (&x)[N], const double (&w)[N]) {
+    if constexpr (N == 3) return wrms3(x[0], x[1], x[2], w[0], w[1], w[2]);
+    else return wrms_inline<N>(x, w);
+}
+
+// ---- get_solution: src/lib.rs:1274-1343 ; returns 0 or B200IDA_ST_BAD_T.  Out of line (called ~12 times per
+// instance); reads phi / psi from the thread's shared-memory column, writes yret to out[0..N), ypret to out[N..2N).
+template <int N>
+__device__ __noinline__ int get_solution_fn(const double* sm, double hh, double hused, double tn, int kused, double t,
+                                            double* out) {
+    const double sgn = (hh > 0.0 || (hh == 0.0 && !signbit(hh))) ? 1.0 : -1.0;
+    const double tfuzz = 100.0 * DBL_EPS * (fabs(tn) + fabs(hh)) * sgn;
+    const double tp = tn - hused - tfuzz;
+    if ((t - tp) * hh < 0.0) return B200IDA_ST_BAD_T;
+    const int kord = (kused == 0) ? 1 : kused;
+    const double delt = t - tn;
+    double c = 1.0, d = 0.0;
+    double gam = delt / sm[(6 * N + 0) * THREAD_BLOCK];
+    // yret = sum_j cvals[j] phi[j], ypret = sum_j dvals[j-1] phi[j], accumulated from 0 in j order
+    double y[N], yp[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        y[i] = 0.0 + c * sm[i * THREAD_BLOCK];
+        yp[i] = 0.0;
+    }
+#pragma unroll 1
+    for (int j = 1; j <= kord; ++j) {
+        const double psi_jm1 = sm[(6 * N + j - 1) * THREAD_BLOCK];
+        d = d * gam + c / psi_jm1;
+        c = c * gam;
+        gam = (delt + psi_jm1) / sm[(6 * N + j) * THREAD_BLOCK];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const double p = sm[(j * N + i) * THREAD_BLOCK];
+            y[i] += c * p;
+            yp[i] += d * p;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        out[i] = y[i];
+        out[N + i] = yp[i];
+    }
+    return 0;
+}
+
 template <class P>
 struct IdaThread {
     static constexpr int N = P::N;
+    static constexpr int SMEM_DOUBLES = 6 * N + 30;  // phi + psi, alpha, beta, sigma, gamma
     using L = Layout;
 
-    // ---- persistent state (src/lib.rs:89-244, src/ida_nls.rs:20-60, src/ida_ls.rs:15-106,
-    //      newton.rs:14-32, dense.rs:13-20) ------------------------------------------------------------
-    double phi[MXORDP1][N];
-    double psi[MXORDP1], alpha[MXORDP1], beta[MXORDP1], sigma[MXORDP1], gamma[MXORDP1];
+    // ---- shared-memory resident arrays (run-time indexed by the order) ------------------------------
+    double* sm;  // this thread's column: element f at sm[f * THREAD_BLOCK]
+    __device__ __forceinline__ double& phi(int j, int i) { return sm[(j * N + i) * THREAD_BLOCK]; }
+    __device__ __forceinline__ double& psi(int j) { return sm[(6 * N + j) * THREAD_BLOCK]; }
+    __device__ __forceinline__ double& alpha(int j) { return sm[(6 * N + 6 + j) * THREAD_BLOCK]; }
+    __device__ __forceinline__ double& beta(int j) { return sm[(6 * N + 12 + j) * THREAD_BLOCK]; }
+    __device__ __forceinline__ double& sigma(int j) { return sm[(6 * N + 18 + j) * THREAD_BLOCK]; }
+    __device__ __forceinline__ double& gamma(int j) { return sm[(6 * N + 24 + j) * THREAD_BLOCK]; }
+
+    // ---- register state (src/lib.rs:89-244, src/ida_nls.rs:20-60, src/ida_ls.rs:15-106,
+    //      newton.rs:14-32, dense.rs:13-20) ---------------------------------------------------------------
     double ee[N], ewt[N], yy[N], yp[N];
     double J[N][N];
     int piv[N];
@@ -46,19 +127,11 @@ struct IdaThread {
     double yypredict[N], yppredict[N], delta[N], oldnrm;
     P prob;
 
-    // ---- HBM <-> registers ---------------------------------------------------------------------------
+    // ---- HBM <-> registers / shared memory -----------------------------------------------------------
     __device__ __forceinline__ void load(const double* __restrict__ ds, const int* __restrict__ is, int64_t B, int64_t b) {
         constexpr Layout lay(N);
-#pragma unroll
-        for (int j = 0; j < MXORDP1; ++j) {
-#pragma unroll
-            for (int i = 0; i < N; ++i) phi[j][i] = ds[(int64_t)lay.phi(j, i) * B + b];
-            psi[j] = ds[(int64_t)lay.psi(j) * B + b];
-            alpha[j] = ds[(int64_t)lay.alpha(j) * B + b];
-            beta[j] = ds[(int64_t)lay.beta(j) * B + b];
-            sigma[j] = ds[(int64_t)lay.sigma(j) * B + b];
-            gamma[j] = ds[(int64_t)lay.gamma(j) * B + b];
-        }
+#pragma unroll 1
+        for (int f = 0; f < SMEM_DOUBLES; ++f) sm[f * THREAD_BLOCK] = ds[(int64_t)f * B + b];  // phi..gamma are fields 0..6N+29
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             ee[i] = ds[(int64_t)lay.ee(i) * B + b];
@@ -81,18 +154,10 @@ struct IdaThread {
 #undef LD_I
     }
 
-    __device__ __forceinline__ void store(double* __restrict__ ds, int* __restrict__ is, int64_t B, int64_t b) const {
+    __device__ __forceinline__ void store(double* __restrict__ ds, int* __restrict__ is, int64_t B, int64_t b) {
         constexpr Layout lay(N);
-#pragma unroll
-        for (int j = 0; j < MXORDP1; ++j) {
-#pragma unroll
-            for (int i = 0; i < N; ++i) ds[(int64_t)lay.phi(j, i) * B + b] = phi[j][i];
-            ds[(int64_t)lay.psi(j) * B + b] = psi[j];
-            ds[(int64_t)lay.alpha(j) * B + b] = alpha[j];
-            ds[(int64_t)lay.beta(j) * B + b] = beta[j];
-            ds[(int64_t)lay.sigma(j) * B + b] = sigma[j];
-            ds[(int64_t)lay.gamma(j) * B + b] = gamma[j];
-        }
+#pragma unroll 1
+        for (int f = 0; f < SMEM_DOUBLES; ++f) ds[(int64_t)f * B + b] = sm[f * THREAD_BLOCK];
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             ds[(int64_t)lay.ee(i) * B + b] = ee[i];
@@ -115,21 +180,10 @@ struct IdaThread {
 #undef ST_I
     }
 
-    // ---- WRMS norm: src/norm_rms.rs:31-38 (ordered fold from 0) -----------------------------------------
-    __device__ __forceinline__ static double wrms(const double (&x)[N], const double (&w)[N]) {
-        double acc = 0.0;
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            const double p = x[i] * w[i];
-            acc = acc + p * p;
-        }
-        return sqrt(acc / (double)N);
-    }
-
     // ---- TolControlSV::ewt_set: src/tol_control.rs:71-82 -------------------------------------------------
     __device__ __forceinline__ void ewt_set(const TolN<N>& tol) {
 #pragma unroll
-        for (int i = 0; i < N; ++i) ewt[i] = 1.0 / (tol.rtol * fabs(phi[0][i]) + tol.atol[i]);
+        for (int i = 0; i < N; ++i) ewt[i] = 1.0 / (tol.rtol * fabs(phi(0, i)) + tol.atol[i]);
     }
 
     // ---- set_coeffs: src/lib.rs:722-782 ----------------------------------------------------------------
@@ -137,48 +191,49 @@ struct IdaThread {
         if (hh != hused || kk != kused) ns = 0;
         ns = min(ns + 1, kused + 2);
         if (kk + 1 >= ns) {
-            beta[0] = 1.0;
-            alpha[0] = 1.0;
+            beta(0) = 1.0;
+            alpha(0) = 1.0;
             double temp1 = hh;
-            gamma[0] = 0.0;
-            sigma[0] = 1.0;
-#pragma unroll
-            for (int i = 1; i <= MAXORD; ++i) {
-                if (i <= kk) {
-                    const double temp2 = psi[i - 1];
-                    psi[i - 1] = temp1;
-                    beta[i] = beta[i - 1] * psi[i - 1] / temp2;
-                    temp1 = temp2 + hh;
-                    alpha[i] = hh / temp1;
-                    sigma[i] = (double)i * sigma[i - 1] * alpha[i];
-                    gamma[i] = gamma[i - 1] + alpha[i - 1] / hh;
-                }
+            gamma(0) = 0.0;
+            sigma(0) = 1.0;
+            double beta_prev = 1.0, alpha_prev = 1.0, sigma_prev = 1.0, gamma_prev = 0.0;
+#pragma unroll 1
+            for (int i = 1; i <= kk; ++i) {
+                const double temp2 = psi(i - 1);
+                psi(i - 1) = temp1;
+                const double b_i = beta_prev * temp1 / temp2;
+                temp1 = temp2 + hh;
+                const double a_i = hh / temp1;
+                const double s_i = (double)i * sigma_prev * a_i;
+                const double g_i = gamma_prev + alpha_prev / hh;
+                beta(i) = b_i;
+                alpha(i) = a_i;
+                sigma(i) = s_i;
+                gamma(i) = g_i;
+                beta_prev = b_i;
+                alpha_prev = a_i;
+                sigma_prev = s_i;
+                gamma_prev = g_i;
             }
-#pragma unroll
-            for (int i = 1; i <= MAXORD; ++i)
-                if (i == kk) psi[i] = temp1;
+            psi(kk) = temp1;
         }
         double alphas = 0.0, alpha0 = 0.0;
-#pragma unroll
-        for (int i = 0; i < MAXORD; ++i) {
-            if (i < kk) {
-                alphas -= 1.0 / (double)(i + 1);
-                alpha0 -= alpha[i];
-            }
+#pragma unroll 1
+        for (int i = 0; i < kk; ++i) {
+            alphas -= 1.0 / (double)(i + 1);
+            alpha0 -= alpha(i);
         }
         cjlast = cj;
         cj = -alphas / hh;
-        const double akk = pick6(alpha, kk);
+        const double akk = alpha(kk);
         double ck = fabs(akk + alphas - alpha0);
         ck = fmax(ck, akk);
+#pragma unroll 1
+        for (int j = ns; j <= kk; ++j) {
+            const double bj = beta(j);
 #pragma unroll
-        for (int j = 1; j <= MAXORD; ++j) {
-            if (j >= ns && j <= kk) {
-#pragma unroll
-                for (int i = 0; i < N; ++i) phi[j][i] *= beta[j];
-            }
+            for (int i = 0; i < N; ++i) phi(j, i) *= bj;
         }
-        // j = 0 is only reachable with ns == 0, which set_coeffs never leaves (ns >= 1)
         return ck;
     }
 
@@ -186,21 +241,17 @@ struct IdaThread {
     __device__ __forceinline__ void predict() {
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            yypredict[i] = 0.0;
+            yypredict[i] = 0.0 + phi(0, i);
             yppredict[i] = 0.0;
         }
+#pragma unroll 1
+        for (int j = 1; j <= kk; ++j) {
+            const double gj = gamma(j);
 #pragma unroll
-        for (int j = 0; j <= MAXORD; ++j) {
-            if (j <= kk) {
-#pragma unroll
-                for (int i = 0; i < N; ++i) yypredict[i] += phi[j][i];
-            }
-        }
-#pragma unroll
-        for (int j = 1; j <= MAXORD; ++j) {
-            if (j <= kk) {
-#pragma unroll
-                for (int i = 0; i < N; ++i) yppredict[i] += gamma[j] * phi[j][i];
+            for (int i = 0; i < N; ++i) {
+                const double p = phi(j, i);
+                yypredict[i] += p;
+                yppredict[i] += gj * p;
             }
         }
     }
@@ -316,14 +367,14 @@ struct IdaThread {
 
     // ---- IdaNLProblem::ctest: src/ida_nls.rs:218-266 ; 1 converged, 0 continue, -1 recover ----------------
     __device__ __forceinline__ int nls_ctest(int m, const double (&del)[N], double tol) {
-        const double delnrm = wrms(del, ewt);
+        const double delnrm = wrms<N>(del, ewt);
         if (m == 0) {
             oldnrm = delnrm;
             if (delnrm <= 0.0001 * toldel) return 1;
         } else {
             const double base = delnrm / oldnrm;
             const double arg = 1.0 / (double)m;
-            const double rate = detpow::det_pow(base, arg);
+            const double rate = pow_noinline(base, arg);
             if (rate > RATEMAX) return -1;
             ss = rate / (1.0 - rate);
         }
@@ -349,6 +400,7 @@ struct IdaThread {
 
         double nd[N];  // Newton.delta
         int ret = 0;
+#pragma unroll 1
         for (;;) {  // at most two passes: the second with a fresh Jacobian
 #pragma unroll
             for (int i = 0; i < N; ++i) delta[i] = 0.0;
@@ -363,6 +415,7 @@ struct IdaThread {
             int curiter = 0;
 #pragma unroll
             for (int i = 0; i < N; ++i) ee[i] = 0.0;  // y = y0 = 0
+#pragma unroll 1
             for (;;) {
                 nni += 1;
 #pragma unroll
@@ -406,36 +459,22 @@ struct IdaThread {
     // ---- test_error: src/lib.rs:967-1039 -------------------------------------------------------------------
     __device__ __forceinline__ bool test_error(double ck, double& err_k, double& err_km1) {
         const double scalar_kk = (double)kk;
-        const double enorm_k = wrms(ee, ewt);
-        err_k = pick6(sigma, kk) * enorm_k;
+        const double enorm_k = wrms<N>(ee, ewt);
+        err_k = sigma(kk) * enorm_k;
         const double terr_k = err_k * (scalar_kk + 1.0);
         err_km1 = 0.0;
         int knew_ = kk;
         if (kk > 1) {
-            double phk[N], phkm1[N];
 #pragma unroll
-            for (int i = 0; i < N; ++i) {
-                double a = phi[1][i], c = phi[0][i];
-#pragma unroll
-                for (int j = 2; j <= MAXORD; ++j) {
-                    if (kk == j) {
-                        a = phi[j][i];
-                        c = phi[j - 1][i];
-                    }
-                }
-                phk[i] = a;
-                phkm1[i] = c;
-            }
-#pragma unroll
-            for (int i = 0; i < N; ++i) delta[i] = phk[i] + ee[i];
-            const double enorm_km1 = wrms(delta, ewt);
-            err_km1 = pick6(sigma, kk - 1) * enorm_km1;
+            for (int i = 0; i < N; ++i) delta[i] = phi(kk, i) + ee[i];
+            const double enorm_km1 = wrms<N>(delta, ewt);
+            err_km1 = sigma(kk - 1) * enorm_km1;
             const double terr_km1 = scalar_kk * err_km1;
             if (kk > 2) {
 #pragma unroll
-                for (int i = 0; i < N; ++i) delta[i] += phkm1[i];
-                const double enorm_km2 = wrms(delta, ewt);
-                const double err_km2 = pick6(sigma, kk - 2) * enorm_km2;
+                for (int i = 0; i < N; ++i) delta[i] += phi(kk - 1, i);
+                const double enorm_km2 = wrms<N>(delta, ewt);
+                const double err_km2 = sigma(kk - 2) * enorm_km2;
                 const double terr_km2 = (scalar_kk - 1.0) * err_km2;
                 if (fmax(terr_km1, terr_km2) <= terr_k) knew_ = kk - 1;
             } else {
@@ -449,16 +488,13 @@ struct IdaThread {
     // ---- restore: src/lib.rs:1044-1083 -----------------------------------------------------------------------
     __device__ __forceinline__ void restore(double saved_t) {
         tn = saved_t;
+#pragma unroll 1
+        for (int j = 1; j <= kk; ++j) psi(j - 1) = psi(j) - hh;
+#pragma unroll 1
+        for (int j = ns; j <= kk; ++j) {
+            const double c = 1.0 / beta(j);
 #pragma unroll
-        for (int j = 1; j <= MAXORD; ++j)
-            if (j <= kk) psi[j - 1] = psi[j] - hh;
-#pragma unroll
-        for (int j = 1; j <= MAXORD; ++j) {
-            if (j >= ns && j <= kk) {
-                const double c = 1.0 / beta[j];
-#pragma unroll
-                for (int i = 0; i < N; ++i) phi[j][i] *= c;
-            }
+            for (int i = 0; i < N; ++i) phi(j, i) *= c;
         }
     }
 
@@ -473,7 +509,7 @@ struct IdaThread {
                 kk = knew;
                 const double base = 2.0 * err_knew + 0.0001;
                 const double arg = 1.0 / (double)(kk + 1);
-                rr = 0.9 * detpow::det_pow(base, -arg);
+                rr = 0.9 * pow_noinline(base, -arg);
                 rr = fmax(0.25, fmin(0.9, rr));
                 hh *= rr;
                 return 0;
@@ -500,11 +536,9 @@ struct IdaThread {
 
     // ---- reset: src/lib.rs:1249-1252 (scales ALL of phi, like the reference) ---------------------------------
     __device__ __forceinline__ void reset() {
-        psi[0] = hh;
-#pragma unroll
-        for (int j = 0; j < MXORDP1; ++j)
-#pragma unroll
-            for (int i = 0; i < N; ++i) phi[j][i] *= rr;
+        psi(0) = hh;
+#pragma unroll 1
+        for (int f = 0; f < MXORDP1 * N; ++f) sm[f * THREAD_BLOCK] *= rr;
     }
 
     // ---- complete_step: src/impl_complete_step.rs:22-177 -------------------------------------------------------
@@ -534,13 +568,8 @@ struct IdaThread {
             } else {
                 double t[N];
 #pragma unroll
-                for (int i = 0; i < N; ++i) {
-                    double p = phi[2][i];  // kk + 1 in 2..5 here (1 <= kk <= 4)
-#pragma unroll
-                    for (int j = 3; j <= MAXORD; ++j) p = (kk + 1 == j) ? phi[j][i] : p;
-                    t[i] = ee[i] - p;
-                }
-                const double enorm = wrms(t, ewt);
+                for (int i = 0; i < N; ++i) t[i] = ee[i] - phi(kk + 1, i);
+                const double enorm = wrms<N>(t, ewt);
                 err_kp1 = enorm / (double)(kk + 2);
                 const double terr_k = (double)(kk + 1) * err_k;
                 const double terr_kp1 = (double)(kk + 2) * err_kp1;
@@ -567,7 +596,7 @@ struct IdaThread {
             {
                 const double base = 2.0 * err_knew + 0.0001;
                 const double arg = -(1.0 / (double)(kk + 1));
-                rr = detpow::det_pow(base, arg);
+                rr = pow_noinline(base, arg);
             }
             if (rr >= 2.0) {
                 hnew = 2.0 * hh;
@@ -581,72 +610,33 @@ struct IdaThread {
         }
         if (kused < MAXORD) {
 #pragma unroll
-            for (int j = 1; j <= MAXORD; ++j) {
-                if (j == kused + 1) {
-#pragma unroll
-                    for (int i = 0; i < N; ++i) phi[j][i] = ee[i];
-                }
-            }
+            for (int i = 0; i < N; ++i) phi(kused + 1, i) = ee[i];
         }
         double tmp[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) tmp[i] = ee[i];
+#pragma unroll 1
+        for (int j = kused; j >= 0; --j) {
 #pragma unroll
-        for (int j = MAXORD; j >= 0; --j) {
-            if (j <= kused) {
-#pragma unroll
-                for (int i = 0; i < N; ++i) {
-                    tmp[i] += phi[j][i];
-                    phi[j][i] = tmp[i];
-                }
+            for (int i = 0; i < N; ++i) {
+                tmp[i] += phi(j, i);
+                phi(j, i) = tmp[i];
             }
         }
     }
 
-    // ---- get_solution: src/lib.rs:1274-1343 ; returns 0 or B200IDA_ST_BAD_T ------------------------------------
+    // ---- get_solution: src/lib.rs:1274-1343 (out-of-line body: get_solution_fn below the class) -----------------
     __device__ __forceinline__ int get_solution(double t) {
-        const double sgn = (hh > 0.0 || (hh == 0.0 && !signbit(hh))) ? 1.0 : -1.0;
-        const double tfuzz = 100.0 * DBL_EPS * (fabs(tn) + fabs(hh)) * sgn;
-        const double tp = tn - hused - tfuzz;
-        if ((t - tp) * hh < 0.0) return B200IDA_ST_BAD_T;
-        const int kord = (kused == 0) ? 1 : kused;
-        const double delt = t - tn;
-        double c = 1.0, d = 0.0;
-        double gam = delt / psi[0];
-        double cvals[MXORDP1], dvals[MXORDP1];
-        cvals[0] = c;
+        double out[2 * N];
+        const int r = get_solution_fn<N>(sm, hh, hused, tn, kused, t, out);
+        if (r == 0) {
 #pragma unroll
-        for (int j = 1; j <= MAXORD; ++j) {
-            cvals[j] = 0.0;
-            dvals[j - 1] = 0.0;
-            if (j <= kord) {
-                d = d * gam + c / psi[j - 1];
-                c = c * gam;
-                gam = (delt + psi[j - 1]) / psi[j];
-                cvals[j] = c;
-                dvals[j - 1] = d;
+            for (int i = 0; i < N; ++i) {
+                yy[i] = out[i];
+                yp[i] = out[N + i];
             }
         }
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            yy[i] = 0.0;
-            yp[i] = 0.0;
-        }
-#pragma unroll
-        for (int j = 0; j <= MAXORD; ++j) {
-            if (j <= kord) {
-#pragma unroll
-                for (int i = 0; i < N; ++i) yy[i] += cvals[j] * phi[j][i];
-            }
-        }
-#pragma unroll
-        for (int j = 1; j <= MAXORD; ++j) {
-            if (j <= kord) {
-#pragma unroll
-                for (int i = 0; i < N; ++i) yp[i] += dvals[j - 1] * phi[j][i];
-            }
-        }
-        return 0;
+        return r;
     }
 
     // ---- first-call block of solve(): src/impl_solve.rs:84-173 ; returns 0 or B200IDA_ST_ILL_INPUT ---------------
@@ -659,20 +649,20 @@ struct IdaThread {
         if (tdist == 0.0) return B200IDA_ST_ILL_INPUT;
         const double troundoff = 2.0 * DBL_EPS * (fabs(tn) + fabs(tout));
         if (tdist < troundoff) return B200IDA_ST_ILL_INPUT;
-        hh = 0.0;  // hin: no setter exists in the reference
-        {
-            hh = 0.001 * tdist;
-            const double ypnorm = wrms(phi[1], ewt);
-            if (ypnorm > 2.0 / hh) hh = 0.5 / ypnorm;
-            if (tout < tn) hh = -hh;
-        }
+        hh = 0.001 * tdist;  // hin = 0: no setter exists in the reference
+        double p1[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) p1[i] = phi(1, i);
+        const double ypnorm = wrms<N>(p1, ewt);
+        if (ypnorm > 2.0 / hh) hh = 0.5 / ypnorm;
+        if (tout < tn) hh = -hh;
         const double rh = fabs(hh) * HMAX_INV;
         if (rh > 1.0) hh /= rh;
         h0u = hh;
         kk = 0;
         kused = 0;
 #pragma unroll
-        for (int i = 0; i < N; ++i) phi[1][i] *= hh;
+        for (int i = 0; i < N; ++i) phi(1, i) = p1[i] * hh;
         eps_newt = EPCON;
         toldel = 0.0001 * eps_newt;
         return 0;
@@ -693,6 +683,7 @@ struct IdaThread {
         double saved_t = 0.0, tout = 0.0;
         int ncf = 0, nef = 0;
 
+#pragma unroll 1
         while (it < lad.ntout) {
             if (need_prologue) {
                 need_prologue = false;
@@ -745,7 +736,10 @@ struct IdaThread {
                         call_status = B200IDA_ST_BAD_EWT;
                         call_done = true;
                     } else {
-                        const double nrm = wrms(phi[0], ewt);
+                        double p0[N];
+#pragma unroll
+                        for (int i = 0; i < N; ++i) p0[i] = phi(0, i);
+                        const double nrm = wrms<N>(p0, ewt);
                         tolsf = DBL_EPS * nrm;
                         if (tolsf > 1.0) {
                             tolsf *= 10.0;
@@ -761,7 +755,7 @@ struct IdaThread {
                                 kk = 1;
                                 kused = 0;
                                 hused = 0.0;
-                                psi[0] = hh;
+                                psi(0) = hh;
                                 cj = 1.0 / hh;
                                 phase = 0;
                                 ns = 0;

@@ -291,14 +291,24 @@ __global__ void __launch_bounds__(256) wrms_thread(const double* __restrict__ x,
     out[b] = sqrt(acc / (double)n);
 }
 
-// AoS <-> SoA transposes used when a large-n SoA batch has to go through the AoS in-place kernel
-__global__ void transpose_to_aos(const double* __restrict__ soa, double* __restrict__ aos, int64_t rows, int64_t B) {
+// SoA <-> AoS conversions used when a large-n SoA batch has to go through the in-place AoS kernel.
+// Matrices: SoA element (i, j, b) at (i*n + j)*B + b  <->  AoS column-major b*n*n + j*n + i.
+__global__ void mat_soa_to_aos(const double* __restrict__ soa, double* __restrict__ aos, int n, int64_t B) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= rows * B) return;
+    if (e >= (int64_t)n * n * B) return;
     const int64_t r = e / B, b = e % B;
-    aos[b * rows + r] = soa[e];
+    const int i = (int)(r / n), j = (int)(r % n);
+    aos[b * n * n + (int64_t)j * n + i] = soa[e];
 }
-__global__ void transpose_to_soa(const double* __restrict__ aos, double* __restrict__ soa, int64_t rows, int64_t B) {
+__global__ void mat_aos_to_soa(const double* __restrict__ aos, double* __restrict__ soa, int n, int64_t B) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (int64_t)n * n * B) return;
+    const int64_t r = e / B, b = e % B;
+    const int i = (int)(r / n), j = (int)(r % n);
+    soa[e] = aos[b * n * n + (int64_t)j * n + i];
+}
+// vectors (any 8-byte element): SoA (i, b) at i*B + b  <->  AoS b*n + i
+__global__ void vec_aos_to_soa(const double* __restrict__ aos, double* __restrict__ soa, int64_t rows, int64_t B) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= rows * B) return;
     const int64_t r = e / B, b = e % B;
@@ -360,12 +370,12 @@ static int getrf_dev(double* A, int64_t* piv, int32_t* info, int n, int64_t B, i
     const int64_t rows = (int64_t)n * n;
     B200_CUDA_TRY(tmp.alloc((size_t)rows * B * sizeof(double)));
     const unsigned tg = (unsigned)((rows * B + 255) / 256);
-    transpose_to_aos<<<tg, 256, 0, st>>>(A, tmp.as<double>(), rows, B);
+    mat_soa_to_aos<<<tg, 256, 0, st>>>(A, tmp.as<double>(), n, B);
     B200_CUDA_TRY(ptmp.alloc((size_t)n * B * sizeof(int64_t)));
     getrf_cta<false, false><<<grid, CTA_THREADS, 0, st>>>(tmp.as<double>(), ptmp.as<int64_t>(), info, n, B);
-    transpose_to_soa<<<tg, 256, 0, st>>>(tmp.as<double>(), A, rows, B);
+    mat_aos_to_soa<<<tg, 256, 0, st>>>(tmp.as<double>(), A, n, B);
     // pivots: int64 has the same width as double, reuse the transpose kernel bit-for-bit
-    transpose_to_soa<<<(unsigned)(((int64_t)n * B + 255) / 256), 256, 0, st>>>(
+    vec_aos_to_soa<<<(unsigned)(((int64_t)n * B + 255) / 256), 256, 0, st>>>(
         reinterpret_cast<const double*>(ptmp.as<int64_t>()), reinterpret_cast<double*>(piv), n, B);
     B200_CUDA_TRY(cudaGetLastError());
     B200_CUDA_TRY(cudaStreamSynchronize(st));  // scratch freed on return
