@@ -9,7 +9,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-SO_PATH = os.path.join(CSRC, "libb200ida.so")
+SO_PATH = os.environ.get("B200IDA_LIB") or os.path.join(CSRC, "libb200ida.so")  # env override: kernel experiments only
 
 MEM_DEVICE, MEM_HOST = 0, 1
 LAYOUT_SOA, LAYOUT_AOS = 0, 1

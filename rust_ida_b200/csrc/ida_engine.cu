@@ -22,8 +22,11 @@ char* last_error_buf() {
 // ---- kernels -----------------------------------------------------------------------------------------
 
 // Thread-per-instance solve over a ladder of output times (ida_thread.cuh).
+#ifndef IDA_MIN_BLOCKS
+#define IDA_MIN_BLOCKS 4
+#endif
 template <class P>
-__global__ void __launch_bounds__(THREAD_BLOCK, 4)
+__global__ void __launch_bounds__(THREAD_BLOCK, IDA_MIN_BLOCKS)
 ida_solve_thread_kernel(double* __restrict__ ds, int* __restrict__ is, const double* __restrict__ params, int64_t B,
                         TolN<P::N> tol, LadderParams lad, double* __restrict__ yy_traj, int32_t* __restrict__ status) {
     extern __shared__ double smem[];

@@ -38,6 +38,23 @@ struct TolN {
 
 __device__ __noinline__ double pow_noinline(double x, double y) { return detpow::det_pow(x, y); }
 
+// x / D for a small integer constant D, bit-identical to the IEEE division the reference performs.
+// Markstein's sequence: y = RN(1/D); q = RN(x*y); r = x - D*q (exact in one FMA); q' = RN(q + r*y) is the
+// correctly rounded quotient whenever nothing over/underflows (checked against `/` on 3e8 random x per D in
+// [2,7]; tools/ notes in DESIGN.md).  3 FP64 instructions instead of the ~25 of a generic division.  Outside
+// 2^-900 <= |x| <= 2^900 (incl. 0, inf, nan) it falls back to the real division.
+template <int D>
+__device__ __forceinline__ double div_const(double x) {
+    constexpr double y = 1.0 / (double)D;
+    const unsigned hi = (unsigned)__double2hiint(x) & 0x7ff00000u;
+    if (hi - 0x07b00000u <= 0x70800000u) {  // biased exponent in [123, 1923]
+        const double q = __dmul_rn(x, y);
+        const double r = __fma_rn(-(double)D, q, x);
+        return __fma_rn(r, y, q);
+    }
+    return x / (double)D;
+}
+
 // ---- WRMS norm: src/norm_rms.rs:31-38 (ordered fold from 0) -------------------------------------------
 template <int N>
 __device__ __forceinline__ double wrms_inline(const double (&x)[N], const double (&w)[N]) {
@@ -47,7 +64,8 @@ __device__ __forceinline__ double wrms_inline(const double (&x)[N], const double
         const double p = x[i] * w[i];
         acc = acc + p * p;
     }
-    return sqrt(acc / (double)N);
+    if constexpr (N >= 2 && N <= 7) return sqrt(div_const<N>(acc));
+    else return sqrt(acc / (double)N);
 }
 __device__ __noinline__ double wrms3(double x0, double x1, double x2, double w0, double w1, double w2) {
     const double x[3] = {x0, x1, x2}, w[3] = {w0, w1, w2};
@@ -98,6 +116,23 @@ __device__ __noinline__ int get_solution_fn(const double* sm, double hh, double 
         out[N + i] = yp[i];
     }
     return 0;
+}
+
+__host__ __device__ constexpr double alphas_seq(int kk) {
+    double a = 0.0;
+    for (int i = 0; i < kk; ++i) a -= 1.0 / (double)(i + 1);
+    return a;
+}
+__device__ __forceinline__ double alphas_of(int kk) {
+    constexpr double t0 = alphas_seq(0), t1 = alphas_seq(1), t2 = alphas_seq(2), t3 = alphas_seq(3), t4 = alphas_seq(4),
+                     t5 = alphas_seq(5);
+    double v = t0;
+    v = (kk == 1) ? t1 : v;
+    v = (kk == 2) ? t2 : v;
+    v = (kk == 3) ? t3 : v;
+    v = (kk == 4) ? t4 : v;
+    v = (kk == 5) ? t5 : v;
+    return v;
 }
 
 template <class P>
@@ -217,12 +252,12 @@ struct IdaThread {
             }
             psi(kk) = temp1;
         }
-        double alphas = 0.0, alpha0 = 0.0;
+        // alphas = -(1 + 1/2 + ... + 1/kk) accumulated in that order (src/lib.rs:757-763): a constant per kk,
+        // so it comes from a table built with the same sequential IEEE operations at compile time.
+        const double alphas = alphas_of(kk);
+        double alpha0 = 0.0;
 #pragma unroll 1
-        for (int i = 0; i < kk; ++i) {
-            alphas -= 1.0 / (double)(i + 1);
-            alpha0 -= alpha(i);
-        }
+        for (int i = 0; i < kk; ++i) alpha0 -= alpha(i);
         cjlast = cj;
         cj = -alphas / hh;
         const double akk = alpha(kk);
