@@ -23,7 +23,7 @@ char* last_error_buf() {
 
 // Thread-per-instance solve over a ladder of output times (ida_thread.cuh).
 #ifndef IDA_MIN_BLOCKS
-#define IDA_MIN_BLOCKS 4
+#define IDA_MIN_BLOCKS 3  // 168 regs, 12 warps/SM: measured faster than 4 (128 regs + spills) and 2
 #endif
 template <class P>
 __global__ void __launch_bounds__(THREAD_BLOCK, IDA_MIN_BLOCKS)
