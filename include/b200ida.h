@@ -127,6 +127,17 @@ int b200ida_destroy(b200ida_ensemble* e);
  * (src/lib.rs:278-405) -- all counters, phi, psi.. are reset. */
 int b200ida_reinit(b200ida_ensemble* e, const double* params, const double* yy0, const double* yp0, int mem);
 
+/* Which kernel family integrates the ensemble (all give bit-identical results; tests check that):
+ *   AUTO    thread-per-instance for the n = 3 problems, warp-per-system for n <= 32, CTA-per-system above
+ *   THREAD  one thread per instance, state in registers + a shared-memory column (csrc/ida_thread.cuh)
+ *   WARP    one warp per instance, state in a per-warp shared-memory arena (csrc/ida_team.cuh), n <= 32
+ *   CTA     one CTA per instance, LU factors resident in shared memory (csrc/ida_team.cuh), n <= 256 */
+#define B200IDA_KERNEL_AUTO 0
+#define B200IDA_KERNEL_THREAD 1
+#define B200IDA_KERNEL_WARP 2
+#define B200IDA_KERNEL_CTA 3
+int b200ida_set_kernel(b200ida_ensemble* e, int kernel);
+
 /* Ida::solve(tout, &mut tret, IdaTask::Normal) for every instance -- src/impl_solve.rs:69-376.
  * One kernel launch; returns after enqueueing (device outputs) or after copying `status` back (host).
  *   status [out, may be NULL]  [batch] B200IDA_ST_*, in memory space `mem`. */

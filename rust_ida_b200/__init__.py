@@ -14,8 +14,8 @@ from . import _lib
 from ._lib import B200IdaError, build, device_count
 from .ida import Ida, IdaSolveStatus, IdaTask
 from .linear import Dense, LSolverType, LUFactFail, norm_wrms
-from .problems import Lorenz63, Roberts
+from .problems import Heat2D, Lorenz63, Roberts
 from .tol_control import TolControlSS, TolControlSV
 
 __all__ = ["Ida", "IdaTask", "IdaSolveStatus", "Dense", "LSolverType", "LUFactFail", "norm_wrms", "Roberts",
-           "Lorenz63", "TolControlSV", "TolControlSS", "B200IdaError", "build", "device_count"]
+           "Lorenz63", "Heat2D", "TolControlSV", "TolControlSS", "B200IdaError", "build", "device_count"]

@@ -9,6 +9,7 @@
 
 #include "host_util.h"
 #include "ida_common.cuh"
+#include "ida_team.cuh"
 #include "ida_thread.cuh"
 #include "problems.cuh"
 
@@ -38,6 +39,31 @@ ida_solve_thread_kernel(double* __restrict__ ds, int* __restrict__ is, const dou
     s.load(ds, is, B, b);
     s.solve_ladder(lad, tol, yy_traj, status, B, b);
     s.store(ds, is, B, b);
+}
+
+// Team-per-instance solve (ida_team.cuh): persistent teams (warps or whole CTAs) stride over the ensemble.
+template <class Team>
+__global__ void ida_solve_team_kernel(double* __restrict__ ds, int* __restrict__ is, const double* __restrict__ params,
+                                      int64_t B, int n, int kind, int nparams, double rtol, const double* __restrict__ atol,
+                                      LadderParams lad, double* __restrict__ yy_traj, int32_t* __restrict__ status,
+                                      unsigned arena_bytes) {
+    extern __shared__ __align__(16) unsigned char team_smem[];
+    const int tpc = Team::teams_per_cta();
+    IdaTeam<Team> s;
+    s.bind(team_smem + (size_t)Team::team_in_cta() * arena_bytes, n);
+    s.rtol = rtol;
+    s.atol = atol;
+    s.prob.kind = kind;
+    s.prob.n = n;
+    int M = 1;
+    while (M * M < n) ++M;
+    s.prob.M = M;
+    for (int64_t b = (int64_t)blockIdx.x * tpc + Team::team_in_cta(); b < B; b += (int64_t)gridDim.x * tpc) {
+        for (int k = 0; k < 4; ++k) s.prob.p[k] = k < nparams ? params[(int64_t)k * B + b] : 0.0;
+        s.load(ds, is, B, b);
+        s.solve_ladder(lad, yy_traj, status, B, b);
+        s.store(ds, is, B, b);
+    }
 }
 
 // Ida::new (src/lib.rs:278-405): phi[0] = yy0, phi[1] = yp0, yy = yy0, yp = yp0 (src/ida_nls.rs:82-83),
@@ -103,6 +129,8 @@ struct b200ida_ensemble {
     double* dstate = nullptr;  // [ndouble][B]
     int* istate = nullptr;     // [nint][B]
     double* params = nullptr;  // [nparams][B]
+    double* d_atol = nullptr;  // [n]
+    int kernel = B200IDA_KERNEL_AUTO;
 };
 
 static int check_mem(int mem) { return (mem == B200IDA_MEM_DEVICE || mem == B200IDA_MEM_HOST) ? 0 : -1; }
@@ -159,6 +187,15 @@ int b200ida_create(b200ida_ensemble** out, int problem, int n, int64_t batch, in
     switch (problem) {
     case B200IDA_PROBLEM_ROBERTS: need_n = Roberts::N; need_p = Roberts::NP; break;
     case B200IDA_PROBLEM_LORENZ63: need_n = Lorenz63::N; need_p = Lorenz63::NP; break;
+    case B200IDA_PROBLEM_HEAT2D: {
+        int M = 1;
+        while (M * M < n) ++M;
+        if (M * M != n || M < 3 || n > 256)
+            return set_error(B200IDA_ERR_ARG, "b200ida_create: heat2d needs n = M*M with 3 <= M <= 16 (got n=%d)", n);
+        need_n = n;
+        need_p = 1;
+        break;
+    }
     default: return set_error(B200IDA_ERR_UNSUPPORTED, "b200ida_create: problem %d has no kernel", problem);
     }
     if (n != need_n || nparams != need_p)
@@ -184,7 +221,9 @@ int b200ida_create(b200ida_ensemble** out, int problem, int n, int64_t batch, in
     cudaError_t err;
     if ((err = cudaMalloc(&e->dstate, nd * sizeof(double))) != cudaSuccess ||
         (err = cudaMalloc(&e->istate, ni * sizeof(int))) != cudaSuccess ||
-        (err = cudaMalloc(&e->params, (size_t)nparams * batch * sizeof(double))) != cudaSuccess) {
+        (err = cudaMalloc(&e->params, (size_t)nparams * batch * sizeof(double))) != cudaSuccess ||
+        (err = cudaMalloc(&e->d_atol, (size_t)n * sizeof(double))) != cudaSuccess ||
+        (err = cudaMemcpy(e->d_atol, atol, (size_t)n * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) {
         b200ida_destroy(e);
         return set_error(B200IDA_ERR_CUDA, "b200ida_create: cudaMalloc -> %s", cudaGetErrorString(err));
     }
@@ -203,6 +242,7 @@ int b200ida_destroy(b200ida_ensemble* e) {
     if (e->dstate) cudaFree(e->dstate);
     if (e->istate) cudaFree(e->istate);
     if (e->params) cudaFree(e->params);
+    if (e->d_atol) cudaFree(e->d_atol);
     delete e;
     return B200IDA_OK;
 }
@@ -233,27 +273,54 @@ int b200ida_solve_ladder(b200ida_ensemble* e, const double* touts, int ntout, in
             d_stat = statb.as<int32_t>();
         }
     }
-    const int tb = THREAD_BLOCK;
-    const unsigned grid = (unsigned)((e->B + tb - 1) / tb);
-    const size_t smem = (size_t)IdaThread<Roberts>::SMEM_DOUBLES * tb * sizeof(double);  // n = 3 for both problems
-    switch (e->problem) {
-    case B200IDA_PROBLEM_ROBERTS: {
+    int kernel = e->kernel;
+    if (kernel == B200IDA_KERNEL_AUTO)
+        kernel = (e->n == 3 && e->problem != B200IDA_PROBLEM_HEAT2D) ? B200IDA_KERNEL_THREAD
+                 : (e->n <= 32 ? B200IDA_KERNEL_WARP : B200IDA_KERNEL_CTA);
+    if (kernel == B200IDA_KERNEL_THREAD) {
+        if (e->n != 3 || e->problem == B200IDA_PROBLEM_HEAT2D)
+            return set_error(B200IDA_ERR_UNSUPPORTED, "thread-per-instance kernels exist for the n = 3 problems only");
+        const int tb = THREAD_BLOCK;
+        const unsigned grid = (unsigned)((e->B + tb - 1) / tb);
+        const size_t smem = (size_t)IdaThread<Roberts>::SMEM_DOUBLES * tb * sizeof(double);
         TolN<3> tol;
         tol.rtol = e->rtol;
         for (int i = 0; i < 3; ++i) tol.atol[i] = e->atol[i];
-        ida_solve_thread_kernel<Roberts><<<grid, tb, smem, e->stream>>>(e->dstate, e->istate, e->params, e->B, tol, lad,
-                                                                     d_traj, d_stat);
-        break;
-    }
-    case B200IDA_PROBLEM_LORENZ63: {
-        TolN<3> tol;
-        tol.rtol = e->rtol;
-        for (int i = 0; i < 3; ++i) tol.atol[i] = e->atol[i];
-        ida_solve_thread_kernel<Lorenz63><<<grid, tb, smem, e->stream>>>(e->dstate, e->istate, e->params, e->B, tol, lad,
-                                                                      d_traj, d_stat);
-        break;
-    }
-    default: return set_error(B200IDA_ERR_UNSUPPORTED, "no kernel for problem %d", e->problem);
+        if (e->problem == B200IDA_PROBLEM_ROBERTS) {
+            B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_thread_kernel<Roberts>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ida_solve_thread_kernel<Roberts><<<grid, tb, smem, e->stream>>>(e->dstate, e->istate, e->params, e->B, tol, lad,
+                                                                            d_traj, d_stat);
+        } else {
+            B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_thread_kernel<Lorenz63>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ida_solve_thread_kernel<Lorenz63><<<grid, tb, smem, e->stream>>>(e->dstate, e->istate, e->params, e->B, tol, lad,
+                                                                             d_traj, d_stat);
+        }
+    } else {
+        const bool warp = kernel == B200IDA_KERNEL_WARP;
+        if (warp && e->n > 32) return set_error(B200IDA_ERR_UNSUPPORTED, "warp-per-system needs n <= 32 (n = %d)", e->n);
+        const unsigned arena = (unsigned)team_arena_bytes(e->n);
+        const int tb = warp ? 128 : (e->n <= 128 ? 128 : 256);
+        const int tpc = warp ? tb / 32 : 1;
+        const size_t smem = (size_t)arena * tpc;
+        if (smem > 227 * 1024) return set_error(B200IDA_ERR_UNSUPPORTED, "n = %d does not fit the shared-memory arena", e->n);
+        int sms = 148, occ = 1;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device);
+        if (warp) {
+            B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_team_kernel<WarpTeam>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ida_solve_team_kernel<WarpTeam>, tb, smem));
+        } else {
+            B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_team_kernel<CtaTeam>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ida_solve_team_kernel<CtaTeam>, tb, smem));
+        }
+        if (occ < 1) occ = 1;
+        const int64_t want = (e->B + tpc - 1) / tpc;
+        const unsigned grid = (unsigned)(want < (int64_t)sms * occ ? want : (int64_t)sms * occ);  // persistent teams
+        if (warp)
+            ida_solve_team_kernel<WarpTeam><<<grid, tb, smem, e->stream>>>(e->dstate, e->istate, e->params, e->B, e->n, e->problem,
+                                                                           e->nparams, e->rtol, e->d_atol, lad, d_traj, d_stat, arena);
+        else
+            ida_solve_team_kernel<CtaTeam><<<grid, tb, smem, e->stream>>>(e->dstate, e->istate, e->params, e->B, e->n, e->problem,
+                                                                          e->nparams, e->rtol, e->d_atol, lad, d_traj, d_stat, arena);
     }
     B200_CUDA_TRY(cudaGetLastError());
     if (mem == B200IDA_MEM_HOST) {
@@ -261,6 +328,13 @@ int b200ida_solve_ladder(b200ida_ensemble* e, const double* touts, int ntout, in
         if (status) B200_CUDA_TRY(cudaMemcpyAsync(status, d_stat, stat_bytes, cudaMemcpyDeviceToHost, e->stream));
         B200_CUDA_TRY(cudaStreamSynchronize(e->stream));
     }
+    return B200IDA_OK;
+}
+
+int b200ida_set_kernel(b200ida_ensemble* e, int kernel) {
+    if (!e || kernel < B200IDA_KERNEL_AUTO || kernel > B200IDA_KERNEL_CTA)
+        return set_error(B200IDA_ERR_ARG, "b200ida_set_kernel: bad argument");
+    e->kernel = kernel;
     return B200IDA_OK;
 }
 

@@ -66,6 +66,12 @@ class Ida:
 
     __del__ = close
 
+    KERNELS = {"auto": 0, "thread": 1, "warp": 2, "cta": 3}
+
+    def set_kernel(self, kernel):
+        """choose the kernel family ("auto", "thread", "warp", "cta"); results are bit-identical"""
+        _lib.check(_lib.lib().b200ida_set_kernel(self._h, self.KERNELS[kernel]))
+
     def reinit(self, yy0, yp0, params=None):
         """fresh Ida::new state for every instance (t = 0, counters 0), keeping the device allocation"""
         py, m1 = B.describe(yy0, np.float64, "yy0")

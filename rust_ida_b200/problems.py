@@ -63,6 +63,46 @@ class Lorenz63(EnsembleProblem):
         return yy0, np.ascontiguousarray(yp0)
 
 
+class Heat2D(EnsembleProblem):
+    """2-D heat equation as a DAE on an M x M grid (n = M*M), after SUNDIALS idaHeat2D: interior
+    u' = coeff * (5-point Laplacian numerator), boundary rows algebraic u = 0.  Not in the reference
+    (SURVEY.md 8d config 5); params row (coeff), nominal coeff = 1/dx^2, dx = 1/(M-1)."""
+    kind, nparams = PROBLEM_HEAT2D, 1
+
+    def __init__(self, params, M=10):
+        self.M = int(M)
+        self.n = self.M * self.M
+        super().__init__(params)
+
+    @staticmethod
+    def nominal_coeff(M):
+        dx = 1.0 / (M - 1)
+        return 1.0 / (dx * dx)
+
+    @staticmethod
+    def consistent_ic(params, M=10):
+        """u0 = 16 x(1-x) y(1-y); u0' = coeff * laplacian on the interior, 0 on the boundary"""
+        p = np.asarray(params)
+        batch = p.shape[1]
+        dx = 1.0 / (M - 1)
+        xs = np.arange(M) * dx
+        u = 16.0 * np.outer(xs * (1.0 - xs), xs * (1.0 - xs))  # [row j (y), col i (x)]
+        u[0, :] = u[-1, :] = 0.0
+        u[:, 0] = u[:, -1] = 0.0
+        lap = np.zeros_like(u)
+        lap[1:-1, 1:-1] = (u[1:-1, :-2] + u[1:-1, 2:] - 2.0 * u[1:-1, 1:-1]) + (u[:-2, 1:-1] + u[2:, 1:-1] - 2.0 * u[1:-1, 1:-1])
+        yy0 = np.repeat(u.reshape(-1, 1), batch, axis=1).copy()
+        yp0 = np.ascontiguousarray(lap.reshape(-1, 1) * p[0][None, :])
+        return yy0, yp0
+
+
+def heat_ensemble_params(batch, M=10, seed=1234, spread=0.1, first_id=0):
+    """coeff = (1/dx^2) (1 + spread*u), u ~ U(-1,1) keyed by instance id (config 5)."""
+    ids = np.arange(first_id, first_id + batch, dtype=np.uint64)
+    c = Heat2D.nominal_coeff(M) * (1.0 + spread * (2.0 * splitmix64_uniform(seed, ids, 0) - 1.0))
+    return np.ascontiguousarray(c[None, :])
+
+
 def splitmix64_uniform(seed, ids, stream):
     """counter-based U[0,1): splitmix64 of (seed, instance id, stream) -- identical parameters for any
     sharding of the ensemble."""

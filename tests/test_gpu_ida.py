@@ -15,12 +15,14 @@ pytestmark = pytest.mark.gpu
 COUNTERS = ("nst", "nre", "nje", "nni", "netf", "ncfn", "nsetups", "nattempts")
 
 
-def run_engine(problem_cls, params, yy0, yp0, rtol, atol, touts, ladder, device_buffers=False):
+def run_engine(problem_cls, params, yy0, yp0, rtol, atol, touts, ladder, device_buffers=False, kernel="auto",
+               problem_kw=None):
     import torch
     import rust_ida_b200 as r
     if device_buffers:
         params, yy0, yp0 = (torch.from_numpy(np.ascontiguousarray(v)).cuda() for v in (params, yy0, yp0))
-    ida = r.Ida(problem_cls(params), yy0, yp0, r.TolControlSV(rtol, atol))
+    ida = r.Ida(problem_cls(params, **(problem_kw or {})), yy0, yp0, r.TolControlSV(rtol, atol))
+    ida.set_kernel(kernel)
     if ladder:
         status, traj = ida.solve_ladder(touts)
     else:
@@ -158,3 +160,48 @@ def test_split_ensemble_equals_whole():
     assert np.array_equal(np.concatenate([q["counters"]["nst"] for q in parts]), whole["counters"]["nst"])
     # shard parameters are keyed by instance id, so shards can generate their own slice
     assert np.array_equal(roberts_ensemble_params(667, seed=99, first_id=333), p[:, 333:])
+
+
+@pytest.mark.parametrize("kernel", ["warp", "cta"])
+def test_team_kernels_match_oracle_on_roberts(kernel):
+    """warp-per-system and CTA-per-system kernels (csrc/ida_team.cuh) on the n = 3 problem: bit-identical to the
+    oracle (and therefore to the thread-per-instance kernel)."""
+    from rust_ida_b200 import Roberts
+    from rust_ida_b200.problems import roberts_ensemble_params
+    ob, _ = oracle_with_detpow()
+    B = 777
+    p = roberts_ensemble_params(B, seed=4321)
+    yy0, yp0 = Roberts.consistent_ic(p)
+    ref = ob.ensemble_solve(ob.PK_ROBERTS, 3, p, yy0, yp0, ROBERTS_RTOL, ROBERTS_ATOL, ROBERTS_TOUTS, nthreads=8,
+                            want_traj=True)
+    g = run_engine(Roberts, p, yy0, yp0, ROBERTS_RTOL, ROBERTS_ATOL, ROBERTS_TOUTS, ladder=True, kernel=kernel)
+    compare(g, ref)
+
+
+@pytest.mark.parametrize("M,kernel,B", [(4, "warp", 300), (5, "warp", 130), (4, "cta", 64), (10, "cta", 700), (10, "auto", 41)])
+def test_heat2d_parity(M, kernel, B):
+    """config 5 at test size: 2-D heat DAE (n = M*M; 10x10 -> dense n = 100, CTA-per-system with the LU factors
+    resident in shared memory), coefficient perturbed +-10 % per instance."""
+    from rust_ida_b200 import Heat2D
+    from rust_ida_b200.problems import heat_ensemble_params
+    ob, _ = oracle_with_detpow()
+    n = M * M
+    p = heat_ensemble_params(B, M=M, seed=1234)
+    yy0, yp0 = Heat2D.consistent_ic(p, M)
+    touts = 0.01 * 2.0 ** np.arange(11)
+    rtol, atol = 1e-6, np.full(n, 1e-8)
+    ref = ob.ensemble_solve(ob.PK_HEAT2D, n, p, yy0, yp0, rtol, atol, touts, nthreads=8, want_traj=True)
+    g = run_engine(Heat2D, p, yy0, yp0, rtol, atol, touts, ladder=True, kernel=kernel, problem_kw={"M": M})
+    compare(g, ref)
+    assert (g["status"] == 0).all() and g["counters"]["nje"].min() > 5
+
+
+def test_thread_kernel_rejects_large_n():
+    import rust_ida_b200 as r
+    from rust_ida_b200.problems import heat_ensemble_params
+    p = heat_ensemble_params(4, M=4)
+    yy0, yp0 = r.Heat2D.consistent_ic(p, 4)
+    ida = r.Ida(r.Heat2D(p, M=4), yy0, yp0, r.TolControlSV(1e-6, np.full(16, 1e-8)))
+    ida.set_kernel("thread")
+    with pytest.raises(r.B200IdaError):
+        ida.solve(0.01)
