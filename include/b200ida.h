@@ -127,6 +127,18 @@ int b200ida_destroy(b200ida_ensemble* e);
  * (src/lib.rs:278-405) -- all counters, phi, psi.. are reset. */
 int b200ida_reinit(b200ida_ensemble* e, const double* params, const double* yy0, const double* yp0, int mem);
 
+/* Instance reordering (process-wide default, read by b200ida_create / b200ida_reinit-with-params).
+ * Lanes of a warp advance in lockstep, so the engine may store instances internally in an order that puts
+ * instances with similar parameters in the same warp (Morton order of the min/max-normalised parameter
+ * vector): they take similar step / Newton / retry decisions and diverge less.  Purely internal: every
+ * input and output of this ABI stays in the caller's instance order, and per-instance results are
+ * bit-identical with or without it (instances are independent).
+ *   OFF never, ON always, AUTO (default) for the thread-per-instance kernels when batch >= 4096. */
+#define B200IDA_REORDER_OFF 0
+#define B200IDA_REORDER_ON 1
+#define B200IDA_REORDER_AUTO 2
+int b200ida_set_default_reorder(int mode);
+
 /* Which kernel family integrates the ensemble (all give bit-identical results; tests check that):
  *   AUTO    thread-per-instance for the n = 3 problems, warp-per-system for n <= 32, CTA-per-system above
  *   THREAD  one thread per instance, state in registers + a shared-memory column (csrc/ida_thread.cuh)

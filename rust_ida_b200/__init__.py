@@ -12,10 +12,10 @@ No CPU fallback: compute calls raise if libb200ida.so or a CUDA device is missin
 """
 from . import _lib
 from ._lib import B200IdaError, build, device_count
-from .ida import Ida, IdaSolveStatus, IdaTask
+from .ida import Ida, IdaSolveStatus, IdaTask, set_default_reorder
 from .linear import Dense, LSolverType, LUFactFail, norm_wrms
 from .problems import Heat2D, Lorenz63, Roberts
 from .tol_control import TolControlSS, TolControlSV
 
 __all__ = ["Ida", "IdaTask", "IdaSolveStatus", "Dense", "LSolverType", "LUFactFail", "norm_wrms", "Roberts",
-           "Lorenz63", "Heat2D", "TolControlSV", "TolControlSS", "B200IdaError", "build", "device_count"]
+           "Lorenz63", "Heat2D", "TolControlSV", "TolControlSS", "B200IdaError", "build", "device_count", "set_default_reorder"]

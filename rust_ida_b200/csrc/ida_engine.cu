@@ -7,6 +7,8 @@
 
 #include <new>
 
+#include <cub/cub.cuh>
+
 #include "host_util.h"
 #include "ida_common.cuh"
 #include "ida_team.cuh"
@@ -29,15 +31,17 @@ char* last_error_buf() {
 template <class P>
 __global__ void __launch_bounds__(THREAD_BLOCK, IDA_MIN_BLOCKS)
 ida_solve_thread_kernel(double* __restrict__ ds, int* __restrict__ is, const double* __restrict__ params, int64_t B,
-                        TolN<P::N> tol, LadderParams lad, double* __restrict__ yy_traj, int32_t* __restrict__ status) {
+                        TolN<P::N> tol, LadderParams lad, double* __restrict__ yy_traj, int32_t* __restrict__ status,
+                        const int* __restrict__ perm) {
     extern __shared__ double smem[];
-    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // slot
     if (b >= B) return;
+    const int64_t ob = perm ? (int64_t)perm[b] : b;  // caller-visible instance id of this slot
     IdaThread<P> s;
     s.sm = smem + threadIdx.x;
     s.prob.load(params, B, b);
     s.load(ds, is, B, b);
-    s.solve_ladder(lad, tol, yy_traj, status, B, b);
+    s.solve_ladder(lad, tol, yy_traj, status, B, ob);
     s.store(ds, is, B, b);
 }
 
@@ -46,7 +50,7 @@ template <class Team>
 __global__ void ida_solve_team_kernel(double* __restrict__ ds, int* __restrict__ is, const double* __restrict__ params,
                                       int64_t B, int n, int kind, int nparams, double rtol, const double* __restrict__ atol,
                                       LadderParams lad, double* __restrict__ yy_traj, int32_t* __restrict__ status,
-                                      unsigned arena_bytes) {
+                                      unsigned arena_bytes, const int* __restrict__ perm) {
     extern __shared__ __align__(16) unsigned char team_smem[];
     const int tpc = Team::teams_per_cta();
     IdaTeam<Team> s;
@@ -61,7 +65,7 @@ __global__ void ida_solve_team_kernel(double* __restrict__ ds, int* __restrict__
     for (int64_t b = (int64_t)blockIdx.x * tpc + Team::team_in_cta(); b < B; b += (int64_t)gridDim.x * tpc) {
         for (int k = 0; k < 4; ++k) s.prob.p[k] = k < nparams ? params[(int64_t)k * B + b] : 0.0;
         s.load(ds, is, B, b);
-        s.solve_ladder(lad, yy_traj, status, B, b);
+        s.solve_ladder(lad, yy_traj, status, B, perm ? (int64_t)perm[b] : b);
         s.store(ds, is, B, b);
     }
 }
@@ -69,12 +73,13 @@ __global__ void ida_solve_team_kernel(double* __restrict__ ds, int* __restrict__
 // Ida::new (src/lib.rs:278-405): phi[0] = yy0, phi[1] = yp0, yy = yy0, yp = yp0 (src/ida_nls.rs:82-83),
 // tolsf = 1, everything else 0 (the state buffers are zeroed before this kernel).
 __global__ void ida_init_kernel(double* __restrict__ ds, const double* __restrict__ yy0, const double* __restrict__ yp0,
-                                int n, int64_t B) {
+                                int n, int64_t B, const int* __restrict__ perm) {
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
+    const int64_t ob = perm ? (int64_t)perm[b] : b;
     const Layout lay(n);
     for (int i = 0; i < n; ++i) {
-        const double y = yy0[(int64_t)i * B + b], yp = yp0[(int64_t)i * B + b];
+        const double y = yy0[(int64_t)i * B + ob], yp = yp0[(int64_t)i * B + ob];
         ds[(int64_t)lay.phi(0, i) * B + b] = y;
         ds[(int64_t)lay.phi(1, i) * B + b] = yp;
         ds[(int64_t)lay.yy(i) * B + b] = y;
@@ -83,9 +88,40 @@ __global__ void ida_init_kernel(double* __restrict__ ds, const double* __restric
     ds[(int64_t)lay.scal(Layout::TOLSF) * B + b] = 1.0;
 }
 
-__global__ void widen_i32_kernel(const int* __restrict__ src, int64_t* __restrict__ dst, int64_t n) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dst[i] = (int64_t)src[i];
+// slot order -> caller order: dst[r][perm[s]] = (TD)src[r][s]  (perm == nullptr: identity)
+template <class TS, class TD>
+__global__ void unpermute_kernel(const TS* __restrict__ src, TD* __restrict__ dst, int rows, int64_t B,
+                                 const int* __restrict__ perm) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= B) return;
+    const int64_t o = perm ? (int64_t)perm[s] : s;
+    for (int r = 0; r < rows; ++r) dst[(int64_t)r * B + o] = (TD)src[(int64_t)r * B + s];
+}
+// caller order -> slot order: dst[r][s] = src[r][perm[s]]
+__global__ void permute_rows_kernel(const double* __restrict__ src, double* __restrict__ dst, int rows, int64_t B,
+                                    const int* __restrict__ perm) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= B) return;
+    const int64_t o = perm ? (int64_t)perm[s] : s;
+    for (int r = 0; r < rows; ++r) dst[(int64_t)r * B + s] = src[(int64_t)r * B + o];
+}
+// Morton key of the (min/max-normalised) parameter vector of each instance: instances that are close in
+// parameter space get adjacent slots, so the lanes of a warp take similar step/Newton/retry decisions.
+__global__ void order_key_kernel(const double* __restrict__ params, const double* __restrict__ lo, const double* __restrict__ hi,
+                                 int nparams, int64_t B, unsigned* __restrict__ keys, int* __restrict__ ids) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int bits = 30 / nparams > 10 ? 10 : 30 / nparams;
+    unsigned key = 0;
+    for (int j = 0; j < nparams; ++j) {
+        const double range = hi[j] - lo[j];
+        double u = range > 0.0 ? (params[(int64_t)j * B + b] - lo[j]) / range : 0.0;
+        u = u < 0.0 ? 0.0 : (u > 1.0 ? 1.0 : u);
+        unsigned q = (unsigned)(u * (double)((1u << bits) - 1u));
+        for (int k = 0; k < bits; ++k) key |= ((q >> k) & 1u) << (k * nparams + j);
+    }
+    keys[b] = key;
+    ids[b] = (int)b;
 }
 
 __global__ void detpow_kernel(const double* __restrict__ x, const double* __restrict__ y, double* __restrict__ out,
@@ -131,9 +167,79 @@ struct b200ida_ensemble {
     double* params = nullptr;  // [nparams][B]
     double* d_atol = nullptr;  // [n]
     int kernel = B200IDA_KERNEL_AUTO;
+    int* perm = nullptr;  // [B] slot -> caller-visible instance id, or null (identity)
 };
 
+static int g_reorder_mode = B200IDA_REORDER_AUTO;
+
+// (re)build e->perm from parameters that are already on the device in CALLER order
+static int build_order(b200ida_ensemble* e, const double* d_params_caller_order) {
+    const bool want = g_reorder_mode == B200IDA_REORDER_ON ||
+                      (g_reorder_mode == B200IDA_REORDER_AUTO && e->problem != B200IDA_PROBLEM_HEAT2D && e->B >= 4096);
+    if (!want || e->nparams < 1 || e->nparams > 8 || e->B >= (int64_t)1 << 31) {
+        if (e->perm) cudaFree(e->perm);
+        e->perm = nullptr;
+        return B200IDA_OK;
+    }
+    const int64_t B = e->B;
+    const int P = e->nparams;
+    cudaStream_t st = e->stream;
+    if (!e->perm) B200_CUDA_TRY(cudaMalloc(&e->perm, (size_t)B * sizeof(int)));
+    DevBuf lohi, keys, keys2, ids, tmp;
+    B200_CUDA_TRY(lohi.alloc(2 * (size_t)P * sizeof(double)));
+    B200_CUDA_TRY(keys.alloc((size_t)B * sizeof(unsigned)));
+    B200_CUDA_TRY(keys2.alloc((size_t)B * sizeof(unsigned)));
+    B200_CUDA_TRY(ids.alloc((size_t)B * sizeof(int)));
+    double* lo = lohi.as<double>();
+    double* hi = lo + P;
+    size_t tb1 = 0, tb2 = 0, tb3 = 0;
+    cub::DeviceReduce::Min(nullptr, tb1, d_params_caller_order, lo, (int)B, st);
+    cub::DeviceReduce::Max(nullptr, tb2, d_params_caller_order, hi, (int)B, st);
+    cub::DeviceRadixSort::SortPairs(nullptr, tb3, keys.as<unsigned>(), keys2.as<unsigned>(), ids.as<int>(), e->perm, (int)B, 0, 32, st);
+    size_t tbytes = tb1 > tb2 ? tb1 : tb2;
+    tbytes = tbytes > tb3 ? tbytes : tb3;
+    B200_CUDA_TRY(tmp.alloc(tbytes));
+    for (int j = 0; j < P; ++j) {
+        B200_CUDA_TRY(cub::DeviceReduce::Min(tmp.p, tbytes, d_params_caller_order + (size_t)j * B, lo + j, (int)B, st));
+        B200_CUDA_TRY(cub::DeviceReduce::Max(tmp.p, tbytes, d_params_caller_order + (size_t)j * B, hi + j, (int)B, st));
+    }
+    const int tb = 256;
+    order_key_kernel<<<(unsigned)((B + tb - 1) / tb), tb, 0, st>>>(d_params_caller_order, lo, hi, P, B, keys.as<unsigned>(), ids.as<int>());
+    B200_CUDA_TRY(cudaGetLastError());
+    B200_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp.p, tbytes, keys.as<unsigned>(), keys2.as<unsigned>(), ids.as<int>(), e->perm, (int)B, 0, 32, st));
+    B200_CUDA_TRY(cudaStreamSynchronize(st));  // scratch freed on return
+    return B200IDA_OK;
+}
+
 static int check_mem(int mem) { return (mem == B200IDA_MEM_DEVICE || mem == B200IDA_MEM_HOST) ? 0 : -1; }
+
+// slot-ordered state rows -> caller-ordered output (device or host), converting TS -> TD
+template <class TS, class TD>
+static int rows_out(b200ida_ensemble* e, TD* dst, const TS* src, int rows, int mem) {
+    if (!dst) return B200IDA_OK;
+    const int64_t B = e->B;
+    const int tb = 256;
+    const unsigned grid = (unsigned)((B + tb - 1) / tb);
+    if (mem == B200IDA_MEM_DEVICE) {
+        unpermute_kernel<TS, TD><<<grid, tb, 0, e->stream>>>(src, dst, rows, B, e->perm);
+        B200_CUDA_TRY(cudaGetLastError());
+        return B200IDA_OK;
+    }
+    const size_t bytes = (size_t)rows * B * sizeof(TD);
+    if (!e->perm && sizeof(TS) == sizeof(TD)) {  // identity order, same type: straight copy
+        B200_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, e->stream));
+        B200_CUDA_TRY(cudaStreamSynchronize(e->stream));
+        return B200IDA_OK;
+    }
+    DevBuf tmp;
+    B200_CUDA_TRY(tmp.alloc(bytes));
+    unpermute_kernel<TS, TD><<<grid, tb, 0, e->stream>>>(src, tmp.as<TD>(), rows, B, e->perm);
+    B200_CUDA_TRY(cudaGetLastError());
+    B200_CUDA_TRY(cudaMemcpyAsync(dst, tmp.p, bytes, cudaMemcpyDeviceToHost, e->stream));
+    B200_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return B200IDA_OK;
+}
+
 
 extern "C" {
 
@@ -162,7 +268,22 @@ int b200ida_reinit(b200ida_ensemble* e, const double* params, const double* yy0,
     const size_t vbytes = (size_t)n * batch * sizeof(double);
     B200_CUDA_TRY(cudaMemsetAsync(e->dstate, 0, nd * sizeof(double), st));
     B200_CUDA_TRY(cudaMemsetAsync(e->istate, 0, ni * sizeof(int), st));
-    if (params) B200_CUDA_TRY(cudaMemcpyAsync(e->params, params, (size_t)e->nparams * batch * sizeof(double), kind, st));
+    if (params) {
+        // new parameters: bring them to the device in caller order, rebuild the slot order, store them by slot
+        const size_t pbytes = (size_t)e->nparams * batch * sizeof(double);
+        DevBuf pb;
+        const double* dp = params;
+        if (mem == B200IDA_MEM_HOST) {
+            B200_CUDA_TRY(pb.alloc(pbytes));
+            B200_CUDA_TRY(cudaMemcpyAsync(pb.p, params, pbytes, kind, st));
+            dp = pb.as<double>();
+        }
+        int rc = build_order(e, dp);
+        if (rc != B200IDA_OK) return rc;
+        permute_rows_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, st>>>(dp, e->params, e->nparams, batch, e->perm);
+        B200_CUDA_TRY(cudaGetLastError());
+        if (mem == B200IDA_MEM_HOST) B200_CUDA_TRY(cudaStreamSynchronize(st));
+    }
     if (mem == B200IDA_MEM_HOST) {
         B200_CUDA_TRY(y0b.alloc(vbytes));
         B200_CUDA_TRY(yp0b.alloc(vbytes));
@@ -172,7 +293,7 @@ int b200ida_reinit(b200ida_ensemble* e, const double* params, const double* yy0,
         dyp0 = yp0b.as<double>();
     }
     const int tb = 256;
-    ida_init_kernel<<<(unsigned)((batch + tb - 1) / tb), tb, 0, st>>>(e->dstate, dy0, dyp0, n, batch);
+    ida_init_kernel<<<(unsigned)((batch + tb - 1) / tb), tb, 0, st>>>(e->dstate, dy0, dyp0, n, batch, e->perm);
     B200_CUDA_TRY(cudaGetLastError());
     if (mem == B200IDA_MEM_HOST) B200_CUDA_TRY(cudaStreamSynchronize(st));  // scratch is freed on return
     return B200IDA_OK;
@@ -243,6 +364,7 @@ int b200ida_destroy(b200ida_ensemble* e) {
     if (e->istate) cudaFree(e->istate);
     if (e->params) cudaFree(e->params);
     if (e->d_atol) cudaFree(e->d_atol);
+    if (e->perm) cudaFree(e->perm);
     delete e;
     return B200IDA_OK;
 }
@@ -289,11 +411,11 @@ int b200ida_solve_ladder(b200ida_ensemble* e, const double* touts, int ntout, in
         if (e->problem == B200IDA_PROBLEM_ROBERTS) {
             B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_thread_kernel<Roberts>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             ida_solve_thread_kernel<Roberts><<<grid, tb, smem, e->stream>>>(e->dstate, e->istate, e->params, e->B, tol, lad,
-                                                                            d_traj, d_stat);
+                                                                            d_traj, d_stat, e->perm);
         } else {
             B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_thread_kernel<Lorenz63>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             ida_solve_thread_kernel<Lorenz63><<<grid, tb, smem, e->stream>>>(e->dstate, e->istate, e->params, e->B, tol, lad,
-                                                                             d_traj, d_stat);
+                                                                             d_traj, d_stat, e->perm);
         }
     } else {
         const bool warp = kernel == B200IDA_KERNEL_WARP;
@@ -317,10 +439,10 @@ int b200ida_solve_ladder(b200ida_ensemble* e, const double* touts, int ntout, in
         const unsigned grid = (unsigned)(want < (int64_t)sms * occ ? want : (int64_t)sms * occ);  // persistent teams
         if (warp)
             ida_solve_team_kernel<WarpTeam><<<grid, tb, smem, e->stream>>>(e->dstate, e->istate, e->params, e->B, e->n, e->problem,
-                                                                           e->nparams, e->rtol, e->d_atol, lad, d_traj, d_stat, arena);
+                                                                           e->nparams, e->rtol, e->d_atol, lad, d_traj, d_stat, arena, e->perm);
         else
             ida_solve_team_kernel<CtaTeam><<<grid, tb, smem, e->stream>>>(e->dstate, e->istate, e->params, e->B, e->n, e->problem,
-                                                                          e->nparams, e->rtol, e->d_atol, lad, d_traj, d_stat, arena);
+                                                                          e->nparams, e->rtol, e->d_atol, lad, d_traj, d_stat, arena, e->perm);
     }
     B200_CUDA_TRY(cudaGetLastError());
     if (mem == B200IDA_MEM_HOST) {
@@ -342,41 +464,14 @@ int b200ida_solve(b200ida_ensemble* e, double tout, int itask, int32_t* status, 
     return b200ida_solve_ladder(e, &tout, 1, itask, nullptr, status, mem);
 }
 
-static int copy_out(b200ida_ensemble* e, void* dst, const void* src, size_t bytes, int mem) {
-    if (!dst) return B200IDA_OK;
-    B200_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, mem == B200IDA_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice,
-                                  e->stream));
-    return B200IDA_OK;
-}
-
 int b200ida_get_state(b200ida_ensemble* e, double* yy, double* yp, double* tret, int mem) {
     if (!e || check_mem(mem)) return set_error(B200IDA_ERR_ARG, "b200ida_get_state: bad argument");
     B200_CUDA_TRY(cudaSetDevice(e->device));
     const Layout lay(e->n);
     int rc;
-    if ((rc = copy_out(e, yy, e->dstate + (size_t)lay.yy(0) * e->B, (size_t)e->n * e->B * sizeof(double), mem))) return rc;
-    if ((rc = copy_out(e, yp, e->dstate + (size_t)lay.yp(0) * e->B, (size_t)e->n * e->B * sizeof(double), mem))) return rc;
-    if ((rc = copy_out(e, tret, e->dstate + (size_t)lay.scal(Layout::TRET) * e->B, (size_t)e->B * sizeof(double), mem))) return rc;
-    if (mem == B200IDA_MEM_HOST) B200_CUDA_TRY(cudaStreamSynchronize(e->stream));
-    return B200IDA_OK;
-}
-
-static int widen_out(b200ida_ensemble* e, int64_t* dst, int field, int mem) {
-    if (!dst) return B200IDA_OK;
-    const int* src = e->istate + (size_t)field * e->B;
-    const int tb = 256;
-    const unsigned grid = (unsigned)((e->B + tb - 1) / tb);
-    if (mem == B200IDA_MEM_DEVICE) {
-        widen_i32_kernel<<<grid, tb, 0, e->stream>>>(src, dst, e->B);
-        B200_CUDA_TRY(cudaGetLastError());
-        return B200IDA_OK;
-    }
-    DevBuf tmp;
-    B200_CUDA_TRY(tmp.alloc((size_t)e->B * sizeof(int64_t)));
-    widen_i32_kernel<<<grid, tb, 0, e->stream>>>(src, tmp.as<int64_t>(), e->B);
-    B200_CUDA_TRY(cudaGetLastError());
-    B200_CUDA_TRY(cudaMemcpyAsync(dst, tmp.p, (size_t)e->B * sizeof(int64_t), cudaMemcpyDeviceToHost, e->stream));
-    B200_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    if ((rc = rows_out<double, double>(e, yy, e->dstate + (size_t)lay.yy(0) * e->B, e->n, mem))) return rc;
+    if ((rc = rows_out<double, double>(e, yp, e->dstate + (size_t)lay.yp(0) * e->B, e->n, mem))) return rc;
+    if ((rc = rows_out<double, double>(e, tret, e->dstate + (size_t)lay.scal(Layout::TRET) * e->B, 1, mem))) return rc;
     return B200IDA_OK;
 }
 
@@ -384,15 +479,16 @@ int b200ida_get_counters(b200ida_ensemble* e, int64_t* nst, int64_t* nre, int64_
                          int64_t* ncfn, int64_t* nsetups, int64_t* nattempts, int mem) {
     if (!e || check_mem(mem)) return set_error(B200IDA_ERR_ARG, "b200ida_get_counters: bad argument");
     B200_CUDA_TRY(cudaSetDevice(e->device));
+    const size_t B = (size_t)e->B;
     int rc;
-    if ((rc = widen_out(e, nst, Layout::NST, mem))) return rc;
-    if ((rc = widen_out(e, nre, Layout::NRE, mem))) return rc;
-    if ((rc = widen_out(e, nje, Layout::NJE, mem))) return rc;
-    if ((rc = widen_out(e, nni, Layout::NNI, mem))) return rc;
-    if ((rc = widen_out(e, netf, Layout::NETF, mem))) return rc;
-    if ((rc = widen_out(e, ncfn, Layout::NCFN, mem))) return rc;
-    if ((rc = widen_out(e, nsetups, Layout::NSETUPS, mem))) return rc;
-    if ((rc = widen_out(e, nattempts, Layout::NATT, mem))) return rc;
+    if ((rc = rows_out<int, int64_t>(e, nst, e->istate + (size_t)Layout::NST * B, 1, mem))) return rc;
+    if ((rc = rows_out<int, int64_t>(e, nre, e->istate + (size_t)Layout::NRE * B, 1, mem))) return rc;
+    if ((rc = rows_out<int, int64_t>(e, nje, e->istate + (size_t)Layout::NJE * B, 1, mem))) return rc;
+    if ((rc = rows_out<int, int64_t>(e, nni, e->istate + (size_t)Layout::NNI * B, 1, mem))) return rc;
+    if ((rc = rows_out<int, int64_t>(e, netf, e->istate + (size_t)Layout::NETF * B, 1, mem))) return rc;
+    if ((rc = rows_out<int, int64_t>(e, ncfn, e->istate + (size_t)Layout::NCFN * B, 1, mem))) return rc;
+    if ((rc = rows_out<int, int64_t>(e, nsetups, e->istate + (size_t)Layout::NSETUPS * B, 1, mem))) return rc;
+    if ((rc = rows_out<int, int64_t>(e, nattempts, e->istate + (size_t)Layout::NATT * B, 1, mem))) return rc;
     return B200IDA_OK;
 }
 
@@ -403,13 +499,18 @@ int b200ida_get_step_info(b200ida_ensemble* e, int32_t* kused, int32_t* kcur, do
     const Layout lay(e->n);
     const size_t B = (size_t)e->B;
     int rc;
-    if ((rc = copy_out(e, kused, e->istate + (size_t)Layout::KUSED * B, B * sizeof(int32_t), mem))) return rc;
-    if ((rc = copy_out(e, kcur, e->istate + (size_t)Layout::KK * B, B * sizeof(int32_t), mem))) return rc;
-    if ((rc = copy_out(e, hused, e->dstate + (size_t)lay.scal(Layout::HUSED) * B, B * sizeof(double), mem))) return rc;
-    if ((rc = copy_out(e, hcur, e->dstate + (size_t)lay.scal(Layout::HH) * B, B * sizeof(double), mem))) return rc;
-    if ((rc = copy_out(e, tcur, e->dstate + (size_t)lay.scal(Layout::TN) * B, B * sizeof(double), mem))) return rc;
-    if ((rc = copy_out(e, h0u, e->dstate + (size_t)lay.scal(Layout::H0U) * B, B * sizeof(double), mem))) return rc;
-    if (mem == B200IDA_MEM_HOST) B200_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    if ((rc = rows_out<int, int32_t>(e, kused, e->istate + (size_t)Layout::KUSED * B, 1, mem))) return rc;
+    if ((rc = rows_out<int, int32_t>(e, kcur, e->istate + (size_t)Layout::KK * B, 1, mem))) return rc;
+    if ((rc = rows_out<double, double>(e, hused, e->dstate + (size_t)lay.scal(Layout::HUSED) * B, 1, mem))) return rc;
+    if ((rc = rows_out<double, double>(e, hcur, e->dstate + (size_t)lay.scal(Layout::HH) * B, 1, mem))) return rc;
+    if ((rc = rows_out<double, double>(e, tcur, e->dstate + (size_t)lay.scal(Layout::TN) * B, 1, mem))) return rc;
+    if ((rc = rows_out<double, double>(e, h0u, e->dstate + (size_t)lay.scal(Layout::H0U) * B, 1, mem))) return rc;
+    return B200IDA_OK;
+}
+
+int b200ida_set_default_reorder(int mode) {
+    if (mode < B200IDA_REORDER_OFF || mode > B200IDA_REORDER_AUTO) return set_error(B200IDA_ERR_ARG, "b200ida_set_default_reorder: bad mode");
+    g_reorder_mode = mode;
     return B200IDA_OK;
 }
 

@@ -28,7 +28,16 @@
 
 namespace b200ida {
 
-constexpr int THREAD_BLOCK = 128;  // threads per CTA of the thread-per-instance kernels
+#ifndef IDA_THREAD_BLOCK
+#define IDA_THREAD_BLOCK 128
+#endif
+#ifndef IDA_WRMS_INLINE
+#define IDA_WRMS_INLINE 0
+#endif
+#ifndef IDA_POW_INLINE
+#define IDA_POW_INLINE 0
+#endif
+constexpr int THREAD_BLOCK = IDA_THREAD_BLOCK;  // threads per CTA of the thread-per-instance kernels
 
 template <int N>
 struct TolN {
@@ -36,7 +45,19 @@ struct TolN {
     double atol[N];
 };
 
+#ifndef IDA_DIV_NOINLINE
+#define IDA_DIV_NOINLINE 0
+#endif
+#if IDA_DIV_NOINLINE
+__device__ __noinline__ double ddiv(double a, double b) { return a / b; }
+#else
+__device__ __forceinline__ double ddiv(double a, double b) { return a / b; }
+#endif
+#if IDA_POW_INLINE
+__device__ __forceinline__ double pow_noinline(double x, double y) { return detpow::det_pow(x, y); }
+#else
 __device__ __noinline__ double pow_noinline(double x, double y) { return detpow::det_pow(x, y); }
+#endif
 
 // x / D for a small integer constant D, bit-identical to the IEEE division the reference performs.
 // Markstein's sequence: y = RN(1/D); q = RN(x*y); r = x - D*q (exact in one FMA); q' = RN(q + r*y) is the
@@ -73,7 +94,7 @@ __device__ __noinline__ double wrms3(double x0, double x1, double x2, double w0,
 }
 template <int N>
 __device__ __forceinline__ double wrms(const double (&x)[N], const double (&w)[N]) {
-    if constexpr (N == 3) return wrms3(x[0], x[1], x[2], w[0], w[1], w[2]);
+    if constexpr (N == 3 && !IDA_WRMS_INLINE) return wrms3(x[0], x[1], x[2], w[0], w[1], w[2]);
     else return wrms_inline<N>(x, w);
 }
 
@@ -218,7 +239,7 @@ struct IdaThread {
     // ---- TolControlSV::ewt_set: src/tol_control.rs:71-82 -------------------------------------------------
     __device__ __forceinline__ void ewt_set(const TolN<N>& tol) {
 #pragma unroll
-        for (int i = 0; i < N; ++i) ewt[i] = 1.0 / (tol.rtol * fabs(phi(0, i)) + tol.atol[i]);
+        for (int i = 0; i < N; ++i) ewt[i] = ddiv(1.0, tol.rtol * fabs(phi(0, i)) + tol.atol[i]);
     }
 
     // ---- set_coeffs: src/lib.rs:722-782 ----------------------------------------------------------------
@@ -236,11 +257,11 @@ struct IdaThread {
             for (int i = 1; i <= kk; ++i) {
                 const double temp2 = psi(i - 1);
                 psi(i - 1) = temp1;
-                const double b_i = beta_prev * temp1 / temp2;
+                const double b_i = ddiv(beta_prev * temp1, temp2);
                 temp1 = temp2 + hh;
-                const double a_i = hh / temp1;
+                const double a_i = ddiv(hh, temp1);
                 const double s_i = (double)i * sigma_prev * a_i;
-                const double g_i = gamma_prev + alpha_prev / hh;
+                const double g_i = gamma_prev + ddiv(alpha_prev, hh);
                 beta(i) = b_i;
                 alpha(i) = a_i;
                 sigma(i) = s_i;
@@ -259,7 +280,7 @@ struct IdaThread {
 #pragma unroll 1
         for (int i = 0; i < kk; ++i) alpha0 -= alpha(i);
         cjlast = cj;
-        cj = -alphas / hh;
+        cj = ddiv(-alphas, hh);
         const double akk = alpha(kk);
         double ck = fabs(akk + alphas - alpha0);
         ck = fmax(ck, akk);
@@ -318,7 +339,7 @@ struct IdaThread {
                     }
                 }
             }
-            const double mult = 1.0 / J[k][k];
+            const double mult = ddiv(1.0, J[k][k]);
 #pragma unroll
             for (int i = k + 1; i < N; ++i) J[i][k] *= mult;
 #pragma unroll
@@ -354,12 +375,12 @@ struct IdaThread {
         }
 #pragma unroll
         for (int k = N - 1; k >= 1; --k) {
-            b[k] /= J[k][k];
+            b[k] = ddiv(b[k], J[k][k]);
             const double bk = b[k];
 #pragma unroll
             for (int i = 0; i < k; ++i) b[i] -= J[i][k] * bk;
         }
-        b[0] /= J[0][0];
+        b[0] = ddiv(b[0], J[0][0]);
     }
 
     // ---- IdaNLProblem::sys: src/ida_nls.rs:118-153 ------------------------------------------------------
@@ -394,7 +415,7 @@ struct IdaThread {
     __device__ __forceinline__ void nls_lsolve(double (&b)[N]) const {
         getrs(b);
         if (cjratio != 1.0) {
-            const double f = 2.0 / (1.0 + cjratio);
+            const double f = ddiv(2.0, 1.0 + cjratio);
 #pragma unroll
             for (int i = 0; i < N; ++i) b[i] *= f;
         }
@@ -407,11 +428,11 @@ struct IdaThread {
             oldnrm = delnrm;
             if (delnrm <= 0.0001 * toldel) return 1;
         } else {
-            const double base = delnrm / oldnrm;
+            const double base = ddiv(delnrm, oldnrm);
             const double arg = 1.0 / (double)m;
             const double rate = pow_noinline(base, arg);
             if (rate > RATEMAX) return -1;
-            ss = rate / (1.0 - rate);
+            ss = ddiv(rate, 1.0 - rate);
         }
         if (ss * delnrm <= tol) return 1;
         return 0;
@@ -427,7 +448,7 @@ struct IdaThread {
             ss = 20.0;
             call_lsetup = true;
         }
-        cjratio = cj / cjold;
+        cjratio = ddiv(cj, cjold);
         const double temp1 = (1.0 - XRATE) / (1.0 + XRATE);
         const double temp2 = 1.0 / temp1;
         if (cjratio < temp1 || cjratio > temp2) call_lsetup = true;
@@ -527,7 +548,7 @@ struct IdaThread {
         for (int j = 1; j <= kk; ++j) psi(j - 1) = psi(j) - hh;
 #pragma unroll 1
         for (int j = ns; j <= kk; ++j) {
-            const double c = 1.0 / beta(j);
+            const double c = ddiv(1.0, beta(j));
 #pragma unroll
             for (int i = 0; i < N; ++i) phi(j, i) *= c;
         }

@@ -32,6 +32,12 @@ class IdaSolveStatus(enum.IntEnum):
     BadTimeValue = -8     # src/lib.rs:1286-1292
 
 
+def set_default_reorder(mode):
+    """"off" | "on" | "auto": internal warp-coherence ordering of instances (include/b200ida.h); results and
+    the caller-visible instance order are unaffected."""
+    _lib.check(_lib.lib().b200ida_set_default_reorder({"off": 0, "on": 1, "auto": 2}[mode]))
+
+
 class Ida:
     """Ida<P, Dense, Newton, TolControlSV> for a whole ensemble."""
 

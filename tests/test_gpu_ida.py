@@ -221,3 +221,47 @@ def test_cpp_host_mirror_example():
     assert out.returncode == 0, out.stdout + out.stderr
     assert "steps 362  res evals 537  jac evals 60  nonlin iters 537  err test fails 15  conv fails 0" in out.stdout
     assert "4.00000e+10  4.86409e-08   1.94564e-13   1.00000e+00" in " ".join(out.stdout.split("\n")[-3].split()) or True
+
+
+@pytest.mark.parametrize("mode", ["on", "off"])
+@pytest.mark.parametrize("device_buffers", [False, True])
+def test_internal_reordering_is_invisible(mode, device_buffers):
+    """warp-coherence reordering (Morton order of the parameter vectors) is internal: every output stays in the
+    caller's instance order and is bit-identical with it on or off, for both solve() and solve_ladder()."""
+    import rust_ida_b200 as r
+    from rust_ida_b200 import Roberts
+    from rust_ida_b200.problems import roberts_ensemble_params
+    ob, _ = oracle_with_detpow()
+    B = 1531
+    p = roberts_ensemble_params(B, seed=77)
+    yy0, yp0 = Roberts.consistent_ic(p)
+    touts = ROBERTS_TOUTS[:7]
+    ref = ob.ensemble_solve(ob.PK_ROBERTS, 3, p, yy0, yp0, ROBERTS_RTOL, ROBERTS_ATOL, touts, nthreads=8, want_traj=True)
+    r.set_default_reorder(mode)
+    try:
+        for ladder in (True, False):
+            g = run_engine(Roberts, p, yy0, yp0, ROBERTS_RTOL, ROBERTS_ATOL, touts, ladder, device_buffers)
+            compare(g, ref)
+    finally:
+        r.set_default_reorder("auto")
+
+
+def test_reinit_with_new_parameters_rebuilds_order():
+    import rust_ida_b200 as r
+    from rust_ida_b200 import Roberts
+    from rust_ida_b200.problems import roberts_ensemble_params
+    ob, _ = oracle_with_detpow()
+    B = 5000  # >= 4096: AUTO reorders
+    p1 = roberts_ensemble_params(B, seed=1)
+    p2 = roberts_ensemble_params(B, seed=2)
+    yy0, yp0 = Roberts.consistent_ic(p1)
+    ida = r.Ida(Roberts(p1), yy0, yp0, r.TolControlSV(ROBERTS_RTOL, ROBERTS_ATOL))
+    ida.solve_ladder(ROBERTS_TOUTS[:3], want_traj=False)
+    yy0b, yp0b = Roberts.consistent_ic(p2)
+    ida.reinit(yy0b, yp0b, params=p2)
+    st, traj = ida.solve_ladder(ROBERTS_TOUTS[:4])
+    ref = ob.ensemble_solve(ob.PK_ROBERTS, 3, p2, yy0b, yp0b, ROBERTS_RTOL, ROBERTS_ATOL, ROBERTS_TOUTS[:4], nthreads=8,
+                            want_traj=True)
+    assert_bit_equal(traj, ref["yy_traj"], "traj after reinit")
+    assert np.array_equal(ida.get_num_steps(), ref["counters"]["nst"])
+    assert_bit_equal(ida.get_last_step(), ref["hused"], "hused")
