@@ -22,6 +22,7 @@
 #pragma once
 #include "detpow.h"
 #include "ida_common.cuh"
+#include "lu_team.cuh"
 
 namespace b200ida {
 
@@ -135,6 +136,7 @@ struct TeamScalars {
     int kk, kused, knew, phase, ns, setup_done, jcur;
     int nst, nre, nje, nni, netf, ncfn, nsetups, nlscf, natt;
     int flag, info, nstloc, ncf, nef, it, call_status, curiter;
+    LuShared lu;
 };
 
 __host__ __device__ inline size_t team_arena_bytes(int n) {
@@ -339,84 +341,22 @@ struct IdaTeam {
         Team::sync();
     }
 
-    // ---- dense_get_rf on the arena's J (crates/linear/src/dense.rs:86-158); S->info = 0 or 1-based column ------
+    // ---- dense_get_rf on the arena's J (crates/linear/src/dense.rs:86-158) via lu_team.cuh; S->info = 0 or the
+    //      1-based singular column ------------------------------------------------------------------------------
     __device__ void getrf() {
-        if (leader()) S->info = 0;
-        for (int k = 0; k < n; ++k) {
-            Team::sync();
-            if (leader()) {
-                // pivot search in index order: first row with strictly largest |a_ik| (dense.rs:109-116)
-                const double* col = J + (size_t)k * n;
-                int l = k;
-                double best = fabs(col[k]);
-                for (int i = k + 1; i < n; ++i) {
-                    const double v = fabs(col[i]);
-                    if (v > best) {
-                        best = v;
-                        l = i;
-                    }
-                }
-                piv[k] = l;
-                if (col[l] == 0.0) S->info = k + 1;
-            }
-            Team::sync();
-            if (S->info != 0) break;
-            const int l = piv[k];
-            if (l != k) {
-                for (int c = t; c < n; c += T) {
-                    const double v = J[(size_t)c * n + k];
-                    J[(size_t)c * n + k] = J[(size_t)c * n + l];
-                    J[(size_t)c * n + l] = v;
-                }
-                Team::sync();
-            }
-            const double mult = 1.0 / J[(size_t)k * n + k];
-            Team::sync();
-            for (int i = k + 1 + t; i < n; i += T) J[(size_t)k * n + i] *= mult;
-            Team::sync();
-            const int m = n - k - 1;
-            for (int e = t; e < m * m; e += T) {
-                const int i = k + 1 + e % m, j = k + 1 + e / m;
-                const double a_kj = J[(size_t)j * n + k];
-                if (a_kj != 0.0) J[(size_t)j * n + i] -= a_kj * J[(size_t)k * n + i];
-            }
-        }
+        Team::sync();
+        lu_factor<Team::T == 32>(J, n, n, &S->lu, piv);
+        if (leader()) S->info = S->lu.info;
         Team::sync();
     }
 
     // ---- dense_get_rs on nd (crates/linear/src/dense.rs:165-206) + cjratio rescale (src/ida_ls.rs:406-410) ------
     __device__ void lsolve() {
-        double* b = nd;
-        if (leader()) {
-            for (int k = 0; k < n; ++k) {
-                const int pk = piv[k];
-                if (pk != k) {
-                    const double v = b[k];
-                    b[k] = b[pk];
-                    b[pk] = v;
-                }
-            }
-        }
-        Team::sync();
-        for (int k = 0; k < n - 1; ++k) {
-            const double bk = b[k];
-            Team::sync();
-            for (int i = k + 1 + t; i < n; i += T) b[i] -= J[(size_t)k * n + i] * bk;
-            Team::sync();
-        }
-        for (int k = n - 1; k >= 1; --k) {
-            if (leader()) b[k] /= J[(size_t)k * n + k];
-            Team::sync();
-            const double bk = b[k];
-            for (int i = t; i < k; i += T) b[i] -= J[(size_t)k * n + i] * bk;
-            Team::sync();
-        }
-        if (leader()) b[0] /= J[0];
-        Team::sync();
+        lu_solve<Team::T == 32>(J, n, n, piv, nd);
         const double cjratio = S->cjratio;
         if (cjratio != 1.0) {
             const double f = 2.0 / (1.0 + cjratio);
-            for (int i = t; i < n; i += T) b[i] *= f;
+            for (int i = t; i < n; i += T) nd[i] *= f;
             Team::sync();
         }
     }

@@ -17,6 +17,7 @@
 //                     memory when it fits (n <= 160), else factored in place in global memory / L2.
 #include "host_util.h"
 #include "ida_common.cuh"
+#include "lu_team.cuh"
 
 namespace b200ida {
 
@@ -141,140 +142,81 @@ __global__ void __launch_bounds__(128) getrs_thread_soa(const double* __restrict
     for (int i = 0; i < N; ++i) bx[(size_t)i * B + b] = x[i];
 }
 
-// ---- CTA-per-system, shared memory (or in-place global when the matrix does not fit) ----------------
+// ---- group-per-system kernels on lu_team.cuh: one warp (n <= 32) or one CTA (n <= 256) per matrix ----------
 constexpr int CTA_THREADS = 256;
-constexpr int SMEM_MAX_N = 160;  // 160*160*8 = 204,800 B <= 227 KB
+constexpr int WARPS_PER_CTA = 4;   // warp-per-system kernels
+constexpr int SMEM_MAX_N = 160;    // CTA kernels stage the matrix in shared memory up to here (161*160*8 B)
 
-template <bool SOA, bool SMEM>
-__global__ void __launch_bounds__(CTA_THREADS) getrf_cta(double* __restrict__ A, int64_t* __restrict__ piv,
-                                                         int32_t* __restrict__ info, int n, int64_t B) {
-    extern __shared__ double sm[];
-    __shared__ int s_l;
-    __shared__ double s_red_v[CTA_THREADS / 32];
-    __shared__ int s_red_i[CTA_THREADS / 32];
-    const int tid = threadIdx.x;
-    for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
-        double* M;    // column-major view, leading dimension n
+__host__ __device__ inline int lu_ld(int n) { return n | 1; }  // odd leading dimension: conflict-free row swaps
+__host__ __device__ inline size_t lu_group_smem_bytes(int n) {
+    // matrix (ld x n doubles) + rhs/pivot staging (n doubles + n ints) + LuShared, 16-byte aligned
+    size_t b = (size_t)lu_ld(n) * n * sizeof(double) + (size_t)n * sizeof(double) + ((size_t)n * sizeof(int) + 15) / 16 * 16 + sizeof(LuShared);
+    return (b + 15) / 16 * 16;
+}
+
+// WARP = true : blockDim = 32*WARPS_PER_CTA, each warp factors its own matrices (grid-stride over the batch)
+// WARP = false: the whole CTA factors one matrix at a time; SMEM = false works in place in global memory (AoS only)
+template <bool SOA, bool WARP, bool SMEM>
+__global__ void __launch_bounds__(CTA_THREADS) getrf_group(double* __restrict__ A, int64_t* __restrict__ piv,
+                                                           int32_t* __restrict__ info, int n, int64_t B, unsigned group_bytes) {
+    extern __shared__ __align__(16) unsigned char lu_smem[];
+    using G = LuGroup<WARP>;
+    const int gi = WARP ? (int)(threadIdx.x >> 5) : 0, ng = WARP ? (int)(blockDim.x >> 5) : 1;
+    unsigned char* base = lu_smem + (size_t)gi * group_bytes;
+    const int ld = SMEM ? lu_ld(n) : n;
+    double* Ms = reinterpret_cast<double*>(base);
+    int* pivs = reinterpret_cast<int*>(base + (SMEM ? (size_t)ld * n * sizeof(double) : 0) + (size_t)n * sizeof(double));
+    LuShared* sh = reinterpret_cast<LuShared*>(reinterpret_cast<unsigned char*>(pivs) + ((size_t)n * sizeof(int) + 15) / 16 * 16);
+    const int tid = G::tid(), nt = G::nthreads(), nw = G::nwarps(), w = G::warp(), lane = tid & 31;
+    for (int64_t b = (int64_t)blockIdx.x * ng + gi; b < B; b += (int64_t)gridDim.x * ng) {
+        double* M = Ms;
         if (SMEM) {
-            for (int e = tid; e < n * n; e += CTA_THREADS) sm[e] = A[mat_idx<SOA>(e % n, e / n, n, b, B)];
-            M = sm;
-            __syncthreads();
+            for (int j = w; j < n; j += nw)
+                for (int i = lane; i < n; i += 32) Ms[(size_t)j * ld + i] = A[mat_idx<SOA>(i, j, n, b, B)];
         } else {
-            M = A + (size_t)b * n * n;  // AoS only (dispatch guarantees it)
+            M = A + (size_t)b * n * n;
         }
-        int inf = 0;
-        for (int k = 0; k < n; ++k) {
-            // pivot search: l = k; for i > k: if |a_ik| > |a_lk| then l = i   (dense.rs:109-116).
-            // i.e. the lowest-index maximum over rows k..n-1, where a NaN never wins and a NaN in row k
-            // keeps l = k.
-            const double vk = fabs(M[(size_t)k * n + k]);
-            double best = -1.0;
-            int bi = 0x7fffffff;
-            for (int i = k + tid; i < n; i += CTA_THREADS) {
-                const double v = fabs(M[(size_t)k * n + i]);
-                if (v > best) {
-                    best = v;
-                    bi = i;
-                }
-            }
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                const double ov = __shfl_down_sync(0xffffffffu, best, off);
-                const int oi = __shfl_down_sync(0xffffffffu, bi, off);
-                if (ov > best || (ov == best && oi < bi)) {
-                    best = ov;
-                    bi = oi;
-                }
-            }
-            if ((tid & 31) == 0) {
-                s_red_v[tid >> 5] = best;
-                s_red_i[tid >> 5] = bi;
-            }
-            __syncthreads();
-            if (tid == 0) {
-                double bv = s_red_v[0];
-                int bidx = s_red_i[0];
-                for (int w = 1; w < CTA_THREADS / 32; ++w) {
-                    if (s_red_v[w] > bv || (s_red_v[w] == bv && s_red_i[w] < bidx)) {
-                        bv = s_red_v[w];
-                        bidx = s_red_i[w];
-                    }
-                }
-                if (vk != vk) bidx = k;  // NaN in row k: nothing compares greater
-                s_l = bidx;
-                piv[SOA ? ((size_t)k * B + b) : ((size_t)b * n + k)] = bidx;
-            }
-            __syncthreads();
-            const int l = s_l;
-            if (M[(size_t)k * n + l] == 0.0) {
-                inf = k + 1;
-                break;
-            }
-            if (l != k) {
-                for (int c = tid; c < n; c += CTA_THREADS) {
-                    const double t = M[(size_t)c * n + k];
-                    M[(size_t)c * n + k] = M[(size_t)c * n + l];
-                    M[(size_t)c * n + l] = t;
-                }
-                __syncthreads();
-            }
-            const double mult = 1.0 / M[(size_t)k * n + k];
-            __syncthreads();
-            for (int i = k + 1 + tid; i < n; i += CTA_THREADS) M[(size_t)k * n + i] *= mult;
-            __syncthreads();
-            const int m = n - k - 1;
-            for (int e = tid; e < m * m; e += CTA_THREADS) {
-                const int i = k + 1 + e % m, j = k + 1 + e / m;
-                const double a_kj = M[(size_t)j * n + k];
-                if (a_kj != 0.0) M[(size_t)j * n + i] -= a_kj * M[(size_t)k * n + i];
-            }
-            __syncthreads();
-        }
+        G::sync();
+        lu_factor<WARP>(M, ld, n, sh, pivs);
         if (SMEM) {
-            __syncthreads();
-            for (int e = tid; e < n * n; e += CTA_THREADS) A[mat_idx<SOA>(e % n, e / n, n, b, B)] = sm[e];
+            for (int j = w; j < n; j += nw)
+                for (int i = lane; i < n; i += 32) A[mat_idx<SOA>(i, j, n, b, B)] = Ms[(size_t)j * ld + i];
         }
+        const int inf = sh->info;
+        for (int k = tid; k < n; k += nt) piv[SOA ? ((size_t)k * B + b) : ((size_t)b * n + k)] = (inf == 0 || k < inf) ? pivs[k] : 0;
         if (tid == 0) info[b] = inf;
-        __syncthreads();
+        G::sync();
     }
 }
 
-template <bool SOA>
-__global__ void __launch_bounds__(CTA_THREADS) getrs_cta(const double* __restrict__ A, const int64_t* __restrict__ piv,
-                                                         double* __restrict__ bx, int n, int64_t B) {
-    __shared__ double x[256];
-    const int tid = threadIdx.x;
-    for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
-        for (int i = tid; i < n; i += CTA_THREADS) x[i] = bx[vec_idx<SOA>(i, n, b, B)];
-        __syncthreads();
-        if (tid == 0) {
-            for (int k = 0; k < n; ++k) {
-                const int pk = (int)piv[SOA ? ((size_t)k * B + b) : ((size_t)b * n + k)];
-                if (pk != k) {
-                    const double t = x[k];
-                    x[k] = x[pk];
-                    x[pk] = t;
-                }
-            }
+template <bool SOA, bool WARP, bool SMEM>
+__global__ void __launch_bounds__(CTA_THREADS) getrs_group(const double* __restrict__ A, const int64_t* __restrict__ piv,
+                                                           double* __restrict__ bx, int n, int64_t B, unsigned group_bytes) {
+    extern __shared__ __align__(16) unsigned char lu_smem[];
+    using G = LuGroup<WARP>;
+    const int gi = WARP ? (int)(threadIdx.x >> 5) : 0, ng = WARP ? (int)(blockDim.x >> 5) : 1;
+    unsigned char* base = lu_smem + (size_t)gi * group_bytes;
+    const int ld = SMEM ? lu_ld(n) : n;
+    double* Ms = reinterpret_cast<double*>(base);
+    double* xs = reinterpret_cast<double*>(base + (SMEM ? (size_t)ld * n * sizeof(double) : 0));
+    int* pivs = reinterpret_cast<int*>(xs + n);
+    const int tid = G::tid(), nt = G::nthreads(), nw = G::nwarps(), w = G::warp(), lane = tid & 31;
+    for (int64_t b = (int64_t)blockIdx.x * ng + gi; b < B; b += (int64_t)gridDim.x * ng) {
+        const double* M = Ms;
+        if (SMEM) {
+            for (int j = w; j < n; j += nw)
+                for (int i = lane; i < n; i += 32) Ms[(size_t)j * ld + i] = A[mat_idx<SOA>(i, j, n, b, B)];
+        } else {
+            M = A + (size_t)b * n * n;
         }
-        __syncthreads();
-        for (int k = 0; k < n - 1; ++k) {
-            const double bk = x[k];
-            __syncthreads();
-            for (int i = k + 1 + tid; i < n; i += CTA_THREADS) x[i] -= A[mat_idx<SOA>(i, k, n, b, B)] * bk;
-            __syncthreads();
+        for (int i = tid; i < n; i += nt) {
+            xs[i] = bx[vec_idx<SOA>(i, n, b, B)];
+            pivs[i] = (int)piv[SOA ? ((size_t)i * B + b) : ((size_t)b * n + i)];
         }
-        for (int k = n - 1; k >= 1; --k) {
-            if (tid == 0) x[k] /= A[mat_idx<SOA>(k, k, n, b, B)];
-            __syncthreads();
-            const double bk = x[k];
-            for (int i = tid; i < k; i += CTA_THREADS) x[i] -= A[mat_idx<SOA>(i, k, n, b, B)] * bk;
-            __syncthreads();
-        }
-        if (tid == 0) x[0] /= A[mat_idx<SOA>(0, 0, n, b, B)];
-        __syncthreads();
-        for (int i = tid; i < n; i += CTA_THREADS) bx[vec_idx<SOA>(i, n, b, B)] = x[i];
-        __syncthreads();
+        G::sync();
+        lu_solve<WARP>(M, ld, n, pivs, xs);
+        for (int i = tid; i < n; i += nt) bx[vec_idx<SOA>(i, n, b, B)] = xs[i];
+        G::sync();
     }
 }
 
@@ -307,6 +249,12 @@ __global__ void mat_aos_to_soa(const double* __restrict__ aos, double* __restric
     const int i = (int)(r / n), j = (int)(r % n);
     soa[e] = aos[b * n * n + (int64_t)j * n + i];
 }
+__global__ void vec_soa_to_aos(const double* __restrict__ soa, double* __restrict__ aos, int64_t rows, int64_t B) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= rows * B) return;
+    const int64_t r = e / B, b = e % B;
+    aos[b * rows + r] = soa[e];
+}
 // vectors (any 8-byte element): SoA (i, b) at i*B + b  <->  AoS b*n + i
 __global__ void vec_aos_to_soa(const double* __restrict__ aos, double* __restrict__ soa, int64_t rows, int64_t B) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -330,6 +278,82 @@ static int sm_count() {
     return sms;
 }
 
+// launch the group-per-system getrf (FACTOR) or getrs kernel for any n <= 256
+template <class K>
+static int launch_cfg(K kernel, int threads, size_t smem, int64_t groups_needed, int groups_per_cta, unsigned* grid) {
+    B200_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem));
+    if (occ < 1) occ = 1;
+    const int64_t want = (groups_needed + groups_per_cta - 1) / groups_per_cta;
+    const int64_t cap = (int64_t)sm_count() * occ;
+    *grid = (unsigned)(want < cap ? want : cap);
+    return B200IDA_OK;
+}
+
+template <bool FACTOR>
+static int launch_group(double* A, int64_t* piv, int32_t* info, double* bx, int n, int64_t B, bool soa, cudaStream_t st) {
+    const unsigned gb = (unsigned)lu_group_smem_bytes(n);
+    unsigned grid = 1;
+    int rc;
+#define LAUNCH(SOA_, WARP_, SMEM_, threads, smem, gpc)                                                                   \
+    do {                                                                                                               \
+        if (FACTOR) {                                                                                                  \
+            if ((rc = launch_cfg(getrf_group<SOA_, WARP_, SMEM_>, threads, smem, B, gpc, &grid))) return rc;             \
+            getrf_group<SOA_, WARP_, SMEM_><<<grid, threads, smem, st>>>(A, piv, info, n, B, gb);                        \
+        } else {                                                                                                       \
+            if ((rc = launch_cfg(getrs_group<SOA_, WARP_, SMEM_>, threads, smem, B, gpc, &grid))) return rc;             \
+            getrs_group<SOA_, WARP_, SMEM_><<<grid, threads, smem, st>>>(A, piv, bx, n, B, gb);                          \
+        }                                                                                                              \
+    } while (0)
+    if (n <= 32) {
+        const int threads = 32 * WARPS_PER_CTA;
+        const size_t smem = (size_t)gb * WARPS_PER_CTA;
+        if (soa) LAUNCH(true, true, true, threads, smem, WARPS_PER_CTA);
+        else LAUNCH(false, true, true, threads, smem, WARPS_PER_CTA);
+    } else if (n <= SMEM_MAX_N) {
+        const int threads = n <= 64 ? 128 : CTA_THREADS;
+        if (soa) LAUNCH(true, false, true, threads, (size_t)gb, 1);
+        else LAUNCH(false, false, true, threads, (size_t)gb, 1);
+    } else {
+        // too big for shared memory: factor / solve in place in global memory (L2-resident), AoS only
+        const size_t smem = (size_t)n * sizeof(double) + ((size_t)n * sizeof(int) + 15) / 16 * 16 + sizeof(LuShared) + 16;
+        if (!soa) {
+            LAUNCH(false, false, false, CTA_THREADS, smem, 1);
+        } else {
+            DevBuf tmp, ptmp, xtmp;
+            B200_CUDA_TRY(tmp.alloc((size_t)n * n * B * sizeof(double)));
+            B200_CUDA_TRY(ptmp.alloc((size_t)n * B * sizeof(int64_t)));
+            const unsigned tg = (unsigned)(((int64_t)n * n * B + 255) / 256), vg = (unsigned)(((int64_t)n * B + 255) / 256);
+            mat_soa_to_aos<<<tg, 256, 0, st>>>(A, tmp.as<double>(), n, B);
+            double* A0 = A;
+            int64_t* piv0 = piv;
+            double* bx0 = bx;
+            A = tmp.as<double>();
+            if (FACTOR) {
+                piv = ptmp.as<int64_t>();
+                LAUNCH(false, false, false, CTA_THREADS, smem, 1);
+                mat_aos_to_soa<<<tg, 256, 0, st>>>(tmp.as<double>(), A0, n, B);
+                vec_aos_to_soa<<<vg, 256, 0, st>>>(reinterpret_cast<const double*>(ptmp.as<int64_t>()), reinterpret_cast<double*>(piv0), n, B);
+            } else {
+                B200_CUDA_TRY(xtmp.alloc((size_t)n * B * sizeof(double)));
+                vec_soa_to_aos<<<vg, 256, 0, st>>>(reinterpret_cast<const double*>(piv0), reinterpret_cast<double*>(ptmp.as<int64_t>()), n, B);
+                vec_soa_to_aos<<<vg, 256, 0, st>>>(bx0, xtmp.as<double>(), n, B);
+                piv = ptmp.as<int64_t>();
+                bx = xtmp.as<double>();
+                LAUNCH(false, false, false, CTA_THREADS, smem, 1);
+                vec_aos_to_soa<<<vg, 256, 0, st>>>(xtmp.as<double>(), bx0, n, B);
+            }
+            B200_CUDA_TRY(cudaGetLastError());
+            B200_CUDA_TRY(cudaStreamSynchronize(st));  // scratch freed on return
+            return B200IDA_OK;
+        }
+    }
+#undef LAUNCH
+    B200_CUDA_TRY(cudaGetLastError());
+    return B200IDA_OK;
+}
+
 // device-pointer implementations -------------------------------------------------------------------------
 static int getrf_dev(double* A, int64_t* piv, int32_t* info, int n, int64_t B, int layout, cudaStream_t st) {
     const bool soa = layout == B200IDA_LAYOUT_SOA;
@@ -347,39 +371,7 @@ static int getrf_dev(double* A, int64_t* piv, int32_t* info, int n, int64_t B, i
         B200_CUDA_TRY(cudaGetLastError());
         return B200IDA_OK;
     }
-    const unsigned grid = (unsigned)(B < (int64_t)sm_count() * 8 ? B : (int64_t)sm_count() * 8);
-    if (n <= SMEM_MAX_N) {
-        const size_t smem = (size_t)n * n * sizeof(double);
-        if (soa) {
-            B200_CUDA_TRY(cudaFuncSetAttribute(getrf_cta<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            getrf_cta<true, true><<<grid, CTA_THREADS, smem, st>>>(A, piv, info, n, B);
-        } else {
-            B200_CUDA_TRY(cudaFuncSetAttribute(getrf_cta<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            getrf_cta<false, true><<<grid, CTA_THREADS, smem, st>>>(A, piv, info, n, B);
-        }
-        B200_CUDA_TRY(cudaGetLastError());
-        return B200IDA_OK;
-    }
-    // n > SMEM_MAX_N: in-place in global memory on an AoS copy
-    if (!soa) {
-        getrf_cta<false, false><<<grid, CTA_THREADS, 0, st>>>(A, piv, info, n, B);
-        B200_CUDA_TRY(cudaGetLastError());
-        return B200IDA_OK;
-    }
-    DevBuf tmp, ptmp;
-    const int64_t rows = (int64_t)n * n;
-    B200_CUDA_TRY(tmp.alloc((size_t)rows * B * sizeof(double)));
-    const unsigned tg = (unsigned)((rows * B + 255) / 256);
-    mat_soa_to_aos<<<tg, 256, 0, st>>>(A, tmp.as<double>(), n, B);
-    B200_CUDA_TRY(ptmp.alloc((size_t)n * B * sizeof(int64_t)));
-    getrf_cta<false, false><<<grid, CTA_THREADS, 0, st>>>(tmp.as<double>(), ptmp.as<int64_t>(), info, n, B);
-    mat_aos_to_soa<<<tg, 256, 0, st>>>(tmp.as<double>(), A, n, B);
-    // pivots: int64 has the same width as double, reuse the transpose kernel bit-for-bit
-    vec_aos_to_soa<<<(unsigned)(((int64_t)n * B + 255) / 256), 256, 0, st>>>(
-        reinterpret_cast<const double*>(ptmp.as<int64_t>()), reinterpret_cast<double*>(piv), n, B);
-    B200_CUDA_TRY(cudaGetLastError());
-    B200_CUDA_TRY(cudaStreamSynchronize(st));  // scratch freed on return
-    return B200IDA_OK;
+    return launch_group<true>(A, piv, info, nullptr, n, B, soa, st);
 }
 
 static int getrs_dev(const double* LU, const int64_t* piv, double* bx, int n, int64_t B, int layout, cudaStream_t st) {
@@ -398,11 +390,7 @@ static int getrs_dev(const double* LU, const int64_t* piv, double* bx, int n, in
         B200_CUDA_TRY(cudaGetLastError());
         return B200IDA_OK;
     }
-    const unsigned grid = (unsigned)(B < (int64_t)sm_count() * 8 ? B : (int64_t)sm_count() * 8);
-    if (soa) getrs_cta<true><<<grid, CTA_THREADS, 0, st>>>(LU, piv, bx, n, B);
-    else getrs_cta<false><<<grid, CTA_THREADS, 0, st>>>(LU, piv, bx, n, B);
-    B200_CUDA_TRY(cudaGetLastError());
-    return B200IDA_OK;
+    return launch_group<false>(const_cast<double*>(LU), const_cast<int64_t*>(piv), nullptr, bx, n, B, soa, st);
 }
 
 static int wrms_dev(const double* x, const double* w, double* out, int n, int64_t B, int layout, cudaStream_t st) {

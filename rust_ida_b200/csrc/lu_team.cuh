@@ -1,0 +1,211 @@
+// lu_team.cuh -- dense partial-pivot LU and triangular solves executed by a GROUP of threads (one warp or one
+// whole CTA) on one column-major matrix that sits in shared memory (or, for matrices too big for it, in global
+// memory).  Shared by the Level-1 batched kernels (linalg_batched.cu) and the team IDA kernels (ida_team.cuh).
+//
+// Semantics are bit-for-bit dense_get_rf / dense_get_rs (crates/linear/src/dense.rs:86-206):
+//   pivot = first row with strictly largest |a_ik| (a NaN never wins; a NaN in row k keeps l = k); whole-row swap;
+//   l_ik = a_ik * (1/a_kk); a_ij -= a_kj * l_ik with column j skipped when a_kj == 0; zero pivot -> k+1 and stop.
+// Within elimination step k every a_ij update is one mul and one sub that depend only on step k-1, so spreading
+// (i, j) over threads changes no rounding; only the k loop is sequential.  Built with -fmad=false.
+//
+// Schedule per step k (2 group barriers):
+//   [A] swap rows k,l in every column j != k and rewrite column k as (pivot, multipliers)   -- threads over j / i
+//   barrier
+//   [B] trailing update, column j -> warp (j-k-1) mod nwarps, rows -> lanes, multipliers cached in registers;
+//       warp 0 owns column k+1, so as soon as it has updated it, it runs the pivot search of step k+1
+//       (look-ahead) while the other warps finish their columns
+//   barrier
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200ida {
+
+struct LuShared {  // per-group scratch in shared memory
+    double pv;     // pivot value a_lk
+    double mult;   // 1 / pv
+    double akk;    // a_kk before the swap
+    int l;         // pivot row
+    int info;      // 0 or 1-based column of the zero pivot
+};
+
+template <bool WARP>
+struct LuGroup {
+    __device__ __forceinline__ static int nthreads() { return WARP ? 32 : (int)blockDim.x; }
+    __device__ __forceinline__ static int tid() { return WARP ? (int)(threadIdx.x & 31) : (int)threadIdx.x; }
+    __device__ __forceinline__ static int nwarps() { return WARP ? 1 : (int)(blockDim.x >> 5); }
+    __device__ __forceinline__ static int warp() { return WARP ? 0 : (int)(threadIdx.x >> 5); }
+    __device__ __forceinline__ static void sync() {
+        if (WARP) __syncwarp();
+        else __syncthreads();
+    }
+};
+
+// pivot search of column k by ONE warp (all 32 lanes call it); publishes l / pv / akk / info and piv[k]
+template <class PivT>
+__device__ __forceinline__ void lu_pivot_search(const double* M, int ld, int n, int k, LuShared* sh, PivT* piv) {
+    const int lane = threadIdx.x & 31;
+    const double* col = M + (size_t)k * ld;
+    double best = -1.0;
+    int bi = 0x7fffffff;
+    for (int i = k + lane; i < n; i += 32) {
+        const double v = fabs(col[i]);
+        if (v > best) {  // NaN fails '>' ; ascending i keeps the lowest index on ties
+            best = v;
+            bi = i;
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, best, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+        if (ov > best || (ov == best && oi < bi)) {
+            best = ov;
+            bi = oi;
+        }
+    }
+    if (lane == 0) {
+        const double akk = col[k];
+        if (akk != akk || bi >= n) bi = k;  // NaN in row k (or nothing comparable): the reference keeps l = k
+        const double pv = col[bi];
+        sh->l = bi;
+        sh->pv = pv;
+        sh->mult = 1.0 / pv;
+        sh->akk = akk;
+        if (pv == 0.0) sh->info = k + 1;
+        piv[k] = (PivT)bi;
+    }
+}
+
+// In-place LU of the n x n column-major matrix M (leading dimension ld).  Every thread of the group calls it.
+// On return (after the final barrier) sh->info holds 0 or the 1-based singular column, piv[0..n) the pivot rows.
+template <bool WARP, int RMAX, class PivT>
+__device__ __forceinline__ void lu_factor_r(double* M, int ld, int n, LuShared* sh, PivT* piv) {
+    using G = LuGroup<WARP>;  // RMAX = rows per lane = ceil(n / 32): the multiplier cache and the update loop are unrolled to it
+    const int tid = G::tid(), nt = G::nthreads(), nw = G::nwarps(), w = G::warp(), lane = tid & 31;
+    if (tid == 0) sh->info = 0;
+    G::sync();
+    if (w == 0) lu_pivot_search(M, ld, n, 0, sh, piv);
+    G::sync();
+    for (int k = 0; k < n; ++k) {
+        if (sh->info != 0) break;  // uniform: written before the barrier that precedes this read
+        const int l = sh->l;
+        const double pv = sh->pv, akk = sh->akk, mult = sh->mult;
+        // [A] row swap outside column k, then column k := (pivot, multipliers)
+        if (l != k) {
+            for (int j = tid; j < n; j += nt) {
+                if (j != k) {
+                    double* c = M + (size_t)j * ld;
+                    const double t = c[k];
+                    c[k] = c[l];
+                    c[l] = t;
+                }
+            }
+        }
+        {
+            double* ck = M + (size_t)k * ld;
+            for (int i = k + tid; i < n; i += nt) {
+                if (i == k) {
+                    ck[k] = pv;
+                } else {
+                    const double v = (i == l) ? akk : ck[i];
+                    ck[i] = v * mult;
+                }
+            }
+        }
+        G::sync();
+        // [B] trailing update with look-ahead pivot search
+        double lik[RMAX];
+        const double* ck = M + (size_t)k * ld;
+#pragma unroll
+        for (int r = 0; r < RMAX; ++r) {
+            const int i = k + 1 + lane + 32 * r;
+            lik[r] = (i < n) ? ck[i] : 0.0;
+        }
+        // two columns per trip: all loads are issued before the stores so the two updates overlap
+        for (int j0 = k + 1 + w; j0 < n; j0 += 2 * nw) {
+            const int j1 = j0 + nw;
+            const bool has1 = j1 < n;
+            double* c0 = M + (size_t)j0 * ld;
+            double* c1 = M + (size_t)(has1 ? j1 : j0) * ld;
+            const double a0 = c0[k];
+            const double a1 = has1 ? c1[k] : 0.0;
+            double v0[RMAX], v1[RMAX];
+#pragma unroll
+            for (int r = 0; r < RMAX; ++r) {
+                const int i = k + 1 + lane + 32 * r;
+                v0[r] = (i < n) ? c0[i] : 0.0;
+                v1[r] = (i < n && has1) ? c1[i] : 0.0;
+            }
+            if (a0 != 0.0) {
+#pragma unroll
+                for (int r = 0; r < RMAX; ++r) {
+                    const int i = k + 1 + lane + 32 * r;
+                    if (i < n) c0[i] = v0[r] - a0 * lik[r];
+                }
+            }
+            if (has1 && a1 != 0.0) {
+#pragma unroll
+                for (int r = 0; r < RMAX; ++r) {
+                    const int i = k + 1 + lane + 32 * r;
+                    if (i < n) c1[i] = v1[r] - a1 * lik[r];
+                }
+            }
+            if (w == 0 && j0 == k + 1) {
+                __syncwarp();
+                lu_pivot_search(M, ld, n, k + 1, sh, piv);
+            }
+        }
+        G::sync();
+    }
+}
+
+// dispatch on ceil(n/32) so that small systems do not issue predicated-off row slots
+template <bool WARP, class PivT>
+__device__ __forceinline__ void lu_factor(double* M, int ld, int n, LuShared* sh, PivT* piv) {
+    if (n <= 32) lu_factor_r<WARP, 1>(M, ld, n, sh, piv);
+    else if (n <= 64) lu_factor_r<WARP, 2>(M, ld, n, sh, piv);
+    else if (n <= 128) lu_factor_r<WARP, 4>(M, ld, n, sh, piv);
+    else lu_factor_r<WARP, 8>(M, ld, n, sh, piv);
+}
+
+// Solve with the factors: b := A^{-1} b, all in shared (or global) memory; every thread of the group calls it.
+// The substitutions are a chain of 2n dependent steps with O(n) work each, so they run on ONE warp (lanes own rows
+// lane, lane+32, ...; one __syncwarp per step) and, in a CTA group, the other warps just wait at the final barrier.
+template <bool WARP, class PivT>
+__device__ __forceinline__ void lu_solve(const double* M, int ld, int n, const PivT* piv, double* b) {
+    using G = LuGroup<WARP>;
+    const int lane = threadIdx.x & 31;
+    G::sync();
+    if (G::warp() == 0) {
+        if (lane == 0) {
+            for (int k = 0; k < n; ++k) {
+                const int pk = (int)piv[k];
+                if (pk != k) {
+                    const double t = b[k];
+                    b[k] = b[pk];
+                    b[pk] = t;
+                }
+            }
+        }
+        __syncwarp();
+        for (int k = 0; k < n - 1; ++k) {
+            const double bk = b[k];
+            const double* ck = M + (size_t)k * ld;
+            for (int i = k + 1 + lane; i < n; i += 32) b[i] -= ck[i] * bk;
+            __syncwarp();
+        }
+        for (int k = n - 1; k >= 1; --k) {
+            const double* ck = M + (size_t)k * ld;
+            if (lane == 0) b[k] /= ck[k];
+            __syncwarp();
+            const double bk = b[k];
+            for (int i = lane; i < k; i += 32) b[i] -= ck[i] * bk;
+            __syncwarp();
+        }
+        if (lane == 0) b[0] /= M[0];
+    }
+    G::sync();
+}
+
+}  // namespace b200ida

@@ -1,0 +1,104 @@
+#!/usr/bin/env python3
+"""Single-GPU measurements of the other BASELINE.json configs (the headline config[1] is bench.py):
+
+  lorenz   config[2]  Lorenz-63 as a DAE, 4 * 2^20 instance parameter sweep, t_end = 5 (10 output times)
+  heat     config[4]  2-D heat DAE, 10x10 grid (dense n = 100), 65,536 instances, CTA-per-system kernel
+  kernels  Roberts, 2^17 instances: thread-per-instance vs warp-per-system vs CTA-per-system on identical inputs
+           ("measure warp-per-system against thread-per-system and let the numbers decide")
+
+One JSON line each: instances/s with inputs resident in HBM, CUDA-event timing, best of --reps.
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def timed_solve(ida, yy0, yp0, touts, reps):
+    import torch
+    best = 1e30
+    for rep in range(reps + 1):
+        ida.reinit(yy0, yp0)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        status, _ = ida.solve_ladder(touts, want_traj=False)
+        e1.record()
+        torch.cuda.synchronize()
+        if rep > 0 or reps == 0:
+            best = min(best, e0.elapsed_time(e1))
+    return best, status
+
+
+def main():
+    import torch
+    import rust_ida_b200 as r
+    from rust_ida_b200.problems import (Heat2D, Lorenz63, Roberts, heat_ensemble_params, lorenz_ensemble_params,
+                                        roberts_ensemble_params)
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--which", default="lorenz,heat,kernels")
+    ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--lorenz-batch", type=int, default=4 << 20)
+    ap.add_argument("--heat-batch", type=int, default=65536)
+    args = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    to_dev = lambda *a: [torch.from_numpy(np.ascontiguousarray(v)).to(dev) for v in a]
+
+    if "lorenz" in args.which:
+        B = args.lorenz_batch
+        p = lorenz_ensemble_params(B, seed=1234)
+        yy0, yp0 = Lorenz63.consistent_ic(p)
+        pd, y0, yp = to_dev(p, yy0, yp0)
+        ida = r.Ida(Lorenz63(pd), y0, yp, r.TolControlSV(1e-6, np.full(3, 1e-8)))
+        touts = 0.5 * np.arange(1, 11)
+        ms, st = timed_solve(ida, y0, yp, touts, args.reps)
+        nst = ida.get_num_steps()
+        print(json.dumps({"config": "lorenz63 DAE ensemble", "batch": B, "n": 3, "kernel": "thread", "ms": ms,
+                          "instances_per_s": B / (ms * 1e-3), "all_success": bool((st == 0).all().item()),
+                          "nst_min_max_mean": [int(nst.min()), int(nst.max()), float(nst.double().mean())]}), flush=True)
+        ida.close()
+
+    if "heat" in args.which:
+        B, M = args.heat_batch, 10
+        p = heat_ensemble_params(B, M=M, seed=1234)
+        yy0, yp0 = Heat2D.consistent_ic(p, M)
+        pd, y0, yp = to_dev(p, yy0, yp0)
+        ida = r.Ida(Heat2D(pd, M=M), y0, yp, r.TolControlSV(1e-6, np.full(M * M, 1e-8)))
+        touts = 0.01 * 2.0 ** np.arange(11)
+        ms, st = timed_solve(ida, y0, yp, touts, max(1, args.reps - 1))
+        nst, nje, nni = ida.get_num_steps(), ida.get_num_jac_evals(), ida.get_num_nonlin_solv_iters()
+        n = M * M
+        lu_flops = sum((n - k - 1) + 2 * (n - k - 1) ** 2 for k in range(n))
+        flops = float(nje.sum()) * lu_flops + float(nni.sum()) * (2 * n * n)
+        print(json.dumps({"config": "heat2d 10x10 DAE ensemble", "batch": B, "n": n, "kernel": "cta", "ms": ms,
+                          "instances_per_s": B / (ms * 1e-3), "all_success": bool((st == 0).all().item()),
+                          "nst_mean": float(nst.double().mean()), "nje_mean": float(nje.double().mean()),
+                          "lu_plus_solve_gflops": flops / (ms * 1e-3) * 1e-9}), flush=True)
+        ida.close()
+
+    if "kernels" in args.which:
+        B = 1 << 17
+        p = roberts_ensemble_params(B, seed=1234)
+        yy0, yp0 = Roberts.consistent_ic(p)
+        pd, y0, yp = to_dev(p, yy0, yp0)
+        touts = 0.4 * 10.0 ** np.arange(12)
+        ref = None
+        for kern in ("thread", "warp", "cta"):
+            ida = r.Ida(Roberts(pd), y0, yp, r.TolControlSV(1e-4, [1e-8, 1e-6, 1e-6]))
+            ida.set_kernel(kern)
+            ms, st = timed_solve(ida, y0, yp, touts, 1)
+            yy = ida.get_yy().cpu().numpy()
+            same = True if ref is None else bool(np.array_equal(ref.view(np.uint64), yy.view(np.uint64)))
+            ref = yy if ref is None else ref
+            print(json.dumps({"config": "roberts ensemble, kernel family comparison", "batch": B, "n": 3, "kernel": kern,
+                              "ms": ms, "instances_per_s": B / (ms * 1e-3), "bit_identical_to_thread_kernel": same}), flush=True)
+            ida.close()
+
+
+if __name__ == "__main__":
+    main()
