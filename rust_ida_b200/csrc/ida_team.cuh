@@ -140,8 +140,8 @@ struct TeamScalars {
 };
 
 __host__ __device__ inline size_t team_arena_bytes(int n) {
-    // phi[6][n] + 10 n-vectors + J[n][n] as doubles, pivots as ints, scalars; 16-byte aligned pieces
-    size_t d = (size_t)16 * n + (size_t)n * n;
+    // phi[6][n] + 11 n-vectors + J[n][n] as doubles, pivots as ints, scalars; 16-byte aligned pieces
+    size_t d = (size_t)17 * n + (size_t)n * n;
     size_t bytes = d * sizeof(double) + ((size_t)n * sizeof(int) + 15) / 16 * 16 + (sizeof(TeamScalars) + 15) / 16 * 16;
     return (bytes + 15) / 16 * 16;
 }
@@ -150,7 +150,7 @@ template <class Team>
 struct IdaTeam {
     int n, T, t;
     // arena views
-    double *phi, *ee, *ewt, *yy, *yp, *yypred, *yppred, *delta, *nd, *tmp, *prod, *J;
+    double *phi, *ee, *ewt, *yy, *yp, *yypred, *yppred, *delta, *nd, *tmp, *prod, *rdiag, *J;
     int* piv;
     TeamScalars* S;
     TeamProblem prob;
@@ -173,6 +173,7 @@ struct IdaTeam {
         nd = d;             d += n;
         tmp = d;            d += n;
         prod = d;           d += n;
+        rdiag = d;          d += n;
         J = d;              d += (size_t)n * n;
         piv = reinterpret_cast<int*>(d);
         S = reinterpret_cast<TeamScalars*>(reinterpret_cast<unsigned char*>(piv) + ((size_t)n * sizeof(int) + 15) / 16 * 16);
@@ -192,6 +193,8 @@ struct IdaTeam {
             piv[i] = is[(int64_t)lay.piv(i) * B + b];
         }
         for (int e = t; e < n * n; e += T) J[e] = ds[(int64_t)lay.J(e % n, e / n) * B + b];
+        Team::sync();
+        for (int k = t; k < n; k += T) rdiag[k] = 1.0 / J[(size_t)k * n + k];  // not persisted; from the stored factors
         if (leader()) {
             for (int j = 0; j < MXORDP1; ++j) {
                 S->psi[j] = ds[(int64_t)lay.psi(j) * B + b];
@@ -347,12 +350,13 @@ struct IdaTeam {
         Team::sync();
         lu_factor<Team::T == 32>(J, n, n, &S->lu, piv);
         if (leader()) S->info = S->lu.info;
+        for (int k = t; k < n; k += T) rdiag[k] = 1.0 / J[(size_t)k * n + k];
         Team::sync();
     }
 
     // ---- dense_get_rs on nd (crates/linear/src/dense.rs:165-206) + cjratio rescale (src/ida_ls.rs:406-410) ------
     __device__ void lsolve() {
-        lu_solve<Team::T == 32>(J, n, n, piv, nd);
+        lu_solve<Team::T == 32>(J, n, n, piv, nd, rdiag);
         const double cjratio = S->cjratio;
         if (cjratio != 1.0) {
             const double f = 2.0 / (1.0 + cjratio);

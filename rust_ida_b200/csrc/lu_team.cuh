@@ -19,6 +19,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "exact_div.cuh"
+
 namespace b200ida {
 
 struct LuShared {  // per-group scratch in shared memory
@@ -170,40 +172,92 @@ __device__ __forceinline__ void lu_factor(double* M, int ld, int n, LuShared* sh
 }
 
 // Solve with the factors: b := A^{-1} b, all in shared (or global) memory; every thread of the group calls it.
-// The substitutions are a chain of 2n dependent steps with O(n) work each, so they run on ONE warp (lanes own rows
-// lane, lane+32, ...; one __syncwarp per step) and, in a CTA group, the other warps just wait at the final barrier.
-template <bool WARP, class PivT>
-__device__ __forceinline__ void lu_solve(const double* M, int ld, int n, const PivT* piv, double* b) {
-    using G = LuGroup<WARP>;
+// The substitutions are a chain of 2n dependent steps with O(n) work each, so they run on ONE warp and, in a CTA
+// group, the other warps wait at the final barrier.  The right-hand side lives in REGISTERS (lane owns rows lane,
+// lane+32, ...), the pivot-row value of each step is broadcast with a shuffle, and the column of L/U is read from
+// shared memory with loads that do not depend on the chain -- so a step costs one shuffle + mul + sub of latency
+// instead of a shared-memory store->load round trip per row slot.
+// rdiag (optional): rdiag[k] = RN(1 / u_kk), computed off the critical path; the division of the back substitution
+// then costs 3 dependent instructions instead of ~10 (exact_div.cuh) and stays bit-identical.
+template <int RMAX, class PivT>
+__device__ __forceinline__ void lu_solve_warp_r(const double* M, int ld, int n, const PivT* piv, double* b, const double* rdiag) {
     const int lane = threadIdx.x & 31;
-    G::sync();
-    if (G::warp() == 0) {
-        if (lane == 0) {
-            for (int k = 0; k < n; ++k) {
-                const int pk = (int)piv[k];
-                if (pk != k) {
-                    const double t = b[k];
-                    b[k] = b[pk];
-                    b[pk] = t;
-                }
+    if (lane == 0) {
+        for (int k = 0; k < n; ++k) {
+            const int pk = (int)piv[k];
+            if (pk != k) {
+                const double t = b[k];
+                b[k] = b[pk];
+                b[pk] = t;
             }
         }
-        __syncwarp();
-        for (int k = 0; k < n - 1; ++k) {
-            const double bk = b[k];
-            const double* ck = M + (size_t)k * ld;
-            for (int i = k + 1 + lane; i < n; i += 32) b[i] -= ck[i] * bk;
-            __syncwarp();
+    }
+    __syncwarp();
+    double x[RMAX];
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r) {
+        const int i = lane + 32 * r;
+        x[r] = (i < n) ? b[i] : 0.0;
+    }
+    for (int k = 0; k < n - 1; ++k) {
+        const double* ck = M + (size_t)k * ld;
+        double c[RMAX];
+#pragma unroll
+        for (int r = 0; r < RMAX; ++r) {
+            const int i = lane + 32 * r;
+            c[r] = (i > k && i < n) ? ck[i] : 0.0;
         }
-        for (int k = n - 1; k >= 1; --k) {
-            const double* ck = M + (size_t)k * ld;
-            if (lane == 0) b[k] /= ck[k];
-            __syncwarp();
-            const double bk = b[k];
-            for (int i = lane; i < k; i += 32) b[i] -= ck[i] * bk;
-            __syncwarp();
+        const int r0 = k >> 5;
+        double xv = x[0];
+#pragma unroll
+        for (int r = 1; r < RMAX; ++r) xv = (r == r0) ? x[r] : xv;
+        const double bk = __shfl_sync(0xffffffffu, xv, k & 31);
+#pragma unroll
+        for (int r = 0; r < RMAX; ++r) {
+            const int i = lane + 32 * r;
+            if (i > k && i < n) x[r] -= c[r] * bk;
         }
-        if (lane == 0) b[0] /= M[0];
+    }
+    for (int k = n - 1; k >= 0; --k) {
+        const double* ck = M + (size_t)k * ld;
+        const double ukk = ck[k];
+        const double y = rdiag ? rdiag[k] : 0.0;
+        double c[RMAX];
+#pragma unroll
+        for (int r = 0; r < RMAX; ++r) {
+            const int i = lane + 32 * r;
+            c[r] = (i < k) ? ck[i] : 0.0;
+        }
+        const int r0 = k >> 5;
+        double xv = x[0];
+#pragma unroll
+        for (int r = 1; r < RMAX; ++r) xv = (r == r0) ? x[r] : xv;
+        if (lane == (k & 31)) xv = rdiag ? div_by_recip(xv, ukk, y) : xv / ukk;
+        const double bk = __shfl_sync(0xffffffffu, xv, k & 31);
+#pragma unroll
+        for (int r = 0; r < RMAX; ++r) {
+            const int i = lane + 32 * r;
+            if (i == k) x[r] = bk;
+            else if (i < k) x[r] -= c[r] * bk;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r) {
+        const int i = lane + 32 * r;
+        if (i < n) b[i] = x[r];
+    }
+}
+
+template <bool WARP, class PivT>
+__device__ __forceinline__ void lu_solve(const double* M, int ld, int n, const PivT* piv, double* b,
+                                         const double* rdiag = nullptr) {
+    using G = LuGroup<WARP>;
+    G::sync();
+    if (G::warp() == 0) {
+        if (n <= 32) lu_solve_warp_r<1>(M, ld, n, piv, b, rdiag);
+        else if (n <= 64) lu_solve_warp_r<2>(M, ld, n, piv, b, rdiag);
+        else if (n <= 128) lu_solve_warp_r<4>(M, ld, n, piv, b, rdiag);
+        else lu_solve_warp_r<8>(M, ld, n, piv, b, rdiag);
     }
     G::sync();
 }
