@@ -168,6 +168,40 @@ struct b200ida_ensemble {
     double* d_atol = nullptr;  // [n]
     int kernel = B200IDA_KERNEL_AUTO;
     int* perm = nullptr;  // [B] slot -> caller-visible instance id, or null (identity)
+    // persistent device scratch for the host-buffer (end-to-end) entry points and the order builder: a few blocks
+    // grown on demand, sub-allocated per API call (scratch_reset() rewinds), freed only by destroy -- so there is no
+    // cudaMalloc / cudaFree (and no implicit device synchronisation) on the per-step path once warmed up
+    static constexpr int MAX_BLOCKS = 16;
+    void* blk[MAX_BLOCKS] = {nullptr};
+    size_t blk_cap[MAX_BLOCKS] = {0}, blk_used[MAX_BLOCKS] = {0};
+    int nblk = 0;
+    void scratch_reset() {
+        for (int i = 0; i < nblk; ++i) blk_used[i] = 0;
+    }
+    cudaError_t scratch_take(size_t bytes, void** out) {
+        bytes = (bytes + 255) / 256 * 256;
+        if (bytes == 0) bytes = 256;
+        for (int i = 0; i < nblk; ++i) {
+            if (blk_cap[i] - blk_used[i] >= bytes) {
+                *out = static_cast<unsigned char*>(blk[i]) + blk_used[i];
+                blk_used[i] += bytes;
+                return cudaSuccess;
+            }
+        }
+        if (nblk == MAX_BLOCKS) return cudaErrorMemoryAllocation;
+        const size_t cap = bytes > ((size_t)32 << 20) ? bytes : ((size_t)32 << 20);
+        cudaError_t err = cudaMalloc(&blk[nblk], cap);
+        if (err != cudaSuccess) return err;
+        blk_cap[nblk] = cap;
+        blk_used[nblk] = bytes;
+        *out = blk[nblk];
+        ++nblk;
+        return cudaSuccess;
+    }
+    void scratch_free() {
+        for (int i = 0; i < nblk; ++i) cudaFree(blk[i]);
+        nblk = 0;
+    }
 };
 
 static int g_reorder_mode = B200IDA_REORDER_AUTO;
@@ -185,30 +219,31 @@ static int build_order(b200ida_ensemble* e, const double* d_params_caller_order)
     const int P = e->nparams;
     cudaStream_t st = e->stream;
     if (!e->perm) B200_CUDA_TRY(cudaMalloc(&e->perm, (size_t)B * sizeof(int)));
-    DevBuf lohi, keys, keys2, ids, tmp;
-    B200_CUDA_TRY(lohi.alloc(2 * (size_t)P * sizeof(double)));
-    B200_CUDA_TRY(keys.alloc((size_t)B * sizeof(unsigned)));
-    B200_CUDA_TRY(keys2.alloc((size_t)B * sizeof(unsigned)));
-    B200_CUDA_TRY(ids.alloc((size_t)B * sizeof(int)));
-    double* lo = lohi.as<double>();
-    double* hi = lo + P;
     size_t tb1 = 0, tb2 = 0, tb3 = 0;
-    cub::DeviceReduce::Min(nullptr, tb1, d_params_caller_order, lo, (int)B, st);
-    cub::DeviceReduce::Max(nullptr, tb2, d_params_caller_order, hi, (int)B, st);
-    cub::DeviceRadixSort::SortPairs(nullptr, tb3, keys.as<unsigned>(), keys2.as<unsigned>(), ids.as<int>(), e->perm, (int)B, 0, 32, st);
+    cub::DeviceReduce::Min(nullptr, tb1, d_params_caller_order, (double*)nullptr, (int)B, st);
+    cub::DeviceReduce::Max(nullptr, tb2, d_params_caller_order, (double*)nullptr, (int)B, st);
+    cub::DeviceRadixSort::SortPairs(nullptr, tb3, (unsigned*)nullptr, (unsigned*)nullptr, (int*)nullptr, (int*)nullptr, (int)B, 0, 32, st);
     size_t tbytes = tb1 > tb2 ? tb1 : tb2;
     tbytes = tbytes > tb3 ? tbytes : tb3;
-    B200_CUDA_TRY(tmp.alloc(tbytes));
+    void *p_lohi, *p_keys, *p_keys2, *p_ids, *p_tmp;
+    B200_CUDA_TRY(e->scratch_take(2 * (size_t)P * sizeof(double), &p_lohi));
+    B200_CUDA_TRY(e->scratch_take((size_t)B * sizeof(unsigned), &p_keys));
+    B200_CUDA_TRY(e->scratch_take((size_t)B * sizeof(unsigned), &p_keys2));
+    B200_CUDA_TRY(e->scratch_take((size_t)B * sizeof(int), &p_ids));
+    B200_CUDA_TRY(e->scratch_take(tbytes, &p_tmp));
+    double* lo = static_cast<double*>(p_lohi);
+    double* hi = lo + P;
+    unsigned *keys = static_cast<unsigned*>(p_keys), *keys2 = static_cast<unsigned*>(p_keys2);
+    int* ids = static_cast<int*>(p_ids);
     for (int j = 0; j < P; ++j) {
-        B200_CUDA_TRY(cub::DeviceReduce::Min(tmp.p, tbytes, d_params_caller_order + (size_t)j * B, lo + j, (int)B, st));
-        B200_CUDA_TRY(cub::DeviceReduce::Max(tmp.p, tbytes, d_params_caller_order + (size_t)j * B, hi + j, (int)B, st));
+        B200_CUDA_TRY(cub::DeviceReduce::Min(p_tmp, tbytes, d_params_caller_order + (size_t)j * B, lo + j, (int)B, st));
+        B200_CUDA_TRY(cub::DeviceReduce::Max(p_tmp, tbytes, d_params_caller_order + (size_t)j * B, hi + j, (int)B, st));
     }
     const int tb = 256;
-    order_key_kernel<<<(unsigned)((B + tb - 1) / tb), tb, 0, st>>>(d_params_caller_order, lo, hi, P, B, keys.as<unsigned>(), ids.as<int>());
+    order_key_kernel<<<(unsigned)((B + tb - 1) / tb), tb, 0, st>>>(d_params_caller_order, lo, hi, P, B, keys, ids);
     B200_CUDA_TRY(cudaGetLastError());
-    B200_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp.p, tbytes, keys.as<unsigned>(), keys2.as<unsigned>(), ids.as<int>(), e->perm, (int)B, 0, 32, st));
-    B200_CUDA_TRY(cudaStreamSynchronize(st));  // scratch freed on return
-    return B200IDA_OK;
+    B200_CUDA_TRY(cub::DeviceRadixSort::SortPairs(p_tmp, tbytes, keys, keys2, ids, e->perm, (int)B, 0, 32, st));
+    return B200IDA_OK;  // scratch is persistent and stream-ordered: no synchronisation needed
 }
 
 static int check_mem(int mem) { return (mem == B200IDA_MEM_DEVICE || mem == B200IDA_MEM_HOST) ? 0 : -1; }
@@ -231,11 +266,12 @@ static int rows_out(b200ida_ensemble* e, TD* dst, const TS* src, int rows, int m
         B200_CUDA_TRY(cudaStreamSynchronize(e->stream));
         return B200IDA_OK;
     }
-    DevBuf tmp;
-    B200_CUDA_TRY(tmp.alloc(bytes));
-    unpermute_kernel<TS, TD><<<grid, tb, 0, e->stream>>>(src, tmp.as<TD>(), rows, B, e->perm);
+    void* tmp;
+    e->scratch_reset();
+    B200_CUDA_TRY(e->scratch_take(bytes, &tmp));
+    unpermute_kernel<TS, TD><<<grid, tb, 0, e->stream>>>(src, static_cast<TD*>(tmp), rows, B, e->perm);
     B200_CUDA_TRY(cudaGetLastError());
-    B200_CUDA_TRY(cudaMemcpyAsync(dst, tmp.p, bytes, cudaMemcpyDeviceToHost, e->stream));
+    B200_CUDA_TRY(cudaMemcpyAsync(dst, tmp, bytes, cudaMemcpyDeviceToHost, e->stream));
     B200_CUDA_TRY(cudaStreamSynchronize(e->stream));
     return B200IDA_OK;
 }
@@ -263,7 +299,7 @@ int b200ida_reinit(b200ida_ensemble* e, const double* params, const double* yy0,
     const size_t nd = (size_t)lay.ndouble() * batch, ni = (size_t)lay.nint() * batch;
     cudaStream_t st = e->stream;
     const cudaMemcpyKind kind = (mem == B200IDA_MEM_HOST) ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
-    DevBuf y0b, yp0b;
+    e->scratch_reset();
     const double *dy0 = yy0, *dyp0 = yp0;
     const size_t vbytes = (size_t)n * batch * sizeof(double);
     B200_CUDA_TRY(cudaMemsetAsync(e->dstate, 0, nd * sizeof(double), st));
@@ -271,31 +307,33 @@ int b200ida_reinit(b200ida_ensemble* e, const double* params, const double* yy0,
     if (params) {
         // new parameters: bring them to the device in caller order, rebuild the slot order, store them by slot
         const size_t pbytes = (size_t)e->nparams * batch * sizeof(double);
-        DevBuf pb;
         const double* dp = params;
         if (mem == B200IDA_MEM_HOST) {
-            B200_CUDA_TRY(pb.alloc(pbytes));
-            B200_CUDA_TRY(cudaMemcpyAsync(pb.p, params, pbytes, kind, st));
-            dp = pb.as<double>();
+            void* pb;
+            B200_CUDA_TRY(e->scratch_take(pbytes, &pb));
+            B200_CUDA_TRY(cudaMemcpyAsync(pb, params, pbytes, kind, st));
+            dp = static_cast<double*>(pb);
         }
         int rc = build_order(e, dp);
         if (rc != B200IDA_OK) return rc;
         permute_rows_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, st>>>(dp, e->params, e->nparams, batch, e->perm);
         B200_CUDA_TRY(cudaGetLastError());
-        if (mem == B200IDA_MEM_HOST) B200_CUDA_TRY(cudaStreamSynchronize(st));
     }
     if (mem == B200IDA_MEM_HOST) {
-        B200_CUDA_TRY(y0b.alloc(vbytes));
-        B200_CUDA_TRY(yp0b.alloc(vbytes));
-        B200_CUDA_TRY(cudaMemcpyAsync(y0b.p, yy0, vbytes, kind, st));
-        B200_CUDA_TRY(cudaMemcpyAsync(yp0b.p, yp0, vbytes, kind, st));
-        dy0 = y0b.as<double>();
-        dyp0 = yp0b.as<double>();
+        void *y0b, *yp0b;
+        B200_CUDA_TRY(e->scratch_take(vbytes, &y0b));
+        B200_CUDA_TRY(e->scratch_take(vbytes, &yp0b));
+        B200_CUDA_TRY(cudaMemcpyAsync(y0b, yy0, vbytes, kind, st));
+        B200_CUDA_TRY(cudaMemcpyAsync(yp0b, yp0, vbytes, kind, st));
+        dy0 = static_cast<double*>(y0b);
+        dyp0 = static_cast<double*>(yp0b);
     }
     const int tb = 256;
     ida_init_kernel<<<(unsigned)((batch + tb - 1) / tb), tb, 0, st>>>(e->dstate, dy0, dyp0, n, batch, e->perm);
     B200_CUDA_TRY(cudaGetLastError());
-    if (mem == B200IDA_MEM_HOST) B200_CUDA_TRY(cudaStreamSynchronize(st));  // scratch is freed on return
+    // host buffers: the caller may reuse them as soon as we return, so wait for the H2D copies; the device scratch
+    // itself is persistent and stream-ordered
+    if (mem == B200IDA_MEM_HOST) B200_CUDA_TRY(cudaStreamSynchronize(st));
     return B200IDA_OK;
 }
 
@@ -365,6 +403,7 @@ int b200ida_destroy(b200ida_ensemble* e) {
     if (e->params) cudaFree(e->params);
     if (e->d_atol) cudaFree(e->d_atol);
     if (e->perm) cudaFree(e->perm);
+    e->scratch_free();
     delete e;
     return B200IDA_OK;
 }
@@ -380,19 +419,20 @@ int b200ida_solve_ladder(b200ida_ensemble* e, const double* touts, int ntout, in
     lad.ntout = ntout;
     for (int i = 0; i < MAX_TOUTS; ++i) lad.touts[i] = i < ntout ? touts[i] : 0.0;
 
-    DevBuf trajb, statb;
     double* d_traj = yy_traj;
     int32_t* d_stat = status;
     const size_t traj_bytes = (size_t)ntout * e->n * e->B * sizeof(double);
     const size_t stat_bytes = (size_t)ntout * e->B * sizeof(int32_t);
     if (mem == B200IDA_MEM_HOST) {
+        e->scratch_reset();
+        void* sp;
         if (yy_traj) {
-            B200_CUDA_TRY(trajb.alloc(traj_bytes));
-            d_traj = trajb.as<double>();
+            B200_CUDA_TRY(e->scratch_take(traj_bytes, &sp));
+            d_traj = static_cast<double*>(sp);
         }
         if (status) {
-            B200_CUDA_TRY(statb.alloc(stat_bytes));
-            d_stat = statb.as<int32_t>();
+            B200_CUDA_TRY(e->scratch_take(stat_bytes, &sp));
+            d_stat = static_cast<int32_t*>(sp);
         }
     }
     int kernel = e->kernel;
