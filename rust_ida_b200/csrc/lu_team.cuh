@@ -79,11 +79,59 @@ __device__ __forceinline__ void lu_pivot_search(const double* M, int ld, int n, 
     }
 }
 
+// trailing update of elimination step k for the columns of one warp, R = ceil((n-k-1)/32) row slots per lane
+// (compile-time, so no predicated-off slots are issued); two columns per trip with all loads ahead of the stores.
+// Warp 0 owns column k+1 and runs the pivot search of step k+1 as soon as that column is final (look-ahead).
+template <int R, class PivT>
+__device__ __forceinline__ void lu_update_cols(double* M, int ld, int n, int k, int w, int nw, int lane, LuShared* sh, PivT* piv) {
+    const double* ck = M + (size_t)k * ld;
+    const int i0 = k + 1 + lane;
+    double lik[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) lik[r] = (i0 + 32 * r < n) ? ck[i0 + 32 * r] : 0.0;
+    // column ownership: with several warps, warp 0 takes ONLY column k+1 and then does the look-ahead pivot search
+    // (a serial chain: reduction, a division), while warps 1.. share columns k+2.. round-robin -- so the step's
+    // critical path is max(search, update) instead of their sum.  A single-warp group takes everything.
+    const bool split = nw > 1;
+    const int jbeg = !split ? k + 1 : (w == 0 ? k + 1 : k + 1 + w);
+    const int jstep = !split ? 1 : nw - 1;
+    const int jend = (split && w == 0) ? k + 2 : n;
+    for (int j0 = jbeg; j0 < jend && j0 < n; j0 += 2 * jstep) {
+        const int j1 = j0 + jstep;
+        const bool has1 = j1 < jend && j1 < n;
+        double* c0 = M + (size_t)j0 * ld;
+        double* c1 = M + (size_t)(has1 ? j1 : j0) * ld;
+        const double a0 = c0[k];
+        const double a1 = has1 ? c1[k] : 0.0;
+        double v0[R], v1[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const bool in = (r + 1 < R) || (i0 + 32 * r < n);  // only the last slot can be ragged
+            v0[r] = in ? c0[i0 + 32 * r] : 0.0;
+            v1[r] = in ? c1[i0 + 32 * r] : 0.0;
+        }
+        if (a0 != 0.0) {
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                if ((r + 1 < R) || (i0 + 32 * r < n)) c0[i0 + 32 * r] = v0[r] - a0 * lik[r];
+        }
+        if (has1 && a1 != 0.0) {
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                if ((r + 1 < R) || (i0 + 32 * r < n)) c1[i0 + 32 * r] = v1[r] - a1 * lik[r];
+        }
+        if (w == 0 && j0 == k + 1) {
+            __syncwarp();
+            lu_pivot_search(M, ld, n, k + 1, sh, piv);
+        }
+    }
+}
+
 // In-place LU of the n x n column-major matrix M (leading dimension ld).  Every thread of the group calls it.
 // On return (after the final barrier) sh->info holds 0 or the 1-based singular column, piv[0..n) the pivot rows.
 template <bool WARP, int RMAX, class PivT>
 __device__ __forceinline__ void lu_factor_r(double* M, int ld, int n, LuShared* sh, PivT* piv) {
-    using G = LuGroup<WARP>;  // RMAX = rows per lane = ceil(n / 32): the multiplier cache and the update loop are unrolled to it
+    using G = LuGroup<WARP>;  // RMAX = ceil(n / 32): upper bound of the row slots per lane
     const int tid = G::tid(), nt = G::nthreads(), nw = G::nwarps(), w = G::warp(), lane = tid & 31;
     if (tid == 0) sh->info = 0;
     G::sync();
@@ -117,46 +165,19 @@ __device__ __forceinline__ void lu_factor_r(double* M, int ld, int n, LuShared* 
         }
         G::sync();
         // [B] trailing update with look-ahead pivot search
-        double lik[RMAX];
-        const double* ck = M + (size_t)k * ld;
-#pragma unroll
-        for (int r = 0; r < RMAX; ++r) {
-            const int i = k + 1 + lane + 32 * r;
-            lik[r] = (i < n) ? ck[i] : 0.0;
-        }
-        // two columns per trip: all loads are issued before the stores so the two updates overlap
-        for (int j0 = k + 1 + w; j0 < n; j0 += 2 * nw) {
-            const int j1 = j0 + nw;
-            const bool has1 = j1 < n;
-            double* c0 = M + (size_t)j0 * ld;
-            double* c1 = M + (size_t)(has1 ? j1 : j0) * ld;
-            const double a0 = c0[k];
-            const double a1 = has1 ? c1[k] : 0.0;
-            double v0[RMAX], v1[RMAX];
-#pragma unroll
-            for (int r = 0; r < RMAX; ++r) {
-                const int i = k + 1 + lane + 32 * r;
-                v0[r] = (i < n) ? c0[i] : 0.0;
-                v1[r] = (i < n && has1) ? c1[i] : 0.0;
-            }
-            if (a0 != 0.0) {
-#pragma unroll
-                for (int r = 0; r < RMAX; ++r) {
-                    const int i = k + 1 + lane + 32 * r;
-                    if (i < n) c0[i] = v0[r] - a0 * lik[r];
-                }
-            }
-            if (has1 && a1 != 0.0) {
-#pragma unroll
-                for (int r = 0; r < RMAX; ++r) {
-                    const int i = k + 1 + lane + 32 * r;
-                    if (i < n) c1[i] = v1[r] - a1 * lik[r];
-                }
-            }
-            if (w == 0 && j0 == k + 1) {
-                __syncwarp();
-                lu_pivot_search(M, ld, n, k + 1, sh, piv);
-            }
+        const int R = (n - k - 1 + 31) >> 5;  // row slots needed at this step (uniform)
+        if (RMAX >= 8 && R > 4) {
+            if (R == 8) lu_update_cols<8>(M, ld, n, k, w, nw, lane, sh, piv);
+            else if (R == 7) lu_update_cols<7>(M, ld, n, k, w, nw, lane, sh, piv);
+            else if (R == 6) lu_update_cols<6>(M, ld, n, k, w, nw, lane, sh, piv);
+            else lu_update_cols<5>(M, ld, n, k, w, nw, lane, sh, piv);
+        } else if (RMAX >= 4 && R > 2) {
+            if (R == 4) lu_update_cols<4>(M, ld, n, k, w, nw, lane, sh, piv);
+            else lu_update_cols<3>(M, ld, n, k, w, nw, lane, sh, piv);
+        } else if (RMAX >= 2 && R == 2) {
+            lu_update_cols<2>(M, ld, n, k, w, nw, lane, sh, piv);
+        } else if (R >= 1) {
+            lu_update_cols<1>(M, ld, n, k, w, nw, lane, sh, piv);
         }
         G::sync();
     }
