@@ -461,7 +461,7 @@ int b200ida_solve_ladder(b200ida_ensemble* e, const double* touts, int ntout, in
         const bool warp = kernel == B200IDA_KERNEL_WARP;
         if (warp && e->n > 32) return set_error(B200IDA_ERR_UNSUPPORTED, "warp-per-system needs n <= 32 (n = %d)", e->n);
         const unsigned arena = (unsigned)team_arena_bytes(e->n);
-        const int tb = warp ? 128 : (e->n <= 64 ? 128 : 256);
+        const int tb = warp ? 128 : (e->n <= 128 ? 128 : 256);
         const int tpc = warp ? tb / 32 : 1;
         const size_t smem = (size_t)arena * tpc;
         if (smem > 227 * 1024) return set_error(B200IDA_ERR_UNSUPPORTED, "n = %d does not fit the shared-memory arena", e->n);
