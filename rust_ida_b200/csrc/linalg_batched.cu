@@ -142,6 +142,114 @@ __global__ void __launch_bounds__(128) getrs_thread_soa(const double* __restrict
     for (int i = 0; i < N; ++i) bx[(size_t)i * B + b] = x[i];
 }
 
+// ---- warp-per-system, REGISTER resident, AoS, n == N in {16, 32} -------------------------------------------------
+// Lane i holds row i of the matrix in registers for the whole factorisation; the pivot row is broadcast with
+// shuffles, so an elimination step is N independent (shuffle, mul, sub) chains with no shared-memory traffic.
+// Rows are never moved: each lane tracks the LOGICAL position of its row (what the reference's whole-row swaps
+// would have produced) and writes the row there at the end; the arithmetic on each element is unchanged.
+// one elimination step with compile-time k (template recursion forces the full unroll that keeps row[] in registers)
+template <int N, int K>
+__device__ __forceinline__ void lu_regs_step(double (&row)[N], int lane, int& pos, int& inf, int& mypiv) {
+    if (inf == 0) {
+        const double x = row[K];
+        const bool cand = pos >= K && lane < N;
+        double v = (cand && x == x) ? fabs(x) : -1.0;  // NaN never wins
+        int p = cand ? pos : 0x7fffffff;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, v, off);
+            const int op = __shfl_xor_sync(0xffffffffu, p, off);
+            if (ov > v || (ov == v && op < p)) {
+                v = ov;
+                p = op;
+            }
+        }
+        const int lk = __ffs(__ballot_sync(0xffffffffu, pos == K && lane < N)) - 1;  // lane holding logical row K
+        const double xk = __shfl_sync(0xffffffffu, x, lk);
+        int l = p;
+        if (xk != xk || l > N) l = K;  // NaN in row K (or nothing comparable): the reference keeps l = K
+        const int lw = __ffs(__ballot_sync(0xffffffffu, pos == l && lane < N)) - 1;  // lane holding the pivot row
+        const double pv = __shfl_sync(0xffffffffu, x, lw);
+        if (lane == K) mypiv = l;
+        if (pv == 0.0) {
+            inf = K + 1;
+        } else {
+            if (lane == lw) pos = K;
+            else if (lane == lk) pos = l;
+            const double mult = 1.0 / pv;
+            const bool below = pos > K && lane < N;
+            const double lik = x * mult;
+            if (below) row[K] = lik;
+#pragma unroll
+            for (int j = K + 1; j < N; ++j) {
+                const double a_kj = __shfl_sync(0xffffffffu, row[j], lw);
+                if (below && a_kj != 0.0) row[j] -= a_kj * lik;
+            }
+        }
+    }
+    if constexpr (K + 1 < N) lu_regs_step<N, K + 1>(row, lane, pos, inf, mypiv);
+}
+
+template <int N>
+__global__ void __launch_bounds__(128) getrf_warp_regs(double* __restrict__ A, int64_t* __restrict__ piv,
+                                                       int32_t* __restrict__ info, int64_t B) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wpg = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); b < B; b += wpg) {
+        double* Ab = A + (size_t)b * N * N;
+        double row[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) row[j] = (lane < N) ? Ab[j * N + lane] : 0.0;
+        int pos = lane;  // logical row index of the data this lane holds
+        int inf = 0;
+        int mypiv = 0;   // lane k keeps piv[k]
+        lu_regs_step<N, 0>(row, lane, pos, inf, mypiv);
+        if (lane < N) {
+#pragma unroll
+            for (int j = 0; j < N; ++j) Ab[j * N + pos] = row[j];
+            piv[(size_t)b * N + lane] = (inf == 0 || lane < inf) ? mypiv : 0;
+        }
+        if (lane == 0) info[b] = inf;
+    }
+}
+
+template <int N>
+__global__ void __launch_bounds__(128) getrs_warp_regs(const double* __restrict__ A, const int64_t* __restrict__ piv,
+                                                       double* __restrict__ bx, int64_t B) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wpg = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); b < B; b += wpg) {
+        const double* Ab = A + (size_t)b * N * N;
+        double row[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) row[j] = (lane < N) ? Ab[j * N + lane] : 1.0;
+        double x = (lane < N) ? bx[(size_t)b * N + lane] : 0.0;
+        const int pl = (lane < N) ? (int)piv[(size_t)b * N + lane] : 0;
+#pragma unroll
+        for (int k = 0; k < N; ++k) {  // apply the pivots in order: swap x_k <-> x_{p_k}
+            const int pk = __shfl_sync(0xffffffffu, pl, k);
+            const double xk = __shfl_sync(0xffffffffu, x, k), xp = __shfl_sync(0xffffffffu, x, pk);
+            if (pk != k) {
+                if (lane == k) x = xp;
+                else if (lane == pk) x = xk;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < N - 1; ++k) {
+            const double bk = __shfl_sync(0xffffffffu, x, k);
+            if (lane > k) x -= row[k] * bk;
+        }
+#pragma unroll
+        for (int k = N - 1; k >= 1; --k) {
+            if (lane == k) x /= row[k];
+            const double bk = __shfl_sync(0xffffffffu, x, k);
+            if (lane < k) x -= row[k] * bk;
+        }
+        if (lane == 0) x /= row[0];
+        if (lane < N) bx[(size_t)b * N + lane] = x;
+    }
+}
+
 // ---- group-per-system kernels on lu_team.cuh: one warp (n <= 32) or one CTA (n <= 256) per matrix ----------
 constexpr int CTA_THREADS = 256;
 constexpr int WARPS_PER_CTA = 4;   // warp-per-system kernels
@@ -306,7 +414,18 @@ static int launch_group(double* A, int64_t* piv, int32_t* info, double* bx, int 
             getrs_group<SOA_, WARP_, SMEM_><<<grid, threads, smem, st>>>(A, piv, bx, n, B, gb);                          \
         }                                                                                                              \
     } while (0)
-    if (n <= 32) {
+    if (!soa && (n == 16 || n == 32)) {
+        const int threads = 128, wpc = 4;
+        const int64_t want = (B + wpc - 1) / wpc, cap = (int64_t)sm_count() * 16;
+        const unsigned g = (unsigned)(want < cap ? want : cap);
+        if (FACTOR) {
+            if (n == 16) getrf_warp_regs<16><<<g, threads, 0, st>>>(A, piv, info, B);
+            else getrf_warp_regs<32><<<g, threads, 0, st>>>(A, piv, info, B);
+        } else {
+            if (n == 16) getrs_warp_regs<16><<<g, threads, 0, st>>>(A, piv, bx, B);
+            else getrs_warp_regs<32><<<g, threads, 0, st>>>(A, piv, bx, B);
+        }
+    } else if (n <= 32) {
         const int threads = 32 * WARPS_PER_CTA;
         const size_t smem = (size_t)gb * WARPS_PER_CTA;
         if (soa) LAUNCH(true, true, true, threads, smem, WARPS_PER_CTA);
