@@ -27,7 +27,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
@@ -47,7 +46,7 @@ OPS_PER_ATTEMPT = 98244.0 / 377.0
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=1 << 20, help="instances per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
@@ -58,37 +57,47 @@ def parse():
 
 # ---- clocks sampler (nvidia-smi during the timed region) -----------------------------------------------------
 class ClockSampler:
+    """one `nvidia-smi -lms 50` process for the duration of the timed region (B200_PROFILING.md clocks line)"""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.samples, self.reasons = [], set()
         self.max_mhz = None
-        self._stop = threading.Event()
-        self._t = threading.Thread(target=self._run, daemon=True)
-
-    def _run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
-                self.samples.append(float(out[0]))
-                self.max_mhz = float(out[1])
-                for nm, v in zip(names, out[2:]):
-                    if v.strip().lower().startswith("active"):
-                        self.reasons.add(nm)
-            except Exception:
-                pass
-            self._stop.wait(0.2)
+        self.proc = None
 
     def __enter__(self):
-        self._t.start()
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            time.sleep(0.15)  # let the first samples land before the timed region starts
+        except Exception:
+            self.proc = None
         return self
 
     def __exit__(self, *a):
-        self._stop.set()
-        self._t.join(timeout=6)
+        if self.proc is None:
+            return
+        time.sleep(0.06)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            try:
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for nm, v in zip(self.NAMES, f[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
 
     def summary(self):
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
