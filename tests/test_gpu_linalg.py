@@ -136,3 +136,35 @@ def test_wrms_bit_exact(n, batch, layout):
     assert_bit_equal(out, ref, "wrms")
     # the reference's own pin: wrms(-0.5, 0.5, n=32) == 0.25
     assert r.norm_wrms(np.full((32, 1), -0.5), np.full((32, 1), 0.5))[0] == 0.25
+
+
+@pytest.mark.parametrize("layout", ["soa", "aos"])
+@pytest.mark.parametrize("n,batch", [(1, 1), (1, 77), (2, 1), (2, 33), (5, 1), (7, 129), (9, 3), (17, 2), (31, 5), (33, 1), (65, 2)])
+def test_edge_sizes(n, batch, layout):
+    """smallest systems, single-system batches and sizes that straddle the kernel dispatch boundaries"""
+    a, b = gen_matrices(n, batch, seed=99)
+    lu_ref, piv_ref, x_ref, info_ref = oracle_lu(a, b)
+    lu, piv, x, info = run_gpu(a, b, layout, device_buffers=(batch % 2 == 1))
+    assert np.array_equal(info, info_ref) and np.array_equal(piv, piv_ref)
+    assert_bit_equal(lu, lu_ref, "LU n=%d" % n)
+    assert_bit_equal(x, x_ref, "x n=%d" % n)
+
+
+@pytest.mark.parametrize("layout,n", [("aos", 16), ("aos", 32), ("soa", 8), ("aos", 48)])
+def test_pivot_ties_and_nan_follow_the_reference(layout, n):
+    """ties pick the FIRST row with the largest |a_ik|; a NaN never wins the `>` test and a NaN in row k keeps l = k
+    (crates/linear/src/dense.rs:109-116) -- checked on every kernel family"""
+    rng = np.random.default_rng(3)
+    a = rng.integers(-3, 4, size=(6, n, n)).astype(np.float64)  # many exact ties and zeros
+    a += np.eye(n)[None] * 0.5
+    a[1, 3, 0] = np.nan
+    a[2, 0, 0] = np.nan
+    a[3, n - 1, 2] = np.inf
+    b = rng.normal(size=(6, n))
+    lu_ref, piv_ref, x_ref, info_ref = oracle_lu(a, b)
+    lu, piv, x, info = run_gpu(a, b, layout, device_buffers=False)
+    assert np.array_equal(info, info_ref)
+    ok = info_ref == 0
+    assert np.array_equal(piv[ok], piv_ref[ok])
+    assert_bit_equal(lu[ok], lu_ref[ok], "LU with ties/NaN")
+    assert_bit_equal(x[ok], x_ref[ok], "x with ties/NaN")

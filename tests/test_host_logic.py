@@ -1,0 +1,72 @@
+"""Host-side logic that needs no GPU: problem descriptors, parameter generators, tolerance control, argument
+checking of the Python mirror of the reference interfaces."""
+import numpy as np
+import pytest
+
+import rust_ida_b200 as r
+from rust_ida_b200 import _lib
+from rust_ida_b200.problems import (Heat2D, Lorenz63, Roberts, heat_ensemble_params, lorenz_ensemble_params,
+                                    roberts_ensemble_params, splitmix64_uniform)
+
+
+def test_splitmix_uniform_range_and_determinism():
+    u = splitmix64_uniform(1234, np.arange(100000), 0)
+    assert u.min() >= 0.0 and u.max() < 1.0 and abs(u.mean() - 0.5) < 0.01
+    assert np.array_equal(u, splitmix64_uniform(1234, np.arange(100000), 0))
+    assert not np.array_equal(u, splitmix64_uniform(1234, np.arange(100000), 1))
+
+
+def test_roberts_descriptor_matches_reference_example():
+    p = Roberts.default(2).params
+    assert p[:, 0].tolist() == [0.04, 1.0e4, 3.0e7]           # src/sample_problems/roberts.rs:58-59
+    yy0, yp0 = Roberts.consistent_ic(p)
+    assert yy0[:, 0].tolist() == [1.0, 0.0, 0.0]               # examples/roberts.rs:67
+    assert yp0[:, 0].tolist() == [-0.04, 0.04, 0.0]            # examples/roberts.rs:68
+    assert Roberts(p).model_size() == 3                        # ModelSpec::model_size
+    with pytest.raises(ValueError):
+        Roberts(np.zeros((2, 4)))
+
+
+def test_lorenz_and_heat_descriptors():
+    p = lorenz_ensemble_params(1000)
+    assert (p[0] >= 8).all() and (p[0] <= 12).all() and (p[1] >= 20).all() and (p[1] <= 35).all()
+    yy0, yp0 = Lorenz63.consistent_ic(p)
+    np.testing.assert_allclose(yp0[0], p[0] * 0.0)             # p (y1 - y0) = 0 at y = (1,1,1)
+    h = heat_ensemble_params(16, M=10)
+    assert abs(h / 81.0 - 1).max() <= 0.1
+    y, yp = Heat2D.consistent_ic(h, 10)
+    assert y.shape == (100, 16) and (y[:10] == 0).all() and (yp[:10] == 0).all() and y.max() <= 1.0
+    assert Heat2D(h, M=10).model_size() == 100
+    # the residual of the consistent IC is zero on the interior (checked with the oracle's residual)
+    from oracle import binding as ob
+    res = ob.res(ob.PK_HEAT2D, h[:, 0], y[:, 0].copy(), yp[:, 0].copy())
+    assert np.abs(res).max() < 1e-12
+
+
+def test_tol_control():
+    sv = r.TolControlSV.new(1e-4, [1e-8, 1e-6, 1e-6])
+    assert sv.ida_rtol == 1e-4 and sv.atol_vector(3).tolist() == [1e-8, 1e-6, 1e-6]
+    with pytest.raises(ValueError):
+        sv.atol_vector(4)
+    ss = r.TolControlSS(1e-4, 1e-4)                            # src/tests/*.rs use TolControlSS::new(1e-4, 1e-4)
+    assert ss.atol_vector(3).tolist() == [1e-4] * 3
+
+
+def test_dense_mirror_metadata_and_shape_checks():
+    d = r.Dense.new(3, 5)
+    assert d.get_type() == r.LSolverType.Direct and d.num_iters() == 0 and d.res_norm() == 0.0
+    assert d.set_scaling_vectors(None, None) is None
+    if _lib.device_count() == 0:
+        with pytest.raises(r.B200IdaError):
+            d.setup(np.zeros((3, 3, 5)))
+
+
+def test_status_enum_matches_header():
+    import os, re
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "b200ida.h")).read()
+    codes = dict(re.findall(r"#define B200IDA_ST_(\w+)\s+\(?(-?\d+)\)?", hdr))
+    assert int(codes["SUCCESS"]) == r.IdaSolveStatus.Success
+    assert int(codes["TOO_MUCH_WORK"]) == r.IdaSolveStatus.TooMuchWork
+    assert int(codes["LSETUP_FAIL"]) == r.IdaSolveStatus.LinearSetupFail
+    assert int(codes["BAD_T"]) == r.IdaSolveStatus.BadTimeValue
+    assert len(codes) == len(r.IdaSolveStatus)
