@@ -21,6 +21,9 @@ __device__ __forceinline__ double div_by_recip(double x, double d, double y) {
         const double r = __fma_rn(-d, q, x);
         return __fma_rn(r, y, q);
     }
+    if (x == 0.0 && ed - 1u < 0x7feu) {  // (+-0) / finite non-zero normal: a signed zero, no need for the slow path
+        return __hiloint2double((__double2hiint(x) ^ __double2hiint(d)) & (int)0x80000000, 0);
+    }
     return x / d;
 }
 

@@ -200,6 +200,55 @@ __device__ __forceinline__ void lu_factor(double* M, int ld, int n, LuShared* sh
 // instead of a shared-memory store->load round trip per row slot.
 // rdiag (optional): rdiag[k] = RN(1 / u_kk), computed off the critical path; the division of the back substitution
 // then costs 3 dependent instructions instead of ~10 (exact_div.cuh) and stays bit-identical.
+// forward / backward sweeps over the 32 pivots owned by register slot R0 (compile-time), so the owner value is
+// x[R0] without a select chain and only the slots that can still change are touched
+template <int RMAX, int R0>
+__device__ __forceinline__ void lu_fwd_block(const double* M, int ld, int n, int lane, double (&x)[RMAX]) {
+    const int kend = (32 * R0 + 32 < n - 1) ? 32 * R0 + 32 : n - 1;
+    for (int k = 32 * R0; k < kend; ++k) {
+        const double* ck = M + (size_t)k * ld;
+        const int kk = k & 31;
+        double c[RMAX];
+#pragma unroll
+        for (int r = R0; r < RMAX; ++r) {
+            const int i = lane + 32 * r;
+            c[r] = (i < n) ? ck[i] : 0.0;
+        }
+        const double bk = __shfl_sync(0xffffffffu, x[R0], kk);
+        if (lane > kk) x[R0] -= c[R0] * bk;
+#pragma unroll
+        for (int r = R0 + 1; r < RMAX; ++r)
+            if (lane + 32 * r < n) x[r] -= c[r] * bk;
+    }
+    if constexpr (R0 + 1 < RMAX) {
+        if (32 * (R0 + 1) < n - 1) lu_fwd_block<RMAX, R0 + 1>(M, ld, n, lane, x);
+    }
+}
+template <int RMAX, int R0>
+__device__ __forceinline__ void lu_bwd_block(const double* M, int ld, int n, int lane, double (&x)[RMAX], const double* rdiag) {
+    if (32 * R0 < n) {
+        const int kbeg = (32 * R0 + 31 < n - 1) ? 32 * R0 + 31 : n - 1;
+        for (int k = kbeg; k >= 32 * R0; --k) {
+            const double* ck = M + (size_t)k * ld;
+            const int kk = k & 31;
+            const double ukk = ck[k];
+            const double y = rdiag ? rdiag[k] : 0.0;
+            double c[RMAX];
+#pragma unroll
+            for (int r = 0; r < R0; ++r) c[r] = ck[lane + 32 * r];  // rows < 32*R0 <= k: always in range
+            c[R0] = (lane < kk) ? ck[lane + 32 * R0] : 0.0;
+            double xv = x[R0];
+            if (lane == kk) xv = rdiag ? div_by_recip(xv, ukk, y) : xv / ukk;
+            const double bk = __shfl_sync(0xffffffffu, xv, kk);
+            if (lane == kk) x[R0] = bk;
+            else if (lane < kk) x[R0] -= c[R0] * bk;
+#pragma unroll
+            for (int r = 0; r < R0; ++r) x[r] -= c[r] * bk;
+        }
+    }
+    if constexpr (R0 > 0) lu_bwd_block<RMAX, R0 - 1>(M, ld, n, lane, x, rdiag);
+}
+
 template <int RMAX, class PivT>
 __device__ __forceinline__ void lu_solve_warp_r(const double* M, int ld, int n, const PivT* piv, double* b, const double* rdiag) {
     const int lane = threadIdx.x & 31;
@@ -220,48 +269,8 @@ __device__ __forceinline__ void lu_solve_warp_r(const double* M, int ld, int n, 
         const int i = lane + 32 * r;
         x[r] = (i < n) ? b[i] : 0.0;
     }
-    for (int k = 0; k < n - 1; ++k) {
-        const double* ck = M + (size_t)k * ld;
-        double c[RMAX];
-#pragma unroll
-        for (int r = 0; r < RMAX; ++r) {
-            const int i = lane + 32 * r;
-            c[r] = (i > k && i < n) ? ck[i] : 0.0;
-        }
-        const int r0 = k >> 5;
-        double xv = x[0];
-#pragma unroll
-        for (int r = 1; r < RMAX; ++r) xv = (r == r0) ? x[r] : xv;
-        const double bk = __shfl_sync(0xffffffffu, xv, k & 31);
-#pragma unroll
-        for (int r = 0; r < RMAX; ++r) {
-            const int i = lane + 32 * r;
-            if (i > k && i < n) x[r] -= c[r] * bk;
-        }
-    }
-    for (int k = n - 1; k >= 0; --k) {
-        const double* ck = M + (size_t)k * ld;
-        const double ukk = ck[k];
-        const double y = rdiag ? rdiag[k] : 0.0;
-        double c[RMAX];
-#pragma unroll
-        for (int r = 0; r < RMAX; ++r) {
-            const int i = lane + 32 * r;
-            c[r] = (i < k) ? ck[i] : 0.0;
-        }
-        const int r0 = k >> 5;
-        double xv = x[0];
-#pragma unroll
-        for (int r = 1; r < RMAX; ++r) xv = (r == r0) ? x[r] : xv;
-        if (lane == (k & 31)) xv = rdiag ? div_by_recip(xv, ukk, y) : xv / ukk;
-        const double bk = __shfl_sync(0xffffffffu, xv, k & 31);
-#pragma unroll
-        for (int r = 0; r < RMAX; ++r) {
-            const int i = lane + 32 * r;
-            if (i == k) x[r] = bk;
-            else if (i < k) x[r] -= c[r] * bk;
-        }
-    }
+    lu_fwd_block<RMAX, 0>(M, ld, n, lane, x);
+    lu_bwd_block<RMAX, RMAX - 1>(M, ld, n, lane, x, rdiag);
 #pragma unroll
     for (int r = 0; r < RMAX; ++r) {
         const int i = lane + 32 * r;
