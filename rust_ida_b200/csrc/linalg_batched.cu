@@ -18,6 +18,7 @@
 #include "host_util.h"
 #include "ida_common.cuh"
 #include "lu_team.cuh"
+#include "lu_blocked.cuh"
 
 namespace b200ida {
 
@@ -399,6 +400,98 @@ static int launch_cfg(K kernel, int threads, size_t smem, int64_t groups_needed,
     return B200IDA_OK;
 }
 
+
+// ---- CTA-per-system blocked LU (lu_blocked.cuh), 33 <= n <= 160: matrix resident in shared memory ---------------------
+__host__ __device__ inline size_t lub_smem_bytes(int n) {
+    size_t b = (size_t)lu_ld(n) * n * sizeof(double);
+    b = (b + 15) / 16 * 16 + (lub_ub_bytes(n) + 15) / 16 * 16 + ((size_t)n * sizeof(int) + 15) / 16 * 16 + sizeof(LubCtl);
+    return (b + 15) / 16 * 16;
+}
+constexpr int lub_threads(int RP) { return RP <= 2 ? 128 : 256; }
+constexpr int lub_min_ctas(int RP) { return RP <= 2 ? 4 : (RP <= 4 ? 2 : 1); }
+
+template <bool SOA, int RP>
+__global__ void __launch_bounds__(lub_threads(RP), lub_min_ctas(RP))
+    getrf_blocked(double* __restrict__ A, int64_t* __restrict__ piv, int32_t* __restrict__ info, int n, int64_t B) {
+    extern __shared__ __align__(16) unsigned char lu_smem[];
+    const int ld = lu_ld(n);
+    double* Ms = reinterpret_cast<double*>(lu_smem);
+    size_t off = ((size_t)ld * n * sizeof(double) + 15) / 16 * 16;
+    double* Ub = reinterpret_cast<double*>(lu_smem + off);
+    off += (lub_ub_bytes(n) + 15) / 16 * 16;
+    int* pivs = reinterpret_cast<int*>(lu_smem + off);
+    off += ((size_t)n * sizeof(int) + 15) / 16 * 16;
+    LubCtl* ctl = reinterpret_cast<LubCtl*>(lu_smem + off);
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+        // stage: warp per column (4 columns in flight), lanes along the rows -> coalesced, no index divisions
+        LUB_T(ts0);
+        if (SOA) {
+            const int w = tid >> 5, nw = nt >> 5, lane = tid & 31;
+            for (int j = 4 * w; j < n; j += 4 * nw) {
+                for (int i = lane; i < n; i += 32) {
+                    double v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (j + u < n) v[u] = A[mat_idx<SOA>(i, j + u, n, b, B)];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (j + u < n) Ms[(j + u) * ld + i] = v[u];
+                }
+            }
+        } else {
+            // AoS: the matrix is n*n contiguous doubles; 8-byte asynchronous copies (LDGSTS) straight into the padded
+            // shared-memory columns, all in flight at once, no registers and no per-load round trip
+            const double* Ab = A + (size_t)b * n * n;
+            const unsigned sbase = (unsigned)__cvta_generic_to_shared(Ms);
+            const int w = tid >> 5, nw = nt >> 5, lane = tid & 31;
+            for (int j = w; j < n; j += nw) {
+                const double* src = Ab + (size_t)j * n;
+                const unsigned dst = sbase + (unsigned)(j * ld) * 8u;
+                for (int i = lane; i < n; i += 32)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (unsigned)i * 8u), "l"(src + i) : "memory");
+            }
+            asm volatile("cp.async.wait_all;" ::: "memory");
+        }
+        __syncthreads();
+        LUB_T(ts1);
+        LUB_ACC(7, ts0, ts1);
+        lub_factor<RP>(Ms, ld, n, ctl, pivs, Ub);
+        {
+            const int w = tid >> 5, nw = nt >> 5, lane = tid & 31;
+            for (int j = 4 * w; j < n; j += 4 * nw) {
+                for (int i = lane; i < n; i += 32) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (j + u < n) A[mat_idx<SOA>(i, j + u, n, b, B)] = Ms[(j + u) * ld + i];
+                }
+            }
+        }
+        const int inf = ctl->info;
+        for (int k = tid; k < n; k += nt) piv[SOA ? ((size_t)k * B + b) : ((size_t)b * n + k)] = (inf == 0 || k < inf) ? pivs[k] : 0;
+        if (tid == 0) info[b] = inf;
+        __syncthreads();
+    }
+}
+
+template <bool SOA, int RP>
+static int launch_getrf_blocked(double* A, int64_t* piv, int32_t* info, int n, int64_t B, cudaStream_t st) {
+    const size_t smem = lub_smem_bytes(n);
+    unsigned grid = 1;
+    int rc;
+    if ((rc = launch_cfg(getrf_blocked<SOA, RP>, lub_threads(RP), smem, B, 1, &grid))) return rc;
+    getrf_blocked<SOA, RP><<<grid, lub_threads(RP), smem, st>>>(A, piv, info, n, B);
+    B200_CUDA_TRY(cudaGetLastError());
+    return B200IDA_OK;
+}
+template <bool SOA>
+static int launch_getrf_blocked_n(double* A, int64_t* piv, int32_t* info, int n, int64_t B, cudaStream_t st) {
+    if (n <= 64) return launch_getrf_blocked<SOA, 2>(A, piv, info, n, B, st);
+    if (n <= 96) return launch_getrf_blocked<SOA, 3>(A, piv, info, n, B, st);
+    if (n <= 128) return launch_getrf_blocked<SOA, 4>(A, piv, info, n, B, st);
+    return launch_getrf_blocked<SOA, 5>(A, piv, info, n, B, st);
+}
+
 template <bool FACTOR>
 static int launch_group(double* A, int64_t* piv, int32_t* info, double* bx, int n, int64_t B, bool soa, cudaStream_t st) {
     const unsigned gb = (unsigned)lu_group_smem_bytes(n);
@@ -490,6 +583,8 @@ static int getrf_dev(double* A, int64_t* piv, int32_t* info, int n, int64_t B, i
         B200_CUDA_TRY(cudaGetLastError());
         return B200IDA_OK;
     }
+    if (n > 32 && n <= SMEM_MAX_N)
+        return soa ? launch_getrf_blocked_n<true>(A, piv, info, n, B, st) : launch_getrf_blocked_n<false>(A, piv, info, n, B, st);
     return launch_group<true>(A, piv, info, nullptr, n, B, soa, st);
 }
 
@@ -537,6 +632,17 @@ static int check_common(const void* a, const void* b, int n, int64_t batch, int 
 using namespace b200ida;
 
 extern "C" {
+
+#ifdef LUB_PROFILE
+int b200ida_debug_lub_prof(unsigned long long* out16, int reset) {
+    if (out16) cudaMemcpyFromSymbol(out16, b200ida::lub_prof, 32 * sizeof(unsigned long long));
+    if (reset) {
+        unsigned long long z[32] = {0};
+        cudaMemcpyToSymbol(b200ida::lub_prof, z, sizeof(z));
+    }
+    return 0;
+}
+#endif
 
 int b200ida_getrf_batched(double* A, int64_t* piv, int32_t* info, int n, int64_t batch, int layout, int mem,
                           void* stream) {

@@ -1,0 +1,496 @@
+// lu_blocked.cuh -- blocked, register-tiled partial-pivot LU of ONE column-major matrix that sits in shared memory,
+// executed by a whole CTA.  Used by the Level-1 batched getrf for 33 <= n <= 160 (linalg_batched.cu) and by the
+// CTA-per-system IDA kernel (ida_team.cuh) for the iteration matrix of the heat problem (n = 100).
+//
+// Semantics are bit-for-bit dense_get_rf (crates/linear/src/dense.rs:86-158): pivot = first row with strictly
+// largest |a_ik| (a NaN never wins; a NaN in row k keeps l = k); whole-row swap; l_ik = a_ik * (1/a_kk);
+// a_ij -= a_kj * l_ik with column j skipped when a_kj == 0; zero pivot -> info = k+1 and stop.
+//
+// Why blocking is bit-exact.  The final value of a_ij is  (..((a_ij - l_i0 u_0j) - l_i1 u_1j) - ..), one un-fused
+// multiply and one subtract per k, in increasing k.  The unblocked reference interleaves the k-steps of different
+// (i, j); any schedule that keeps, for each (i, j), the k-order and the operands is bit-identical.  Here NB = 8
+// consecutive k-steps are applied to a register tile before it goes back to shared memory, which divides the
+// shared-memory traffic of the trailing update by NB (the unblocked lu_team.cuh kernel is bound by it).
+// Built with -fmad=false.
+//
+// One block step (columns kb .. kb+nb), two CTA barriers (the panel of the NEXT step runs inside [U], see lub_factor):
+//   [P] panel: warp 0 eliminates the nb columns of the (n-kb) x nb panel in shared memory (lane = row, 32-row
+//       slots), arg-max by warp integer reductions, never moving rows: each lane tracks the LOGICAL position the
+//       reference's row swaps would have given its rows.  It permutes the panel to the logical positions at the end
+//       and publishes the list of row moves (src -> dst, at most 2 nb) of this panel.
+//   [S] every other column (one thread per column): apply the row moves; right of the panel also the nb-step
+//       unit-lower solve that produces the U rows kb..kb+nb (kept in registers, chain of nb), copied to Ub.
+//   [U] trailing update: warps own (64-row x 4-column) register tiles; per tile 8 loads + 8 stores of the matrix
+//       against 2*2*4*8 FP64 operations, multipliers cached in registers across the tiles of a row block,
+//       U values read as 16-byte broadcasts from Ub.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200ida {
+
+#ifdef LUB_PROFILE  // debug build only: per-phase clock accumulation (tools/prof_lub.py)
+__device__ unsigned long long lub_prof[32];
+#define LUB_ACC2(i, a, b) lub_acc[i] += (unsigned long long)((b) - (a))
+#define LUB_ACC2_DECL unsigned long long lub_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define LUB_ACC2_FLUSH do { if (threadIdx.x == 0 && blockIdx.x == 0) { for (int i_ = 0; i_ < 8; ++i_) lub_prof[16 + i_] += lub_acc[i_]; } } while (0)
+#define LUB_T(var) const long long var = clock64()
+#define LUB_ACC(i, a, b) do { if ((threadIdx.x == 0 || threadIdx.x == 32) && blockIdx.x == 0) atomicAdd(&lub_prof[(i) + (threadIdx.x ? 8 : 0)], (unsigned long long)((b) - (a))); } while (0)
+#else
+#define LUB_T(var)
+#define LUB_ACC(i, a, b)
+#define LUB_ACC2(i, a, b)
+#define LUB_ACC2_DECL
+#define LUB_ACC2_FLUSH
+#endif
+
+constexpr int LUB_NB = 8;                   // panel width = k-steps fused in registers
+constexpr int LUB_CT = 4;                   // columns per register tile in [U]
+constexpr int LUB_MAXMOVES = 2 * LUB_NB;    // a panel of nb pivots moves at most 2 nb rows
+
+struct LubCtl {  // per-CTA control block in shared memory
+    int info;    // 0 or the 1-based column of the zero pivot
+    int nmoves;  // row moves of the current panel
+    int ndone;   // panel columns actually eliminated (== nb unless a zero pivot stopped the panel)
+    int pad;
+    int src[LUB_MAXMOVES];
+    int dst[LUB_MAXMOVES];
+};
+
+__host__ __device__ inline int lub_ldu(int n) { return (n + 7) & ~3; }  // row pitch of Ub (multiple of 4, >= n + 3)
+// scratch after the matrix: Ub (LUB_NB x ldu doubles) followed by the per-column zero flags (ldu bytes)
+__host__ __device__ inline size_t lub_ub_bytes(int n) { return (size_t)LUB_NB * lub_ldu(n) * sizeof(double) + (size_t)lub_ldu(n); }
+
+// ---- [P] panel factorisation by one warp, panel resident in shared memory ------------------------------------------------
+// Lane = row (32-row slots, R of them hold rows).  Rows are NOT moved while the panel is eliminated: pos[r] is the
+// LOGICAL position the reference's row swaps would have given register row r; the panel is permuted once at the end.
+// Per column: arg-max by three warp integer reductions (redux.sync) on the IEEE bit pattern of |a_ik| (for finite
+// non-negative doubles the bit pattern orders like the value; NaN maps below every candidate so it never wins; ties
+// go to the lowest logical position, which also carries the physical row in its low bits), exact reciprocal of the
+// pivot started from the reduced |pivot| bits while its sign is fetched, right-looking update of the remaining panel
+// columns straight in shared memory.
+// shared-memory accesses by 32-bit shared-window address: no generic-address arithmetic in the serial chain
+__device__ __forceinline__ double lub_lds(unsigned a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void lub_sts(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+
+// step-c update of the ND panel columns right of column c: v -= a_d * x for the rows still active; a zero pivot-row
+// entry a_d skips column d like the reference (select on the result, so the block stays straight-line code)
+template <int R, int ND>
+__device__ __forceinline__ void lub_panel_update(const unsigned (&ra)[R], unsigned pa, unsigned ldb, const double (&x)[R],
+                                                 const bool (&act)[R]) {
+    double a[ND], v[ND][R];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) a[d] = lub_lds(pa + (unsigned)(d + 1) * ldb);
+#pragma unroll
+    for (int d = 0; d < ND; ++d)
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[d][r] = lub_lds(ra[r] + (unsigned)(d + 1) * ldb);
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+        const bool nz = a[d] != 0.0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const double t = v[d][r] - a[d] * x[r];
+            if (act[r] && nz) lub_sts(ra[r] + (unsigned)(d + 1) * ldb, t);
+        }
+    }
+}
+
+template <int R>
+__device__ __noinline__ void lub_panel(double* M, int ld, int n, int kb, int nb, LubCtl* ctl, int* pivs) {
+    // One warp, in-order issue: the cost of a column step is (instructions issued) x (4..8 cycles), so the loop is
+    // written for instruction count -- 32-bit shared addresses advanced per column, a "pivoted" flag per row
+    // instead of position compares, unconditional loads (rows beyond the matrix alias row n-1; their results are
+    // never stored) and predicated lone stores, so the body is straight-line code.
+    const int lane = threadIdx.x & 31;
+    LUB_ACC2_DECL;
+    const unsigned mbase = (unsigned)__cvta_generic_to_shared(M);
+    const unsigned ldb = (unsigned)ld * 8u;
+    unsigned ra[R];   // shared address of (row r, current column)
+    unsigned pp[R];   // (logical position << 16) | physical row
+    bool act[R];      // row exists and has not been chosen as a pivot yet
+    int rowc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int row = kb + lane + 32 * r;
+        act[r] = row < n;
+        rowc[r] = act[r] ? row : n - 1;
+        ra[r] = mbase + (unsigned)(kb * ld + rowc[r]) * 8u;
+        pp[r] = ((unsigned)rowc[r] << 16) | (unsigned)rowc[r];
+    }
+    unsigned colb = mbase + (unsigned)(kb * ld) * 8u;  // shared address of (row 0, current column)
+    int ndone = nb, info = 0;
+#pragma unroll 1
+    for (int c = 0; c < nb; ++c) {
+        const int k = kb + c;
+        LUB_T(p0);
+        double x[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) x[r] = lub_lds(ra[r]);
+        // lane-local best candidate: key = bits of |x| (NaN -> -1, not a candidate -> -2), ties -> lowest position
+        int bhi = -2;
+        unsigned blo = 0u, bpp = 0xffffffffu;
+        bool nank = false;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const bool isnan_ = x[r] != x[r];
+            const int hi = isnan_ ? -1 : (__double2hiint(x[r]) & 0x7fffffff);
+            const unsigned lo = isnan_ ? 0xffffffffu : (unsigned)__double2loint(x[r]);
+            const bool gt = hi > bhi || (hi == bhi && (lo > blo || (lo == blo && pp[r] < bpp)));
+            const bool take = act[r] && gt;
+            bhi = take ? hi : bhi;
+            blo = take ? lo : blo;
+            bpp = take ? pp[r] : bpp;
+            nank = nank || (isnan_ && (pp[r] >> 16) == (unsigned)k);
+        }
+        LUB_T(p1);
+        LUB_ACC2(0, p0, p1);
+        const int mhi = __reduce_max_sync(0xffffffffu, bhi);
+        const unsigned mlo = __reduce_max_sync(0xffffffffu, (bhi == mhi) ? blo : 0u);
+        unsigned mpp = __reduce_min_sync(0xffffffffu, (bhi == mhi && blo == mlo) ? bpp : 0xffffffffu);
+        const bool forced = mhi < 0 || __any_sync(0xffffffffu, nank);  // nothing comparable, or NaN in row k: l = k
+        // reciprocal of |pivot| from the reduced bits, off the critical path of the sign fetch
+        double mult = __drcp_rn(__hiloint2double(mhi, (int)mlo));
+        if (forced) {  // warp-uniform, rare
+            unsigned pk = 0xffffffffu;
+#pragma unroll
+            for (int r = 0; r < R; ++r) pk = (act[r] && (pp[r] >> 16) == (unsigned)k) ? pp[r] : pk;
+            mpp = __reduce_min_sync(0xffffffffu, pk);
+        }
+        const int l = (int)(mpp >> 16), physl = (int)(mpp & 0xffffu);
+        LUB_T(p2);
+        LUB_ACC2(1, p1, p2);
+        const unsigned pvoff = (unsigned)physl * 8u;
+        const double pv = lub_lds(colb + pvoff);
+        if (forced) mult = 1.0 / pv;
+        else mult = (pv < 0.0) ? -mult : mult;
+        if (lane == 0) pivs[k] = l;
+        if (pv == 0.0) {
+            info = k + 1;
+            ndone = c;
+            break;
+        }
+        LUB_T(p3);
+        LUB_ACC2(2, p2, p3);
+        // logical positions: the pivot row goes to k, the row that sat at k goes to l; multipliers below the pivot
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const bool isl = pp[r] == mpp;
+            const bool isk = (pp[r] >> 16) == (unsigned)k;
+            const unsigned low = pp[r] & 0xffffu;
+            pp[r] = isl ? (((unsigned)k << 16) | low) : (isk ? (((unsigned)l << 16) | low) : pp[r]);
+            act[r] = act[r] && !isl;
+            x[r] = x[r] * mult;
+            if (act[r]) lub_sts(ra[r], x[r]);
+        }
+        LUB_T(p4);
+        LUB_ACC2(3, p3, p4);
+        // right-looking update of the remaining nd panel columns: all loads, then the arithmetic, then the stores
+        // (specialised on nd so that nothing is issued for columns that do not exist)
+        switch (nb - 1 - c) {
+        case 7: lub_panel_update<R, 7>(ra, colb + pvoff, ldb, x, act); break;
+        case 6: lub_panel_update<R, 6>(ra, colb + pvoff, ldb, x, act); break;
+        case 5: lub_panel_update<R, 5>(ra, colb + pvoff, ldb, x, act); break;
+        case 4: lub_panel_update<R, 4>(ra, colb + pvoff, ldb, x, act); break;
+        case 3: lub_panel_update<R, 3>(ra, colb + pvoff, ldb, x, act); break;
+        case 2: lub_panel_update<R, 2>(ra, colb + pvoff, ldb, x, act); break;
+        case 1: lub_panel_update<R, 1>(ra, colb + pvoff, ldb, x, act); break;
+        default: break;
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) ra[r] += ldb;
+        colb += ldb;
+        LUB_T(p5);
+        LUB_ACC2(4, p4, p5);
+        __syncwarp();
+        LUB_T(p6);
+        LUB_ACC2(5, p5, p6);
+    }
+    __syncwarp();
+    LUB_T(q0);
+    // permute the panel to the logical positions (two columns per trip), publish the row moves for the other columns
+    bool moved[R];
+    bool anymoved = false;
+    int posc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int pos = (int)(pp[r] >> 16);
+        moved[r] = kb + lane + 32 * r < n && pos != rowc[r];
+        anymoved = anymoved || moved[r];
+        posc[r] = moved[r] ? pos : rowc[r];
+    }
+    if (__any_sync(0xffffffffu, anymoved)) {
+#pragma unroll 1
+        for (int c = 0; c < nb; c += 2) {
+            double* Mc = M + (kb + c) * ld;
+            const int o1 = (c + 1 < nb) ? ld : 0;  // odd width: the second column of the trip is the first again
+            double t0[R], t1[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                t0[r] = Mc[rowc[r]];
+                t1[r] = Mc[o1 + rowc[r]];
+            }
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if (moved[r]) Mc[posc[r]] = t0[r];
+            }
+            if (o1 != 0) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if (moved[r]) Mc[o1 + posc[r]] = t1[r];
+                }
+            }
+        }
+    }
+    int base = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const unsigned m = __ballot_sync(0xffffffffu, moved[r]);
+        const int idx = base + __popc(m & ((1u << lane) - 1u));
+        if (moved[r]) ctl->src[idx] = rowc[r];
+        if (moved[r]) ctl->dst[idx] = posc[r];
+        base += __popc(m);
+    }
+    if (lane >= base && lane < LUB_MAXMOVES) {  // unused slots: a valid row, so [S] can load unconditionally
+        ctl->src[lane] = kb;
+        ctl->dst[lane] = kb;
+    }
+    if (lane == 0) {
+        ctl->nmoves = base;
+        ctl->ndone = ndone;
+        if (info != 0) ctl->info = info;
+    }
+    __syncwarp();
+    LUB_T(q1);
+    LUB_ACC2(6, q0, q1);
+    LUB_ACC2_FLUSH;
+}
+
+// dispatch on the number of 32-row slots that still hold rows, so later (shorter) panels issue no dead instructions
+template <int RP>
+__device__ __forceinline__ void lub_panel_any(double* M, int ld, int n, int kb, int nb, LubCtl* ctl, int* pivs) {
+    const int nr = (n - kb + 31) >> 5;
+    if (RP >= 5 && nr >= 5) lub_panel<5>(M, ld, n, kb, nb, ctl, pivs);
+    else if (RP >= 4 && nr == 4) lub_panel<4>(M, ld, n, kb, nb, ctl, pivs);
+    else if (RP >= 3 && nr == 3) lub_panel<3>(M, ld, n, kb, nb, ctl, pivs);
+    else if (RP >= 2 && nr == 2) lub_panel<2>(M, ld, n, kb, nb, ctl, pivs);
+    else lub_panel<1>(M, ld, n, kb, nb, ctl, pivs);
+}
+
+// ---- [S] row moves for the columns outside the panel + the U rows of the columns right of it --------------------------
+// zcol[j] (right columns): 0 = no zero among the nbd U values of column j, 2 = all zero, 1 = mixed
+__device__ __noinline__ void lub_swap_solve(double* M, int ld, int n, int kb, int nbp, int nbd, const LubCtl* ctl,
+                                            double* Ub, unsigned char* zcol, int ldu, int tid, int nt) {
+    // loads unconditional (unused move slots point at a valid row), stores predicated: see lub_panel
+    const int nm = ctl->nmoves;
+    int src[LUB_MAXMOVES], dst[LUB_MAXMOVES];
+#pragma unroll
+    for (int m = 0; m < LUB_MAXMOVES; ++m) {
+        src[m] = ctl->src[m];
+        dst[m] = ctl->dst[m];
+    }
+    for (int j = tid; j < n; j += nt) {
+        if (j >= kb && j < kb + nbp) continue;
+        double* col = M + j * ld;
+        if (nm > 0) {  // CTA-uniform
+            double tmp[LUB_MAXMOVES];
+#pragma unroll
+            for (int m = 0; m < LUB_MAXMOVES; ++m) tmp[m] = col[src[m]];
+#pragma unroll
+            for (int m = 0; m < LUB_MAXMOVES; ++m)
+                if (m < nm) col[dst[m]] = tmp[m];
+        }
+        if (j >= kb + nbp) {  // right of the panel: kb + LUB_NB <= n here, so rows kb..kb+7 exist
+            double u[LUB_NB];
+#pragma unroll
+            for (int c = 0; c < LUB_NB; ++c) u[c] = col[kb + c];
+            int nz = 0;
+#pragma unroll
+            for (int c = 0; c < LUB_NB; ++c) {
+                const double uc = u[c];
+                const bool on = c < nbd && uc != 0.0;
+                nz += on ? 1 : 0;
+                const double* lc = M + (kb + c) * ld + kb;
+#pragma unroll
+                for (int i = c + 1; i < LUB_NB; ++i) {
+                    const double t = u[i] - uc * lc[i];
+                    u[i] = (on && i < nbd) ? t : u[i];
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < LUB_NB; ++c)
+                if (c < nbd) {
+                    col[kb + c] = u[c];
+                    Ub[c * ldu + j] = u[c];
+                }
+            zcol[j] = (nz == nbd) ? 0 : (nz == 0 ? 2 : 1);
+        }
+    }
+}
+
+// ---- [U] trailing update with K = nbd fused k-steps per register tile -----------------------------------------------------
+// EXACT = false: every U value of the tile is non-zero, plain multiply / subtract.  EXACT = true: a zero u_kj skips
+// the update of column j at step k like the reference does (it matters for signed zeros and non-finite multipliers).
+template <bool TWO, bool EXACT, bool FULL>
+__device__ __forceinline__ void lub_tile(double* M, int ld, int n, int K, int i0, int j0, const double (&l0)[LUB_NB],
+                                         const double (&l1)[LUB_NB], const double* Ub, int ldu) {
+    // FULL: K == LUB_NB and the whole (32|64) x 4 tile is inside the matrix -> no predicates at all.
+    // Otherwise loads use clamped (valid) addresses and only the stores are predicated (see lub_panel).
+    const bool v0 = FULL || i0 < n, v1 = TWO && (FULL || i0 + 32 < n);
+    const int i0c = v0 ? i0 : n - 1, i1c = v1 ? i0 + 32 : n - 1;
+    double* c0 = M + j0 * ld;
+    double a0[LUB_CT], a1[LUB_CT];
+    int jo[LUB_CT];
+#pragma unroll
+    for (int cc = 0; cc < LUB_CT; ++cc) {
+        jo[cc] = (FULL || j0 + cc < n) ? cc * ld : 0;
+        a0[cc] = c0[jo[cc] + i0c];
+        if (TWO) a1[cc] = c0[jo[cc] + i1c];
+    }
+    const double* ur = Ub + j0;
+#pragma unroll
+    for (int k = 0; k < LUB_NB; ++k) {
+        if (FULL || k < K) {
+            const double2 ua = *reinterpret_cast<const double2*>(ur + k * ldu);
+            const double2 ub = *reinterpret_cast<const double2*>(ur + k * ldu + 2);
+            const double u[LUB_CT] = {ua.x, ua.y, ub.x, ub.y};
+#pragma unroll
+            for (int cc = 0; cc < LUB_CT; ++cc) {
+                if (!EXACT || u[cc] != 0.0) {
+                    a0[cc] -= u[cc] * l0[k];
+                    if (TWO) a1[cc] -= u[cc] * l1[k];
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int cc = 0; cc < LUB_CT; ++cc) {
+        const bool ok = FULL || j0 + cc < n;
+        if (ok && v0) c0[jo[cc] + i0c] = a0[cc];
+        if (TWO && ok && v1) c0[jo[cc] + i1c] = a1[cc];
+    }
+}
+
+// rows >= kb + K, columns [c0, c1); warp w of nw takes a contiguous chunk of (row block, column tile) items.
+// RB = rows per block: 64 (two register rows per lane) for the bulk, 32 to spread a narrow strip over more warps.
+template <int RB>
+__device__ __noinline__ void lub_update(double* M, int ld, int n, int kb, int K, int c0, int c1, const double* Ub,
+                                        const unsigned char* zcol, int ldu, int w, int nw, int lane) {
+    const int r0 = kb + K;
+    const int nrows = n - r0, ncols = c1 - c0;
+    if (nrows <= 0 || ncols <= 0 || K <= 0) return;
+    const int nrb = (nrows + RB - 1) / RB, nct = (ncols + LUB_CT - 1) / LUB_CT;
+    const int items = nrb * nct, chunk = (items + nw - 1) / nw;
+    int it = w * chunk;
+    if (it >= items) return;
+    const int itend = (it + chunk < items) ? it + chunk : items;
+    int rb = it / nct, ct = it - rb * nct;
+    int cur_rb = -1;
+    double l0[LUB_NB], l1[LUB_NB];
+    for (; it < itend; ++it) {
+        const int j0 = c0 + ct * LUB_CT;
+        const unsigned zf = *reinterpret_cast<const unsigned*>(zcol + j0);  // flags of the tile's 4 columns
+        if (zf != 0x02020202u) {  // else every u_kj is zero: nothing to do
+            const int ib = r0 + rb * RB;
+            const int i0 = ib + lane;
+            const bool two = RB == 64 && ib + 32 < n;  // warp-uniform
+            if (rb != cur_rb) {
+                cur_rb = rb;
+#pragma unroll
+                for (int k = 0; k < LUB_NB; ++k) {
+                    const int kc = (k < K) ? k : 0;
+                    const double* ckc = M + (kb + kc) * ld;
+                    l0[k] = ckc[i0 < n ? i0 : n - 1];
+                    if (RB == 64) l1[k] = ckc[i0 + 32 < n ? i0 + 32 : n - 1];
+                }
+            }
+            const bool full = K == LUB_NB && j0 + LUB_CT <= c1 && ib + (two ? 64 : 32) <= n;
+            if (zf == 0u) {
+                if (two) {
+                    if (full) lub_tile<true, false, true>(M, ld, n, K, i0, j0, l0, l1, Ub, ldu);
+                    else lub_tile<true, false, false>(M, ld, n, K, i0, j0, l0, l1, Ub, ldu);
+                } else {
+                    if (full) lub_tile<false, false, true>(M, ld, n, K, i0, j0, l0, l1, Ub, ldu);
+                    else lub_tile<false, false, false>(M, ld, n, K, i0, j0, l0, l1, Ub, ldu);
+                }
+            } else {
+                if (two) lub_tile<true, true, false>(M, ld, n, K, i0, j0, l0, l1, Ub, ldu);
+                else lub_tile<false, true, false>(M, ld, n, K, i0, j0, l0, l1, Ub, ldu);
+            }
+        }
+        if (++ct == nct) {
+            ct = 0;
+            ++rb;
+        }
+    }
+}
+
+// In-place LU of the n x n column-major matrix M (leading dimension ld) in shared memory.  Every thread of the CTA
+// calls it (blockDim.x a multiple of 32, at least 64).  RP >= ceil(n / 32).  Ub: lub_ub_bytes(n) of shared scratch,
+// 16-byte aligned.  On return (after a barrier) ctl->info holds 0 or the 1-based singular column, pivs[0..n) the pivot
+// rows; after a zero pivot in column k the matrix is the reference's partially factored state (steps < k applied).
+//
+// Look-ahead: in block step kb all warps first bring the NEXT panel (columns kb+nb .. kb+2nb) up to date; then warp 0
+// eliminates it while warps 1.. update the rest of the trailing matrix, so the serial pivot chain of one panel
+// overlaps the parallel update of the previous one; three CTA barriers per block step.
+template <int RP>
+__device__ __forceinline__ void lub_factor(double* M, int ld, int n, LubCtl* ctl, int* pivs, double* Ub) {
+    const int tid = threadIdx.x, nt = blockDim.x, w = tid >> 5, nw = nt >> 5, lane = tid & 31;
+    const int ldu = lub_ldu(n);
+    unsigned char* zcol = reinterpret_cast<unsigned char*>(Ub + LUB_NB * ldu);
+    if (tid == 0) ctl->info = 0;
+    for (int j = n + tid; j < ldu; j += nt) zcol[j] = 0;
+    __syncthreads();
+    LUB_T(t0);
+    if (w == 0) lub_panel_any<RP>(M, ld, n, 0, n < LUB_NB ? n : LUB_NB, ctl, pivs);
+    LUB_T(t1);
+    __syncthreads();
+    LUB_ACC(0, t0, t1);
+    for (int kb = 0; kb < n; kb += LUB_NB) {
+        const int nb = (n - kb < LUB_NB) ? n - kb : LUB_NB;
+        const int nbd = ctl->ndone;
+        const int info = ctl->info;
+        LUB_T(ta);
+        lub_swap_solve(M, ld, n, kb, nb, nbd, ctl, Ub, zcol, ldu, tid, nt);
+        LUB_T(tb);
+        __syncthreads();
+        LUB_T(tc);
+        const int c0 = kb + nb;                                  // first column right of this panel
+        const int nb2 = (n - c0 < LUB_NB) ? n - c0 : LUB_NB;     // width of the next panel (<= 0: none)
+        if (nb2 > 0) {
+            // the strip that becomes the next panel first, spread over all warps in 32-row blocks
+            lub_update<32>(M, ld, n, kb, nbd, c0, c0 + nb2, Ub, zcol, ldu, w, nw, lane);
+            LUB_T(td);
+            __syncthreads();
+            LUB_T(te);
+            // warp w runs on scheduler (sub-partition) w % 4: the panel warp's serial chain must not queue behind
+            // FP64-saturating update warps, so with 8 warps warp 4 (same scheduler as warp 0) sits the update out
+            if (w == 0) {
+                if (info == 0) lub_panel_any<RP>(M, ld, n, c0, nb2, ctl, pivs);
+            } else if (nw <= 4) {
+                lub_update<64>(M, ld, n, kb, nbd, c0 + nb2, n, Ub, zcol, ldu, w - 1, nw - 1, lane);
+            } else if ((w & 3) != 0) {
+                lub_update<64>(M, ld, n, kb, nbd, c0 + nb2, n, Ub, zcol, ldu, w - 1 - (w >> 2), nw - (nw >> 2), lane);
+            }
+            LUB_T(tf);
+            LUB_ACC(3, tc, td);
+            LUB_ACC(4, td, te);
+            LUB_ACC(5, te, tf);
+            __syncthreads();
+            LUB_T(tg);
+            LUB_ACC(6, tf, tg);
+        } else {
+            __syncthreads();
+        }
+        LUB_ACC(1, ta, tb);
+        LUB_ACC(2, tb, tc);
+        if (info != 0) break;  // uniform: read before warp 0 could overwrite it
+    }
+}
+
+}  // namespace b200ida
