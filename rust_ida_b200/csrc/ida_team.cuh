@@ -23,6 +23,7 @@
 #include "detpow.h"
 #include "ida_common.cuh"
 #include "lu_team.cuh"
+#include "lu_blocked.cuh"
 
 namespace b200ida {
 
@@ -77,10 +78,9 @@ struct TeamProblem {
         }
         }
     }
-    // J(i, j) = dF_i/dy_j + cj dF_i/dy'_j for the whole row i (J already zeroed), column-major ld = n
-    __device__ __forceinline__ void jac_row(int i, double cj, const double* yy, double* J) const {
-        const int n_ = n;
-        auto A = [&](int r, int c) -> double& { return J[(size_t)c * n_ + r]; };
+    // J(i, j) = dF_i/dy_j + cj dF_i/dy'_j for the whole row i (J already zeroed), column-major, leading dimension ld
+    __device__ __forceinline__ void jac_row(int i, double cj, const double* yy, double* J, int ld) const {
+        auto A = [&](int r, int c) -> double& { return J[(size_t)c * ld + r]; };
         switch (kind) {
         case B200IDA_PROBLEM_ROBERTS:  // src/sample_problems/roberts.rs:80-90
             if (i == 0) {
@@ -139,19 +139,25 @@ struct TeamScalars {
     LuShared lu;
 };
 
+// leading dimension of the iteration matrix in the arena: odd, so that row accesses (pivot-row moves) are
+// shared-memory bank-conflict free as well as column accesses
+__host__ __device__ inline int team_ldj(int n) { return n | 1; }
 __host__ __device__ inline size_t team_arena_bytes(int n) {
-    // phi[6][n] + 11 n-vectors + J[n][n] as doubles, pivots as ints, scalars; 16-byte aligned pieces
-    size_t d = (size_t)17 * n + (size_t)n * n;
-    size_t bytes = d * sizeof(double) + ((size_t)n * sizeof(int) + 15) / 16 * 16 + (sizeof(TeamScalars) + 15) / 16 * 16;
+    // phi[6][n] + 11 n-vectors + J[ldj][n] (+1 pad) as doubles, the blocked-LU scratch (lu_blocked.cuh), pivots as ints,
+    // scalars; 16-byte aligned pieces
+    size_t d = (size_t)17 * n + (size_t)team_ldj(n) * n + 1;
+    size_t bytes = (d * sizeof(double) + 15) / 16 * 16 + (lub_ub_bytes(n) + 15) / 16 * 16 + 2 * (((size_t)n * sizeof(int) + 15) / 16 * 16) +
+                   (sizeof(LubCtl) + 15) / 16 * 16 + (sizeof(TeamScalars) + 15) / 16 * 16;
     return (bytes + 15) / 16 * 16;
 }
 
 template <class Team>
 struct IdaTeam {
-    int n, T, t;
+    int n, T, t, ldj;
     // arena views
-    double *phi, *ee, *ewt, *yy, *yp, *yypred, *yppred, *delta, *nd, *tmp, *prod, *rdiag, *J;
-    int* piv;
+    double *phi, *ee, *ewt, *yy, *yp, *yypred, *yppred, *delta, *nd, *tmp, *prod, *rdiag, *J, *Ub;
+    int *piv, *perm;
+    LubCtl* lub;
     TeamScalars* S;
     TeamProblem prob;
     const double* atol;  // global, [n]
@@ -174,9 +180,18 @@ struct IdaTeam {
         tmp = d;            d += n;
         prod = d;           d += n;
         rdiag = d;          d += n;
-        J = d;              d += (size_t)n * n;
-        piv = reinterpret_cast<int*>(d);
-        S = reinterpret_cast<TeamScalars*>(reinterpret_cast<unsigned char*>(piv) + ((size_t)n * sizeof(int) + 15) / 16 * 16);
+        ldj = team_ldj(n);
+        J = d;              d += (size_t)ldj * n + 1;
+        unsigned char* q = arena + ((size_t)(d - reinterpret_cast<double*>(arena)) * sizeof(double) + 15) / 16 * 16;
+        Ub = reinterpret_cast<double*>(q);
+        q += (lub_ub_bytes(n) + 15) / 16 * 16;
+        piv = reinterpret_cast<int*>(q);
+        q += ((size_t)n * sizeof(int) + 15) / 16 * 16;
+        perm = reinterpret_cast<int*>(q);
+        q += ((size_t)n * sizeof(int) + 15) / 16 * 16;
+        lub = reinterpret_cast<LubCtl*>(q);
+        q += (sizeof(LubCtl) + 15) / 16 * 16;
+        S = reinterpret_cast<TeamScalars*>(q);
     }
     __device__ __forceinline__ bool leader() const { return t == 0; }
     __device__ __forceinline__ double* PHI(int j) const { return phi + (size_t)j * n; }
@@ -192,9 +207,10 @@ struct IdaTeam {
             yp[i] = ds[(int64_t)lay.yp(i) * B + b];
             piv[i] = is[(int64_t)lay.piv(i) * B + b];
         }
-        for (int e = t; e < n * n; e += T) J[e] = ds[(int64_t)lay.J(e % n, e / n) * B + b];
+        for (int e = t; e < n * n; e += T) J[(e / n) * ldj + e % n] = ds[(int64_t)lay.J(e % n, e / n) * B + b];
         Team::sync();
-        for (int k = t; k < n; k += T) rdiag[k] = 1.0 / J[(size_t)k * n + k];  // not persisted; from the stored factors
+        for (int k = t; k < n; k += T) rdiag[k] = 1.0 / J[(size_t)k * ldj + k];  // not persisted; from the stored factors
+        if (t == T - 1) lu_build_perm(n, piv, perm);                              // likewise
         if (leader()) {
             for (int j = 0; j < MXORDP1; ++j) {
                 S->psi[j] = ds[(int64_t)lay.psi(j) * B + b];
@@ -227,7 +243,7 @@ struct IdaTeam {
             ds[(int64_t)lay.yp(i) * B + b] = yp[i];
             is[(int64_t)lay.piv(i) * B + b] = piv[i];
         }
-        for (int e = t; e < n * n; e += T) ds[(int64_t)lay.J(e % n, e / n) * B + b] = J[e];
+        for (int e = t; e < n * n; e += T) ds[(int64_t)lay.J(e % n, e / n) * B + b] = J[(e / n) * ldj + e % n];
         if (leader()) {
             for (int j = 0; j < MXORDP1; ++j) {
                 ds[(int64_t)lay.psi(j) * B + b] = S->psi[j];
@@ -344,19 +360,31 @@ struct IdaTeam {
         Team::sync();
     }
 
-    // ---- dense_get_rf on the arena's J (crates/linear/src/dense.rs:86-158) via lu_team.cuh; S->info = 0 or the
-    //      1-based singular column ------------------------------------------------------------------------------
+    // ---- dense_get_rf on the arena's J (crates/linear/src/dense.rs:86-158); S->info = 0 or the 1-based singular
+    //      column.  CTA teams with n > 32 use the blocked, look-ahead factorisation of lu_blocked.cuh (bit-identical to
+    //      the unblocked one), warp teams and small systems the group LU of lu_team.cuh -------------------------------
     __device__ void getrf() {
         Team::sync();
-        lu_factor<Team::T == 32>(J, n, n, &S->lu, piv);
-        if (leader()) S->info = S->lu.info;
-        for (int k = t; k < n; k += T) rdiag[k] = 1.0 / J[(size_t)k * n + k];
+        if (Team::T == 0 && n > 32) {
+            lub_factor<5>(J, ldj, n, lub, piv, Ub);
+            if (leader()) S->info = lub->info;
+        } else {
+            lu_factor<Team::T == 32>(J, ldj, n, &S->lu, piv);
+            if (leader()) S->info = S->lu.info;
+        }
+        for (int k = t; k < n; k += T) rdiag[k] = 1.0 / J[(size_t)k * ldj + k];
+        if (t == T - 1) lu_build_perm(n, piv, perm);
         Team::sync();
     }
 
     // ---- dense_get_rs on nd (crates/linear/src/dense.rs:165-206) + cjratio rescale (src/ida_ls.rs:406-410) ------
     __device__ void lsolve() {
-        lu_solve<Team::T == 32>(J, n, n, piv, nd, rdiag);
+        if (Team::T == 0 && n > 32) {
+            Team::sync();
+            lu_solve_cta_blocked(J, ldj, n, perm, nd, tmp, rdiag);
+        } else {
+            lu_solve<Team::T == 32>(J, ldj, n, piv, nd, rdiag);
+        }
         const double cjratio = S->cjratio;
         if (cjratio != 1.0) {
             const double f = 2.0 / (1.0 + cjratio);
@@ -367,10 +395,10 @@ struct IdaTeam {
 
     // ---- IdaNLProblem::setup (src/ida_nls.rs:156-187, src/ida_ls.rs:232-290) ---------------------------------
     __device__ void nls_setup() {
-        for (int e = t; e < n * n; e += T) J[e] = 0.0;
+        for (int e = t; e < ldj * n; e += T) J[e] = 0.0;
         Team::sync();
         const double cj = S->cj;
-        for (int i = t; i < n; i += T) prob.jac_row(i, cj, yy, J);
+        for (int i = t; i < n; i += T) prob.jac_row(i, cj, yy, J, ldj);
         Team::sync();
         getrf();
         if (leader()) {

@@ -492,6 +492,170 @@ static int launch_getrf_blocked_n(double* A, int64_t* piv, int32_t* info, int n,
     return launch_getrf_blocked<SOA, 5>(A, piv, info, n, B, st);
 }
 
+// ---- warp-per-system streaming getrs (AoS, n > 32): every element of the factors is used exactly once, so the
+// matrix is never staged -- each warp streams its matrix from HBM/L2 straight into registers, one chunk of columns
+// ahead of the substitution chain (register double buffer), and only the triangle each sweep needs is fetched
+// (32-row slot granularity: ~n^2 + 32n doubles in total).  The right-hand side lives in registers (lane owns rows
+// lane, lane+32, ..), a step of the chain is one shuffle + mul + sub; the divisions of the backward sweep use
+// the exact reciprocal sequence (exact_div.cuh) with 1/u_kk computed as soon as the column arrives, off the chain.
+template <int NS, int CB>
+__device__ __forceinline__ void gs_load_fwd(const double* __restrict__ Mg, int n, int k0, int kend, int rbase, int lane,
+                                            double (&c)[CB][NS]) {
+#pragma unroll
+    for (int q = 0; q < CB; ++q) {
+        const int k = k0 + q;
+        const double* col = Mg + (size_t)(k < kend ? k : kend - 1) * n;
+#pragma unroll
+        for (int r = 0; r < NS; ++r) {
+            const int i = lane + 32 * (rbase + r);
+            c[q][r] = (k < kend && i < n) ? __ldg(col + i) : 0.0;
+        }
+    }
+}
+
+template <int RMAX, int R0>
+__device__ __forceinline__ void gs_fwd_block(const double* __restrict__ Mg, int n, int lane, double (&x)[RMAX]) {
+    constexpr int NS = RMAX - R0;               // slots R0 .. RMAX-1 hold the rows below the pivots of this block
+    constexpr int CB = (NS >= 5) ? 4 : 8;       // columns per chunk (register budget)
+    const int kbeg = 32 * R0;
+    const int kend = (kbeg + 32 < n - 1) ? kbeg + 32 : n - 1;
+    if (kbeg < kend) {
+        double cur[CB][NS], nxt[CB][NS];
+        gs_load_fwd<NS, CB>(Mg, n, kbeg, kend, R0, lane, cur);
+        for (int k0 = kbeg; k0 < kend; k0 += CB) {
+            gs_load_fwd<NS, CB>(Mg, n, k0 + CB, kend, R0, lane, nxt);  // predicated off past the block
+#pragma unroll
+            for (int q = 0; q < CB; ++q) {
+                const int k = k0 + q;
+                if (k < kend) {  // warp-uniform
+                    const int kk = k & 31;
+                    const double bk = __shfl_sync(0xffffffffu, x[R0], kk);
+                    const double t0 = x[R0] - cur[q][0] * bk;
+                    x[R0] = (lane > kk) ? t0 : x[R0];
+#pragma unroll
+                    for (int r = 1; r < NS; ++r) {
+                        const double t = x[R0 + r] - cur[q][r] * bk;
+                        x[R0 + r] = (lane + 32 * (R0 + r) < n) ? t : x[R0 + r];
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < CB; ++q)
+#pragma unroll
+                for (int r = 0; r < NS; ++r) cur[q][r] = nxt[q][r];
+        }
+    }
+    if constexpr (R0 + 1 < RMAX) gs_fwd_block<RMAX, R0 + 1>(Mg, n, lane, x);
+}
+
+// backward chunk: columns k0, k0-1, .., k0-CB+1 (descending), rows of slots 0..R0; rd = 1/u_kk of each column
+template <int NS, int CB>
+__device__ __forceinline__ void gs_load_bwd(const double* __restrict__ Mg, int n, int k0, int kbeg, int lane,
+                                            double (&c)[CB][NS], double (&ud)[CB], double (&rd)[CB]) {
+#pragma unroll
+    for (int q = 0; q < CB; ++q) {
+        const int k = k0 - q;
+        const bool on = k >= kbeg;
+        const double* col = Mg + (size_t)(on ? k : kbeg) * n;
+#pragma unroll
+        for (int r = 0; r < NS; ++r) {
+            const int i = lane + 32 * r;
+            c[q][r] = (on && i < k) ? __ldg(col + i) : 0.0;  // strictly above the diagonal
+        }
+        ud[q] = on ? __ldg(col + k) : 1.0;  // same address for the whole warp
+        rd[q] = 1.0 / ud[q];
+    }
+}
+
+template <int RMAX, int R0>
+__device__ __forceinline__ void gs_bwd_block(const double* __restrict__ Mg, int n, int lane, double (&x)[RMAX]) {
+    constexpr int NS = R0 + 1;                  // slots 0 .. R0 hold the rows above the pivots of this block
+    constexpr int CB = (NS >= 5) ? 4 : 8;
+    const int kbeg = 32 * R0;
+    if (kbeg < n) {
+        const int ktop = (kbeg + 31 < n - 1) ? kbeg + 31 : n - 1;
+        double cur[CB][NS], nxt[CB][NS], udc[CB], rdc[CB], udn[CB], rdn[CB];
+        gs_load_bwd<NS, CB>(Mg, n, ktop, kbeg, lane, cur, udc, rdc);
+        for (int k0 = ktop; k0 >= kbeg; k0 -= CB) {
+            gs_load_bwd<NS, CB>(Mg, n, k0 - CB, kbeg, lane, nxt, udn, rdn);
+#pragma unroll
+            for (int q = 0; q < CB; ++q) {
+                const int k = k0 - q;
+                if (k >= kbeg) {  // warp-uniform
+                    const int kk = k & 31;
+                    double xv = x[R0];
+                    if (lane == kk) xv = div_by_recip(xv, udc[q], rdc[q]);
+                    const double bk = __shfl_sync(0xffffffffu, xv, kk);
+                    const double t0 = x[R0] - cur[q][R0] * bk;
+                    x[R0] = (lane == kk) ? bk : ((lane < kk) ? t0 : x[R0]);
+#pragma unroll
+                    for (int r = 0; r < R0; ++r) x[r] -= cur[q][r] * bk;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < CB; ++q) {
+#pragma unroll
+                for (int r = 0; r < NS; ++r) cur[q][r] = nxt[q][r];
+                udc[q] = udn[q];
+                rdc[q] = rdn[q];
+            }
+        }
+    }
+    if constexpr (R0 > 0) gs_bwd_block<RMAX, R0 - 1>(Mg, n, lane, x);
+}
+
+constexpr int GS_WARPS = 4;  // warps (= systems in flight) per CTA
+template <int RMAX>
+__global__ void __launch_bounds__(32 * GS_WARPS) getrs_stream(const double* __restrict__ A, const int64_t* __restrict__ piv,
+                                                               double* __restrict__ bx, int n, int64_t B) {
+    extern __shared__ __align__(16) unsigned char lu_smem[];
+    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    double* xs = reinterpret_cast<double*>(lu_smem) + (size_t)wi * n;
+    int* ps = reinterpret_cast<int*>(lu_smem + (size_t)GS_WARPS * n * sizeof(double)) + (size_t)wi * n;
+    for (int64_t b = (int64_t)blockIdx.x * GS_WARPS + wi; b < B; b += (int64_t)gridDim.x * GS_WARPS) {
+        const double* Mg = A + (size_t)b * n * n;
+        for (int i = lane; i < n; i += 32) {
+            xs[i] = bx[(size_t)b * n + i];
+            ps[i] = (int)piv[(size_t)b * n + i];
+        }
+        __syncwarp();
+        if (lane == 0) {  // the row interchanges, in order (dense.rs:176-181)
+            for (int k = 0; k < n; ++k) {
+                const int pk = ps[k];
+                if (pk != k) {
+                    const double t = xs[k];
+                    xs[k] = xs[pk];
+                    xs[pk] = t;
+                }
+            }
+        }
+        __syncwarp();
+        double x[RMAX];
+#pragma unroll
+        for (int r = 0; r < RMAX; ++r) {
+            const int i = lane + 32 * r;
+            x[r] = (i < n) ? xs[i] : 0.0;
+        }
+        gs_fwd_block<RMAX, 0>(Mg, n, lane, x);
+        gs_bwd_block<RMAX, RMAX - 1>(Mg, n, lane, x);
+#pragma unroll
+        for (int r = 0; r < RMAX; ++r) {
+            const int i = lane + 32 * r;
+            if (i < n) bx[(size_t)b * n + i] = x[r];
+        }
+        __syncwarp();
+    }
+}
+
+template <int RMAX>
+static int launch_getrs_stream(const double* A, const int64_t* piv, double* bx, int n, int64_t B, cudaStream_t st) {
+    const size_t smem = (size_t)GS_WARPS * n * (sizeof(double) + sizeof(int));
+    const int64_t want = (B + GS_WARPS - 1) / GS_WARPS, cap = (int64_t)sm_count() * 8;
+    getrs_stream<RMAX><<<(unsigned)(want < cap ? want : cap), 32 * GS_WARPS, smem, st>>>(A, piv, bx, n, B);
+    B200_CUDA_TRY(cudaGetLastError());
+    return B200IDA_OK;
+}
+
 template <bool FACTOR>
 static int launch_group(double* A, int64_t* piv, int32_t* info, double* bx, int n, int64_t B, bool soa, cudaStream_t st) {
     const unsigned gb = (unsigned)lu_group_smem_bytes(n);
@@ -603,6 +767,11 @@ static int getrs_dev(const double* LU, const int64_t* piv, double* bx, int n, in
         }
         B200_CUDA_TRY(cudaGetLastError());
         return B200IDA_OK;
+    }
+    if (!soa && n > 32) {
+        if (n <= 64) return launch_getrs_stream<2>(LU, piv, bx, n, B, st);
+        if (n <= 128) return launch_getrs_stream<4>(LU, piv, bx, n, B, st);
+        return launch_getrs_stream<8>(LU, piv, bx, n, B, st);
     }
     return launch_group<false>(const_cast<double*>(LU), const_cast<int64_t*>(piv), nullptr, bx, n, B, soa, st);
 }

@@ -284,7 +284,7 @@ __device__ __forceinline__ void lub_panel_any(double* M, int ld, int n, int kb, 
 
 // ---- [S] row moves for the columns outside the panel + the U rows of the columns right of it --------------------------
 // zcol[j] (right columns): 0 = no zero among the nbd U values of column j, 2 = all zero, 1 = mixed
-__device__ __noinline__ void lub_swap_solve(double* M, int ld, int n, int kb, int nbp, int nbd, const LubCtl* ctl,
+static __device__ __noinline__ void lub_swap_solve(double* M, int ld, int n, int kb, int nbp, int nbd, const LubCtl* ctl,
                                             double* Ub, unsigned char* zcol, int ldu, int tid, int nt) {
     // loads unconditional (unused move slots point at a valid row), stores predicated: see lub_panel
     const int nm = ctl->nmoves;

@@ -292,4 +292,95 @@ __device__ __forceinline__ void lu_solve(const double* M, int ld, int n, const P
     G::sync();
 }
 
+// ---- blocked triangular solves for a whole CTA (n > 32) -----------------------------------------------------------------
+// The 2n-step substitution chain is split into 32 x 32 diagonal blocks (one warp, right-hand side in registers, one
+// shuffle + mul + sub per step) and the off-diagonal panels below / above them, which are independent per row: row i
+// subtracts l_ik x_k for the 32 pivots of the block in the reference's order (ascending k in the forward sweep,
+// descending in the backward sweep), a chain of subtractions with no shuffles, and the rows are spread over all
+// warps.  Per element the operations and their order are those of dense_get_rs (dense.rs:165-206), so the result is
+// bit-identical to the single-warp chain; the critical path drops from 2n full-height steps to 2n single-slot steps.
+// perm (optional): perm[i] = source row of row i after the row interchanges (built once per factorisation by
+// lu_build_perm), so that the interchanges are one parallel gather instead of a serial loop per solve.
+template <class PivT>
+__device__ __forceinline__ void lu_build_perm(int n, const PivT* piv, int* perm) {  // one thread
+    for (int i = 0; i < n; ++i) perm[i] = i;
+    for (int k = 0; k < n; ++k) {
+        const int pk = (int)piv[k];
+        if (pk != k) {
+            const int t = perm[k];
+            perm[k] = perm[pk];
+            perm[pk] = t;
+        }
+    }
+}
+
+__device__ __forceinline__ void lu_solve_cta_blocked(const double* M, int ld, int n, const int* perm, double* b, double* tmp,
+                                                     const double* rdiag) {
+    const int tid = threadIdx.x, nt = blockDim.x, w = tid >> 5, nw = nt >> 5, lane = tid & 31;
+    const int nblk = (n + 31) >> 5;
+    // row interchanges: b := P b
+    for (int i = tid; i < n; i += nt) tmp[i] = b[perm[i]];
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) b[i] = tmp[i];
+    __syncthreads();
+    // forward sweep, unit lower triangle
+    for (int R0 = 0; R0 < nblk; ++R0) {
+        const int k0 = 32 * R0;
+        const int kend = (k0 + 32 < n) ? k0 + 32 : n;
+        if (w == 0) {
+            const int i = k0 + lane;
+            const int ic = i < n ? i : n - 1;
+            double x = b[ic];
+#pragma unroll 4
+            for (int k = k0; k < kend - 1; ++k) {
+                const double c = M[(size_t)k * ld + ic];
+                const double bk = __shfl_sync(0xffffffffu, x, k - k0);
+                const double t = x - c * bk;
+                x = (i > k) ? t : x;
+            }
+            if (i < n) b[i] = x;
+        }
+        __syncthreads();
+        // rows below the block: i = 32 (R0 + 1) + ..; each warp takes whole 32-row slots
+        for (int r = R0 + 1 + w; r < nblk; r += nw) {
+            const int i = 32 * r + lane;
+            const int ic = i < n ? i : n - 1;
+            double acc = b[ic];
+#pragma unroll 8
+            for (int k = k0; k < kend; ++k) acc -= M[(size_t)k * ld + ic] * b[k];
+            if (i < n) b[i] = acc;
+        }
+        __syncthreads();
+    }
+    // backward sweep, upper triangle with the divisions by u_kk
+    for (int R0 = nblk - 1; R0 >= 0; --R0) {
+        const int k0 = 32 * R0;
+        const int ktop = (k0 + 31 < n - 1) ? k0 + 31 : n - 1;
+        if (w == 0) {
+            const int i = k0 + lane;
+            const int ic = i < n ? i : n - 1;
+            double x = b[ic];
+#pragma unroll 4
+            for (int k = ktop; k >= k0; --k) {
+                const double c = M[(size_t)k * ld + ic];  // lane == k - k0 reads u_kk
+                double xv = x;
+                if (i == k) xv = rdiag ? div_by_recip(x, c, rdiag[k]) : x / c;
+                const double bk = __shfl_sync(0xffffffffu, xv, k - k0);
+                const double t = x - c * bk;
+                x = (i == k) ? bk : ((i < k) ? t : x);
+            }
+            if (i < n) b[i] = x;
+        }
+        __syncthreads();
+        for (int r = w; r < R0; r += nw) {
+            const int i = 32 * r + lane;  // always < n
+            double acc = b[i];
+#pragma unroll 8
+            for (int k = ktop; k >= k0; --k) acc -= M[(size_t)k * ld + i] * b[k];
+            b[i] = acc;
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace b200ida
