@@ -41,6 +41,9 @@ SEED = 1234
 # FP64 arithmetic per step attempt of the reference algorithm at n = 3 (each add, mul, div, sqrt, pow counted
 # as ONE op): 98,244 ops / 377 attempts for the default Roberts instance (SURVEY.md 6 / BASELINE.md 2).
 OPS_PER_ATTEMPT = 98244.0 / 377.0
+# algorithmic HBM bytes per instance and launch: the SoA state (10n + 45 + n^2 doubles + 16 + n int32, n = 3) is read
+# once and written once
+ALG_BYTES_PER_INSTANCE = 2 * ((10 * 3 + 45 + 9) * 8 + (16 + 3) * 4)
 
 
 def parse():
@@ -284,6 +287,10 @@ def run_ours(args, rank, world, local_rank):
                          "rust-ida (oracle/), one instance per thread" % (sample, dt)}
 
     total = world * B * args.steps
+    try:
+        hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        hbm_peak = 6650.0  # fallback stated in /opt/skills/guides/B200_PROFILING.md
     line = {
         "metric": "ensemble DAE solves/sec (Roberts, t=4e10)",
         "value": total / (ms * 1e-3), "unit": "instances/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -299,7 +306,15 @@ def run_ours(args, rank, world, local_rank):
                 "d2h_bytes_per_step": d2h, "results_match_device_run": e2e_ok},
         "gpu_launches": args.steps * 3,  # per step: ida_init_kernel, ida_solve_thread_kernel, widen_i32_kernel
         "roofline": {"bound": "fp64", "achieved": achieved_gops, "peak": peak_gops, "unit": "GFLOP/s (un-fused FP64 ops)",
-                     "frac": achieved_gops / peak_gops, "traffic": None,
+                     "frac": achieved_gops / peak_gops,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch at batch 2^20 (ncu --set full,
+                     # profiles/r1e_ida_solve_thread_final_ncu_summary.csv), scaled to this batch
+                     "traffic": int(2181624000 * (B / float(1 << 20))),
+                     "hbm_view": {"algorithmic_bytes_per_launch": B * ALG_BYTES_PER_INSTANCE,
+                                  "achieved_gbs": B * ALG_BYTES_PER_INSTANCE / (kernel_ms * 1e-3) * 1e-9, "peak_gbs": hbm_peak,
+                                  "frac": B * ALG_BYTES_PER_INSTANCE / (kernel_ms * 1e-3) * 1e-9 / hbm_peak,
+                                  "note": "state read once + written once per launch; three orders of magnitude below the "
+                                          "FP64 bound, which is why the roofline above is the FP64 issue rate"},
                      "kernel": "ida_solve_thread_kernel<Roberts>", "kernel_ms": kernel_ms,
                      "ops_per_launch": tot_attempts * OPS_PER_ATTEMPT, "attempts_per_launch": tot_attempts,
                      "peak_source": "measured on this GPU by b200ida_fp64_issue_rate (MEASURED_PEAKS.json has no FP64 entry): "

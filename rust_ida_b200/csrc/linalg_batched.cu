@@ -656,6 +656,44 @@ static int launch_getrs_stream(const double* A, const int64_t* piv, double* bx, 
     return B200IDA_OK;
 }
 
+// ---- CTA-per-system blocked LU for matrices too big for shared memory (161 <= n <= 256): matrix in place in global
+// memory / L2, panels double-buffered in shared memory (lub_factor_global), AoS only ------------------------------------
+__host__ __device__ inline size_t lubg_smem_bytes(int n) {
+    size_t b = (size_t)2 * LUB_NB * (n | 1) * sizeof(double);
+    b = (b + 15) / 16 * 16 + (lub_ub_bytes(n) + 15) / 16 * 16 + ((size_t)n * sizeof(int) + 15) / 16 * 16 + sizeof(LubCtl);
+    return (b + 15) / 16 * 16;
+}
+__global__ void __launch_bounds__(256, 2)
+    getrf_blocked_global(double* __restrict__ A, int64_t* __restrict__ piv, int32_t* __restrict__ info, int n, int64_t B) {
+    extern __shared__ __align__(16) unsigned char lu_smem[];
+    const int ldp = n | 1;
+    double* Pb0 = reinterpret_cast<double*>(lu_smem);
+    double* Pb1 = Pb0 + (size_t)LUB_NB * ldp;
+    size_t off = ((size_t)2 * LUB_NB * ldp * sizeof(double) + 15) / 16 * 16;
+    double* Ub = reinterpret_cast<double*>(lu_smem + off);
+    off += (lub_ub_bytes(n) + 15) / 16 * 16;
+    int* pivs = reinterpret_cast<int*>(lu_smem + off);
+    off += ((size_t)n * sizeof(int) + 15) / 16 * 16;
+    LubCtl* ctl = reinterpret_cast<LubCtl*>(lu_smem + off);
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+        lub_factor_global<8>(A + (size_t)b * n * n, n, ctl, pivs, Ub, Pb0, Pb1);
+        const int inf = ctl->info;
+        for (int k = tid; k < n; k += nt) piv[(size_t)b * n + k] = (inf == 0 || k < inf) ? pivs[k] : 0;
+        if (tid == 0) info[b] = inf;
+        __syncthreads();
+    }
+}
+static int launch_getrf_blocked_global(double* A, int64_t* piv, int32_t* info, int n, int64_t B, cudaStream_t st) {
+    const size_t smem = lubg_smem_bytes(n);
+    unsigned grid = 1;
+    int rc;
+    if ((rc = launch_cfg(getrf_blocked_global, 256, smem, B, 1, &grid))) return rc;
+    getrf_blocked_global<<<grid, 256, smem, st>>>(A, piv, info, n, B);
+    B200_CUDA_TRY(cudaGetLastError());
+    return B200IDA_OK;
+}
+
 template <bool FACTOR>
 static int launch_group(double* A, int64_t* piv, int32_t* info, double* bx, int n, int64_t B, bool soa, cudaStream_t st) {
     const unsigned gb = (unsigned)lu_group_smem_bytes(n);
@@ -695,6 +733,7 @@ static int launch_group(double* A, int64_t* piv, int32_t* info, double* bx, int 
         // too big for shared memory: factor / solve in place in global memory (L2-resident), AoS only
         const size_t smem = (size_t)n * sizeof(double) + ((size_t)n * sizeof(int) + 15) / 16 * 16 + sizeof(LuShared) + 16;
         if (!soa) {
+            if (FACTOR) return launch_getrf_blocked_global(A, piv, info, n, B, st);
             LAUNCH(false, false, false, CTA_THREADS, smem, 1);
         } else {
             DevBuf tmp, ptmp, xtmp;
@@ -708,7 +747,7 @@ static int launch_group(double* A, int64_t* piv, int32_t* info, double* bx, int 
             A = tmp.as<double>();
             if (FACTOR) {
                 piv = ptmp.as<int64_t>();
-                LAUNCH(false, false, false, CTA_THREADS, smem, 1);
+                if ((rc = launch_getrf_blocked_global(A, piv, info, n, B, st))) return rc;
                 mat_aos_to_soa<<<tg, 256, 0, st>>>(tmp.as<double>(), A0, n, B);
                 vec_aos_to_soa<<<vg, 256, 0, st>>>(reinterpret_cast<const double*>(ptmp.as<int64_t>()), reinterpret_cast<double*>(piv0), n, B);
             } else {

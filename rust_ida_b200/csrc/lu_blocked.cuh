@@ -275,7 +275,9 @@ __device__ __noinline__ void lub_panel(double* M, int ld, int n, int kb, int nb,
 template <int RP>
 __device__ __forceinline__ void lub_panel_any(double* M, int ld, int n, int kb, int nb, LubCtl* ctl, int* pivs) {
     const int nr = (n - kb + 31) >> 5;
-    if (RP >= 5 && nr >= 5) lub_panel<5>(M, ld, n, kb, nb, ctl, pivs);
+    if (RP >= 8 && nr >= 7) lub_panel<8>(M, ld, n, kb, nb, ctl, pivs);
+    else if (RP >= 6 && nr == 6) lub_panel<6>(M, ld, n, kb, nb, ctl, pivs);
+    else if (RP >= 5 && nr >= 5) lub_panel<5>(M, ld, n, kb, nb, ctl, pivs);
     else if (RP >= 4 && nr == 4) lub_panel<4>(M, ld, n, kb, nb, ctl, pivs);
     else if (RP >= 3 && nr == 3) lub_panel<3>(M, ld, n, kb, nb, ctl, pivs);
     else if (RP >= 2 && nr == 2) lub_panel<2>(M, ld, n, kb, nb, ctl, pivs);
@@ -284,8 +286,11 @@ __device__ __forceinline__ void lub_panel_any(double* M, int ld, int n, int kb, 
 
 // ---- [S] row moves for the columns outside the panel + the U rows of the columns right of it --------------------------
 // zcol[j] (right columns): 0 = no zero among the nbd U values of column j, 2 = all zero, 1 = mixed
+// (Lp, ldl): the current panel's columns -- column c at Lp + c * ldl, rows by absolute index.  For the matrix resident in
+// shared memory that is M + kb * ld; for the global-memory variant the panel sits in its own shared-memory buffer.
 static __device__ __noinline__ void lub_swap_solve(double* M, int ld, int n, int kb, int nbp, int nbd, const LubCtl* ctl,
-                                            double* Ub, unsigned char* zcol, int ldu, int tid, int nt) {
+                                            const double* Lp, int ldl, double* Ub, unsigned char* zcol, int ldu, int tid,
+                                            int nt) {
     // loads unconditional (unused move slots point at a valid row), stores predicated: see lub_panel
     const int nm = ctl->nmoves;
     int src[LUB_MAXMOVES], dst[LUB_MAXMOVES];
@@ -315,7 +320,7 @@ static __device__ __noinline__ void lub_swap_solve(double* M, int ld, int n, int
                 const double uc = u[c];
                 const bool on = c < nbd && uc != 0.0;
                 nz += on ? 1 : 0;
-                const double* lc = M + (kb + c) * ld + kb;
+                const double* lc = Lp + c * ldl + kb;
 #pragma unroll
                 for (int i = c + 1; i < LUB_NB; ++i) {
                     const double t = u[i] - uc * lc[i];
@@ -379,8 +384,8 @@ __device__ __forceinline__ void lub_tile(double* M, int ld, int n, int K, int i0
 // rows >= kb + K, columns [c0, c1); warp w of nw takes a contiguous chunk of (row block, column tile) items.
 // RB = rows per block: 64 (two register rows per lane) for the bulk, 32 to spread a narrow strip over more warps.
 template <int RB>
-__device__ __noinline__ void lub_update(double* M, int ld, int n, int kb, int K, int c0, int c1, const double* Ub,
-                                        const unsigned char* zcol, int ldu, int w, int nw, int lane) {
+__device__ __noinline__ void lub_update(double* M, int ld, int n, int kb, int K, int c0, int c1, const double* Lp, int ldl,
+                                        const double* Ub, const unsigned char* zcol, int ldu, int w, int nw, int lane) {
     const int r0 = kb + K;
     const int nrows = n - r0, ncols = c1 - c0;
     if (nrows <= 0 || ncols <= 0 || K <= 0) return;
@@ -404,7 +409,7 @@ __device__ __noinline__ void lub_update(double* M, int ld, int n, int kb, int K,
 #pragma unroll
                 for (int k = 0; k < LUB_NB; ++k) {
                     const int kc = (k < K) ? k : 0;
-                    const double* ckc = M + (kb + kc) * ld;
+                    const double* ckc = Lp + kc * ldl;
                     l0[k] = ckc[i0 < n ? i0 : n - 1];
                     if (RB == 64) l1[k] = ckc[i0 + 32 < n ? i0 + 32 : n - 1];
                 }
@@ -456,7 +461,7 @@ __device__ __forceinline__ void lub_factor(double* M, int ld, int n, LubCtl* ctl
         const int nbd = ctl->ndone;
         const int info = ctl->info;
         LUB_T(ta);
-        lub_swap_solve(M, ld, n, kb, nb, nbd, ctl, Ub, zcol, ldu, tid, nt);
+        lub_swap_solve(M, ld, n, kb, nb, nbd, ctl, M + kb * ld, ld, Ub, zcol, ldu, tid, nt);
         LUB_T(tb);
         __syncthreads();
         LUB_T(tc);
@@ -464,7 +469,7 @@ __device__ __forceinline__ void lub_factor(double* M, int ld, int n, LubCtl* ctl
         const int nb2 = (n - c0 < LUB_NB) ? n - c0 : LUB_NB;     // width of the next panel (<= 0: none)
         if (nb2 > 0) {
             // the strip that becomes the next panel first, spread over all warps in 32-row blocks
-            lub_update<32>(M, ld, n, kb, nbd, c0, c0 + nb2, Ub, zcol, ldu, w, nw, lane);
+            lub_update<32>(M, ld, n, kb, nbd, c0, c0 + nb2, M + kb * ld, ld, Ub, zcol, ldu, w, nw, lane);
             LUB_T(td);
             __syncthreads();
             LUB_T(te);
@@ -473,9 +478,9 @@ __device__ __forceinline__ void lub_factor(double* M, int ld, int n, LubCtl* ctl
             if (w == 0) {
                 if (info == 0) lub_panel_any<RP>(M, ld, n, c0, nb2, ctl, pivs);
             } else if (nw <= 4) {
-                lub_update<64>(M, ld, n, kb, nbd, c0 + nb2, n, Ub, zcol, ldu, w - 1, nw - 1, lane);
+                lub_update<64>(M, ld, n, kb, nbd, c0 + nb2, n, M + kb * ld, ld, Ub, zcol, ldu, w - 1, nw - 1, lane);
             } else if ((w & 3) != 0) {
-                lub_update<64>(M, ld, n, kb, nbd, c0 + nb2, n, Ub, zcol, ldu, w - 1 - (w >> 2), nw - (nw >> 2), lane);
+                lub_update<64>(M, ld, n, kb, nbd, c0 + nb2, n, M + kb * ld, ld, Ub, zcol, ldu, w - 1 - (w >> 2), nw - (nw >> 2), lane);
             }
             LUB_T(tf);
             LUB_ACC(3, tc, td);
@@ -490,6 +495,66 @@ __device__ __forceinline__ void lub_factor(double* M, int ld, int n, LubCtl* ctl
         LUB_ACC(1, ta, tb);
         LUB_ACC(2, tb, tc);
         if (info != 0) break;  // uniform: read before warp 0 could overwrite it
+    }
+}
+
+// ---- the same factorisation for a matrix that does not fit in shared memory (161 <= n <= 256) -----------------------------
+// The matrix stays in global memory (column-major, ld = n: it lives in L2 while its CTA works on it); only the panels
+// go through shared memory.  Two panel buffers of LUB_NB full-height columns: Pb[cur] holds the factored panel of the
+// current block step -- the multipliers and L11 the [S] and [U] phases read come from there, not from global -- while
+// warp 0 eliminates the next panel in Pb[nxt].  A factored panel is written back to global right after the barrier that
+// ends its elimination (later panels apply their row moves to it there).  Trailing tiles are read and written once per
+// block step, i.e. the L2 traffic of the update is 1/LUB_NB of the unblocked kernel's.
+__device__ __forceinline__ void lub_panel_copy(double* dst, int ldd, const double* src, int lds, int r0, int n, int ncols,
+                                               int w, int nw, int lane) {
+    for (int c = w; c < ncols; c += nw)
+        for (int i = r0 + lane; i < n; i += 32) dst[c * ldd + i] = src[c * lds + i];
+}
+
+template <int RP>
+__device__ __forceinline__ void lub_factor_global(double* Mg, int n, LubCtl* ctl, int* pivs, double* Ub, double* Pb0,
+                                                  double* Pb1) {
+    const int tid = threadIdx.x, nt = blockDim.x, w = tid >> 5, nw = nt >> 5, lane = tid & 31;
+    const int ld = n, ldp = n | 1, ldu = lub_ldu(n);
+    unsigned char* zcol = reinterpret_cast<unsigned char*>(Ub + LUB_NB * ldu);
+    double* Pcur = Pb0;
+    double* Pnxt = Pb1;
+    if (tid == 0) ctl->info = 0;
+    for (int j = n + tid; j < ldu; j += nt) zcol[j] = 0;
+    const int nb0 = n < LUB_NB ? n : LUB_NB;
+    lub_panel_copy(Pcur, ldp, Mg, ld, 0, n, nb0, w, nw, lane);
+    __syncthreads();
+    if (w == 0) lub_panel_any<RP>(Pcur, ldp, n, 0, nb0, ctl, pivs);  // panel 0: column c of the panel is column c
+    __syncthreads();
+    lub_panel_copy(Mg, ld, Pcur, ldp, 0, n, nb0, w, nw, lane);
+    for (int kb = 0; kb < n; kb += LUB_NB) {
+        const int nb = (n - kb < LUB_NB) ? n - kb : LUB_NB;
+        const int nbd = ctl->ndone;
+        const int info = ctl->info;
+        lub_swap_solve(Mg, ld, n, kb, nb, nbd, ctl, Pcur, ldp, Ub, zcol, ldu, tid, nt);
+        __syncthreads();
+        const int c0 = kb + nb;
+        const int nb2 = (n - c0 < LUB_NB) ? n - c0 : LUB_NB;
+        if (nb2 > 0) {
+            lub_update<32>(Mg, ld, n, kb, nbd, c0, c0 + nb2, Pcur, ldp, Ub, zcol, ldu, w, nw, lane);
+            __syncthreads();
+            lub_panel_copy(Pnxt, ldp, Mg + (size_t)c0 * ld, ld, c0, n, nb2, w, nw, lane);  // rows >= c0 of the strip
+            __syncthreads();
+            if (w == 0) {
+                // lub_panel addresses column kb' + c at M + (kb' + c) * ld: shift the base so that it lands in the buffer
+                if (info == 0) lub_panel_any<RP>(Pnxt - (size_t)c0 * ldp, ldp, n, c0, nb2, ctl, pivs);
+            } else if ((w & 3) != 0 || nw <= 4) {
+                const int uw = nw <= 4 ? w - 1 : w - 1 - (w >> 2), unw = nw <= 4 ? nw - 1 : nw - (nw >> 2);
+                lub_update<64>(Mg, ld, n, kb, nbd, c0 + nb2, n, Pcur, ldp, Ub, zcol, ldu, uw, unw, lane);
+            }
+            __syncthreads();
+            if (info == 0) lub_panel_copy(Mg + (size_t)c0 * ld, ld, Pnxt, ldp, c0, n, nb2, w, nw, lane);
+            double* t = Pcur;
+            Pcur = Pnxt;
+            Pnxt = t;
+        }
+        __syncthreads();
+        if (info != 0) break;
     }
 }
 
