@@ -15,6 +15,7 @@
 //                     [n][n][batch] loads/stores -> HBM-bound (16 n^2 + 8n B/system for getrf).
 //   *_cta             any n <= 256, either layout: one CTA per system; the matrix is staged in shared
 //                     memory when it fits (n <= 160), else factored in place in global memory / L2.
+#include <cstdlib>
 #include "host_util.h"
 #include "ida_common.cuh"
 #include "lu_team.cuh"
@@ -663,7 +664,8 @@ __host__ __device__ inline size_t lubg_smem_bytes(int n) {
     b = (b + 15) / 16 * 16 + (lub_ub_bytes(n) + 15) / 16 * 16 + ((size_t)n * sizeof(int) + 15) / 16 * 16 + sizeof(LubCtl);
     return (b + 15) / 16 * 16;
 }
-__global__ void __launch_bounds__(256, 2)
+template <int NT>
+__global__ void __launch_bounds__(NT, NT <= 128 ? 4 : (NT <= 256 ? 2 : 1))
     getrf_blocked_global(double* __restrict__ A, int64_t* __restrict__ piv, int32_t* __restrict__ info, int n, int64_t B) {
     extern __shared__ __align__(16) unsigned char lu_smem[];
     const int ldp = n | 1;
@@ -688,8 +690,26 @@ static int launch_getrf_blocked_global(double* A, int64_t* piv, int32_t* info, i
     const size_t smem = lubg_smem_bytes(n);
     unsigned grid = 1;
     int rc;
-    if ((rc = launch_cfg(getrf_blocked_global, 256, smem, B, 1, &grid))) return rc;
-    getrf_blocked_global<<<grid, 256, smem, st>>>(A, piv, info, n, B);
+    // few, large systems (one per SM): the trailing update, not the pivot chain, is the long pole -> 16 warps
+    const char* force = getenv("B200IDA_LUBG_THREADS");  // kernel experiments only
+    if (force && atoi(force) == 128) {
+        if ((rc = launch_cfg(getrf_blocked_global<128>, 128, smem, B, 1, &grid))) return rc;
+        getrf_blocked_global<128><<<grid, 128, smem, st>>>(A, piv, info, n, B);
+    } else if (force && atoi(force) == 256) {
+        if ((rc = launch_cfg(getrf_blocked_global<256>, 256, smem, B, 1, &grid))) return rc;
+        getrf_blocked_global<256><<<grid, 256, smem, st>>>(A, piv, info, n, B);
+    } else if (n <= SMEM_MAX_N) {
+        // 115..160: the shared-memory-resident kernel fits one CTA per SM only; four small CTAs per SM on L2-resident
+        // matrices keep four pivot chains in flight instead (measured: n = 128 0.47 -> 0.37 ms)
+        if ((rc = launch_cfg(getrf_blocked_global<128>, 128, smem, B, 1, &grid))) return rc;
+        getrf_blocked_global<128><<<grid, 128, smem, st>>>(A, piv, info, n, B);
+    } else if (B <= (int64_t)sm_count() && n >= 224) {
+        if ((rc = launch_cfg(getrf_blocked_global<512>, 512, smem, B, 1, &grid))) return rc;
+        getrf_blocked_global<512><<<grid, 512, smem, st>>>(A, piv, info, n, B);
+    } else {
+        if ((rc = launch_cfg(getrf_blocked_global<256>, 256, smem, B, 1, &grid))) return rc;
+        getrf_blocked_global<256><<<grid, 256, smem, st>>>(A, piv, info, n, B);
+    }
     B200_CUDA_TRY(cudaGetLastError());
     return B200IDA_OK;
 }
@@ -786,6 +806,7 @@ static int getrf_dev(double* A, int64_t* piv, int32_t* info, int n, int64_t B, i
         B200_CUDA_TRY(cudaGetLastError());
         return B200IDA_OK;
     }
+    if (!soa && n > 32 && (n >= 115 || getenv("B200IDA_LUBG_THREADS"))) return launch_getrf_blocked_global(A, piv, info, n, B, st);
     if (n > 32 && n <= SMEM_MAX_N)
         return soa ? launch_getrf_blocked_n<true>(A, piv, info, n, B, st) : launch_getrf_blocked_n<false>(A, piv, info, n, B, st);
     return launch_group<true>(A, piv, info, nullptr, n, B, soa, st);
