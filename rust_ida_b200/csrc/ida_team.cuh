@@ -469,7 +469,8 @@ struct IdaTeam {
                             decided = true;
                         }
                     } else {
-                        const double rate = detpow::det_pow(delnrm / s.oldnrm, 1.0 / (double)s.curiter);
+                        const double base = delnrm / s.oldnrm;  // pow(x, 1.0) == x bit-for-bit (tests/test_detpow.py)
+                        const double rate = (s.curiter == 1) ? base : detpow::det_pow(base, 1.0 / (double)s.curiter);
                         if (rate > RATEMAX) {
                             c = -1;
                             decided = true;

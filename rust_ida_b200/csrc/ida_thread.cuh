@@ -430,7 +430,10 @@ struct IdaThread {
         } else {
             const double base = ddiv(delnrm, oldnrm);
             const double arg = 1.0 / (double)m;
-            const double rate = pow_noinline(base, arg);
+            // m == 1 (the second Newton iteration, by far the most frequent case): pow(x, 1.0) returns x bit-for-bit
+            // in the reference's libm (tests/test_detpow.py::test_pow_with_exponent_one_is_the_identity), so the
+            // ~60-instruction pow is skipped for the lanes that do not need it
+            const double rate = (m == 1) ? base : pow_noinline(base, arg);
             if (rate > RATEMAX) return -1;
             ss = ddiv(rate, 1.0 - rate);
         }

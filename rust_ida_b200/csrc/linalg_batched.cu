@@ -753,8 +753,8 @@ static int launch_group(double* A, int64_t* piv, int32_t* info, double* bx, int 
         // too big for shared memory: factor / solve in place in global memory (L2-resident), AoS only
         const size_t smem = (size_t)n * sizeof(double) + ((size_t)n * sizeof(int) + 15) / 16 * 16 + sizeof(LuShared) + 16;
         if (!soa) {
-            if (FACTOR) return launch_getrf_blocked_global(A, piv, info, n, B, st);
-            LAUNCH(false, false, false, CTA_THREADS, smem, 1);
+            if constexpr (FACTOR) return launch_getrf_blocked_global(A, piv, info, n, B, st);
+            else LAUNCH(false, false, false, CTA_THREADS, smem, 1);
         } else {
             DevBuf tmp, ptmp, xtmp;
             B200_CUDA_TRY(tmp.alloc((size_t)n * n * B * sizeof(double)));

