@@ -714,6 +714,241 @@ static int launch_getrf_blocked_global(double* A, int64_t* piv, int32_t* info, i
     return B200IDA_OK;
 }
 
+// ---- warp-per-system getrs with TMA-staged shared-memory panels (AoS, even n > 32, 16-byte aligned batch) -----------------
+// Each warp streams its matrix through a private ring of GT_STAGES shared-memory panels of GT_CB columns filled by
+// BULK asynchronous copies (cp.async.bulk, the TMA unit): one instruction per panel column, issued by the first
+// GT_CB lanes in parallel, completion counted in bytes on a per-stage mbarrier the whole warp then waits on.  The
+// copies run GT_STAGES-1 panels ahead of the substitution chain and fetch only the part of each column the sweep
+// needs (rows >= k0 in the forward sweep, rows <= k in the backward sweep), i.e. ~n^2 + 8n doubles per system.
+// Why TMA and not per-element copies: with a handful of warps per SM the kernel is bound by the number of
+// instructions it issues per byte; the same ring filled by 8-byte LDGSTS copies was 1.7-2x slower than no ring at all
+// (DESIGN.md section 5.3).  Even n keeps every column segment 16-byte aligned; other shapes take getrs_stream.
+constexpr int GT_CB = 8;
+constexpr int GT_STAGES = 4;
+constexpr int GT_WARPS = 2;
+
+__device__ __forceinline__ void gt_mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void gt_mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void gt_mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "GT_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra GT_DONE;\n"
+        "bra GT_WAIT;\n"
+        "GT_DONE:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void gt_bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+struct GtPlan {  // chunk schedule of one system: forward chunks 0..nf-1, then the backward chunks
+    int n, nf, ntop, nc, rbb;
+    __device__ __forceinline__ explicit GtPlan(int n_) : n(n_) {
+        nf = (n - 1 + GT_CB - 1) / GT_CB;                    // forward: columns 0 .. n-2
+        rbb = (n + 31) >> 5;                                 // 32-column blocks
+        ntop = (n - 32 * (rbb - 1) + GT_CB - 1) / GT_CB;      // backward chunks of the (ragged) top block
+        nc = nf + ntop + (rbb - 1) * (32 / GT_CB);
+    }
+    __device__ __forceinline__ void bwd(int jb, int& k0, int& klo) const {  // first (highest) column, block start
+        int R0, m;
+        if (jb < ntop) {
+            R0 = rbb - 1;
+            m = jb;
+        } else {
+            R0 = rbb - 2 - (jb - ntop) / (32 / GT_CB);
+            m = (jb - ntop) % (32 / GT_CB);
+        }
+        klo = 32 * R0;
+        const int ktop = (klo + 31 < n - 1) ? klo + 31 : n - 1;
+        k0 = ktop - GT_CB * m;
+    }
+};
+
+// issue chunk j into ring stage j % GT_STAGES: the chunk's columns are contiguous in the column-major matrix, so one
+// elected lane arms the stage's barrier and issues ONE bulk copy of whole columns (the kernel is bound by instructions
+// issued per system, not by bytes: fetching the half of each column the sweep does not use costs less than issuing
+// one trimmed copy per column -- cp.async.bulk is a uniform-datapath instruction, per-lane copies are serialised)
+__device__ __forceinline__ void gt_issue(const GtPlan& P, const double* __restrict__ Mg, unsigned ring, unsigned bars, int j,
+                                         int lane) {
+    if (j >= P.nc || lane != 0) return;
+    const int s = j % GT_STAGES, n = P.n;
+    const unsigned st = ring + (unsigned)(s * GT_CB * n) * 8u, bar = bars + 8u * (unsigned)s;
+    int kmin, ncols;
+    if (j < P.nf) {
+        kmin = j * GT_CB;
+        ncols = (n - 1 - kmin < GT_CB) ? n - 1 - kmin : GT_CB;
+    } else {
+        int k0, klo;
+        P.bwd(j - P.nf, k0, klo);
+        kmin = (k0 - (GT_CB - 1) > klo) ? k0 - (GT_CB - 1) : klo;
+        ncols = k0 - kmin + 1;
+    }
+    const unsigned bytes = (unsigned)(ncols * n) * 8u;
+    gt_mbar_expect_tx(bar, bytes);
+    gt_bulk_g2s(st, Mg + (size_t)kmin * n, bytes, bar);
+}
+
+template <int RMAX, int R0>
+__device__ __forceinline__ void gt_fwd_block(const GtPlan& P, const double* __restrict__ Mg, unsigned ring, unsigned bars,
+                                             const double* ringp, int lane, double (&x)[RMAX], unsigned& phases) {
+    constexpr int NS = RMAX - R0;  // slots R0 .. RMAX-1 hold the rows below the pivots of this block
+    const int n = P.n;
+    const int kend = (32 * R0 + 32 < n - 1) ? 32 * R0 + 32 : n - 1;
+    for (int k0 = 32 * R0; k0 < kend; k0 += GT_CB) {
+        const int j = k0 / GT_CB, s = j % GT_STAGES;
+        gt_issue(P, Mg, ring, bars, j + GT_STAGES - 1, lane);
+        gt_mbar_wait(bars + 8u * (unsigned)s, (phases >> s) & 1u);
+        phases ^= 1u << s;
+        const double* st = ringp + s * GT_CB * n;
+        const int qn = (kend - k0 < GT_CB) ? kend - k0 : GT_CB;
+#pragma unroll 4
+        for (int q = 0; q < qn; ++q) {
+            const int kk = (k0 + q) & 31;
+            double c[NS];
+#pragma unroll
+            for (int r = 0; r < NS; ++r) {
+                const int i = lane + 32 * (R0 + r);
+                c[r] = st[q * n + (i < n ? i : n - 1)];
+            }
+            const double bk = __shfl_sync(0xffffffffu, x[R0], kk);
+            const double t0 = x[R0] - c[0] * bk;
+            x[R0] = (lane > kk && lane + 32 * R0 < n) ? t0 : x[R0];
+#pragma unroll
+            for (int r = 1; r < NS; ++r) {
+                const double t = x[R0 + r] - c[r] * bk;
+                x[R0 + r] = (lane + 32 * (R0 + r) < n) ? t : x[R0 + r];
+            }
+        }
+        __syncwarp();
+    }
+    if constexpr (R0 + 1 < RMAX) {
+        if (32 * (R0 + 1) < n - 1) gt_fwd_block<RMAX, R0 + 1>(P, Mg, ring, bars, ringp, lane, x, phases);
+    }
+}
+
+template <int RMAX, int R0>
+__device__ __forceinline__ void gt_bwd_block(const GtPlan& P, const double* __restrict__ Mg, unsigned ring, unsigned bars,
+                                             const double* ringp, int lane, double (&x)[RMAX], unsigned& phases, int& j) {
+    constexpr int NS = R0 + 1;  // slots 0 .. R0 hold the rows above the pivots of this block
+    const int n = P.n;
+    const int klo = 32 * R0;
+    if (klo < n) {
+        const int ktop = (klo + 31 < n - 1) ? klo + 31 : n - 1;
+        for (int k0 = ktop; k0 >= klo; k0 -= GT_CB, ++j) {
+            const int s = j % GT_STAGES;
+            gt_issue(P, Mg, ring, bars, j + GT_STAGES - 1, lane);
+            gt_mbar_wait(bars + 8u * (unsigned)s, (phases >> s) & 1u);
+            phases ^= 1u << s;
+            const double* st = ringp + s * GT_CB * n;
+            const int qn = (k0 - klo + 1 < GT_CB) ? k0 - klo + 1 : GT_CB;
+            // the lane that owns pivot row k (lane == k & 31) fetches u_kk and its reciprocal for its column of the
+            // panel up front: one division per panel and lane, off the chain
+            const int myq = (k0 - lane) & 31;  // column k0 - myq has k & 31 == lane
+            double myud = 1.0;
+            if (myq < qn) myud = st[(qn - 1 - myq) * n + (k0 - myq)];  // columns ascend in the stage: k0 - q at slot qn-1-q
+            const double myrd = 1.0 / myud;
+#pragma unroll 4
+            for (int q = 0; q < qn; ++q) {
+                const int kk = (k0 - q) & 31;
+                double c[NS];
+#pragma unroll
+                for (int r = 0; r < NS; ++r) c[r] = st[(qn - 1 - q) * n + lane + 32 * r];  // r < R0: always < k; r == R0: used if < k
+                double xv = x[R0];
+                if (lane == kk) xv = div_by_recip(xv, myud, myrd);
+                const double bk = __shfl_sync(0xffffffffu, xv, kk);
+                const double t0 = x[R0] - c[R0] * bk;
+                x[R0] = (lane == kk) ? bk : ((lane < kk) ? t0 : x[R0]);
+#pragma unroll
+                for (int r = 0; r < R0; ++r) x[r] -= c[r] * bk;
+            }
+            __syncwarp();
+        }
+    }
+    if constexpr (R0 > 0) gt_bwd_block<RMAX, R0 - 1>(P, Mg, ring, bars, ringp, lane, x, phases, j);
+}
+
+__host__ __device__ inline size_t gt_warp_smem(int n) {  // ring (16-byte aligned: n even) + rhs + pivots + barriers
+    return ((size_t)GT_STAGES * GT_CB * n * sizeof(double) + (size_t)n * sizeof(double) + (size_t)n * sizeof(int) + 8 * GT_STAGES + 15) / 16 * 16;
+}
+
+template <int RMAX>
+__global__ void __launch_bounds__(32 * GT_WARPS) getrs_tma(const double* __restrict__ A, const int64_t* __restrict__ piv,
+                                                            double* __restrict__ bx, int n, int64_t B) {
+    extern __shared__ __align__(16) unsigned char lu_smem[];
+    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    unsigned char* base = lu_smem + (size_t)wi * gt_warp_smem(n);
+    double* ringp = reinterpret_cast<double*>(base);
+    double* xs = ringp + (size_t)GT_STAGES * GT_CB * n;
+    unsigned long long* barp = reinterpret_cast<unsigned long long*>(xs + n);
+    int* ps = reinterpret_cast<int*>(barp + GT_STAGES);
+    const unsigned ring = (unsigned)__cvta_generic_to_shared(ringp);
+    const unsigned bars = (unsigned)__cvta_generic_to_shared(barp);
+    if (lane == 0) {
+        for (int s = 0; s < GT_STAGES; ++s) gt_mbar_init(bars + 8u * (unsigned)s, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    unsigned phases = 0;  // parity to wait for, one bit per stage
+    const GtPlan P(n);
+    for (int64_t b = (int64_t)blockIdx.x * GT_WARPS + wi; b < B; b += (int64_t)gridDim.x * GT_WARPS) {
+        const double* Mg = A + (size_t)b * n * n;
+        for (int j = 0; j < GT_STAGES - 1; ++j) gt_issue(P, Mg, ring, bars, j, lane);  // the factors start streaming first
+        for (int i = lane; i < n; i += 32) {
+            xs[i] = bx[(size_t)b * n + i];
+            ps[i] = (int)piv[(size_t)b * n + i];
+        }
+        __syncwarp();
+        if (lane == 0) {  // the row interchanges, in order (dense.rs:176-181)
+            for (int k = 0; k < n; ++k) {
+                const int pk = ps[k];
+                if (pk != k) {
+                    const double t = xs[k];
+                    xs[k] = xs[pk];
+                    xs[pk] = t;
+                }
+            }
+        }
+        __syncwarp();
+        double x[RMAX];
+#pragma unroll
+        for (int r = 0; r < RMAX; ++r) {
+            const int i = lane + 32 * r;
+            x[r] = (i < n) ? xs[i] : 0.0;
+        }
+        gt_fwd_block<RMAX, 0>(P, Mg, ring, bars, ringp, lane, x, phases);
+        int j = P.nf;
+        gt_bwd_block<RMAX, RMAX - 1>(P, Mg, ring, bars, ringp, lane, x, phases, j);
+#pragma unroll
+        for (int r = 0; r < RMAX; ++r) {
+            const int i = lane + 32 * r;
+            if (i < n) bx[(size_t)b * n + i] = x[r];
+        }
+        __syncwarp();
+    }
+}
+
+template <int RMAX>
+static int launch_getrs_tma(const double* A, const int64_t* piv, double* bx, int n, int64_t B, cudaStream_t st) {
+    const size_t smem = gt_warp_smem(n) * GT_WARPS;
+    unsigned grid = 1;
+    int rc;
+    if ((rc = launch_cfg(getrs_tma<RMAX>, 32 * GT_WARPS, smem, B, GT_WARPS, &grid))) return rc;
+    getrs_tma<RMAX><<<grid, 32 * GT_WARPS, smem, st>>>(A, piv, bx, n, B);
+    B200_CUDA_TRY(cudaGetLastError());
+    return B200IDA_OK;
+}
+
 template <bool FACTOR>
 static int launch_group(double* A, int64_t* piv, int32_t* info, double* bx, int n, int64_t B, bool soa, cudaStream_t st) {
     const unsigned gb = (unsigned)lu_group_smem_bytes(n);
@@ -827,6 +1062,11 @@ static int getrs_dev(const double* LU, const int64_t* piv, double* bx, int n, in
         }
         B200_CUDA_TRY(cudaGetLastError());
         return B200IDA_OK;
+    }
+    if (!soa && n > 32 && (n & 1) == 0 && (reinterpret_cast<uintptr_t>(LU) & 15) == 0 && !getenv("B200IDA_GETRS_NO_TMA")) {
+        if (n <= 64) return launch_getrs_tma<2>(LU, piv, bx, n, B, st);
+        if (n <= 128) return launch_getrs_tma<4>(LU, piv, bx, n, B, st);
+        return launch_getrs_tma<8>(LU, piv, bx, n, B, st);
     }
     if (!soa && n > 32) {
         if (n <= 64) return launch_getrs_stream<2>(LU, piv, bx, n, B, st);
