@@ -101,7 +101,7 @@ def test_golden_matrices_on_gpu(golden_dir):
         assert_bit_equal(x[:, 0], np.array(it["expect"]["value"]), name)
 
 
-@pytest.mark.parametrize("layout,n", [("soa", 3), ("aos", 3), ("soa", 20), ("aos", 40)])
+@pytest.mark.parametrize("layout,n", [("soa", 3), ("aos", 3), ("soa", 20), ("aos", 40), ("soa", 70), ("aos", 130), ("aos", 200)])
 def test_singular_reports_one_based_column(layout, n):
     import rust_ida_b200 as r
     rng = np.random.default_rng(7)
@@ -150,7 +150,8 @@ def test_edge_sizes(n, batch, layout):
     assert_bit_equal(x, x_ref, "x n=%d" % n)
 
 
-@pytest.mark.parametrize("layout,n", [("aos", 16), ("aos", 32), ("soa", 8), ("aos", 48)])
+@pytest.mark.parametrize("layout,n", [("aos", 16), ("aos", 32), ("soa", 8), ("aos", 48), ("soa", 80), ("aos", 100), ("aos", 130),
+                                      ("aos", 200)])
 def test_pivot_ties_and_nan_follow_the_reference(layout, n):
     """ties pick the FIRST row with the largest |a_ik|; a NaN never wins the `>` test and a NaN in row k keeps l = k
     (crates/linear/src/dense.rs:109-116) -- checked on every kernel family"""
@@ -168,3 +169,44 @@ def test_pivot_ties_and_nan_follow_the_reference(layout, n):
     assert np.array_equal(piv[ok], piv_ref[ok])
     assert_bit_equal(lu[ok], lu_ref[ok], "LU with ties/NaN")
     assert_bit_equal(x[ok], x_ref[ok], "x with ties/NaN")
+
+
+@pytest.mark.parametrize("n", [40, 100, 130, 200])
+def test_singular_leaves_the_reference_partial_factors(n):
+    """after a zero pivot in column k the reference returns with steps < k applied (dense.rs:120-122); the blocked
+    kernels (shared-memory and global-memory variants) must leave exactly that matrix and those pivots behind"""
+    rng = np.random.default_rng(11)
+    a = rng.uniform(0.5, 1.5, size=(3, n, n)) + np.eye(n)[None] * n
+    a[0, :, n // 2 + 3] = 0.0             # a zero column stays zero (a_kj == 0 skips it): zero pivot inside a panel
+    a[1, :, 8] = 0.0                      # zero pivot at the first column of the second panel
+    a[2, :, n - 1] = a[2, :, n - 2]       # (nearly) dependent last columns: zero or tiny pivot at the last step
+    b = np.ones((3, n))
+    lu_ref, piv_ref, _, info_ref = oracle_lu(a, b)
+    lu, piv, _, info = run_gpu(a, b, "aos", device_buffers=True)
+    assert info.tolist() == info_ref.tolist() and info_ref[0] == n // 2 + 4 and info_ref[1] == 9
+    assert_bit_equal(lu, lu_ref, "partial factors n=%d" % n)
+    for k in range(3):
+        m = info_ref[k] if info_ref[k] > 0 else n
+        assert np.array_equal(piv[k, :m], piv_ref[k, :m])
+
+
+@pytest.mark.parametrize("n", [64, 100, 256])
+def test_getrs_unaligned_batch_takes_the_non_tma_path(n):
+    """getrs_tma needs a 16-byte aligned batch (cp.async.bulk); a batch that starts 8 bytes into an allocation must
+    still be solved, bit-exactly, by the register-streaming kernel"""
+    import torch
+    from rust_ida_b200 import _lib
+    batch = 7
+    a, b = gen_matrices(n, batch, seed=5)
+    lu_ref, piv_ref, x_ref, _ = oracle_lu(a, b)
+    L = _lib.lib()
+    buf = torch.zeros(batch * n * n + 1, dtype=torch.float64, device="cuda")
+    A = buf[1:]
+    assert A.data_ptr() % 16 == 8
+    A.copy_(torch.from_numpy(np.ascontiguousarray(lu_ref.transpose(0, 2, 1)).reshape(-1)))
+    piv = torch.from_numpy(piv_ref.astype(np.int64).reshape(-1)).cuda()
+    x = torch.from_numpy(b.copy().reshape(-1)).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(L.b200ida_getrs_batched(A.data_ptr(), piv.data_ptr(), x.data_ptr(), n, batch, _lib.LAYOUT_AOS, _lib.MEM_DEVICE, st))
+    torch.cuda.synchronize()
+    assert_bit_equal(x.cpu().numpy().reshape(batch, n), x_ref, "unaligned getrs n=%d" % n)
