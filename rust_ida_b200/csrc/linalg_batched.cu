@@ -145,73 +145,96 @@ __global__ void __launch_bounds__(128) getrs_thread_soa(const double* __restrict
 }
 
 // ---- warp-per-system, REGISTER resident, AoS, n == N in {16, 32} -------------------------------------------------
-// Lane i holds row i of the matrix in registers for the whole factorisation; the pivot row is broadcast with
-// shuffles, so an elimination step is N independent (shuffle, mul, sub) chains with no shared-memory traffic.
-// Rows are never moved: each lane tracks the LOGICAL position of its row (what the reference's whole-row swaps
-// would have produced) and writes the row there at the end; the arithmetic on each element is unchanged.
+// Lane i holds row i of the matrix in registers for the whole factorisation; N = 16 packs TWO systems into a warp
+// (lanes 0..15 and 16..31, every collective on the half-warp).  Rows are never moved: each lane tracks the LOGICAL
+// position of its row (what the reference's whole-row swaps would have produced) and writes the row there at the
+// end; the arithmetic on each element is unchanged.  Per elimination step: arg-max of |a_ik| by three integer
+// redux.sync on the IEEE bit pattern (NaN below every candidate, ties to the lowest logical position, key carries the
+// lane), exact reciprocal of the pivot in every lane, pivot row broadcast through shared memory, N-1-k independent
+// mul/sub.  The throughput bound is instructions issued per system (6.5 k at N = 32, half of them the update), not bytes.
 // one elimination step with compile-time k (template recursion forces the full unroll that keeps row[] in registers)
 template <int N, int K>
-__device__ __forceinline__ void lu_regs_step(double (&row)[N], int lane, int& pos, int& inf, int& mypiv) {
-    if (inf == 0) {
+__device__ __forceinline__ void lu_regs_step(double (&row)[N], double* prow, unsigned gmask, int gl, int& pos, bool& done, int& inf,
+                                             int& mypiv) {
+    if (inf == 0) {  // uniform over the group
         const double x = row[K];
-        const bool cand = pos >= K && lane < N;
-        double v = (cand && x == x) ? fabs(x) : -1.0;  // NaN never wins
-        int p = cand ? pos : 0x7fffffff;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const double ov = __shfl_xor_sync(0xffffffffu, v, off);
-            const int op = __shfl_xor_sync(0xffffffffu, p, off);
-            if (ov > v || (ov == v && op < p)) {
-                v = ov;
-                p = op;
-            }
+        const bool isnan_ = x != x;
+        const int hi = done ? -2 : (isnan_ ? -1 : (__double2hiint(x) & 0x7fffffff));
+        const unsigned lo = (done || isnan_) ? 0u : (unsigned)__double2loint(x);
+        const unsigned pp = ((unsigned)pos << 8) | (unsigned)gl;
+        const int mhi = __reduce_max_sync(gmask, hi);
+        const unsigned mlo = __reduce_max_sync(gmask, (hi == mhi) ? lo : 0u);
+        unsigned mpp = __reduce_min_sync(gmask, (!done && hi == mhi && lo == mlo) ? pp : 0xffffffffu);
+        const bool atk = pos == K;  // the lane that holds logical row K (not yet a pivot row: positions < K are final)
+        if (mhi < 0 || __any_sync(gmask, atk && isnan_)) {
+            // nothing comparable, or a NaN in row K: the reference keeps l = K
+            mpp = __reduce_min_sync(gmask, atk ? pp : 0xffffffffu);
         }
-        const int lk = __ffs(__ballot_sync(0xffffffffu, pos == K && lane < N)) - 1;  // lane holding logical row K
-        const double xk = __shfl_sync(0xffffffffu, x, lk);
-        int l = p;
-        if (xk != xk || l > N) l = K;  // NaN in row K (or nothing comparable): the reference keeps l = K
-        const int lw = __ffs(__ballot_sync(0xffffffffu, pos == l && lane < N)) - 1;  // lane holding the pivot row
-        const double pv = __shfl_sync(0xffffffffu, x, lw);
-        if (lane == K) mypiv = l;
+        const int l = (int)(mpp >> 8), lw = (int)(mpp & 0xffu);
+        const double pv = __shfl_sync(gmask, x, lw, N);
+        if (gl == K) mypiv = l;
         if (pv == 0.0) {
             inf = K + 1;
         } else {
-            if (lane == lw) pos = K;
-            else if (lane == lk) pos = l;
-            const double mult = 1.0 / pv;
-            const bool below = pos > K && lane < N;
-            const double lik = x * mult;
-            if (below) row[K] = lik;
-#pragma unroll
-            for (int j = K + 1; j < N; ++j) {
-                const double a_kj = __shfl_sync(0xffffffffu, row[j], lw);
-                if (below && a_kj != 0.0) row[j] -= a_kj * lik;
+            const double mult = __drcp_rn(pv);  // == 1.0 / pv (both correctly rounded)
+            if (gl == lw) {
+                pos = K;
+                done = true;
+            } else if (atk) {
+                pos = l;
             }
+            const double lik = x * mult;
+            if (!done) row[K] = lik;
+            // pivot row through shared memory: the owner lane stores row[K+1..N) as 16-byte pairs, everybody reads them
+            // back as broadcasts -- one store + one load per PAIR instead of four 32-bit shuffles.  The a_kj == 0 skip
+            // of the reference stays a per-element test: dropping it is only wrong when a_ij is -0.0 or the multiplier
+            // is not finite, but then it IS wrong, and every cheaper formulation tried loses one of those corners.
+            constexpr int J0 = (K + 1) & ~1;
+            if (gl == lw) {
+#pragma unroll
+                for (int j = J0; j < N; j += 2) *reinterpret_cast<double2*>(prow + j) = make_double2(row[j], row[j + 1]);
+            }
+            __syncwarp(gmask);
+#pragma unroll
+            for (int j = J0; j < N; j += 2) {
+                const double2 a = *reinterpret_cast<const double2*>(prow + j);
+                if (j > K && !done && a.x != 0.0) row[j] -= a.x * lik;
+                if (!done && a.y != 0.0) row[j + 1] -= a.y * lik;
+            }
+            __syncwarp(gmask);
         }
     }
-    if constexpr (K + 1 < N) lu_regs_step<N, K + 1>(row, lane, pos, inf, mypiv);
+    if constexpr (K + 1 < N) lu_regs_step<N, K + 1>(row, prow, gmask, gl, pos, done, inf, mypiv);
 }
 
 template <int N>
 __global__ void __launch_bounds__(128) getrf_warp_regs(double* __restrict__ A, int64_t* __restrict__ piv,
                                                        int32_t* __restrict__ info, int64_t B) {
-    const int lane = threadIdx.x & 31;
+    constexpr int G = 32 / N;  // systems per warp
+    __shared__ __align__(16) double prow_all[4 * 32];  // pivot-row staging: 32 doubles per warp (N per system)
+    const int lane = threadIdx.x & 31, gl = lane & (N - 1), g = lane / N;
+    double* prow = prow_all + (threadIdx.x >> 5) * 32 + g * N;
+    const unsigned gmask = (N == 32) ? 0xffffffffu : (0xffffu << (16 * g));
     const int64_t wpg = (int64_t)gridDim.x * (blockDim.x >> 5);
-    for (int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); b < B; b += wpg) {
-        double* Ab = A + (size_t)b * N * N;
+    const int64_t nwork = (B + G - 1) / G;  // warp-sized work items
+    for (int64_t wk = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); wk < nwork; wk += wpg) {
+        const int64_t b = wk * G + g;
+        const bool live = b < B;  // uniform over the group (a trailing odd system leaves the second half idle)
+        double* Ab = A + (size_t)(live ? b : 0) * N * N;
         double row[N];
 #pragma unroll
-        for (int j = 0; j < N; ++j) row[j] = (lane < N) ? Ab[j * N + lane] : 0.0;
-        int pos = lane;  // logical row index of the data this lane holds
+        for (int j = 0; j < N; ++j) row[j] = live ? Ab[j * N + gl] : (j == gl ? 1.0 : 0.0);
+        int pos = gl;       // logical row index of the data this lane holds
+        bool done = false;  // this lane's row has become a pivot row
         int inf = 0;
-        int mypiv = 0;   // lane k keeps piv[k]
-        lu_regs_step<N, 0>(row, lane, pos, inf, mypiv);
-        if (lane < N) {
+        int mypiv = 0;      // lane k keeps piv[k]
+        lu_regs_step<N, 0>(row, prow, gmask, gl, pos, done, inf, mypiv);
+        if (live) {
 #pragma unroll
             for (int j = 0; j < N; ++j) Ab[j * N + pos] = row[j];
-            piv[(size_t)b * N + lane] = (inf == 0 || lane < inf) ? mypiv : 0;
+            piv[(size_t)b * N + gl] = (inf == 0 || gl < inf) ? mypiv : 0;
+            if (gl == 0) info[b] = inf;
         }
-        if (lane == 0) info[b] = inf;
     }
 }
 
@@ -966,7 +989,8 @@ static int launch_group(double* A, int64_t* piv, int32_t* info, double* bx, int 
     } while (0)
     if (!soa && (n == 16 || n == 32)) {
         const int threads = 128, wpc = 4;
-        const int64_t want = (B + wpc - 1) / wpc, cap = (int64_t)sm_count() * 16;
+        const int64_t items = (FACTOR && n == 16) ? (B + 1) / 2 : B;  // getrf n = 16: two systems per warp
+        const int64_t want = (items + wpc - 1) / wpc, cap = (int64_t)sm_count() * 16;
         const unsigned g = (unsigned)(want < cap ? want : cap);
         if (FACTOR) {
             if (n == 16) getrf_warp_regs<16><<<g, threads, 0, st>>>(A, piv, info, B);
