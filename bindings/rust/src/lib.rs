@@ -33,6 +33,8 @@ extern "C" {
                                  mem: c_int, stream: *mut c_void) -> c_int;
     pub fn b200ida_wrms_batched(x: *const f64, w: *const f64, out: *mut f64, n: c_int, batch: i64, layout: c_int,
                                 mem: c_int, stream: *mut c_void) -> c_int;
+    pub fn b200ida_wrms_masked_batched(x: *const f64, w: *const f64, id: *const u8, out: *mut f64, n: c_int, batch: i64,
+                                       layout: c_int, mem: c_int, stream: *mut c_void) -> c_int;
     pub fn b200ida_create(out: *mut *mut RawEnsemble, problem: c_int, n: c_int, batch: i64, nparams: c_int,
                           params: *const f64, yy0: *const f64, yp0: *const f64, rtol: f64, atol: *const f64,
                           mem: c_int, device: c_int, stream: *mut c_void) -> c_int;

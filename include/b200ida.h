@@ -55,7 +55,8 @@ int b200ida_device_count(void);
  * Replaces, for `batch` independent systems at once:
  *   LSolver::setup   crates/linear/src/traits.rs:52-54  -> Dense::setup / dense_get_rf  crates/linear/src/dense.rs:38-44, 86-158
  *   LSolver::solve   crates/linear/src/traits.rs:70-80  -> Dense::solve / dense_get_rs  crates/linear/src/dense.rs:46-63, 165-206
- *   NormWRMS::norm_wrms  crates/nonlinear/src/norm_wrms.rs:24-33 ; NormRms::norm_wrms  src/norm_rms.rs:31-38
+ *   NormWRMS::norm_wrms  crates/nonlinear/src/norm_wrms.rs:24-33 ; NormRms::norm_wrms  src/norm_rms.rs:31-38 ;
+ *   NormRmsMasked::norm_wrms_masked  src/norm_rms.rs:49-57
  * ===================================================================================================== */
 
 /* In-place LU with partial (row) pivoting of `batch` n x n matrices.
@@ -80,6 +81,14 @@ int b200ida_getrs_batched(const double* LU, const int64_t* piv, double* bx, int 
  * src/norm_rms.rs:32-37).  x, w: SoA [n][batch] or AoS [batch][n]; out: [batch]. */
 int b200ida_wrms_batched(const double* x, const double* w, double* out, int n, int64_t batch, int layout,
                          int mem, void* stream);
+
+/* Masked variant, NormRmsMasked::norm_wrms_masked (src/norm_rms.rs:49-57; what Ida::wrms_norm switches to when
+ * `suppressalg` is set, src/lib.rs:1353-1370):  out[b] = sqrt( (sum_i ((x_i w_i) m_i)^2) / n ),  m_i = id[i] ? 1 : 0,
+ * same fold order; the divisor stays n like the reference.  id: [n] bytes (non-zero = differential component), one
+ * mask for the whole batch (it is a property of the problem, `ida_id` src/lib.rs:122), in the same memory space
+ * as x. */
+int b200ida_wrms_masked_batched(const double* x, const double* w, const unsigned char* id, double* out, int n,
+                                int64_t batch, int layout, int mem, void* stream);
 
 /* =====================================================================================================
  * Level 2 -- ensemble IDA.  One handle = `batch` independent instances of

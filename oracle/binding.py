@@ -43,6 +43,8 @@ def lib():
         L.oracle_getrs.argtypes = [_dp, _i64p, _dp, C.c_int]
         L.oracle_wrms.restype = C.c_double
         L.oracle_wrms.argtypes = [_dp, _dp, C.c_int]
+        L.oracle_wrms_masked.restype = C.c_double
+        L.oracle_wrms_masked.argtypes = [_dp, _dp, np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS"), C.c_int]
         L.oracle_res.argtypes = [C.c_int, C.c_int, _dp, C.c_double, _dp, _dp, _dp]
         L.oracle_jac.argtypes = [C.c_int, C.c_int, _dp, C.c_double, _dp, _dp, _dp]
         L.oracle_unit_new.restype = C.c_void_p
@@ -103,6 +105,14 @@ def wrms(x, w):
     x = np.ascontiguousarray(x, dtype=np.float64)
     w = np.ascontiguousarray(w, dtype=np.float64)
     return lib().oracle_wrms(x, w, x.size)
+
+
+def wrms_masked(x, w, id_):
+    """src/norm_rms.rs:49-57"""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    m = np.ascontiguousarray(np.asarray(id_) != 0, dtype=np.uint8)
+    return lib().oracle_wrms_masked(x, w, m, x.size)
 
 
 def res(kind, params, yy, yp, t=0.0):

@@ -225,6 +225,16 @@ double norm_wrms(const double* x, const double* w, int n) {
     return std::sqrt(acc / (double)n);
 }
 
+// ---- masked WRMS norm: src/norm_rms.rs:49-57 (mask = id ? 1 : 0; ((x*w)*mask)^2 folded from 0, / len, sqrt) ----
+double norm_wrms_masked(const double* x, const double* w, const unsigned char* id, int n) {
+    double acc = 0.0;
+    for (int i = 0; i < n; ++i) {
+        const double p = (x[i] * w[i]) * (id[i] ? 1.0 : 0.0);
+        acc = acc + p * p;
+    }
+    return std::sqrt(acc / (double)n);
+}
+
 // ---- Newton: crates/nonlinear/src/newton.rs:14-32 (state) and :51-167 (solve) -------------------
 // Generic over an NLProblem-like object P providing (crates/nonlinear/src/traits.rs:5-127):
 //   void sys(const double* y, double* f); int setup(const double* y, const double* f, bool jbad)
@@ -816,6 +826,7 @@ void oracle_getrs(const double* a_colmajor, const int64_t* pivot, double* b, int
     dense_get_rs(a_colmajor, pivot, b, n);
 }
 double oracle_wrms(const double* x, const double* w, int n) { return norm_wrms(x, w, n); }
+double oracle_wrms_masked(const double* x, const double* w, const unsigned char* id, int n) { return norm_wrms_masked(x, w, id, n); }
 
 void oracle_res(int kind, int n, const double* params, double t, const double* yy, const double* yp, double* r) {
     Problem p{kind, n, params};

@@ -366,6 +366,21 @@ __global__ void __launch_bounds__(256) wrms_thread(const double* __restrict__ x,
     out[b] = sqrt(acc / (double)n);
 }
 
+// masked norm, src/norm_rms.rs:49-57: ((x_i w_i) m_i)^2 folded in index order, divided by n (not by the mask count)
+template <bool SOA>
+__global__ void __launch_bounds__(256) wrms_masked_thread(const double* __restrict__ x, const double* __restrict__ w,
+                                                          const unsigned char* __restrict__ id, double* __restrict__ out, int n,
+                                                          int64_t B) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double acc = 0.0;
+    for (int i = 0; i < n; ++i) {
+        const double p = (x[vec_idx<SOA>(i, n, b, B)] * w[vec_idx<SOA>(i, n, b, B)]) * (id[i] ? 1.0 : 0.0);
+        acc = acc + p * p;
+    }
+    out[b] = sqrt(acc / (double)n);
+}
+
 // SoA <-> AoS conversions used when a large-n SoA batch has to go through the in-place AoS kernel.
 // Matrices: SoA element (i, j, b) at (i*n + j)*B + b  <->  AoS column-major b*n*n + j*n + i.
 __global__ void mat_soa_to_aos(const double* __restrict__ soa, double* __restrict__ aos, int n, int64_t B) {
@@ -1108,6 +1123,15 @@ static int wrms_dev(const double* x, const double* w, double* out, int n, int64_
     return B200IDA_OK;
 }
 
+static int wrms_masked_dev(const double* x, const double* w, const unsigned char* id, double* out, int n, int64_t B, int layout,
+                           cudaStream_t st) {
+    const unsigned grid = (unsigned)((B + 255) / 256);
+    if (layout == B200IDA_LAYOUT_SOA) wrms_masked_thread<true><<<grid, 256, 0, st>>>(x, w, id, out, n, B);
+    else wrms_masked_thread<false><<<grid, 256, 0, st>>>(x, w, id, out, n, B);
+    B200_CUDA_TRY(cudaGetLastError());
+    return B200IDA_OK;
+}
+
 static int check_common(const void* a, const void* b, int n, int64_t batch, int layout, int mem, const char* who) {
     if (!a || !b || n < 1 || n > 256 || batch < 1 || (layout != B200IDA_LAYOUT_SOA && layout != B200IDA_LAYOUT_AOS) ||
         (mem != B200IDA_MEM_DEVICE && mem != B200IDA_MEM_HOST))
@@ -1197,6 +1221,28 @@ int b200ida_wrms_batched(const double* x, const double* w, double* out, int n, i
     B200_CUDA_TRY(cudaMemcpyAsync(dX.p, x, vb, cudaMemcpyHostToDevice, st));
     B200_CUDA_TRY(cudaMemcpyAsync(dW.p, w, vb, cudaMemcpyHostToDevice, st));
     if ((rc = wrms_dev(dX.as<double>(), dW.as<double>(), dO.as<double>(), n, batch, layout, st))) return rc;
+    B200_CUDA_TRY(cudaMemcpyAsync(out, dO.p, ob, cudaMemcpyDeviceToHost, st));
+    B200_CUDA_TRY(cudaStreamSynchronize(st));
+    return B200IDA_OK;
+}
+
+int b200ida_wrms_masked_batched(const double* x, const double* w, const unsigned char* id, double* out, int n,
+                                int64_t batch, int layout, int mem, void* stream) {
+    int rc = check_common(x, w, n, batch, layout, mem, "b200ida_wrms_masked_batched");
+    if (rc) return rc;
+    if (!out || !id) return set_error(B200IDA_ERR_ARG, "b200ida_wrms_masked_batched: out or id is null");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (mem == B200IDA_MEM_DEVICE) return wrms_masked_dev(x, w, id, out, n, batch, layout, st);
+    DevBuf dX, dW, dI, dO;
+    const size_t vb = (size_t)n * batch * sizeof(double), ob = (size_t)batch * sizeof(double);
+    B200_CUDA_TRY(dX.alloc(vb));
+    B200_CUDA_TRY(dW.alloc(vb));
+    B200_CUDA_TRY(dI.alloc((size_t)n));
+    B200_CUDA_TRY(dO.alloc(ob));
+    B200_CUDA_TRY(cudaMemcpyAsync(dX.p, x, vb, cudaMemcpyHostToDevice, st));
+    B200_CUDA_TRY(cudaMemcpyAsync(dW.p, w, vb, cudaMemcpyHostToDevice, st));
+    B200_CUDA_TRY(cudaMemcpyAsync(dI.p, id, (size_t)n, cudaMemcpyHostToDevice, st));
+    if ((rc = wrms_masked_dev(dX.as<double>(), dW.as<double>(), dI.as<unsigned char>(), dO.as<double>(), n, batch, layout, st))) return rc;
     B200_CUDA_TRY(cudaMemcpyAsync(out, dO.p, ob, cudaMemcpyDeviceToHost, st));
     B200_CUDA_TRY(cudaStreamSynchronize(st));
     return B200IDA_OK;

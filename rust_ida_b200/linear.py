@@ -120,3 +120,28 @@ def norm_wrms(x, w, layout="soa"):
     _lib.check(_lib.lib().b200ida_wrms_batched(px, pw, po, int(n), int(batch), _layout_code(layout), mem,
                                                B.current_stream(mem)))
     return out
+
+
+def norm_wrms_masked(x, w, id_, layout="soa"):
+    """NormRmsMasked::norm_wrms_masked for every system of a batch (src/norm_rms.rs:49-57): components with
+    id == False are left out of the sum, the divisor stays n.  x, w: (n, batch) soa or (batch, n) aos; id_: (n,) bools,
+    one mask for the whole batch (`ida_id`, src/lib.rs:122)."""
+    _lib.require_device()
+    n, batch = (x.shape if layout == "soa" else x.shape[::-1])
+    px, m1 = B.describe(x, np.float64, "x")
+    pw, m2 = B.describe(w, np.float64, "w")
+    mem = B.common_mem(m1, m2)
+    mask = np.ascontiguousarray(np.asarray(id_).reshape(-1) != 0, dtype=np.uint8)
+    if mask.size != n:
+        raise ValueError("id has %d entries, the systems have %d components" % (mask.size, n))
+    if mem == _lib.MEM_DEVICE:
+        import torch
+        mask_t = torch.from_numpy(mask).to(x.device)
+        pm = mask_t.data_ptr()
+    else:
+        pm = mask.ctypes.data
+    out = B.empty_like_space(x, (batch,), np.float64)
+    po, _ = B.describe(out, np.float64, "out")
+    _lib.check(_lib.lib().b200ida_wrms_masked_batched(px, pw, pm, po, int(n), int(batch), _layout_code(layout), mem,
+                                                      B.current_stream(mem)))
+    return out

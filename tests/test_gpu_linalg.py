@@ -210,3 +210,27 @@ def test_getrs_unaligned_batch_takes_the_non_tma_path(n):
     _lib.check(L.b200ida_getrs_batched(A.data_ptr(), piv.data_ptr(), x.data_ptr(), n, batch, _lib.LAYOUT_AOS, _lib.MEM_DEVICE, st))
     torch.cuda.synchronize()
     assert_bit_equal(x.cpu().numpy().reshape(batch, n), x_ref, "unaligned getrs n=%d" % n)
+
+
+@pytest.mark.parametrize("layout", ["soa", "aos"])
+@pytest.mark.parametrize("n,batch,dev", [(3, 1000, True), (32, 257, False), (100, 33, True)])
+def test_wrms_masked_bit_exact(n, batch, layout, dev):
+    """norm_wrms_masked (src/norm_rms.rs:49-57) incl. the reference's own pin (:73-86)"""
+    import torch
+    import rust_ida_b200 as r
+    from oracle import binding as ob
+    rng = np.random.default_rng(n + 1)
+    x = rng.normal(size=(batch, n)) * 10.0 ** rng.integers(-8, 8, size=(batch, 1))
+    w = 1.0 / (1e-4 * np.abs(x) + 1e-8)
+    mask = rng.random(n) < 0.7
+    ref = np.array([ob.wrms_masked(x[k], w[k], mask) for k in range(batch)])
+    X, W = (np.ascontiguousarray(x.T), np.ascontiguousarray(w.T)) if layout == "soa" else (x, w)
+    if dev:
+        out = r.norm_wrms_masked(torch.from_numpy(X).cuda(), torch.from_numpy(W).cuda(), mask, layout=layout).cpu().numpy()
+    else:
+        out = r.norm_wrms_masked(X, W, mask, layout=layout)
+    assert_bit_equal(out, ref, "wrms_masked")
+    m = np.ones(32, dtype=bool)
+    m[-1] = False
+    fac = np.sqrt(np.float64(31) / np.float64(32))
+    assert r.norm_wrms_masked(np.full((32, 1), -0.5), np.full((32, 1), 0.5), m)[0] == fac * 0.5 * 0.5

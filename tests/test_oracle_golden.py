@@ -91,6 +91,16 @@ def test_wrms_golden():
     assert ob.wrms(np.full(32, -0.5), np.full(32, 0.5)) == 0.25
 
 
+def test_wrms_masked_golden():
+    """src/norm_rms.rs:73-86: all components but the last, expect fac * 0.5 * 0.5 with assert_eq!"""
+    n = 32
+    fac = np.sqrt(np.float64(n - 1) / np.float64(n))
+    mask = np.ones(n, dtype=bool)
+    mask[-1] = False
+    assert ob.wrms_masked(np.full(n, -0.5), np.full(n, 0.5), mask) == fac * 0.5 * 0.5
+    assert ob.wrms_masked(np.full(n, -0.5), np.full(n, 0.5), np.ones(n, dtype=bool)) == 0.25
+
+
 # ---- Newton known answer: crates/nonlinear/src/newton.rs:306-343 -------------------------------------
 def test_newton_golden(golden_dir):
     it = {i["name"]: i["value"] for i in load(golden_dir, "newton")["test_newton"]}
