@@ -128,6 +128,15 @@ def auto_cpu_sample(target_s=12.0):
     return max(1024, min(n, 1 << 20))
 
 
+def workload_config(B):
+    """the `config` object both arms print (the reference arm must run on our arm's config)"""
+    return {"workload": "Roberts ensemble, n=3, %d instances per GPU, rate constants +-10%% (splitmix64 seed 1234 "
+                        "keyed by instance id), rtol 1e-4, atol [1e-8,1e-6,1e-6], tout = 0.4*10^i i=0..11 "
+                        "(BASELINE.json configs[1])" % B,
+            "batch_per_gpu": B, "sharding": "contiguous instance-id ranges, no collective in the step loop",
+            "l2": "per-step state (%.0f MB/GPU) is larger than the 126 MB L2" % (B * 0.78e-3)}
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU path for the same metric/config.  rust-ida cannot be built here
     (no Rust toolchain, tree mid-refactor), so this is the oracle port, all host threads, bounded sample."""
@@ -149,8 +158,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "ensemble DAE solves/sec (Roberts, t=4e10)", "value": val, "unit": "instances/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "Roberts ensemble, n=3, rate constants +-10% (splitmix64 seed 1234), rtol 1e-4, "
-                               "atol [1e-8,1e-6,1e-6], tout = 0.4*10^i i=0..11", "batch_per_gpu": args.batch},
+        "config": workload_config(args.batch),
         "cpu_baseline": {"value": val, "unit": "instances/s", "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": val, "unit": "instances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -296,12 +304,7 @@ def run_ours(args, rank, world, local_rank):
         "value": total / (ms * 1e-3), "unit": "instances/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "Roberts ensemble, n=3, %d instances per GPU, rate constants +-10%% (splitmix64 seed 1234 "
-                               "keyed by instance id), rtol 1e-4, atol [1e-8,1e-6,1e-6], tout = 0.4*10^i i=0..11 "
-                               "(BASELINE.json configs[1])" % B,
-                   "batch_per_gpu": B, "sharding": "contiguous instance-id ranges, no collective in the step loop",
-                   "l2": "per-step state (%.0f MB/GPU) is larger than the 126 MB L2" % (B * 0.78e-3),
-                   "parity": "all status==0: %s; nst min/max/mean %d/%d/%.1f" % ((ok,) + nst_minmax)},
+        "config": dict(workload_config(B), parity="all status==0: %s; nst min/max/mean %d/%d/%.1f" % ((ok,) + nst_minmax)),
         "e2e": {"value": world * B * e2e_steps / e2e_s, "unit": "instances/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "results_match_device_run": e2e_ok},
         "gpu_launches": args.steps * 3,  # per step: ida_init_kernel, ida_solve_thread_kernel, widen_i32_kernel
