@@ -318,6 +318,11 @@ def run_ours(args, rank, world, local_rank):
                                   "frac": B * ALG_BYTES_PER_INSTANCE / (kernel_ms * 1e-3) * 1e-9 / hbm_peak,
                                   "note": "state read once + written once per launch; three orders of magnitude below the "
                                           "FP64 bound, which is why the roofline above is the FP64 issue rate"},
+                     # hardware-side view of the same kernel from ncu (profiles/r1e_ida_solve_thread_final_ncu_summary.csv):
+                     # the FP64 pipe is busy 29 % of the cycles, the schedulers issue on 43 % -- division, sqrt and pow
+                     # expand to 10-60 FP64-pipe instructions per algorithmic op, which is the gap to `frac`
+                     "ncu": {"sm__pipe_fp64_cycles_active_pct": 28.96, "smsp__issue_active_pct": 43.32,
+                             "active_lanes_per_instruction": 20.21, "source": "profiles/r1e_ida_solve_thread_final_ncu_summary.csv"},
                      "kernel": "ida_solve_thread_kernel<Roberts>", "kernel_ms": kernel_ms,
                      "ops_per_launch": tot_attempts * OPS_PER_ATTEMPT, "attempts_per_launch": tot_attempts,
                      "peak_source": "measured on this GPU by b200ida_fp64_issue_rate (MEASURED_PEAKS.json has no FP64 entry): "
