@@ -16,6 +16,8 @@
 //   *_cta             any n <= 256, either layout: one CTA per system; the matrix is staged in shared
 //                     memory when it fits (n <= 160), else factored in place in global memory / L2.
 #include <cstdlib>
+#include <mutex>
+#include <vector>
 #include "host_util.h"
 #include "ida_common.cuh"
 #include "lu_team.cuh"
@@ -427,12 +429,42 @@ static int sm_count() {
 }
 
 // launch the group-per-system getrf (FACTOR) or getrs kernel for any n <= 256
+// The attribute / occupancy queries cost several microseconds of host time per call -- comparable to the short
+// kernels they configure -- so their result is cached per (kernel, device, threads, shared-memory size).
+struct LaunchCfgEntry {
+    const void* fn;
+    int dev, threads;
+    size_t smem;
+    int occ;
+};
 template <class K>
 static int launch_cfg(K kernel, int threads, size_t smem, int64_t groups_needed, int groups_per_cta, unsigned* grid) {
-    B200_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 1;
-    B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem));
-    if (occ < 1) occ = 1;
+    static std::mutex mu;
+    static std::vector<LaunchCfgEntry> cache;
+    int dev = 0;
+    B200_CUDA_TRY(cudaGetDevice(&dev));
+    const void* fn = reinterpret_cast<const void*>(kernel);
+    int occ = 0;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        for (const LaunchCfgEntry& e : cache)
+            if (e.fn == fn && e.dev == dev && e.threads == threads && e.smem == smem) occ = e.occ;
+    }
+    if (occ == 0) {
+        // the dynamic shared-memory limit of a kernel is only ever raised (a smaller request after a larger one must
+        // not lower it under a cached configuration)
+        size_t cur = 0;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            for (const LaunchCfgEntry& e : cache)
+                if (e.fn == fn && e.dev == dev && e.smem > cur) cur = e.smem;
+        }
+        if (smem > cur) B200_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem));
+        if (occ < 1) occ = 1;
+        std::lock_guard<std::mutex> lk(mu);
+        cache.push_back({fn, dev, threads, smem, occ});
+    }
     const int64_t want = (groups_needed + groups_per_cta - 1) / groups_per_cta;
     const int64_t cap = (int64_t)sm_count() * occ;
     *grid = (unsigned)(want < cap ? want : cap);
