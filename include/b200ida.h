@@ -173,6 +173,19 @@ int b200ida_solve(b200ida_ensemble* e, double tout, int itask, int32_t* status, 
 int b200ida_solve_ladder(b200ida_ensemble* e, const double* touts /* host */, int ntout, int itask, double* yy_traj,
                          int32_t* status, int mem);
 
+/* Per-attempt state trace of ONE instance -- the device side of the reference's `data_trace` feature, which
+ * serialises the whole solver at the top of every step attempt (src/lib.rs:297-301, 635-639; scripts/data_trace.ipynb).
+ * Until switched off (instance < 0), every b200ida_solve / b200ida_solve_ladder of this handle runs a traced
+ * instantiation of the thread-per-instance kernel (n = 3 problems): when attempt c of `instance` begins, its complete
+ * persistent state is written to row c of
+ *   dtrace [max_attempts][10n + 45 + n^2] doubles: phi[6][n], psi, alpha, beta, sigma, gamma [6 each], ee, ewt, yy, yp [n],
+ *          hh, hused, rr, cj, cjold, cjlast, cjratio, ss, toldel, eps_newt, tn, tretlast, h0u, tolsf, tret, J[n][n] (col-major)
+ *   itrace [max_attempts][16 + n] int32:  kk, kused, knew, phase, ns, setup_done, jcur, nst, nre, nje, nni, netf, ncfn,
+ *          nsetups, nlscf, natt, pivots[n]
+ * and count[0] (reset to 0 here) counts the attempts seen.  All three are DEVICE buffers owned by the caller. */
+int b200ida_set_trace(b200ida_ensemble* e, int64_t instance, double* dtrace, int32_t* itrace, int32_t* count,
+                      int max_attempts);
+
 /* get_yy / get_yp (src/ida_io.rs:11-19) and the tret of the last solve; SoA [n][batch] / [batch]; NULL skips. */
 int b200ida_get_state(b200ida_ensemble* e, double* yy, double* yp, double* tret, int mem);
 

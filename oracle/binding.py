@@ -222,6 +222,28 @@ def ensemble_solve(kind, n, params, yy0, yp0, rtol, atol, touts, nthreads=1, wan
     return out
 
 
+def attempt_trace(kind, params, yy0, yp0, rtol, atol, touts, max_rows=4096):
+    """state at the top of every step attempt (the reference's data_trace frames, src/lib.rs:635-639) in the engine's
+    field order (include/b200ida.h, b200ida_set_trace).  Returns (doubles (attempts, 10n+45+n^2), ints (attempts, 16+n), status)."""
+    yy0 = np.ascontiguousarray(yy0, dtype=np.float64)
+    n = yy0.size
+    touts = np.ascontiguousarray(touts, dtype=np.float64)
+    d = np.zeros((max_rows, 10 * n + 45 + n * n))
+    q = np.zeros((max_rows, 16 + n), dtype=np.int32)
+    st = np.zeros(touts.size, dtype=np.int32)
+    L = lib()
+    L.oracle_attempt_trace.restype = C.c_long
+    L.oracle_attempt_trace.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp, C.c_double, _dp, _dp, C.c_int, _dp,
+                                       np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS"), C.c_long,
+                                       np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")]
+    c = L.oracle_attempt_trace(kind, n, np.ascontiguousarray(params, dtype=np.float64), yy0,
+                               np.ascontiguousarray(yp0, dtype=np.float64), rtol, np.ascontiguousarray(atol, dtype=np.float64),
+                               touts, touts.size, d, q, max_rows, st)
+    if c > max_rows:
+        raise RuntimeError("trace overflow: %d attempts" % c)
+    return d[:c], q[:c], st
+
+
 def single_trace(kind, params, yy0, yp0, rtol, atol, touts):
     yy0 = np.ascontiguousarray(yy0, dtype=np.float64)
     n = yy0.size

@@ -321,6 +321,33 @@ struct Ida {
 
     double* PHI(int j) { return &phi[(size_t)j * n]; }
 
+    // ---- per-attempt state trace in the engine's field order (include/b200ida.h, b200ida_set_trace) --------------
+    double* trace_d = nullptr;
+    int32_t* trace_i = nullptr;
+    long trace_max = 0, trace_count = 0;
+    double trace_tret = 0.0;  // the caller's tret (a local of Ida::solve's caller in the reference)
+    void dump_frame() {
+        const long c = trace_count++;
+        if (c >= trace_max) return;
+        const int nd = 10 * n + 45 + n * n, ni = 16 + n;
+        double* d = trace_d + (size_t)c * nd;
+        int32_t* q = trace_i + (size_t)c * ni;
+        int o = 0;
+        for (int j = 0; j < MXORDP1; ++j)
+            for (int i = 0; i < n; ++i) d[o++] = PHI(j)[i];
+        for (const double* a : {psi, alpha, beta, sigma, gamma})
+            for (int j = 0; j < MXORDP1; ++j) d[o++] = a[j];
+        for (const std::vector<double>* v : {&ee, &ewt, &yy, &yp})
+            for (int i = 0; i < n; ++i) d[o++] = (*v)[i];
+        const double sc[15] = {hh, hused, rr, cj, cjold, cjlast, cjratio, ss, toldel, eps_newt, tn, tretlast, h0u, tolsf, trace_tret};
+        for (double v : sc) d[o++] = v;
+        for (int e = 0; e < n * n; ++e) d[o++] = J[e];  // column-major like the engine
+        const long iv[16] = {kk, kused, knew, phase, ns, setup_done ? 1 : 0, nls.jcur ? 1 : 0, nst, nre, nje, nls.niters, netf, ncfn,
+                             nsetups, nls.nconvfails, nattempts};
+        for (int k = 0; k < 16; ++k) q[k] = (int32_t)iv[k];
+        for (int i = 0; i < n; ++i) q[16 + i] = (int32_t)pivots[i];
+    }
+
     // Ida::new -- src/lib.rs:278-405
     void init(const Problem& p, const double* yy0, const double* yp0, double rtol_, const double* atol_) {
         prob = p;
@@ -658,6 +685,7 @@ struct Ida {
         long ncf = 0, nef = 0;
         double ck, err_k = 0.0, err_km1 = 0.0;
         for (;;) {
+            if (trace_d) dump_frame();  // data_trace frame: state at the top of the attempt (src/lib.rs:635-639)
             nattempts += 1;
             ck = set_coeffs();
             tn += hh;
@@ -1049,6 +1077,26 @@ int oracle_single_trace(int kind, int n, const double* params, const double* yy0
                        ida.nls.nconvfails, ida.nattempts};
     for (int k = 0; k < 9; ++k) counters[k] = c[k];
     return last;
+}
+
+// attempt trace of one instance over a ladder of output times: rows as documented at b200ida_set_trace.
+// Returns the number of attempts seen (may exceed max_rows; only the first max_rows are stored).
+long oracle_attempt_trace(int kind, int n, const double* params, const double* yy0, const double* yp0, double rtol,
+                          const double* atol, const double* touts, int ntout, double* dtrace, int32_t* itrace, long max_rows,
+                          int32_t* status /*[ntout]*/) {
+    Ida ida;
+    Problem p{kind, n, params};
+    ida.init(p, yy0, yp0, rtol, atol);
+    ida.trace_d = dtrace;
+    ida.trace_i = itrace;
+    ida.trace_max = max_rows;
+    double tret = 0.0;
+    for (int it = 0; it < ntout; ++it) {
+        ida.trace_tret = tret;
+        const int st = ida.solve(touts[it], tret);
+        if (status) status[it] = st;
+    }
+    return ida.trace_count;
 }
 
 }  // extern "C"

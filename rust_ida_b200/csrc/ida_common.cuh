@@ -60,6 +60,17 @@ struct LadderParams {
     double touts[MAX_TOUTS];
 };
 
+// per-attempt state trace of ONE instance (the device side of the reference's `data_trace` feature, which serialises
+// the whole solver at the top of every step attempt: src/lib.rs:297-301, 635-639).  Row c of d / i is the instance's
+// complete persistent state (the Layout fields, as doubles / ints) when its c-th attempt begins.
+struct TraceParams {
+    double* d;       // [max][Layout::ndouble()]
+    int* i;          // [max][Layout::nint()]
+    int* count;      // [1] attempts seen so far (rows beyond max are counted, not stored)
+    int max;
+    long long id;    // caller-visible instance id
+};
+
 // select a[k] from a 6-entry register array without dynamic indexing
 __device__ __forceinline__ double pick6(const double (&a)[MXORDP1], int k) {
     double v = a[0];

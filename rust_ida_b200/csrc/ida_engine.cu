@@ -28,11 +28,11 @@ char* last_error_buf() {
 #ifndef IDA_MIN_BLOCKS
 #define IDA_MIN_BLOCKS 3  // 168 regs, 12 warps/SM: measured faster than 4 (128 regs + spills) and 2
 #endif
-template <class P>
+template <class P, bool TRACE = false>
 __global__ void __launch_bounds__(THREAD_BLOCK, IDA_MIN_BLOCKS)
 ida_solve_thread_kernel(double* __restrict__ ds, int* __restrict__ is, const double* __restrict__ params, int64_t B,
                         TolN<P::N> tol, LadderParams lad, double* __restrict__ yy_traj, int32_t* __restrict__ status,
-                        const int* __restrict__ perm) {
+                        const int* __restrict__ perm, TraceParams tr = TraceParams()) {
     extern __shared__ double smem[];
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // slot
     if (b >= B) return;
@@ -41,7 +41,7 @@ ida_solve_thread_kernel(double* __restrict__ ds, int* __restrict__ is, const dou
     s.sm = smem + threadIdx.x;
     s.prob.load(params, B, b);
     s.load(ds, is, B, b);
-    s.solve_ladder(lad, tol, yy_traj, status, B, ob);
+    s.template solve_ladder<TRACE>(lad, tol, yy_traj, status, B, ob, tr);
     s.store(ds, is, B, b);
 }
 
@@ -168,6 +168,7 @@ struct b200ida_ensemble {
     double* d_atol = nullptr;  // [n]
     int kernel = B200IDA_KERNEL_AUTO;
     int* perm = nullptr;  // [B] slot -> caller-visible instance id, or null (identity)
+    TraceParams trace = {nullptr, nullptr, nullptr, 0, -1};  // b200ida_set_trace; id < 0: off
     // persistent device scratch for the host-buffer (end-to-end) entry points and the order builder: a few blocks
     // grown on demand, sub-allocated per API call (scratch_reset() rewinds), freed only by destroy -- so there is no
     // cudaMalloc / cudaFree (and no implicit device synchronisation) on the per-step path once warmed up
@@ -408,6 +409,23 @@ int b200ida_destroy(b200ida_ensemble* e) {
     return B200IDA_OK;
 }
 
+int b200ida_set_trace(b200ida_ensemble* e, int64_t instance, double* dtrace, int32_t* itrace, int32_t* count,
+                      int max_attempts) {
+    if (!e) return set_error(B200IDA_ERR_ARG, "b200ida_set_trace: null handle");
+    if (instance < 0) {
+        e->trace = {nullptr, nullptr, nullptr, 0, -1};
+        return B200IDA_OK;
+    }
+    if (instance >= e->B || !dtrace || !itrace || !count || max_attempts < 1)
+        return set_error(B200IDA_ERR_ARG, "b200ida_set_trace: bad argument (0 <= instance < batch, non-null device buffers)");
+    if (e->n != 3 || e->problem == B200IDA_PROBLEM_HEAT2D)
+        return set_error(B200IDA_ERR_UNSUPPORTED, "b200ida_set_trace: the thread-per-instance kernels (n = 3 problems) only");
+    B200_CUDA_TRY(cudaSetDevice(e->device));
+    B200_CUDA_TRY(cudaMemsetAsync(count, 0, sizeof(int32_t), e->stream));
+    e->trace = {dtrace, reinterpret_cast<int*>(itrace), reinterpret_cast<int*>(count), max_attempts, (long long)instance};
+    return B200IDA_OK;
+}
+
 int b200ida_solve_ladder(b200ida_ensemble* e, const double* touts, int ntout, int itask, double* yy_traj,
                          int32_t* status, int mem) {
     if (!e || !touts || ntout < 1 || ntout > MAX_TOUTS || check_mem(mem))
@@ -448,7 +466,18 @@ int b200ida_solve_ladder(b200ida_ensemble* e, const double* touts, int ntout, in
         TolN<3> tol;
         tol.rtol = e->rtol;
         for (int i = 0; i < 3; ++i) tol.atol[i] = e->atol[i];
-        if (e->problem == B200IDA_PROBLEM_ROBERTS) {
+        if (e->trace.id >= 0) {
+            // traced run: the TRACE instantiation of the same kernel (the production instantiation carries no trace code)
+            if (e->problem == B200IDA_PROBLEM_ROBERTS) {
+                B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_thread_kernel<Roberts, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                ida_solve_thread_kernel<Roberts, true><<<grid, tb, smem, e->stream>>>(e->dstate, e->istate, e->params, e->B, tol, lad,
+                                                                                      d_traj, d_stat, e->perm, e->trace);
+            } else {
+                B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_thread_kernel<Lorenz63, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                ida_solve_thread_kernel<Lorenz63, true><<<grid, tb, smem, e->stream>>>(e->dstate, e->istate, e->params, e->B, tol, lad,
+                                                                                       d_traj, d_stat, e->perm, e->trace);
+            }
+        } else if (e->problem == B200IDA_PROBLEM_ROBERTS) {
             B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_thread_kernel<Roberts>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             ida_solve_thread_kernel<Roberts><<<grid, tb, smem, e->stream>>>(e->dstate, e->istate, e->params, e->B, tol, lad,
                                                                             d_traj, d_stat, e->perm);

@@ -731,8 +731,9 @@ struct IdaThread {
     // Equivalent to calling Ida::solve(touts[k], .., Normal) for k = 0..ntout-1 (src/impl_solve.rs:69-376 with the
     // NORMAL branches of stop_test1/2, src/impl_stop_test.rs:53-65,152-161).  After call k, yy is written to
     // yy_traj[k][.][b] and the call's status to status[k][b] when those pointers are non-null.
+    template <bool TRACE>
     __device__ __forceinline__ void solve_ladder(const LadderParams& lad, const TolN<N>& tol, double* __restrict__ yy_traj,
-                                                 int32_t* __restrict__ status, int64_t B, int64_t b) {
+                                                 int32_t* __restrict__ status, int64_t B, int64_t b, const TraceParams& tr) {
         int it = 0;
         bool need_prologue = true;
         bool in_step = false;
@@ -828,6 +829,14 @@ struct IdaThread {
             }
             if (!call_done) {
                 // one step attempt: src/lib.rs:634-694
+                if constexpr (TRACE) {  // data_trace frame: the whole state at the top of the attempt (src/lib.rs:635-639)
+                    if (b == (int64_t)tr.id) {
+                        constexpr Layout lay(N);
+                        const int c = *tr.count;
+                        if (c < tr.max) store(tr.d + (size_t)c * lay.ndouble(), tr.i + (size_t)c * lay.nint(), 1, 0);
+                        *tr.count = c + 1;
+                    }
+                }
                 natt += 1;
                 const double ck = set_coeffs();
                 tn += hh;

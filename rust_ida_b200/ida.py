@@ -38,6 +38,20 @@ def set_default_reorder(mode):
     _lib.check(_lib.lib().b200ida_set_default_reorder({"off": 0, "on": 1, "auto": 2}[mode]))
 
 
+class AttemptTrace:
+    """device buffers of Ida.trace(); rows() -> (doubles (attempts, 10n+45+n^2), ints (attempts, 16+n)) as numpy"""
+
+    def __init__(self, ida, d, i, count):
+        self.ida, self.d, self.i, self.count = ida, d, i, count
+
+    def rows(self):
+        self.ida.sync()
+        c = int(self.count.cpu()[0])
+        if c > self.d.shape[0]:
+            raise RuntimeError("trace overflow: %d attempts, room for %d" % (c, self.d.shape[0]))
+        return self.d[:c].cpu().numpy(), self.i[:c].cpu().numpy()
+
+
 class Ida:
     """Ida<P, Dense, Newton, TolControlSV> for a whole ensemble."""
 
@@ -116,6 +130,25 @@ class Ida:
 
     def sync(self):
         _lib.check(_lib.lib().b200ida_sync(self._h))
+
+    # ---- per-attempt state trace (the reference's `data_trace` feature, src/lib.rs:297-301, 635-639) --------------
+    def trace(self, instance, max_attempts=4096):
+        """Record the complete solver state of `instance` at the top of every step attempt of the following solves
+        (thread-per-instance kernels).  Returns an AttemptTrace; call .rows() after the solve; trace(None) stops."""
+        import torch
+        if instance is None:
+            _lib.check(_lib.lib().b200ida_set_trace(self._h, -1, None, None, None, 0))
+            self._trace = None
+            return None
+        dev = torch.device("cuda", self.device)
+        nd, ni = 10 * self.n + 45 + self.n * self.n, 16 + self.n
+        t = AttemptTrace(self, torch.zeros((max_attempts, nd), dtype=torch.float64, device=dev),
+                         torch.zeros((max_attempts, ni), dtype=torch.int32, device=dev),
+                         torch.zeros((1,), dtype=torch.int32, device=dev))
+        _lib.check(_lib.lib().b200ida_set_trace(self._h, int(instance), t.d.data_ptr(), t.i.data_ptr(), t.count.data_ptr(),
+                                                int(max_attempts)))
+        self._trace = t  # keeps the device buffers alive while the engine holds their addresses
+        return t
 
     # ---- getters: src/ida_io.rs -----------------------------------------------------------------------------
     def _state(self, which):

@@ -265,3 +265,65 @@ def test_reinit_with_new_parameters_rebuilds_order():
     assert_bit_equal(traj, ref["yy_traj"], "traj after reinit")
     assert np.array_equal(ida.get_num_steps(), ref["counters"]["nst"])
     assert_bit_equal(ida.get_last_step(), ref["hused"], "hused")
+
+
+# ---- per-attempt state trace: the device side of the reference's data_trace feature (src/lib.rs:297-301, 635-639) ------
+TRACE_D_FIELDS = None  # filled lazily: names of the double columns, for readable failures
+
+
+def _trace_names(n):
+    d = ["phi[%d][%d]" % (j, i) for j in range(6) for i in range(n)]
+    for a in ("psi", "alpha", "beta", "sigma", "gamma"):
+        d += ["%s[%d]" % (a, j) for j in range(6)]
+    for v in ("ee", "ewt", "yy", "yp"):
+        d += ["%s[%d]" % (v, i) for i in range(n)]
+    d += ["hh", "hused", "rr", "cj", "cjold", "cjlast", "cjratio", "ss", "toldel", "eps_newt", "tn", "tretlast", "h0u",
+          "tolsf", "tret"]
+    d += ["J[%d][%d]" % (e % n, e // n) for e in range(n * n)]
+    q = ["kk", "kused", "knew", "phase", "ns", "setup_done", "jcur", "nst", "nre", "nje", "nni", "netf", "ncfn", "nsetups",
+         "nlscf", "natt"] + ["piv[%d]" % i for i in range(n)]
+    return d, q
+
+
+@pytest.mark.parametrize("problem,picks", [("roberts", "default+ncfn"), ("lorenz", "spread")])
+def test_every_attempt_of_a_traced_instance_is_bit_identical(problem, picks):
+    """The strongest parity statement the engine can make: for traced instances inside a larger ensemble, the COMPLETE
+    solver state at the top of EVERY step attempt (divided differences, coefficients, error / weight / state vectors,
+    all scalars, the LU factors, pivots and every counter) equals the oracle's, bit for bit -- the reference author's
+    data_trace workflow (scripts/data_trace.ipynb: 377 frames for the default Roberts run) as a GPU-vs-oracle diff."""
+    import torch
+    import rust_ida_b200 as r
+    from rust_ida_b200.problems import lorenz_ensemble_params, roberts_ensemble_params
+    ob, _ = oracle_with_detpow()
+    B = 300
+    if problem == "roberts":
+        cls, kind, rtol, atol, touts = r.Roberts, ob.PK_ROBERTS, ROBERTS_RTOL, ROBERTS_ATOL, ROBERTS_TOUTS
+        p = roberts_ensemble_params(B, seed=1234)
+        p[:, 7] = r.Roberts.DEFAULT  # the reference's own example instance
+    else:
+        cls, kind, rtol, atol, touts = r.Lorenz63, ob.PK_LORENZ63, LORENZ_RTOL, LORENZ_ATOL, LORENZ_TOUTS
+        p = lorenz_ensemble_params(B, seed=1234)
+    yy0, yp0 = cls.consistent_ic(p)
+    ref = ob.ensemble_solve(kind, 3, p, yy0, yp0, rtol, atol, touts, nthreads=8, want_traj=False)
+    picked = [7, 0, B - 1]
+    if problem == "roberts":
+        picked += [int(i) for i in np.nonzero(ref["counters"]["ncfn"] > 0)[0][:2]]  # Newton-recover instances (SURVEY 7.4)
+        picked += [int(np.argmax(ref["counters"]["netf"]))]
+    dn, qn = _trace_names(3)
+    for inst in picked:
+        d_ref, q_ref, _ = ob.attempt_trace(kind, p[:, inst], yy0[:, inst], yp0[:, inst], rtol, atol, touts)
+        ida = r.Ida(cls(p), yy0, yp0, r.TolControlSV(rtol, atol))
+        tr = ida.trace(inst)
+        ida.solve_ladder(touts, want_traj=False)
+        d, q = tr.rows()
+        ida.close()
+        assert d.shape == d_ref.shape and q.shape == q_ref.shape, "attempt counts differ for instance %d" % inst
+        assert d.shape[0] == ref["counters"]["nattempts"][inst]
+        bad_q = np.argwhere(q != q_ref)
+        assert bad_q.size == 0, "instance %d: int field %s differs at attempt %d" % (inst, qn[bad_q[0][1]], bad_q[0][0])
+        bad_d = np.argwhere(d.view(np.uint64) != d_ref.view(np.uint64))
+        assert bad_d.size == 0, "instance %d: field %s differs at attempt %d (%r vs %r)" % (
+            inst, dn[bad_d[0][1]], bad_d[0][0], d[tuple(bad_d[0])], d_ref[tuple(bad_d[0])])
+    if problem == "roberts":
+        d7, _, _ = ob.attempt_trace(kind, p[:, 7], yy0[:, 7], yp0[:, 7], rtol, atol, touts)
+        assert d7.shape[0] == 377  # the frame count of the reference author's notebook
