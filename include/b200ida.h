@@ -175,9 +175,9 @@ int b200ida_solve_ladder(b200ida_ensemble* e, const double* touts /* host */, in
 
 /* Per-attempt state trace of ONE instance -- the device side of the reference's `data_trace` feature, which
  * serialises the whole solver at the top of every step attempt (src/lib.rs:297-301, 635-639; scripts/data_trace.ipynb).
- * Until switched off (instance < 0), every b200ida_solve / b200ida_solve_ladder of this handle runs a traced
- * instantiation of the thread-per-instance kernel (n = 3 problems): when attempt c of `instance` begins, its complete
- * persistent state is written to row c of
+ * Until switched off (instance < 0), every b200ida_solve / b200ida_solve_ladder of this handle records (thread
+ * kernels: a separate traced instantiation; team kernels: a team-uniform test per attempt): when attempt c of
+ * `instance` begins, its complete persistent state is written to row c of
  *   dtrace [max_attempts][10n + 45 + n^2] doubles: phi[6][n], psi, alpha, beta, sigma, gamma [6 each], ee, ewt, yy, yp [n],
  *          hh, hused, rr, cj, cjold, cjlast, cjratio, ss, toldel, eps_newt, tn, tretlast, h0u, tolsf, tret, J[n][n] (col-major)
  *   itrace [max_attempts][16 + n] int32:  kk, kused, knew, phase, ns, setup_done, jcur, nst, nre, nje, nni, netf, ncfn,

@@ -50,13 +50,14 @@ template <class Team>
 __global__ void ida_solve_team_kernel(double* __restrict__ ds, int* __restrict__ is, const double* __restrict__ params,
                                       int64_t B, int n, int kind, int nparams, double rtol, const double* __restrict__ atol,
                                       LadderParams lad, double* __restrict__ yy_traj, int32_t* __restrict__ status,
-                                      unsigned arena_bytes, const int* __restrict__ perm) {
+                                      unsigned arena_bytes, const int* __restrict__ perm, TraceParams tr) {
     extern __shared__ __align__(16) unsigned char team_smem[];
     const int tpc = Team::teams_per_cta();
     IdaTeam<Team> s;
     s.bind(team_smem + (size_t)Team::team_in_cta() * arena_bytes, n);
     s.rtol = rtol;
     s.atol = atol;
+    s.tr = tr;
     s.prob.kind = kind;
     s.prob.n = n;
     int M = 1;
@@ -418,8 +419,6 @@ int b200ida_set_trace(b200ida_ensemble* e, int64_t instance, double* dtrace, int
     }
     if (instance >= e->B || !dtrace || !itrace || !count || max_attempts < 1)
         return set_error(B200IDA_ERR_ARG, "b200ida_set_trace: bad argument (0 <= instance < batch, non-null device buffers)");
-    if (e->n != 3 || e->problem == B200IDA_PROBLEM_HEAT2D)
-        return set_error(B200IDA_ERR_UNSUPPORTED, "b200ida_set_trace: the thread-per-instance kernels (n = 3 problems) only");
     B200_CUDA_TRY(cudaSetDevice(e->device));
     B200_CUDA_TRY(cudaMemsetAsync(count, 0, sizeof(int32_t), e->stream));
     e->trace = {dtrace, reinterpret_cast<int*>(itrace), reinterpret_cast<int*>(count), max_attempts, (long long)instance};
@@ -508,10 +507,10 @@ int b200ida_solve_ladder(b200ida_ensemble* e, const double* touts, int ntout, in
         const unsigned grid = (unsigned)(want < (int64_t)sms * occ ? want : (int64_t)sms * occ);  // persistent teams
         if (warp)
             ida_solve_team_kernel<WarpTeam><<<grid, tb, smem, e->stream>>>(e->dstate, e->istate, e->params, e->B, e->n, e->problem,
-                                                                           e->nparams, e->rtol, e->d_atol, lad, d_traj, d_stat, arena, e->perm);
+                                                                           e->nparams, e->rtol, e->d_atol, lad, d_traj, d_stat, arena, e->perm, e->trace);
         else
             ida_solve_team_kernel<CtaTeam><<<grid, tb, smem, e->stream>>>(e->dstate, e->istate, e->params, e->B, e->n, e->problem,
-                                                                          e->nparams, e->rtol, e->d_atol, lad, d_traj, d_stat, arena, e->perm);
+                                                                          e->nparams, e->rtol, e->d_atol, lad, d_traj, d_stat, arena, e->perm, e->trace);
     }
     B200_CUDA_TRY(cudaGetLastError());
     if (mem == B200IDA_MEM_HOST) {

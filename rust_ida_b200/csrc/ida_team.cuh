@@ -162,6 +162,7 @@ struct IdaTeam {
     TeamProblem prob;
     const double* atol;  // global, [n]
     double rtol;
+    TraceParams tr = {nullptr, nullptr, nullptr, 0, -1};  // b200ida_set_trace
 
     __device__ __forceinline__ void bind(unsigned char* arena, int n_) {
         n = n_;
@@ -873,6 +874,14 @@ struct IdaTeam {
                 Team::sync();
                 int kflag = 0;
                 for (;;) {  // attempts
+                    if (tr.id == (long long)b) {  // team-uniform: data_trace frame of the traced instance (src/lib.rs:635-639)
+                        const Layout lay(n);
+                        const int c = *reinterpret_cast<volatile int*>(tr.count);
+                        if (c < tr.max) store(tr.d + (size_t)c * lay.ndouble(), tr.i + (size_t)c * lay.nint(), 1, 0);
+                        Team::sync();
+                        if (leader()) *tr.count = c + 1;
+                        Team::sync();
+                    }
                     if (leader()) S->natt += 1;
                     set_coeffs();
                     Team::sync();

@@ -327,3 +327,33 @@ def test_every_attempt_of_a_traced_instance_is_bit_identical(problem, picks):
     if problem == "roberts":
         d7, _, _ = ob.attempt_trace(kind, p[:, 7], yy0[:, 7], yp0[:, 7], rtol, atol, touts)
         assert d7.shape[0] == 377  # the frame count of the reference author's notebook
+
+
+@pytest.mark.parametrize("M,kernel", [(10, "cta"), (4, "warp"), (6, "cta")])
+def test_every_attempt_of_a_traced_heat_instance_is_bit_identical(M, kernel):
+    """the same per-attempt statement for the team kernels on the dense heat problem: at the top of every attempt the
+    whole state INCLUDING the n x n LU factors and the pivots (blocked look-ahead LU for n = 100 / 36, group LU for
+    n = 16) equals the oracle's bit for bit"""
+    import rust_ida_b200 as r
+    from rust_ida_b200.problems import heat_ensemble_params
+    ob, _ = oracle_with_detpow()
+    n, B = M * M, 24
+    p = heat_ensemble_params(B, M=M, seed=1234)
+    yy0, yp0 = r.Heat2D.consistent_ic(p, M)
+    touts = 0.01 * 2.0 ** np.arange(11)
+    rtol, atol = 1e-6, np.full(n, 1e-8)
+    dn, qn = _trace_names(n)
+    for inst in (0, 13, B - 1):
+        d_ref, q_ref, _ = ob.attempt_trace(ob.PK_HEAT2D, p[:, inst], yy0[:, inst], yp0[:, inst], rtol, atol, touts)
+        ida = r.Ida(r.Heat2D(p, M=M), yy0, yp0, r.TolControlSV(rtol, atol))
+        ida.set_kernel(kernel)
+        tr = ida.trace(inst, max_attempts=1024)
+        ida.solve_ladder(touts, want_traj=False)
+        d, q = tr.rows()
+        ida.close()
+        assert d.shape == d_ref.shape and q.shape == q_ref.shape and d.shape[0] > 50
+        bad_q = np.argwhere(q != q_ref)
+        assert bad_q.size == 0, "instance %d: int field %s differs at attempt %d" % (inst, qn[bad_q[0][1]], bad_q[0][0])
+        bad_d = np.argwhere(d.view(np.uint64) != d_ref.view(np.uint64))
+        assert bad_d.size == 0, "instance %d: field %s differs at attempt %d (%r vs %r)" % (
+            inst, dn[bad_d[0][1]], bad_d[0][0], d[tuple(bad_d[0])], d_ref[tuple(bad_d[0])])
