@@ -1,6 +1,8 @@
-// lu_blocked.cuh -- blocked, register-tiled partial-pivot LU of ONE column-major matrix that sits in shared memory,
-// executed by a whole CTA.  Used by the Level-1 batched getrf for 33 <= n <= 160 (linalg_batched.cu) and by the
-// CTA-per-system IDA kernel (ida_team.cuh) for the iteration matrix of the heat problem (n = 100).
+// lu_blocked.cuh -- blocked, register-tiled partial-pivot LU of ONE column-major matrix, executed by a whole CTA.
+// lub_factor: the matrix sits in shared memory (Level-1 batched getrf for 33 <= n <= 114, linalg_batched.cu, and the
+// CTA-per-system IDA kernel, ida_team.cuh, for the iteration matrix of the heat problem, n = 100).
+// lub_factor_global (end of file): the matrix stays in global memory / L2 and only the panels go through shared
+// memory (Level-1 getrf for 115 <= n <= 256).
 //
 // Semantics are bit-for-bit dense_get_rf (crates/linear/src/dense.rs:86-158): pivot = first row with strictly
 // largest |a_ik| (a NaN never wins; a NaN in row k keeps l = k); whole-row swap; l_ik = a_ik * (1/a_kk);
@@ -13,7 +15,7 @@
 // shared-memory traffic of the trailing update by NB (the unblocked lu_team.cuh kernel is bound by it).
 // Built with -fmad=false.
 //
-// One block step (columns kb .. kb+nb), two CTA barriers (the panel of the NEXT step runs inside [U], see lub_factor):
+// One block step (columns kb .. kb+nb), three CTA barriers (the panel of the NEXT step runs inside [U], see lub_factor):
 //   [P] panel: warp 0 eliminates the nb columns of the (n-kb) x nb panel in shared memory (lane = row, 32-row
 //       slots), arg-max by warp integer reductions, never moving rows: each lane tracks the LOGICAL position the
 //       reference's row swaps would have given its rows.  It permutes the panel to the logical positions at the end
