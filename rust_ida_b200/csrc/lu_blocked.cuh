@@ -133,43 +133,71 @@ __device__ __noinline__ void lub_panel(double* M, int ld, int n, int kb, int nb,
         double x[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) x[r] = lub_lds(ra[r]);
-        // lane-local best candidate: key = bits of |x| (NaN -> -1, not a candidate -> -2), ties -> lowest position
-        int bhi = -2;
-        unsigned blo = 0u, bpp = 0xffffffffu;
-        bool nank = false;
+        // Fast path (the common case): compare only the high words of |x| -- sign stripped, so for finite values
+        // they order like the values -- and accept the winner when it is unique: exactly one lane holds the maximum
+        // high word, that lane saw it once, and it is finite.  A unique, strictly largest high word means a strictly
+        // largest |x|, so the choice equals the reference's; everything else (equal high words, i.e. possible ties,
+        // and any inf / NaN candidate) takes the full lexicographic path below.
+        int bkey = -1;
+        unsigned bpp = 0xffffffffu;
+        bool tie = false;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const bool isnan_ = x[r] != x[r];
-            const int hi = isnan_ ? -1 : (__double2hiint(x[r]) & 0x7fffffff);
-            const unsigned lo = isnan_ ? 0xffffffffu : (unsigned)__double2loint(x[r]);
-            const bool gt = hi > bhi || (hi == bhi && (lo > blo || (lo == blo && pp[r] < bpp)));
-            const bool take = act[r] && gt;
-            bhi = take ? hi : bhi;
-            blo = take ? lo : blo;
-            bpp = take ? pp[r] : bpp;
-            nank = nank || (isnan_ && (pp[r] >> 16) == (unsigned)k);
+            const int key = act[r] ? (__double2hiint(x[r]) & 0x7fffffff) : -1;
+            const bool gt = key > bkey;
+            tie = gt ? false : (tie || (key == bkey && key >= 0));
+            bkey = gt ? key : bkey;
+            bpp = gt ? pp[r] : bpp;
         }
+        const int mkey = __reduce_max_sync(0xffffffffu, bkey);
+        const unsigned wmask = __ballot_sync(0xffffffffu, bkey == mkey);
+        const bool unique = __popc(wmask) == 1 && !__any_sync(0xffffffffu, tie && bkey == mkey) && mkey < 0x7ff00000;
+        unsigned mpp;
+        bool forced = false;
+        double mult, pv;
+        unsigned pvoff;
         LUB_T(p1);
         LUB_ACC2(0, p0, p1);
-        const int mhi = __reduce_max_sync(0xffffffffu, bhi);
-        const unsigned mlo = __reduce_max_sync(0xffffffffu, (bhi == mhi) ? blo : 0u);
-        unsigned mpp = __reduce_min_sync(0xffffffffu, (bhi == mhi && blo == mlo) ? bpp : 0xffffffffu);
-        const bool forced = mhi < 0 || __any_sync(0xffffffffu, nank);  // nothing comparable, or NaN in row k: l = k
-        // reciprocal of |pivot| from the reduced bits, off the critical path of the sign fetch
-        double mult = __drcp_rn(__hiloint2double(mhi, (int)mlo));
-        if (forced) {  // warp-uniform, rare
-            unsigned pk = 0xffffffffu;
+        if (unique) {  // warp-uniform
+            mpp = __shfl_sync(0xffffffffu, bpp, __ffs(wmask) - 1);
+            pvoff = (mpp & 0xffffu) * 8u;
+            pv = lub_lds(colb + pvoff);
+            mult = __drcp_rn(pv);  // == 1.0 / pv, both correctly rounded
+        } else {
+            // full key = bits of |x| (NaN -> -1, not a candidate -> -2), ties -> lowest logical position
+            int bhi = -2;
+            unsigned blo = 0u;
+            bpp = 0xffffffffu;
+            bool nank = false;
 #pragma unroll
-            for (int r = 0; r < R; ++r) pk = (act[r] && (pp[r] >> 16) == (unsigned)k) ? pp[r] : pk;
-            mpp = __reduce_min_sync(0xffffffffu, pk);
+            for (int r = 0; r < R; ++r) {
+                const bool isnan_ = x[r] != x[r];
+                const int hi = isnan_ ? -1 : (__double2hiint(x[r]) & 0x7fffffff);
+                const unsigned lo = isnan_ ? 0xffffffffu : (unsigned)__double2loint(x[r]);
+                const bool gt = hi > bhi || (hi == bhi && (lo > blo || (lo == blo && pp[r] < bpp)));
+                const bool take = act[r] && gt;
+                bhi = take ? hi : bhi;
+                blo = take ? lo : blo;
+                bpp = take ? pp[r] : bpp;
+                nank = nank || (isnan_ && (pp[r] >> 16) == (unsigned)k);
+            }
+            const int mhi = __reduce_max_sync(0xffffffffu, bhi);
+            const unsigned mlo = __reduce_max_sync(0xffffffffu, (bhi == mhi) ? blo : 0u);
+            mpp = __reduce_min_sync(0xffffffffu, (bhi == mhi && blo == mlo) ? bpp : 0xffffffffu);
+            forced = mhi < 0 || __any_sync(0xffffffffu, nank);  // nothing comparable, or NaN in row k: l = k
+            if (forced) {
+                unsigned pk = 0xffffffffu;
+#pragma unroll
+                for (int r = 0; r < R; ++r) pk = (act[r] && (pp[r] >> 16) == (unsigned)k) ? pp[r] : pk;
+                mpp = __reduce_min_sync(0xffffffffu, pk);
+            }
+            pvoff = (mpp & 0xffffu) * 8u;
+            pv = lub_lds(colb + pvoff);
+            mult = 1.0 / pv;
         }
-        const int l = (int)(mpp >> 16), physl = (int)(mpp & 0xffffu);
+        const int l = (int)(mpp >> 16);
         LUB_T(p2);
         LUB_ACC2(1, p1, p2);
-        const unsigned pvoff = (unsigned)physl * 8u;
-        const double pv = lub_lds(colb + pvoff);
-        if (forced) mult = 1.0 / pv;
-        else mult = (pv < 0.0) ? -mult : mult;
         if (lane == 0) pivs[k] = l;
         if (pv == 0.0) {
             info = k + 1;
