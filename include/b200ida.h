@@ -117,6 +117,8 @@ int b200ida_wrms_masked_batched(const double* x, const double* w, const unsigned
 #define B200IDA_ST_BAD_EWT (-6)       /* an ewt component <= 0, src/impl_solve.rs:272-285 */
 #define B200IDA_ST_ILL_INPUT (-7)     /* tout too close to t0, src/impl_solve.rs:97-109 */
 #define B200IDA_ST_BAD_T (-8)         /* IdaError::BadTimeValue from get_solution, src/lib.rs:1286-1292 */
+#define B200IDA_ST_CLOSE_ROOTS (-9)   /* IdaError::CloseRoots, src/impl_r_check.rs:199-203 */
+#define B200IDA_ST_ROOT 2             /* IdaSolveStatus::Root (src/lib.rs:57-63): internal to a ladder launch, see b200ida_set_roots */
 
 typedef struct b200ida_ensemble b200ida_ensemble; /* opaque */
 
@@ -185,6 +187,26 @@ int b200ida_solve_ladder(b200ida_ensemble* e, const double* touts /* host */, in
  * and count[0] (reset to 0 here) counts the attempts seen.  All three are DEVICE buffers owned by the caller. */
 int b200ida_set_trace(b200ida_ensemble* e, int64_t instance, double* dtrace, int32_t* itrace, int32_t* count,
                       int max_attempts);
+
+/* Rootfinding -- Root::{num_roots, root} (src/traits.rs:72-89), IDARcheck1/2/3 + IDARootfind (src/impl_r_check.rs:32-576),
+ * the Root returns of Ida::solve (src/impl_solve.rs:161-164, 186-227, 335-344) and get_root_info / get_num_g_evals
+ * (src/ida_io.rs:107-117).  Available for the Roberts problem (g0 = y1 - 1e-4, g1 = y3 - 0.01,
+ * src/sample_problems/roberts.rs:99-113) through a separate instantiation of the thread-per-instance kernel.
+ * After b200ida_set_roots(e, max_events > 0, ..) every b200ida_solve_ladder launch plays the caller of
+ * examples/roberts.rs:117-140 on the device: when solve() returns Root for an instance, the event is logged and solve()
+ * is called again for the same tout, so the per-tout status stays Success and
+ *   ev_t      [max_events][batch]      root locations tret, in the order they were found
+ *   ev_iroots [max_events][2][batch]   get_root_info at each event (a Scalar array in the reference: signum(g(tlo)) for
+ *                                      the g_i that crossed, 0 otherwise -- the reference's sign convention, which is the
+ *                                      opposite of SUNDIALS')
+ *   ev_count  [batch]                  events seen (beyond max_events: counted, not stored); reset to 0 here
+ *   nge       [batch], may be NULL     get_num_g_evals after the launch
+ * all DEVICE buffers owned by the caller, indexed by the caller-visible instance id.  Rootfinding never alters the
+ * step sequence (same nst / attempts / states as without).  The reference starts with every g_i INACTIVE
+ * (`ida_gactive` false, src/lib.rs:373; SUNDIALS: active), so roots in the first step are not seen -- kept as is.
+ * max_events <= 0 switches rootfinding off. */
+int b200ida_set_roots(b200ida_ensemble* e, int max_events, double* ev_t, double* ev_iroots, int32_t* ev_count,
+                      int32_t* nge);
 
 /* get_yy / get_yp (src/ida_io.rs:11-19) and the tret of the last solve; SoA [n][batch] / [batch]; NULL skips. */
 int b200ida_get_state(b200ida_ensemble* e, double* yy, double* yp, double* tret, int mem);

@@ -244,6 +244,32 @@ def attempt_trace(kind, params, yy0, yp0, rtol, atol, touts, max_rows=4096):
     return d[:c], q[:c], st
 
 
+def roots_run(kind, params, yy0, yp0, rtol, atol, touts, max_ev=64):
+    """one instance with rootfinding, driven like examples/roberts.rs (solve again after every Root return).
+    Returns dict: t (nev,), iroots (nev, nr), y (nev, n), yy (n,), counters {.., nge}, status (ntout,)."""
+    yy0 = np.ascontiguousarray(yy0, dtype=np.float64)
+    n = yy0.size
+    nr = 2 if kind == PK_ROBERTS else 0
+    touts = np.ascontiguousarray(touts, dtype=np.float64)
+    ev_t = np.zeros(max_ev)
+    ev_r = np.zeros((max_ev, max(nr, 1)))
+    ev_y = np.zeros((max_ev, n))
+    yy = np.zeros(n)
+    cnt = np.zeros(10, dtype=np.int64)
+    st = np.zeros(touts.size, dtype=np.int32)
+    L = lib()
+    L.oracle_roots_run.restype = C.c_long
+    L.oracle_roots_run.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp, C.c_double, _dp, _dp, C.c_int, C.c_long, _dp, _dp, _dp, _dp, _i64p,
+                                   np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")]
+    nev = L.oracle_roots_run(kind, n, np.ascontiguousarray(params, dtype=np.float64), yy0, np.ascontiguousarray(yp0, dtype=np.float64),
+                             rtol, np.ascontiguousarray(atol, dtype=np.float64), touts, touts.size, max_ev, ev_t, ev_r, ev_y, yy, cnt, st)
+    if nev > max_ev:
+        raise RuntimeError("more than %d root events" % max_ev)
+    names = COUNTER_NAMES + ("nge",)
+    return {"t": ev_t[:nev], "iroots": ev_r[:nev, :nr], "y": ev_y[:nev], "yy": yy, "status": st,
+            "counters": {k: int(cnt[i]) for i, k in enumerate(names)}}
+
+
 def single_trace(kind, params, yy0, yp0, rtol, atol, touts):
     yy0 = np.ascontiguousarray(yy0, dtype=np.float64)
     n = yy0.size

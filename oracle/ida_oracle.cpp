@@ -61,6 +61,8 @@ pow_fn_t g_pow = static_cast<double (*)(double, double)>(std::pow);
 // status codes shared with the engine (include/b200ida.h B200IDA_ST_*)
 enum Status : int {
     ST_SUCCESS = 0,
+    ST_ROOT = 2,             // IdaSolveStatus::Root (src/lib.rs:57-63)
+    ST_CLOSE_ROOTS = -9,     // IdaError::CloseRoots (src/impl_r_check.rs:199-203)
     ST_TOO_MUCH_WORK = -1,   // mxstep steps taken (IdaError::IllegalInput in the reference)
     ST_TOO_MUCH_ACC = -2,    // IdaError::TooMuchAccuracy
     ST_ERR_FAIL = -3,        // "IDA_ERR_FAIL"
@@ -78,6 +80,15 @@ struct Problem {
     int kind;
     int n;
     const double* p;  // per-instance parameters
+
+    // Root::num_roots / Root::root -- src/traits.rs:72-89 ; Roberts: src/sample_problems/roberts.rs:99-113
+    int num_roots() const { return kind == PK_ROBERTS ? 2 : 0; }
+    void root(double /*t*/, const double* y, const double* /*yp*/, double* gout) const {
+        if (kind == PK_ROBERTS) {
+            gout[0] = y[0] - 0.0001;
+            gout[1] = y[2] - 0.01;
+        }
+    }
 
     // Residual::res -- src/traits.rs:28-38
     void res(double /*tt*/, const double* yy, const double* yp, double* r) const {
@@ -713,6 +724,218 @@ struct Ida {
         return 0;
     }
 
+    // ---- rootfinding: src/impl_r_check.rs:32-576, state src/lib.rs:198-229 (enabled by enable_roots) -------------
+    int nrtfn = 0;
+    std::vector<double> glo, ghi, grout, iroots;  // iroots is a Scalar array in the reference (src/lib.rs:200)
+    std::vector<char> gactive;                     // initialised FALSE like the reference (src/lib.rs:373; C: TRUE)
+    double tlo = 0, thi = 0, trout = 0, ttol = 0, toutc = 0;
+    bool irfnd = false;
+    long nge = 0;
+    void enable_roots() {
+        nrtfn = prob.num_roots();
+        glo.assign(nrtfn, 0.0);
+        ghi.assign(nrtfn, 0.0);
+        grout.assign(nrtfn, 0.0);
+        iroots.assign(nrtfn, 0.0);
+        gactive.assign(nrtfn, 0);
+    }
+    static double signum(double x) { return (x != x) ? x : (std::signbit(x) ? -1.0 : 1.0); }  // f64::signum
+
+    // IDARcheck1 -- src/impl_r_check.rs:32-105
+    void r_check1() {
+        for (int i = 0; i < nrtfn; ++i) iroots[i] = 0.0;
+        tlo = tn;
+        ttol = (std::fabs(tn) + std::fabs(hh)) * DBL_EPS * 100.0;
+        prob.root(tlo, PHI(0), PHI(1), glo.data());
+        nge = 1;
+        bool zroot = false;
+        for (int i = 0; i < nrtfn; ++i) {
+            if (std::fabs(glo[i]) == 0.0) {
+                gactive[i] = 0;
+                zroot = true;
+            }
+        }
+        if (zroot) {
+            const double hratio = std::max(ttol / std::fabs(hh), 0.1);
+            const double smallh = hratio * hh;
+            const double tplus = tlo + smallh;
+            for (int i = 0; i < n; ++i) yy[i] = PHI(0)[i];
+            for (int i = 0; i < n; ++i) yy[i] += smallh * PHI(1)[i];  // scaled_add
+            prob.root(tplus, yy.data(), PHI(1), ghi.data());
+            nge += 1;
+            for (int i = 0; i < nrtfn; ++i) {
+                if (!gactive[i] && std::fabs(ghi[i]) != 0.0) {
+                    gactive[i] = 1;
+                    glo[i] = ghi[i];
+                }
+            }
+        }
+    }
+
+    // IDARcheck2 -- src/impl_r_check.rs:123-209 ; returns 0 continue, 1 root found, ST_CLOSE_ROOTS
+    int r_check2() {
+        if (!irfnd) return 0;
+        get_solution(tlo);
+        prob.root(tlo, yy.data(), yp.data(), glo.data());
+        nge += 1;
+        for (int i = 0; i < nrtfn; ++i) iroots[i] = 0.0;
+        bool zroot = false;
+        for (int i = 0; i < nrtfn; ++i) {
+            if (gactive[i] && std::fabs(glo[i]) == 0.0) {
+                zroot = true;
+                iroots[i] = 1.0;
+            }
+        }
+        if (zroot) {
+            ttol = (std::fabs(tn) + std::fabs(hh)) * DBL_EPS * 100.0;
+            const double smallh = ttol * signum(hh);
+            const double tplus = tlo + smallh;
+            if ((tplus - tn) * hh >= 0.0) {
+                const double hratio = smallh / hh;
+                for (int i = 0; i < n; ++i) yy[i] += hratio * PHI(1)[i];
+            } else {
+                get_solution(tplus);
+            }
+            prob.root(tplus, yy.data(), yp.data(), ghi.data());
+            nge += 1;
+            bool z2 = false;
+            for (int i = 0; i < nrtfn; ++i) {
+                if (gactive[i]) {
+                    if (std::fabs(ghi[i]) == 0.0) {
+                        if (iroots[i] > 0.0) return ST_CLOSE_ROOTS;  // FoldWhile::Done
+                        z2 = true;
+                        iroots[i] = 1.0;
+                    } else {
+                        if (iroots[i] > 0.0) glo[i] = ghi[i];
+                    }
+                }
+            }
+            if (z2) return 1;
+        }
+        return 0;
+    }
+
+    // one pass over the g_i of root_find: src/impl_r_check.rs:332-369 and :457-492
+    void scan_roots(const std::vector<double>& gx, bool first, int imax_in, bool& zroot, bool& sgnchg, int& imax) const {
+        zroot = false;
+        sgnchg = false;
+        double maxfrac = 0.0;
+        imax = first ? 0 : imax_in;
+        for (int i = 0; i < nrtfn; ++i) {
+            if (!gactive[i]) continue;
+            const bool rootdir_glo_neg = 0.0 * glo[i] <= 0.0;  // rootdir is all zeros (src/lib.rs:368): 0*glo <= 0
+            if (first) {
+                if (std::fabs(gx[i]) == 0.0) {
+                    if (rootdir_glo_neg) zroot = true;
+                } else if (glo[i] * gx[i] < 0.0 && rootdir_glo_neg) {
+                    const double gfrac = std::fabs(gx[i] / (gx[i] - glo[i]));
+                    if (gfrac > maxfrac) {
+                        sgnchg = true;
+                        maxfrac = gfrac;
+                        imax = i;
+                    }
+                }
+            } else {
+                if (std::fabs(gx[i]) == 0.0 && rootdir_glo_neg) {
+                    zroot = true;
+                } else if (glo[i] * gx[i] < 0.0 && rootdir_glo_neg) {
+                    const double gfrac = std::fabs(gx[i] / (gx[i] - glo[i]));
+                    if (gfrac > maxfrac) {
+                        sgnchg = true;
+                        maxfrac = gfrac;
+                        imax = i;
+                    }
+                }
+            }
+        }
+    }
+
+    // IDARootfind (Illinois algorithm) -- src/impl_r_check.rs:330-576 ; returns 0 continue, 1 root found
+    int root_find() {
+        bool zroot, sgnchg;
+        int imax;
+        scan_roots(ghi, true, 0, zroot, sgnchg, imax);
+        if (!sgnchg) {
+            trout = thi;
+            grout = ghi;
+            if (!zroot) return 0;
+            for (int i = 0; i < nrtfn; ++i) {
+                iroots[i] = 0.0;
+                if (gactive[i]) {
+                    const bool rootdir_glo_neg = 0.0 * glo[i] <= 0.0;
+                    if (std::fabs(ghi[i]) == 0.0 && rootdir_glo_neg) iroots[i] = signum(glo[i]);
+                }
+            }
+            return 1;
+        }
+        double alph = 1.0;
+        int side = 0, sideprev = -1;
+        for (;;) {
+            if (std::fabs(thi - tlo) <= ttol) break;
+            alph = (sideprev == side) ? ((side == 2) ? alph * 2.0 : alph * 0.5) : 1.0;
+            double tmid = thi - (thi - tlo) * ghi[imax] / (ghi[imax] - alph * glo[imax]);
+            if (std::fabs(tmid - tlo) < 0.5 * ttol) {
+                const double fracint = std::fabs(thi - tlo) / ttol;
+                const double fracsub = (fracint > 5.0) ? 0.1 : 0.5 / fracint;
+                tmid = tlo + fracsub * (thi - tlo);
+            }
+            if (std::fabs(thi - tmid) < 0.5 * ttol) {
+                const double fracint = std::fabs(thi - tlo) / ttol;
+                const double fracsub = (fracint > 5.0) ? 0.1 : 0.5 / fracint;
+                tmid = thi - fracsub * (thi - tlo);
+            }
+            get_solution(tmid);
+            prob.root(tmid, yy.data(), yp.data(), grout.data());
+            nge += 1;
+            sideprev = side;
+            int imax2;
+            scan_roots(grout, false, imax, zroot, sgnchg, imax2);
+            imax = imax2;
+            if (sgnchg) {
+                thi = tmid;
+                ghi = grout;
+                side = 1;
+                if (std::fabs(thi - tlo) <= ttol) break;
+                continue;
+            }
+            if (zroot) {
+                thi = tmid;
+                ghi = grout;
+                break;
+            }
+            tlo = tmid;
+            glo = grout;
+            side = 2;
+            if (std::fabs(thi - tlo) <= ttol) break;
+        }
+        trout = thi;
+        grout = ghi;
+        for (int i = 0; i < nrtfn; ++i) {
+            iroots[i] = 0.0;
+            if (gactive[i]) {
+                const bool rootdir_glo_neg = 0.0 * glo[i] <= 0.0;
+                if (rootdir_glo_neg && (std::fabs(ghi[i]) == 0.0 || glo[i] * ghi[i] < 0.0)) iroots[i] = signum(glo[i]);
+            }
+        }
+        return 1;
+    }
+
+    // IDARcheck3 -- src/impl_r_check.rs:211-267 ; returns 0 continue, 1 root found
+    int r_check3() {
+        thi = ((toutc - tn) * hh >= 0.0) ? tn : toutc;  // IdaTask::Normal
+        get_solution(thi);
+        prob.root(thi, yy.data(), yp.data(), ghi.data());
+        nge += 1;
+        ttol = (std::fabs(tn) + std::fabs(hh)) * DBL_EPS * 100.0;
+        const int ier = root_find();
+        for (int i = 0; i < nrtfn; ++i)
+            if (!gactive[i] && grout[i] != 0.0) gactive[i] = 1;
+        tlo = trout;
+        glo = grout;
+        if (ier == 1) get_solution(trout);
+        return ier;
+    }
+
     // get_solution -- src/lib.rs:1274-1343 ; returns 0 or ST_BAD_T
     int get_solution(double t) {
         const double sgn = (hh > 0.0 || (hh == 0.0 && !std::signbit(hh))) ? 1.0 : -1.0;  // f64::signum
@@ -745,9 +968,10 @@ struct Ida {
         return 0;
     }
 
-    // solve (IdaTask::Normal, no roots, no tstop) -- src/impl_solve.rs:69-376 with
+    // solve (IdaTask::Normal, optional rootfinding, no tstop) -- src/impl_solve.rs:69-376 with
     // stop_test1/2 NORMAL branches src/impl_stop_test.rs:53-65,152-161
     int solve(double tout, double& tret) {
+        toutc = tout;  // src/impl_solve.rs:78-82 (IdaTask::Normal)
         if (nst == 0) {
             if (!setup_done) {
                 ewt_set(PHI(0));  // initial_setup src/lib.rs:537-545
@@ -770,6 +994,7 @@ struct Ida {
             h0u = hh;
             kk = 0;
             kused = 0;
+            if (nrtfn > 0) r_check1();  // src/impl_solve.rs:161-164, before phi[1] is scaled
             {
                 double* p1 = PHI(1);
                 for (int i = 0; i < n; ++i) p1[i] *= hh;
@@ -779,6 +1004,26 @@ struct Ida {
         }
         long nstloc = 0;
         if (nst > 0) {
+            // root stop checks: src/impl_solve.rs:186-227
+            if (nrtfn > 0) {
+                const int ier2 = r_check2();
+                if (ier2 < 0) return ier2;
+                if (ier2 == 1) {
+                    tretlast = tlo;
+                    tret = tlo;
+                    return ST_ROOT;
+                }
+                const double troundoff = (std::fabs(tn) + std::fabs(hh)) * DBL_EPS * 100.0;
+                if (std::fabs(tn - tretlast) > troundoff) {
+                    if (r_check3() == 1) {
+                        irfnd = true;
+                        tretlast = tlo;
+                        tret = tlo;
+                        return ST_ROOT;
+                    }
+                    irfnd = false;
+                }
+            }
             // stop_test1, NORMAL
             if (tout == tretlast) {
                 tretlast = tout;
@@ -828,6 +1073,13 @@ struct Ida {
                 return sflag;
             }
             nstloc += 1;
+            // root in the last step taken: src/impl_solve.rs:335-344
+            if (nrtfn > 0 && r_check3() == 1) {
+                irfnd = true;
+                tretlast = tlo;
+                tret = tlo;
+                return ST_ROOT;
+            }
             // stop_test2, NORMAL
             if ((tn - tout) * hh >= 0.0) {
                 tret = tout;
@@ -1097,6 +1349,41 @@ long oracle_attempt_trace(int kind, int n, const double* params, const double* y
         if (status) status[it] = st;
     }
     return ida.trace_count;
+}
+
+// One instance with rootfinding, driven like examples/roberts.rs:117-140: for every tout, call solve() again after each
+// Root return.  Events: ev_t[k], ev_iroots[k][nr] (get_root_info), ev_y[k][n]; returns the number of events (may
+// exceed max_ev; only the first max_ev are stored).  out: yy[n], counters[10] = the 9 of oracle_single_trace + nge.
+long oracle_roots_run(int kind, int n, const double* params, const double* yy0, const double* yp0, double rtol, const double* atol,
+                      const double* touts, int ntout, long max_ev, double* ev_t, double* ev_iroots, double* ev_y, double* yy_out,
+                      int64_t* counters, int32_t* status) {
+    Ida ida;
+    Problem p{kind, n, params};
+    ida.init(p, yy0, yp0, rtol, atol);
+    ida.enable_roots();
+    const int nr = ida.nrtfn;
+    long nev = 0;
+    double tret = 0.0;
+    for (int it = 0; it < ntout; ++it) {
+        int st;
+        for (;;) {
+            st = ida.solve(touts[it], tret);
+            if (st != ST_ROOT) break;
+            if (nev < max_ev) {
+                ev_t[nev] = tret;
+                for (int i = 0; i < nr; ++i) ev_iroots[nev * nr + i] = ida.iroots[i];
+                for (int i = 0; i < n; ++i) ev_y[nev * n + i] = ida.yy[i];
+            }
+            nev += 1;
+        }
+        status[it] = st;
+        if (st != 0) break;
+    }
+    for (int i = 0; i < n; ++i) yy_out[i] = ida.yy[i];
+    const long c[10] = {ida.nst, ida.nre, ida.nje, ida.nls.niters, ida.netf, ida.ncfn, ida.nsetups, ida.nls.nconvfails, ida.nattempts,
+                        ida.nge};
+    for (int k = 0; k < 10; ++k) counters[k] = c[k];
+    return nev;
 }
 
 }  // extern "C"

@@ -71,6 +71,19 @@ struct TraceParams {
     long long id;    // caller-visible instance id
 };
 
+// rootfinding (src/impl_r_check.rs): per-instance root state persisted next to the solver state, and the event log
+// a ladder launch fills -- the device plays the caller of examples/roberts.rs:117-140, calling solve() again after
+// every Root return and recording (t, get_root_info) of each.
+struct RootParams {
+    double* rd;         // [4 NR + 5][batch]: glo, ghi, grout, iroots [NR each], tlo, thi, trout, ttol, toutc
+    int* ri;            // [NR + 2][batch]: gactive [NR], irfnd, nge
+    double* ev_t;       // [max_ev][batch] root locations
+    double* ev_iroots;  // [max_ev][NR][batch] get_root_info at each event (a Scalar array in the reference)
+    int* ev_count;      // [batch] events seen (beyond max_ev: counted, not stored)
+    int* nge_out;       // [batch] or null: get_num_g_evals after the launch
+    int max_ev;
+};
+
 // select a[k] from a 6-entry register array without dynamic indexing
 __device__ __forceinline__ double pick6(const double (&a)[MXORDP1], int k) {
     double v = a[0];

@@ -28,11 +28,11 @@ char* last_error_buf() {
 #ifndef IDA_MIN_BLOCKS
 #define IDA_MIN_BLOCKS 3  // 168 regs, 12 warps/SM: measured faster than 4 (128 regs + spills) and 2
 #endif
-template <class P, bool TRACE = false>
+template <class P, bool TRACE = false, bool ROOTS = false>
 __global__ void __launch_bounds__(THREAD_BLOCK, IDA_MIN_BLOCKS)
 ida_solve_thread_kernel(double* __restrict__ ds, int* __restrict__ is, const double* __restrict__ params, int64_t B,
                         TolN<P::N> tol, LadderParams lad, double* __restrict__ yy_traj, int32_t* __restrict__ status,
-                        const int* __restrict__ perm, TraceParams tr = TraceParams()) {
+                        const int* __restrict__ perm, TraceParams tr = TraceParams(), RootParams rp = RootParams()) {
     extern __shared__ double smem[];
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // slot
     if (b >= B) return;
@@ -41,8 +41,13 @@ ida_solve_thread_kernel(double* __restrict__ ds, int* __restrict__ is, const dou
     s.sm = smem + threadIdx.x;
     s.prob.load(params, B, b);
     s.load(ds, is, B, b);
-    s.template solve_ladder<TRACE>(lad, tol, yy_traj, status, B, ob, tr);
+    if constexpr (ROOTS) s.load_roots(rp, B, b);
+    s.template solve_ladder<TRACE, ROOTS>(lad, tol, yy_traj, status, B, ob, tr, rp);
     s.store(ds, is, B, b);
+    if constexpr (ROOTS) {
+        s.store_roots(rp, B, b);
+        if (rp.nge_out) rp.nge_out[ob] = s.nge;
+    }
 }
 
 // Team-per-instance solve (ida_team.cuh): persistent teams (warps or whole CTAs) stride over the ensemble.
@@ -170,6 +175,8 @@ struct b200ida_ensemble {
     int kernel = B200IDA_KERNEL_AUTO;
     int* perm = nullptr;  // [B] slot -> caller-visible instance id, or null (identity)
     TraceParams trace = {nullptr, nullptr, nullptr, 0, -1};  // b200ida_set_trace; id < 0: off
+    RootParams roots = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0};  // b200ida_set_roots; max_ev == 0: off
+    DevBuf root_d, root_i;  // the per-instance root state (engine-owned)
     // persistent device scratch for the host-buffer (end-to-end) entry points and the order builder: a few blocks
     // grown on demand, sub-allocated per API call (scratch_reset() rewinds), freed only by destroy -- so there is no
     // cudaMalloc / cudaFree (and no implicit device synchronisation) on the per-step path once warmed up
@@ -306,6 +313,11 @@ int b200ida_reinit(b200ida_ensemble* e, const double* params, const double* yy0,
     const size_t vbytes = (size_t)n * batch * sizeof(double);
     B200_CUDA_TRY(cudaMemsetAsync(e->dstate, 0, nd * sizeof(double), st));
     B200_CUDA_TRY(cudaMemsetAsync(e->istate, 0, ni * sizeof(int), st));
+    if (e->roots.max_ev > 0) {  // a re-initialised ensemble starts rootfinding afresh (Ida::new, src/lib.rs:360-375)
+        B200_CUDA_TRY(cudaMemsetAsync(e->root_d.p, 0, (size_t)(4 * Roberts::NR + 5) * batch * sizeof(double), st));
+        B200_CUDA_TRY(cudaMemsetAsync(e->root_i.p, 0, (size_t)(Roberts::NR + 2) * batch * sizeof(int), st));
+        B200_CUDA_TRY(cudaMemsetAsync(e->roots.ev_count, 0, (size_t)batch * sizeof(int), st));
+    }
     if (params) {
         // new parameters: bring them to the device in caller order, rebuild the slot order, store them by slot
         const size_t pbytes = (size_t)e->nparams * batch * sizeof(double);
@@ -425,6 +437,28 @@ int b200ida_set_trace(b200ida_ensemble* e, int64_t instance, double* dtrace, int
     return B200IDA_OK;
 }
 
+int b200ida_set_roots(b200ida_ensemble* e, int max_events, double* ev_t, double* ev_iroots, int32_t* ev_count, int32_t* nge) {
+    if (!e) return set_error(B200IDA_ERR_ARG, "b200ida_set_roots: null handle");
+    if (max_events <= 0) {
+        e->roots = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
+        return B200IDA_OK;
+    }
+    if (e->problem != B200IDA_PROBLEM_ROBERTS || e->n != 3)
+        return set_error(B200IDA_ERR_UNSUPPORTED, "b200ida_set_roots: the Roberts problem is the only one with root functions");
+    if (!ev_t || !ev_iroots || !ev_count) return set_error(B200IDA_ERR_ARG, "b200ida_set_roots: null event buffer");
+    B200_CUDA_TRY(cudaSetDevice(e->device));
+    constexpr int NR = Roberts::NR;
+    const size_t db = (size_t)(4 * NR + 5) * e->B * sizeof(double), ib = (size_t)(NR + 2) * e->B * sizeof(int);
+    if (!e->root_d.p) B200_CUDA_TRY(e->root_d.alloc(db));  // the batch size of a handle is fixed
+    if (!e->root_i.p) B200_CUDA_TRY(e->root_i.alloc(ib));
+    B200_CUDA_TRY(cudaMemsetAsync(e->root_d.p, 0, db, e->stream));
+    B200_CUDA_TRY(cudaMemsetAsync(e->root_i.p, 0, ib, e->stream));  // gactive = false, irfnd = false, nge = 0 (src/lib.rs:360-375)
+    B200_CUDA_TRY(cudaMemsetAsync(ev_count, 0, (size_t)e->B * sizeof(int32_t), e->stream));
+    e->roots = {e->root_d.as<double>(), e->root_i.as<int>(), ev_t, ev_iroots, reinterpret_cast<int*>(ev_count),
+                reinterpret_cast<int*>(nge), max_events};
+    return B200IDA_OK;
+}
+
 int b200ida_solve_ladder(b200ida_ensemble* e, const double* touts, int ntout, int itask, double* yy_traj,
                          int32_t* status, int mem) {
     if (!e || !touts || ntout < 1 || ntout > MAX_TOUTS || check_mem(mem))
@@ -465,7 +499,13 @@ int b200ida_solve_ladder(b200ida_ensemble* e, const double* touts, int ntout, in
         TolN<3> tol;
         tol.rtol = e->rtol;
         for (int i = 0; i < 3; ++i) tol.atol[i] = e->atol[i];
-        if (e->trace.id >= 0) {
+        if (e->roots.max_ev > 0) {
+            if (e->problem != B200IDA_PROBLEM_ROBERTS)
+                return set_error(B200IDA_ERR_UNSUPPORTED, "rootfinding: the Roberts problem is the only one with root functions");
+            B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_thread_kernel<Roberts, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ida_solve_thread_kernel<Roberts, false, true><<<grid, tb, smem, e->stream>>>(e->dstate, e->istate, e->params, e->B, tol, lad,
+                                                                                         d_traj, d_stat, e->perm, TraceParams(), e->roots);
+        } else if (e->trace.id >= 0) {
             // traced run: the TRACE instantiation of the same kernel (the production instantiation carries no trace code)
             if (e->problem == B200IDA_PROBLEM_ROBERTS) {
                 B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_thread_kernel<Roberts, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -698,7 +698,262 @@ struct IdaThread {
         return r;
     }
 
+    // ---- rootfinding: src/impl_r_check.rs:32-576 (state src/lib.rs:198-229).  Only instantiated by the ROOTS kernels. --
+    static constexpr int NR = P::NR > 0 ? P::NR : 1;
+    double glo[NR], ghi[NR], grout[NR], iroots[NR];
+    bool gactive[NR];  // FALSE at start like the reference (src/lib.rs:373)
+    double tlo, thi, trout, ttol, toutc;
+    bool irfnd;
+    int nge;
+    __device__ __forceinline__ static double signum(double x) { return (x != x) ? x : (signbit(x) ? -1.0 : 1.0); }
+    __device__ __forceinline__ void eval_root(double t, double (&g)[NR]) {
+        if constexpr (P::NR > 0) prob.root(t, yy, yp, g);
+    }
+    __device__ __forceinline__ void load_roots(const RootParams& rp, int64_t B, int64_t b) {
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+            glo[i] = rp.rd[(int64_t)i * B + b];
+            ghi[i] = rp.rd[(int64_t)(NR + i) * B + b];
+            grout[i] = rp.rd[(int64_t)(2 * NR + i) * B + b];
+            iroots[i] = rp.rd[(int64_t)(3 * NR + i) * B + b];
+            gactive[i] = rp.ri[(int64_t)i * B + b] != 0;
+        }
+        tlo = rp.rd[(int64_t)(4 * NR) * B + b];
+        thi = rp.rd[(int64_t)(4 * NR + 1) * B + b];
+        trout = rp.rd[(int64_t)(4 * NR + 2) * B + b];
+        ttol = rp.rd[(int64_t)(4 * NR + 3) * B + b];
+        toutc = rp.rd[(int64_t)(4 * NR + 4) * B + b];
+        irfnd = rp.ri[(int64_t)NR * B + b] != 0;
+        nge = rp.ri[(int64_t)(NR + 1) * B + b];
+    }
+    __device__ __forceinline__ void store_roots(const RootParams& rp, int64_t B, int64_t b) {
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+            rp.rd[(int64_t)i * B + b] = glo[i];
+            rp.rd[(int64_t)(NR + i) * B + b] = ghi[i];
+            rp.rd[(int64_t)(2 * NR + i) * B + b] = grout[i];
+            rp.rd[(int64_t)(3 * NR + i) * B + b] = iroots[i];
+            rp.ri[(int64_t)i * B + b] = gactive[i] ? 1 : 0;
+        }
+        rp.rd[(int64_t)(4 * NR) * B + b] = tlo;
+        rp.rd[(int64_t)(4 * NR + 1) * B + b] = thi;
+        rp.rd[(int64_t)(4 * NR + 2) * B + b] = trout;
+        rp.rd[(int64_t)(4 * NR + 3) * B + b] = ttol;
+        rp.rd[(int64_t)(4 * NR + 4) * B + b] = toutc;
+        rp.ri[(int64_t)NR * B + b] = irfnd ? 1 : 0;
+        rp.ri[(int64_t)(NR + 1) * B + b] = nge;
+    }
+
+    // IDARcheck1 -- src/impl_r_check.rs:32-105 (called before phi[1] is scaled by hh)
+    __device__ __noinline__ void r_check1() {
+#pragma unroll
+        for (int i = 0; i < NR; ++i) iroots[i] = 0.0;
+        tlo = tn;
+        ttol = (fabs(tn) + fabs(hh)) * DBL_EPS * 100.0;
+        double y0[N], y1[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            y0[i] = phi(0, i);
+            y1[i] = phi(1, i);
+        }
+        if constexpr (P::NR > 0) prob.root(tlo, y0, y1, glo);
+        nge = 1;
+        bool zroot = false;
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+            if (fabs(glo[i]) == 0.0) {
+                gactive[i] = false;
+                zroot = true;
+            }
+        }
+        if (zroot) {
+            const double hratio = fmax(ttol / fabs(hh), 0.1);
+            const double smallh = hratio * hh;
+            const double tplus = tlo + smallh;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                yy[i] = y0[i];
+                yy[i] += smallh * y1[i];
+            }
+            if constexpr (P::NR > 0) prob.root(tplus, yy, y1, ghi);
+            nge += 1;
+#pragma unroll
+            for (int i = 0; i < NR; ++i) {
+                if (!gactive[i] && fabs(ghi[i]) != 0.0) {
+                    gactive[i] = true;
+                    glo[i] = ghi[i];
+                }
+            }
+        }
+    }
+
+    // IDARcheck2 -- src/impl_r_check.rs:123-209 ; 0 continue, 1 root found, B200IDA_ST_CLOSE_ROOTS
+    __device__ __noinline__ int r_check2() {
+        if (!irfnd) return 0;
+        get_solution(tlo);
+        eval_root(tlo, glo);
+        nge += 1;
+        bool zroot = false;
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+            iroots[i] = 0.0;
+            if (gactive[i] && fabs(glo[i]) == 0.0) {
+                zroot = true;
+                iroots[i] = 1.0;
+            }
+        }
+        if (zroot) {
+            ttol = (fabs(tn) + fabs(hh)) * DBL_EPS * 100.0;
+            const double sgn = (hh > 0.0 || (hh == 0.0 && !signbit(hh))) ? 1.0 : -1.0;
+            const double smallh = ttol * sgn;
+            const double tplus = tlo + smallh;
+            if ((tplus - tn) * hh >= 0.0) {
+                const double hratio = smallh / hh;
+#pragma unroll
+                for (int i = 0; i < N; ++i) yy[i] += hratio * phi(1, i);
+            } else {
+                get_solution(tplus);
+            }
+            eval_root(tplus, ghi);
+            nge += 1;
+            bool z2 = false;
+#pragma unroll
+            for (int i = 0; i < NR; ++i) {
+                if (gactive[i]) {
+                    if (fabs(ghi[i]) == 0.0) {
+                        if (iroots[i] > 0.0) return B200IDA_ST_CLOSE_ROOTS;
+                        z2 = true;
+                        iroots[i] = 1.0;
+                    } else if (iroots[i] > 0.0) {
+                        glo[i] = ghi[i];
+                    }
+                }
+            }
+            if (z2) return 1;
+        }
+        return 0;
+    }
+
+    // one pass over the g_i in root_find: src/impl_r_check.rs:332-369 (first) and :457-492
+    __device__ __forceinline__ void scan_roots(const double (&gx)[NR], bool first, bool& zroot, bool& sgnchg, int& imax) const {
+        zroot = false;
+        sgnchg = false;
+        double maxfrac = 0.0;
+        if (first) imax = 0;
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+            if (!gactive[i]) continue;
+            const bool rootdir_glo_neg = 0.0 * glo[i] <= 0.0;  // rootdir is all zeros (src/lib.rs:368)
+            const bool gz = fabs(gx[i]) == 0.0;
+            if (gz && (first || rootdir_glo_neg)) {
+                if (rootdir_glo_neg) zroot = true;
+            } else if (glo[i] * gx[i] < 0.0 && rootdir_glo_neg) {
+                const double gfrac = fabs(gx[i] / (gx[i] - glo[i]));
+                if (gfrac > maxfrac) {
+                    sgnchg = true;
+                    maxfrac = gfrac;
+                    imax = i;
+                }
+            }
+        }
+    }
+    __device__ __forceinline__ double pickr(const double (&a)[NR], int k) const {
+        double v = a[0];
+#pragma unroll
+        for (int j = 1; j < NR; ++j) v = (k == j) ? a[j] : v;
+        return v;
+    }
+
+    // IDARootfind (Illinois) -- src/impl_r_check.rs:330-576 ; 0 continue, 1 root found
+    __device__ __noinline__ int root_find() {
+        bool zroot, sgnchg;
+        int imax = 0;
+        scan_roots(ghi, true, zroot, sgnchg, imax);
+        if (!sgnchg) {
+            trout = thi;
+#pragma unroll
+            for (int i = 0; i < NR; ++i) grout[i] = ghi[i];
+            if (!zroot) return 0;
+#pragma unroll
+            for (int i = 0; i < NR; ++i) {
+                iroots[i] = 0.0;
+                if (gactive[i] && fabs(ghi[i]) == 0.0 && 0.0 * glo[i] <= 0.0) iroots[i] = signum(glo[i]);
+            }
+            return 1;
+        }
+        double alph = 1.0;
+        int side = 0, sideprev = -1;
+#pragma unroll 1
+        for (;;) {
+            if (fabs(thi - tlo) <= ttol) break;
+            alph = (sideprev == side) ? ((side == 2) ? alph * 2.0 : alph * 0.5) : 1.0;
+            const double gh = pickr(ghi, imax), gl = pickr(glo, imax);
+            double tmid = thi - (thi - tlo) * gh / (gh - alph * gl);
+            if (fabs(tmid - tlo) < 0.5 * ttol) {
+                const double fracint = fabs(thi - tlo) / ttol;
+                const double fracsub = (fracint > 5.0) ? 0.1 : 0.5 / fracint;
+                tmid = tlo + fracsub * (thi - tlo);
+            }
+            if (fabs(thi - tmid) < 0.5 * ttol) {
+                const double fracint = fabs(thi - tlo) / ttol;
+                const double fracsub = (fracint > 5.0) ? 0.1 : 0.5 / fracint;
+                tmid = thi - fracsub * (thi - tlo);
+            }
+            get_solution(tmid);
+            eval_root(tmid, grout);
+            nge += 1;
+            sideprev = side;
+            scan_roots(grout, false, zroot, sgnchg, imax);
+            if (sgnchg) {
+                thi = tmid;
+#pragma unroll
+                for (int i = 0; i < NR; ++i) ghi[i] = grout[i];
+                side = 1;
+                if (fabs(thi - tlo) <= ttol) break;
+                continue;
+            }
+            if (zroot) {
+                thi = tmid;
+#pragma unroll
+                for (int i = 0; i < NR; ++i) ghi[i] = grout[i];
+                break;
+            }
+            tlo = tmid;
+#pragma unroll
+            for (int i = 0; i < NR; ++i) glo[i] = grout[i];
+            side = 2;
+            if (fabs(thi - tlo) <= ttol) break;
+        }
+        trout = thi;
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+            grout[i] = ghi[i];
+            iroots[i] = 0.0;
+            if (gactive[i] && 0.0 * glo[i] <= 0.0 && (fabs(ghi[i]) == 0.0 || glo[i] * ghi[i] < 0.0)) iroots[i] = signum(glo[i]);
+        }
+        return 1;
+    }
+
+    // IDARcheck3 -- src/impl_r_check.rs:211-267 ; 0 continue, 1 root found
+    __device__ __noinline__ int r_check3() {
+        thi = ((toutc - tn) * hh >= 0.0) ? tn : toutc;  // IdaTask::Normal
+        get_solution(thi);
+        eval_root(thi, ghi);
+        nge += 1;
+        ttol = (fabs(tn) + fabs(hh)) * DBL_EPS * 100.0;
+        const int ier = root_find();
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+            if (!gactive[i] && grout[i] != 0.0) gactive[i] = true;
+            glo[i] = grout[i];
+        }
+        tlo = trout;
+        if (ier == 1) get_solution(trout);
+        return ier;
+    }
+
     // ---- first-call block of solve(): src/impl_solve.rs:84-173 ; returns 0 or B200IDA_ST_ILL_INPUT ---------------
+    template <bool ROOTS>
     __device__ __forceinline__ int first_call(double tout, const TolN<N>& tol) {
         if (!setup_done) {
             ewt_set(tol);  // initial_setup, src/lib.rs:537-545
@@ -720,6 +975,7 @@ struct IdaThread {
         h0u = hh;
         kk = 0;
         kused = 0;
+        if constexpr (ROOTS) r_check1();  // src/impl_solve.rs:161-164, before phi[1] is scaled
 #pragma unroll
         for (int i = 0; i < N; ++i) phi(1, i) = p1[i] * hh;
         eps_newt = EPCON;
@@ -731,9 +987,10 @@ struct IdaThread {
     // Equivalent to calling Ida::solve(touts[k], .., Normal) for k = 0..ntout-1 (src/impl_solve.rs:69-376 with the
     // NORMAL branches of stop_test1/2, src/impl_stop_test.rs:53-65,152-161).  After call k, yy is written to
     // yy_traj[k][.][b] and the call's status to status[k][b] when those pointers are non-null.
-    template <bool TRACE>
+    template <bool TRACE, bool ROOTS = false>
     __device__ __forceinline__ void solve_ladder(const LadderParams& lad, const TolN<N>& tol, double* __restrict__ yy_traj,
-                                                 int32_t* __restrict__ status, int64_t B, int64_t b, const TraceParams& tr) {
+                                                 int32_t* __restrict__ status, int64_t B, int64_t b, const TraceParams& tr,
+                                                 const RootParams& rp = RootParams()) {
         int it = 0;
         bool need_prologue = true;
         bool in_step = false;
@@ -752,15 +1009,41 @@ struct IdaThread {
                 in_step = false;
                 call_done = false;
                 call_status = 0;
+                if constexpr (ROOTS) toutc = tout;  // src/impl_solve.rs:78-82
                 if (nst == 0) {
-                    const int r = first_call(tout, tol);
+                    const int r = first_call<ROOTS>(tout, tol);
                     if (r != 0) {
                         call_done = true;
                         call_status = r;
                     }
                 } else {
+                    if constexpr (ROOTS) {  // root stop checks: src/impl_solve.rs:186-227
+                        const int ier2 = r_check2();
+                        if (ier2 != 0) {
+                            if (ier2 == 1) {
+                                tretlast = tlo;
+                                tret = tlo;
+                            }
+                            call_status = (ier2 == 1) ? B200IDA_ST_ROOT : ier2;
+                            call_done = true;
+                        } else {
+                            const double troundoff = (fabs(tn) + fabs(hh)) * DBL_EPS * 100.0;
+                            if (fabs(tn - tretlast) > troundoff) {
+                                if (r_check3() == 1) {
+                                    irfnd = true;
+                                    tretlast = tlo;
+                                    tret = tlo;
+                                    call_status = B200IDA_ST_ROOT;
+                                    call_done = true;
+                                } else {
+                                    irfnd = false;
+                                }
+                            }
+                        }
+                    }
                     // stop_test1, NORMAL: src/impl_stop_test.rs:53-65
-                    if (tout == tretlast) {
+                    if (call_done) {
+                    } else if (tout == tretlast) {
                         tretlast = tout;
                         tret = tout;
                         call_done = true;
@@ -854,8 +1137,19 @@ struct IdaThread {
                     for (int i = 0; i < N; ++i) ee[i] *= ck;  // src/lib.rs:708
                     in_step = false;
                     nstloc += 1;
+                    bool root_ret = false;
+                    if constexpr (ROOTS) {  // root in the last step taken: src/impl_solve.rs:335-344
+                        if (r_check3() == 1) {
+                            irfnd = true;
+                            tretlast = tlo;
+                            tret = tlo;
+                            call_status = B200IDA_ST_ROOT;
+                            call_done = true;
+                            root_ret = true;
+                        }
+                    }
                     // stop_test2, NORMAL: src/impl_stop_test.rs:152-161
-                    if ((tn - tout) * hh >= 0.0) {
+                    if (!root_ret && (tn - tout) * hh >= 0.0) {
                         tret = tout;
                         tretlast = tout;
                         get_solution(tout);
@@ -883,6 +1177,21 @@ struct IdaThread {
                     } else if (nst == 0) {
                         reset();
                     }
+                }
+            }
+            if constexpr (ROOTS) {
+                if (call_done && call_status == B200IDA_ST_ROOT) {
+                    // the caller of examples/roberts.rs:117-140: log (t, get_root_info) and call solve() again
+                    const int c = rp.ev_count[b];
+                    if (c < rp.max_ev) {
+                        rp.ev_t[(int64_t)c * B + b] = tret;
+#pragma unroll
+                        for (int i = 0; i < NR; ++i) rp.ev_iroots[((int64_t)c * NR + i) * B + b] = iroots[i];
+                    }
+                    rp.ev_count[b] = c + 1;
+                    call_done = false;
+                    need_prologue = true;
+                    continue;
                 }
             }
             if (call_done) {

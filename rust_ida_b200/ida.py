@@ -30,6 +30,8 @@ class IdaSolveStatus(enum.IntEnum):
     BadErrorWeight = -6   # src/impl_solve.rs:272-285
     IllegalInput = -7     # src/impl_solve.rs:97-109
     BadTimeValue = -8     # src/lib.rs:1286-1292
+    CloseRoots = -9       # IdaError::CloseRoots, src/impl_r_check.rs:199-203
+    Root = 2              # IdaSolveStatus::Root (src/lib.rs:57-63); consumed inside a ladder launch (enable_roots)
 
 
 def set_default_reorder(mode):
@@ -50,6 +52,19 @@ class AttemptTrace:
         if c > self.d.shape[0]:
             raise RuntimeError("trace overflow: %d attempts, room for %d" % (c, self.d.shape[0]))
         return self.d[:c].cpu().numpy(), self.i[:c].cpu().numpy()
+
+
+class RootEvents:
+    """device buffers of Ida.enable_roots(): t (max_events, batch), iroots (max_events, 2, batch) = get_root_info at
+    each event (src/ida_io.rs:115), count (batch,), nge (batch,) = get_num_g_evals (src/ida_io.rs:107)"""
+
+    def __init__(self, ida, t, iroots, count, nge):
+        self.ida, self.t, self.iroots, self.count, self.nge = ida, t, iroots, count, nge
+
+    def numpy(self):
+        self.ida.sync()
+        return {"t": self.t.cpu().numpy(), "iroots": self.iroots.cpu().numpy(), "count": self.count.cpu().numpy(),
+                "nge": self.nge.cpu().numpy()}
 
 
 class Ida:
@@ -130,6 +145,26 @@ class Ida:
 
     def sync(self):
         _lib.check(_lib.lib().b200ida_sync(self._h))
+
+    # ---- rootfinding: src/impl_r_check.rs, Root returns of Ida::solve, get_root_info / get_num_g_evals ----------------
+    def enable_roots(self, max_events=16):
+        """Switch rootfinding on (Roberts: g0 = y1 - 1e-4, g1 = y3 - 0.01).  Every following solve_ladder launch logs
+        the Root returns per instance like the loop of examples/roberts.rs:117-140.  Returns a RootEvents object;
+        enable_roots(0) switches it off."""
+        import torch
+        if not max_events:
+            _lib.check(_lib.lib().b200ida_set_roots(self._h, 0, None, None, None, None))
+            self._roots = None
+            return None
+        dev = torch.device("cuda", self.device)
+        ev = RootEvents(self, torch.zeros((max_events, self.batch), dtype=torch.float64, device=dev),
+                        torch.zeros((max_events, 2, self.batch), dtype=torch.float64, device=dev),
+                        torch.zeros((self.batch,), dtype=torch.int32, device=dev),
+                        torch.zeros((self.batch,), dtype=torch.int32, device=dev))
+        _lib.check(_lib.lib().b200ida_set_roots(self._h, int(max_events), ev.t.data_ptr(), ev.iroots.data_ptr(),
+                                                ev.count.data_ptr(), ev.nge.data_ptr()))
+        self._roots = ev  # keeps the device buffers alive while the engine holds their addresses
+        return ev
 
     # ---- per-attempt state trace (the reference's `data_trace` feature, src/lib.rs:297-301, 635-639) --------------
     def trace(self, instance, max_attempts=4096):

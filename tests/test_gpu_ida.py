@@ -357,3 +357,66 @@ def test_every_attempt_of_a_traced_heat_instance_is_bit_identical(M, kernel):
         bad_d = np.argwhere(d.view(np.uint64) != d_ref.view(np.uint64))
         assert bad_d.size == 0, "instance %d: field %s differs at attempt %d (%r vs %r)" % (
             inst, dn[bad_d[0][1]], bad_d[0][0], d[tuple(bad_d[0])], d_ref[tuple(bad_d[0])])
+
+
+# ---- rootfinding: src/impl_r_check.rs, the Root returns of Ida::solve, get_root_info / get_num_g_evals ------------------
+def test_roberts_root_events_match_the_oracle():
+    """GPU (ROOTS instantiation of the thread kernel, caller loop of examples/roberts.rs:117-140 on the device) vs the
+    oracle's restatement of IDARcheck1/2/3 + IDARootfind, instance by instance: event times and get_root_info
+    bit-identical, get_num_g_evals equal, and the integration itself untouched by rootfinding."""
+    import torch
+    import rust_ida_b200 as r
+    from rust_ida_b200.problems import roberts_ensemble_params
+    ob, _ = oracle_with_detpow()
+    B = 700
+    p = roberts_ensemble_params(B, seed=1234)
+    p[:, 11] = r.Roberts.DEFAULT
+    yy0, yp0 = r.Roberts.consistent_ic(p)
+    plain = run_engine(r.Roberts, p, yy0, yp0, ROBERTS_RTOL, ROBERTS_ATOL, ROBERTS_TOUTS, ladder=True)
+    ida = r.Ida(r.Roberts(p), yy0, yp0, r.TolControlSV(ROBERTS_RTOL, ROBERTS_ATOL))
+    ev = ida.enable_roots(max_events=8)
+    status, traj = ida.solve_ladder(ROBERTS_TOUTS)
+    e = ev.numpy()
+    yy = np.asarray(ida.get_yy())
+    cnt = {k: np.asarray(v) for k, v in ida.counters().items()}
+    ida.close()
+    # rootfinding never alters the step sequence or the returned solution at the output times
+    assert (np.asarray(status) == 0).all()
+    assert_bit_equal(yy, plain["yy"], "final state with / without rootfinding")
+    assert_bit_equal(np.asarray(traj), plain["traj"], "y(tout) with / without rootfinding")
+    for k in COUNTERS:
+        assert np.array_equal(cnt[k], plain["counters"][k]), k
+    assert (e["count"] == 2).all()  # y3 rises through 0.01, later y1 falls through 1e-4
+    for inst in list(range(0, B, 7)) + [11, B - 1]:
+        ref = ob.roots_run(ob.PK_ROBERTS, p[:, inst], yy0[:, inst], yp0[:, inst], ROBERTS_RTOL, ROBERTS_ATOL, ROBERTS_TOUTS)
+        assert e["count"][inst] == ref["t"].size
+        assert_bit_equal(e["t"][:ref["t"].size, inst], ref["t"], "root times of instance %d" % inst)
+        assert_bit_equal(e["iroots"][:ref["t"].size, :, inst], ref["iroots"], "get_root_info of instance %d" % inst)
+        assert e["nge"][inst] == ref["counters"]["nge"]
+    # the reference example's own instance: the two roots of SUNDIALS' idaRoberts_dns (t = 2.6400e-01, 2.0786e+07), with the
+    # reference's sign convention for get_root_info (signum of g at the left end, src/impl_r_check.rs:388,569)
+    assert abs(e["t"][0, 11] - 2.6400e-01) < 5e-5 and abs(e["t"][1, 11] / 2.0786e+07 - 1.0) < 2e-4
+    assert e["iroots"][0, :, 11].tolist() == [0.0, -1.0] and e["iroots"][1, :, 11].tolist() == [1.0, 0.0]
+
+
+def test_root_state_survives_between_launches():
+    """solve(tout) call by call (one launch per tout) must find the same events as the one-launch ladder: the root state
+    (glo, gactive, tlo, irfnd, nge ...) is persistent device state like the rest of the solver"""
+    import rust_ida_b200 as r
+    from rust_ida_b200.problems import roberts_ensemble_params
+    B = 96
+    p = roberts_ensemble_params(B, seed=99)
+    yy0, yp0 = r.Roberts.consistent_ic(p)
+    out = []
+    for split in (False, True):
+        ida = r.Ida(r.Roberts(p), yy0, yp0, r.TolControlSV(ROBERTS_RTOL, ROBERTS_ATOL))
+        ev = ida.enable_roots(max_events=8)
+        if split:
+            for t in ROBERTS_TOUTS:
+                ida.solve_ladder(np.array([t]), want_traj=False)
+        else:
+            ida.solve_ladder(ROBERTS_TOUTS, want_traj=False)
+        out.append(ev.numpy())
+        ida.close()
+    assert np.array_equal(out[0]["count"], out[1]["count"]) and np.array_equal(out[0]["nge"], out[1]["nge"])
+    assert_bit_equal(out[0]["t"], out[1]["t"], "root times, ladder vs call by call")

@@ -69,4 +69,5 @@ def test_status_enum_matches_header():
     assert int(codes["TOO_MUCH_WORK"]) == r.IdaSolveStatus.TooMuchWork
     assert int(codes["LSETUP_FAIL"]) == r.IdaSolveStatus.LinearSetupFail
     assert int(codes["BAD_T"]) == r.IdaSolveStatus.BadTimeValue
+    assert int(codes["CLOSE_ROOTS"]) == r.IdaSolveStatus.CloseRoots and int(codes["ROOT"]) == r.IdaSolveStatus.Root
     assert len(codes) == len(r.IdaSolveStatus)

@@ -230,3 +230,24 @@ def test_roberts_end_to_end():
     ref = np.array([5.2083474251394888e-08, 2.0833390772616859e-13, 9.9999994791631752e-01])
     ewt = 1.0 / (1e-4 * np.abs(ref) + 10.0 * np.array([1e-8, 1e-6, 1e-6]))
     assert ob.wrms(y - ref, ewt) < 1.0
+
+
+# ---- rootfinding (src/impl_r_check.rs): pinned by the example's own problem -------------------------------------------
+def test_oracle_rootfinding_on_the_reference_example():
+    """examples/roberts.rs with its root functions g0 = y1 - 1e-4, g1 = y3 - 0.01 (src/sample_problems/roberts.rs:99-113).
+    The reference has no rootfinding test; the pins are (a) the two root locations SUNDIALS publishes for this very
+    problem (idaRoberts_dns: t = 2.6400e-01 and 2.0786e+07), (b) g_i(y(t_root)) = 0 to the root tolerance, (c) the
+    integration being untouched (362 steps / 377 attempts, same final state), (d) the reference's get_root_info sign
+    convention, signum of g at the left end of the bracketing interval (src/impl_r_check.rs:388, 569)."""
+    touts = 0.4 * 10.0 ** np.arange(12)
+    k = [0.04, 1e4, 3e7]
+    r = ob.roots_run(ob.PK_ROBERTS, k, [1, 0, 0], [-0.04, 0.04, 0], 1e-4, [1e-8, 1e-6, 1e-6], touts)
+    assert (r["status"] == 0).all() and r["t"].size == 2
+    assert abs(r["t"][0] - 2.6400e-01) < 5e-5 and abs(r["t"][1] / 2.0786e+07 - 1.0) < 2e-4
+    assert abs(r["y"][0][2] - 0.01) < 1e-9 and abs(r["y"][1][0] - 1e-4) < 1e-11
+    assert r["iroots"].tolist() == [[0.0, -1.0], [1.0, 0.0]]
+    c = r["counters"]
+    assert (c["nst"], c["nattempts"], c["nre"], c["nje"], c["netf"]) == (362, 377, 537, 60, 15)
+    st, rows, _ = ob.single_trace(ob.PK_ROBERTS, k, [1, 0, 0], [-0.04, 0.04, 0], 1e-4, [1e-8, 1e-6, 1e-6], touts)
+    assert np.array_equal(r["yy"].view(np.uint64), rows[-1][3:].view(np.uint64))  # same final state as without roots
+    assert c["nge"] > c["nst"]  # one g evaluation per step at least (r_check3), plus the Illinois iterations
