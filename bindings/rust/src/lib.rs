@@ -39,6 +39,9 @@ extern "C" {
                           params: *const f64, yy0: *const f64, yp0: *const f64, rtol: f64, atol: *const f64,
                           mem: c_int, device: c_int, stream: *mut c_void) -> c_int;
     pub fn b200ida_destroy(e: *mut RawEnsemble) -> c_int;
+    /// rootfinding (src/impl_r_check.rs): event log per instance, device buffers; max_events <= 0 switches it off
+    pub fn b200ida_set_roots(e: *mut RawEnsemble, max_events: c_int, ev_t: *mut f64, ev_iroots: *mut f64, ev_count: *mut i32,
+                             nge: *mut i32) -> c_int;
     /// per-attempt state trace of one instance (the `data_trace` feature, src/lib.rs:297-301, 635-639); device buffers
     pub fn b200ida_set_trace(e: *mut RawEnsemble, instance: i64, dtrace: *mut f64, itrace: *mut i32, count: *mut i32,
                              max_attempts: c_int) -> c_int;

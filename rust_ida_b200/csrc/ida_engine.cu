@@ -502,8 +502,9 @@ int b200ida_solve_ladder(b200ida_ensemble* e, const double* touts, int ntout, in
         if (e->roots.max_ev > 0) {
             if (e->problem != B200IDA_PROBLEM_ROBERTS)
                 return set_error(B200IDA_ERR_UNSUPPORTED, "rootfinding: the Roberts problem is the only one with root functions");
-            B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_thread_kernel<Roberts, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            ida_solve_thread_kernel<Roberts, false, true><<<grid, tb, smem, e->stream>>>(e->dstate, e->istate, e->params, e->B, tol, lad,
+            const size_t rsmem = (size_t)(IdaThread<Roberts>::SMEM_DOUBLES + IdaThread<Roberts>::ROOT_DOUBLES) * tb * sizeof(double);
+            B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_thread_kernel<Roberts, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
+            ida_solve_thread_kernel<Roberts, false, true><<<grid, tb, rsmem, e->stream>>>(e->dstate, e->istate, e->params, e->B, tol, lad,
                                                                                          d_traj, d_stat, e->perm, TraceParams(), e->roots);
         } else if (e->trace.id >= 0) {
             // traced run: the TRACE instantiation of the same kernel (the production instantiation carries no trace code)

@@ -156,6 +156,185 @@ __device__ __forceinline__ double alphas_of(int kk) {
     return v;
 }
 
+// The Illinois iteration of IDARootfind (src/impl_r_check.rs:402-576) on the root state in the thread's shared-memory
+// column: entered with a sign change of g_imax in (tlo, thi), leaves trout / grout / iroots set and returns the number
+// of g evaluations it made.  Out of line on purpose (see IdaThread::root_find).
+template <class P>
+__device__ __noinline__ int root_illinois(double* sm, P prob, unsigned gmask, int imax, double hh, double hused, double tn,
+                                          int kused) {
+    constexpr int N = P::N, NR = P::NR > 0 ? P::NR : 1, SD = 6 * N + 30;
+    auto rsm = [&](int k) -> double& { return sm[(SD + k) * THREAD_BLOCK]; };
+    auto signum = [](double x) { return (x != x) ? x : (signbit(x) ? -1.0 : 1.0); };
+    int evals = 0;
+    double alph = 1.0;
+    int side = 0, sideprev = -1;
+#pragma unroll 1
+    for (;;) {
+        if (fabs(rsm(4 * NR + 1) - rsm(4 * NR + 0)) <= rsm(4 * NR + 3)) break;
+        alph = (sideprev == side) ? ((side == 2) ? alph * 2.0 : alph * 0.5) : 1.0;
+        const double gh = rsm(1 * NR + imax), gl = rsm(0 * NR + imax);
+        double tmid = rsm(4 * NR + 1) - (rsm(4 * NR + 1) - rsm(4 * NR + 0)) * gh / (gh - alph * gl);
+        if (fabs(tmid - rsm(4 * NR + 0)) < 0.5 * rsm(4 * NR + 3)) {
+            const double fracint = fabs(rsm(4 * NR + 1) - rsm(4 * NR + 0)) / rsm(4 * NR + 3);
+            const double fracsub = (fracint > 5.0) ? 0.1 : 0.5 / fracint;
+            tmid = rsm(4 * NR + 0) + fracsub * (rsm(4 * NR + 1) - rsm(4 * NR + 0));
+        }
+        if (fabs(rsm(4 * NR + 1) - tmid) < 0.5 * rsm(4 * NR + 3)) {
+            const double fracint = fabs(rsm(4 * NR + 1) - rsm(4 * NR + 0)) / rsm(4 * NR + 3);
+            const double fracsub = (fracint > 5.0) ? 0.1 : 0.5 / fracint;
+            tmid = rsm(4 * NR + 1) - fracsub * (rsm(4 * NR + 1) - rsm(4 * NR + 0));
+        }
+        double out[2 * N], y[N], yp[N], g[NR];
+        get_solution_fn<N>(sm, hh, hused, tn, kused, tmid, out);  // t inside the last step: cannot fail
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            y[i] = out[i];
+            yp[i] = out[N + i];
+        }
+        if constexpr (P::NR > 0) prob.root(tmid, y, yp, g);
+#pragma unroll
+        for (int i = 0; i < NR; ++i) rsm(2 * NR + i) = g[i];
+        evals += 1;
+        sideprev = side;
+        // in which subinterval does g change sign: src/impl_r_check.rs:457-492
+        bool zroot = false, sgnchg = false;
+        double maxfrac = 0.0;
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+            if (!((gmask >> i) & 1u)) continue;
+            const double glo_i = rsm(0 * NR + i), gx = rsm(2 * NR + i);
+            const bool rootdir_glo_neg = 0.0 * glo_i <= 0.0;
+            if (fabs(gx) == 0.0 && rootdir_glo_neg) {
+                zroot = true;
+            } else if (glo_i * gx < 0.0 && rootdir_glo_neg) {
+                const double gfrac = fabs(gx / (gx - glo_i));
+                if (gfrac > maxfrac) {
+                    sgnchg = true;
+                    maxfrac = gfrac;
+                    imax = i;
+                }
+            }
+        }
+        if (sgnchg) {
+            rsm(4 * NR + 1) = tmid;
+#pragma unroll
+            for (int i = 0; i < NR; ++i) rsm(1 * NR + i) = rsm(2 * NR + i);
+            side = 1;
+            if (fabs(rsm(4 * NR + 1) - rsm(4 * NR + 0)) <= rsm(4 * NR + 3)) break;
+            continue;
+        }
+        if (zroot) {
+            rsm(4 * NR + 1) = tmid;
+#pragma unroll
+            for (int i = 0; i < NR; ++i) rsm(1 * NR + i) = rsm(2 * NR + i);
+            break;
+        }
+        rsm(4 * NR + 0) = tmid;
+#pragma unroll
+        for (int i = 0; i < NR; ++i) rsm(0 * NR + i) = rsm(2 * NR + i);
+        side = 2;
+        if (fabs(rsm(4 * NR + 1) - rsm(4 * NR + 0)) <= rsm(4 * NR + 3)) break;
+    }
+    rsm(4 * NR + 2) = rsm(4 * NR + 1);
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+        rsm(2 * NR + i) = rsm(1 * NR + i);
+        rsm(3 * NR + i) = 0.0;
+        const double glo_i = rsm(0 * NR + i), ghi_i = rsm(1 * NR + i);
+        if (((gmask >> i) & 1u) && 0.0 * glo_i <= 0.0 && (fabs(ghi_i) == 0.0 || glo_i * ghi_i < 0.0)) rsm(3 * NR + i) = signum(glo_i);
+    }
+    return evals;
+}
+
+// IDARcheck3 + the first pass of IDARootfind (src/impl_r_check.rs:211-267, 330-400) as ONE out-of-line function on the
+// root state in the thread's shared-memory column, so that the step loop of the ROOTS kernel only carries a call: with
+// these ~400 instructions inline the loop outgrew the instruction cache (ncu: 5.0 no_instruction stalls per issue, 2.1x
+// the run time of the plain kernel).  Returns ier | gactive mask << 1 | g evaluations << 8; when ier == 1 the caller
+// still has to interpolate y(trout) (get_solution), everything else is done here.
+template <class P>
+__device__ __noinline__ unsigned root_check3(double* sm, P prob, unsigned gmask, double tn, double hh, double hused, int kused) {
+    constexpr int N = P::N, NR = P::NR > 0 ? P::NR : 1, SD = 6 * N + 30;
+    auto rsm = [&](int k) -> double& { return sm[(SD + k) * THREAD_BLOCK]; };
+    auto signum = [](double x) { return (x != x) ? x : (signbit(x) ? -1.0 : 1.0); };
+    unsigned evals = 1;
+    const bool at_tn = (rsm(4 * NR + 4) - tn) * hh >= 0.0;
+    const double thi = at_tn ? tn : rsm(4 * NR + 4);  // IdaTask::Normal
+    rsm(4 * NR + 1) = thi;
+    {
+        double y[N], yp[N], g[NR];
+        if (at_tn && !P::ROOT_USES_YP) {
+            // get_solution(tn) is the interpolant at delt = 0: c_0 = 1 and every other c_j is 0 * (finite) = 0, so it
+            // returns phi[0] (src/lib.rs:1274-1343) -- evaluated here without its ~10 divisions, once per step.  yy / yp
+            // themselves are not refreshed; every path on which the reference's values would be observed refreshes
+            // them (root return, output time, failure returns, and the mxstep return patched in solve_ladder).
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                y[i] = 0.0 + sm[i * THREAD_BLOCK];
+                yp[i] = 0.0;
+            }
+        } else {
+            double out[2 * N];
+            get_solution_fn<N>(sm, hh, hused, tn, kused, thi, out);
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                y[i] = out[i];
+                yp[i] = out[N + i];
+            }
+        }
+        if constexpr (P::NR > 0) prob.root(thi, y, yp, g);
+#pragma unroll
+        for (int i = 0; i < NR; ++i) rsm(1 * NR + i) = g[i];
+    }
+    rsm(4 * NR + 3) = (fabs(tn) + fabs(hh)) * DBL_EPS * 100.0;
+    // first pass of IDARootfind: sign change in, or zero of, g(thi)
+    bool zroot = false, sgnchg = false;
+    double maxfrac = 0.0;
+    int imax = 0;
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+        if (!((gmask >> i) & 1u)) continue;
+        const double glo_i = rsm(0 * NR + i), ghi_i = rsm(1 * NR + i);
+        const bool rootdir_glo_neg = 0.0 * glo_i <= 0.0;  // rootdir is all zeros (src/lib.rs:368)
+        if (fabs(ghi_i) == 0.0) {
+            if (rootdir_glo_neg) zroot = true;
+        } else if (glo_i * ghi_i < 0.0 && rootdir_glo_neg) {
+            const double gfrac = fabs(ghi_i / (ghi_i - glo_i));
+            if (gfrac > maxfrac) {
+                sgnchg = true;
+                maxfrac = gfrac;
+                imax = i;
+            }
+        }
+    }
+    unsigned ier = 0;
+    if (!sgnchg) {
+        rsm(4 * NR + 2) = thi;
+#pragma unroll
+        for (int i = 0; i < NR; ++i) rsm(2 * NR + i) = rsm(1 * NR + i);
+        if (zroot) {
+            ier = 1;
+#pragma unroll
+            for (int i = 0; i < NR; ++i) {
+                const double glo_i = rsm(0 * NR + i);
+                rsm(3 * NR + i) = 0.0;
+                if (((gmask >> i) & 1u) && fabs(rsm(1 * NR + i)) == 0.0 && 0.0 * glo_i <= 0.0) rsm(3 * NR + i) = signum(glo_i);
+            }
+        }
+    } else {
+        evals += (unsigned)root_illinois<P>(sm, prob, gmask, imax, hh, hused, tn, kused);
+        ier = 1;
+    }
+    // src/impl_r_check.rs:247-258: inactive components that moved away from zero become active; tlo, glo <- trout, grout
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+        const double gr = rsm(2 * NR + i);
+        if (!((gmask >> i) & 1u) && gr != 0.0) gmask |= 1u << i;
+        rsm(0 * NR + i) = gr;
+    }
+    rsm(4 * NR + 0) = rsm(4 * NR + 2);
+    return ier | (gmask << 1) | (evals << 8);
+}
+
 template <class P>
 struct IdaThread {
     static constexpr int N = P::N;
@@ -699,114 +878,134 @@ struct IdaThread {
     }
 
     // ---- rootfinding: src/impl_r_check.rs:32-576 (state src/lib.rs:198-229).  Only instantiated by the ROOTS kernels. --
+    // The 4 NR + 5 doubles of root state live in the thread's shared-memory column behind the solver's arrays (the
+    // ROOTS kernel is launched with SMEM_DOUBLES + ROOT_DOUBLES words per thread): in registers they pushed the kernel
+    // over its 168-register budget and the spills cost 2.5x.
     static constexpr int NR = P::NR > 0 ? P::NR : 1;
-    double glo[NR], ghi[NR], grout[NR], iroots[NR];
+    static constexpr int ROOT_DOUBLES = 4 * NR + 5;
+    __device__ __forceinline__ double& rsm(int k) { return sm[(SMEM_DOUBLES + k) * THREAD_BLOCK]; }
+    __device__ __forceinline__ const double& rsm(int k) const { return sm[(SMEM_DOUBLES + k) * THREAD_BLOCK]; }
     bool gactive[NR];  // FALSE at start like the reference (src/lib.rs:373)
-    double tlo, thi, trout, ttol, toutc;
     bool irfnd;
     int nge;
     __device__ __forceinline__ static double signum(double x) { return (x != x) ? x : (signbit(x) ? -1.0 : 1.0); }
-    __device__ __forceinline__ void eval_root(double t, double (&g)[NR]) {
-        if constexpr (P::NR > 0) prob.root(t, yy, yp, g);
+    enum { GLO = 0, GHI = 1, GROUT = 2 };  // which array of the root state
+    __device__ __forceinline__ void eval_root(double t, int which) {  // g(t, yy, yp) -> array `which`
+        if constexpr (P::NR > 0) {
+            double g[NR];
+            prob.root(t, yy, yp, g);
+#pragma unroll
+            for (int i = 0; i < NR; ++i) rsm(which * NR + i) = g[i];
+        }
     }
     __device__ __forceinline__ void load_roots(const RootParams& rp, int64_t B, int64_t b) {
 #pragma unroll
         for (int i = 0; i < NR; ++i) {
-            glo[i] = rp.rd[(int64_t)i * B + b];
-            ghi[i] = rp.rd[(int64_t)(NR + i) * B + b];
-            grout[i] = rp.rd[(int64_t)(2 * NR + i) * B + b];
-            iroots[i] = rp.rd[(int64_t)(3 * NR + i) * B + b];
+            rsm(0 * NR + (i)) = rp.rd[(int64_t)i * B + b];
+            rsm(1 * NR + (i)) = rp.rd[(int64_t)(NR + i) * B + b];
+            rsm(2 * NR + (i)) = rp.rd[(int64_t)(2 * NR + i) * B + b];
+            rsm(3 * NR + (i)) = rp.rd[(int64_t)(3 * NR + i) * B + b];
             gactive[i] = rp.ri[(int64_t)i * B + b] != 0;
         }
-        tlo = rp.rd[(int64_t)(4 * NR) * B + b];
-        thi = rp.rd[(int64_t)(4 * NR + 1) * B + b];
-        trout = rp.rd[(int64_t)(4 * NR + 2) * B + b];
-        ttol = rp.rd[(int64_t)(4 * NR + 3) * B + b];
-        toutc = rp.rd[(int64_t)(4 * NR + 4) * B + b];
+        rsm(4 * NR + 0) = rp.rd[(int64_t)(4 * NR) * B + b];
+        rsm(4 * NR + 1) = rp.rd[(int64_t)(4 * NR + 1) * B + b];
+        rsm(4 * NR + 2) = rp.rd[(int64_t)(4 * NR + 2) * B + b];
+        rsm(4 * NR + 3) = rp.rd[(int64_t)(4 * NR + 3) * B + b];
+        rsm(4 * NR + 4) = rp.rd[(int64_t)(4 * NR + 4) * B + b];
         irfnd = rp.ri[(int64_t)NR * B + b] != 0;
         nge = rp.ri[(int64_t)(NR + 1) * B + b];
     }
     __device__ __forceinline__ void store_roots(const RootParams& rp, int64_t B, int64_t b) {
 #pragma unroll
         for (int i = 0; i < NR; ++i) {
-            rp.rd[(int64_t)i * B + b] = glo[i];
-            rp.rd[(int64_t)(NR + i) * B + b] = ghi[i];
-            rp.rd[(int64_t)(2 * NR + i) * B + b] = grout[i];
-            rp.rd[(int64_t)(3 * NR + i) * B + b] = iroots[i];
+            rp.rd[(int64_t)i * B + b] = rsm(0 * NR + (i));
+            rp.rd[(int64_t)(NR + i) * B + b] = rsm(1 * NR + (i));
+            rp.rd[(int64_t)(2 * NR + i) * B + b] = rsm(2 * NR + (i));
+            rp.rd[(int64_t)(3 * NR + i) * B + b] = rsm(3 * NR + (i));
             rp.ri[(int64_t)i * B + b] = gactive[i] ? 1 : 0;
         }
-        rp.rd[(int64_t)(4 * NR) * B + b] = tlo;
-        rp.rd[(int64_t)(4 * NR + 1) * B + b] = thi;
-        rp.rd[(int64_t)(4 * NR + 2) * B + b] = trout;
-        rp.rd[(int64_t)(4 * NR + 3) * B + b] = ttol;
-        rp.rd[(int64_t)(4 * NR + 4) * B + b] = toutc;
+        rp.rd[(int64_t)(4 * NR) * B + b] = rsm(4 * NR + 0);
+        rp.rd[(int64_t)(4 * NR + 1) * B + b] = rsm(4 * NR + 1);
+        rp.rd[(int64_t)(4 * NR + 2) * B + b] = rsm(4 * NR + 2);
+        rp.rd[(int64_t)(4 * NR + 3) * B + b] = rsm(4 * NR + 3);
+        rp.rd[(int64_t)(4 * NR + 4) * B + b] = rsm(4 * NR + 4);
         rp.ri[(int64_t)NR * B + b] = irfnd ? 1 : 0;
         rp.ri[(int64_t)(NR + 1) * B + b] = nge;
     }
 
     // IDARcheck1 -- src/impl_r_check.rs:32-105 (called before phi[1] is scaled by hh)
-    __device__ __noinline__ void r_check1() {
+    __device__ __forceinline__ void r_check1() {
 #pragma unroll
-        for (int i = 0; i < NR; ++i) iroots[i] = 0.0;
-        tlo = tn;
-        ttol = (fabs(tn) + fabs(hh)) * DBL_EPS * 100.0;
+        for (int i = 0; i < NR; ++i) rsm(3 * NR + (i)) = 0.0;
+        rsm(4 * NR + 0) = tn;
+        rsm(4 * NR + 3) = (fabs(tn) + fabs(hh)) * DBL_EPS * 100.0;
         double y0[N], y1[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             y0[i] = phi(0, i);
             y1[i] = phi(1, i);
         }
-        if constexpr (P::NR > 0) prob.root(tlo, y0, y1, glo);
+        if constexpr (P::NR > 0) {
+            double g[NR];
+            prob.root(rsm(4 * NR + 0), y0, y1, g);
+#pragma unroll
+            for (int i = 0; i < NR; ++i) rsm(GLO * NR + i) = g[i];
+        }
         nge = 1;
         bool zroot = false;
 #pragma unroll
         for (int i = 0; i < NR; ++i) {
-            if (fabs(glo[i]) == 0.0) {
+            if (fabs(rsm(0 * NR + (i))) == 0.0) {
                 gactive[i] = false;
                 zroot = true;
             }
         }
         if (zroot) {
-            const double hratio = fmax(ttol / fabs(hh), 0.1);
+            const double hratio = fmax(rsm(4 * NR + 3) / fabs(hh), 0.1);
             const double smallh = hratio * hh;
-            const double tplus = tlo + smallh;
+            const double tplus = rsm(4 * NR + 0) + smallh;
 #pragma unroll
             for (int i = 0; i < N; ++i) {
                 yy[i] = y0[i];
                 yy[i] += smallh * y1[i];
             }
-            if constexpr (P::NR > 0) prob.root(tplus, yy, y1, ghi);
+            if constexpr (P::NR > 0) {
+                double g[NR];
+                prob.root(tplus, yy, y1, g);
+#pragma unroll
+                for (int i = 0; i < NR; ++i) rsm(GHI * NR + i) = g[i];
+            }
             nge += 1;
 #pragma unroll
             for (int i = 0; i < NR; ++i) {
-                if (!gactive[i] && fabs(ghi[i]) != 0.0) {
+                if (!gactive[i] && fabs(rsm(1 * NR + (i))) != 0.0) {
                     gactive[i] = true;
-                    glo[i] = ghi[i];
+                    rsm(0 * NR + (i)) = rsm(1 * NR + (i));
                 }
             }
         }
     }
 
     // IDARcheck2 -- src/impl_r_check.rs:123-209 ; 0 continue, 1 root found, B200IDA_ST_CLOSE_ROOTS
-    __device__ __noinline__ int r_check2() {
+    __device__ __forceinline__ int r_check2() {
         if (!irfnd) return 0;
-        get_solution(tlo);
-        eval_root(tlo, glo);
+        get_solution(rsm(4 * NR + 0));
+        eval_root(rsm(4 * NR + 0), GLO);
         nge += 1;
         bool zroot = false;
 #pragma unroll
         for (int i = 0; i < NR; ++i) {
-            iroots[i] = 0.0;
-            if (gactive[i] && fabs(glo[i]) == 0.0) {
+            rsm(3 * NR + (i)) = 0.0;
+            if (gactive[i] && fabs(rsm(0 * NR + (i))) == 0.0) {
                 zroot = true;
-                iroots[i] = 1.0;
+                rsm(3 * NR + (i)) = 1.0;
             }
         }
         if (zroot) {
-            ttol = (fabs(tn) + fabs(hh)) * DBL_EPS * 100.0;
+            rsm(4 * NR + 3) = (fabs(tn) + fabs(hh)) * DBL_EPS * 100.0;
             const double sgn = (hh > 0.0 || (hh == 0.0 && !signbit(hh))) ? 1.0 : -1.0;
-            const double smallh = ttol * sgn;
-            const double tplus = tlo + smallh;
+            const double smallh = rsm(4 * NR + 3) * sgn;
+            const double tplus = rsm(4 * NR + 0) + smallh;
             if ((tplus - tn) * hh >= 0.0) {
                 const double hratio = smallh / hh;
 #pragma unroll
@@ -814,18 +1013,18 @@ struct IdaThread {
             } else {
                 get_solution(tplus);
             }
-            eval_root(tplus, ghi);
+            eval_root(tplus, GHI);
             nge += 1;
             bool z2 = false;
 #pragma unroll
             for (int i = 0; i < NR; ++i) {
                 if (gactive[i]) {
-                    if (fabs(ghi[i]) == 0.0) {
-                        if (iroots[i] > 0.0) return B200IDA_ST_CLOSE_ROOTS;
+                    if (fabs(rsm(1 * NR + (i))) == 0.0) {
+                        if (rsm(3 * NR + (i)) > 0.0) return B200IDA_ST_CLOSE_ROOTS;
                         z2 = true;
-                        iroots[i] = 1.0;
-                    } else if (iroots[i] > 0.0) {
-                        glo[i] = ghi[i];
+                        rsm(3 * NR + (i)) = 1.0;
+                    } else if (rsm(3 * NR + (i)) > 0.0) {
+                        rsm(0 * NR + (i)) = rsm(1 * NR + (i));
                     }
                 }
             }
@@ -834,122 +1033,17 @@ struct IdaThread {
         return 0;
     }
 
-    // one pass over the g_i in root_find: src/impl_r_check.rs:332-369 (first) and :457-492
-    __device__ __forceinline__ void scan_roots(const double (&gx)[NR], bool first, bool& zroot, bool& sgnchg, int& imax) const {
-        zroot = false;
-        sgnchg = false;
-        double maxfrac = 0.0;
-        if (first) imax = 0;
+    // IDARcheck3 -- src/impl_r_check.rs:211-267 ; 0 continue, 1 root found (body: root_check3 above, out of line)
+    __device__ __forceinline__ int r_check3() {
+        unsigned gmask = 0;
 #pragma unroll
-        for (int i = 0; i < NR; ++i) {
-            if (!gactive[i]) continue;
-            const bool rootdir_glo_neg = 0.0 * glo[i] <= 0.0;  // rootdir is all zeros (src/lib.rs:368)
-            const bool gz = fabs(gx[i]) == 0.0;
-            if (gz && (first || rootdir_glo_neg)) {
-                if (rootdir_glo_neg) zroot = true;
-            } else if (glo[i] * gx[i] < 0.0 && rootdir_glo_neg) {
-                const double gfrac = fabs(gx[i] / (gx[i] - glo[i]));
-                if (gfrac > maxfrac) {
-                    sgnchg = true;
-                    maxfrac = gfrac;
-                    imax = i;
-                }
-            }
-        }
-    }
-    __device__ __forceinline__ double pickr(const double (&a)[NR], int k) const {
-        double v = a[0];
+        for (int i = 0; i < NR; ++i) gmask |= gactive[i] ? (1u << i) : 0u;
+        const unsigned r = root_check3<P>(sm, prob, gmask, tn, hh, hused, kused);
 #pragma unroll
-        for (int j = 1; j < NR; ++j) v = (k == j) ? a[j] : v;
-        return v;
-    }
-
-    // IDARootfind (Illinois) -- src/impl_r_check.rs:330-576 ; 0 continue, 1 root found
-    __device__ __noinline__ int root_find() {
-        bool zroot, sgnchg;
-        int imax = 0;
-        scan_roots(ghi, true, zroot, sgnchg, imax);
-        if (!sgnchg) {
-            trout = thi;
-#pragma unroll
-            for (int i = 0; i < NR; ++i) grout[i] = ghi[i];
-            if (!zroot) return 0;
-#pragma unroll
-            for (int i = 0; i < NR; ++i) {
-                iroots[i] = 0.0;
-                if (gactive[i] && fabs(ghi[i]) == 0.0 && 0.0 * glo[i] <= 0.0) iroots[i] = signum(glo[i]);
-            }
-            return 1;
-        }
-        double alph = 1.0;
-        int side = 0, sideprev = -1;
-#pragma unroll 1
-        for (;;) {
-            if (fabs(thi - tlo) <= ttol) break;
-            alph = (sideprev == side) ? ((side == 2) ? alph * 2.0 : alph * 0.5) : 1.0;
-            const double gh = pickr(ghi, imax), gl = pickr(glo, imax);
-            double tmid = thi - (thi - tlo) * gh / (gh - alph * gl);
-            if (fabs(tmid - tlo) < 0.5 * ttol) {
-                const double fracint = fabs(thi - tlo) / ttol;
-                const double fracsub = (fracint > 5.0) ? 0.1 : 0.5 / fracint;
-                tmid = tlo + fracsub * (thi - tlo);
-            }
-            if (fabs(thi - tmid) < 0.5 * ttol) {
-                const double fracint = fabs(thi - tlo) / ttol;
-                const double fracsub = (fracint > 5.0) ? 0.1 : 0.5 / fracint;
-                tmid = thi - fracsub * (thi - tlo);
-            }
-            get_solution(tmid);
-            eval_root(tmid, grout);
-            nge += 1;
-            sideprev = side;
-            scan_roots(grout, false, zroot, sgnchg, imax);
-            if (sgnchg) {
-                thi = tmid;
-#pragma unroll
-                for (int i = 0; i < NR; ++i) ghi[i] = grout[i];
-                side = 1;
-                if (fabs(thi - tlo) <= ttol) break;
-                continue;
-            }
-            if (zroot) {
-                thi = tmid;
-#pragma unroll
-                for (int i = 0; i < NR; ++i) ghi[i] = grout[i];
-                break;
-            }
-            tlo = tmid;
-#pragma unroll
-            for (int i = 0; i < NR; ++i) glo[i] = grout[i];
-            side = 2;
-            if (fabs(thi - tlo) <= ttol) break;
-        }
-        trout = thi;
-#pragma unroll
-        for (int i = 0; i < NR; ++i) {
-            grout[i] = ghi[i];
-            iroots[i] = 0.0;
-            if (gactive[i] && 0.0 * glo[i] <= 0.0 && (fabs(ghi[i]) == 0.0 || glo[i] * ghi[i] < 0.0)) iroots[i] = signum(glo[i]);
-        }
-        return 1;
-    }
-
-    // IDARcheck3 -- src/impl_r_check.rs:211-267 ; 0 continue, 1 root found
-    __device__ __noinline__ int r_check3() {
-        thi = ((toutc - tn) * hh >= 0.0) ? tn : toutc;  // IdaTask::Normal
-        get_solution(thi);
-        eval_root(thi, ghi);
-        nge += 1;
-        ttol = (fabs(tn) + fabs(hh)) * DBL_EPS * 100.0;
-        const int ier = root_find();
-#pragma unroll
-        for (int i = 0; i < NR; ++i) {
-            if (!gactive[i] && grout[i] != 0.0) gactive[i] = true;
-            glo[i] = grout[i];
-        }
-        tlo = trout;
-        if (ier == 1) get_solution(trout);
-        return ier;
+        for (int i = 0; i < NR; ++i) gactive[i] = ((r >> (1 + i)) & 1u) != 0;
+        nge += (int)(r >> 8);
+        if (r & 1u) get_solution(rsm(4 * NR + 2));  // y(trout), y'(trout)
+        return (int)(r & 1u);
     }
 
     // ---- first-call block of solve(): src/impl_solve.rs:84-173 ; returns 0 or B200IDA_ST_ILL_INPUT ---------------
@@ -1009,7 +1103,7 @@ struct IdaThread {
                 in_step = false;
                 call_done = false;
                 call_status = 0;
-                if constexpr (ROOTS) toutc = tout;  // src/impl_solve.rs:78-82
+                if constexpr (ROOTS) rsm(4 * NR + 4) = tout;  // src/impl_solve.rs:78-82
                 if (nst == 0) {
                     const int r = first_call<ROOTS>(tout, tol);
                     if (r != 0) {
@@ -1021,8 +1115,8 @@ struct IdaThread {
                         const int ier2 = r_check2();
                         if (ier2 != 0) {
                             if (ier2 == 1) {
-                                tretlast = tlo;
-                                tret = tlo;
+                                tretlast = rsm(4 * NR + 0);
+                                tret = rsm(4 * NR + 0);
                             }
                             call_status = (ier2 == 1) ? B200IDA_ST_ROOT : ier2;
                             call_done = true;
@@ -1031,8 +1125,8 @@ struct IdaThread {
                             if (fabs(tn - tretlast) > troundoff) {
                                 if (r_check3() == 1) {
                                     irfnd = true;
-                                    tretlast = tlo;
-                                    tret = tlo;
+                                    tretlast = rsm(4 * NR + 0);
+                                    tret = rsm(4 * NR + 0);
                                     call_status = B200IDA_ST_ROOT;
                                     call_done = true;
                                 } else {
@@ -1061,6 +1155,7 @@ struct IdaThread {
             if (!call_done && !in_step) {
                 // top of the step loop: src/impl_solve.rs:246-311
                 if (nstloc >= MXSTEP) {
+                    if constexpr (ROOTS) get_solution(tn);  // what the reference's r_check3 left in yy / yp (see r_check3)
                     tret = tn;
                     tretlast = tn;
                     call_status = B200IDA_ST_TOO_MUCH_WORK;
@@ -1141,8 +1236,8 @@ struct IdaThread {
                     if constexpr (ROOTS) {  // root in the last step taken: src/impl_solve.rs:335-344
                         if (r_check3() == 1) {
                             irfnd = true;
-                            tretlast = tlo;
-                            tret = tlo;
+                            tretlast = rsm(4 * NR + 0);
+                            tret = rsm(4 * NR + 0);
                             call_status = B200IDA_ST_ROOT;
                             call_done = true;
                             root_ret = true;
@@ -1186,7 +1281,7 @@ struct IdaThread {
                     if (c < rp.max_ev) {
                         rp.ev_t[(int64_t)c * B + b] = tret;
 #pragma unroll
-                        for (int i = 0; i < NR; ++i) rp.ev_iroots[((int64_t)c * NR + i) * B + b] = iroots[i];
+                        for (int i = 0; i < NR; ++i) rp.ev_iroots[((int64_t)c * NR + i) * B + b] = rsm(3 * NR + i);
                     }
                     rp.ev_count[b] = c + 1;
                     call_done = false;

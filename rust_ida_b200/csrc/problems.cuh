@@ -15,6 +15,7 @@ struct Roberts {
     static constexpr int N = 3;
     static constexpr int NP = 3;
     static constexpr int NR = 2;  // Root::num_roots, roberts.rs:99-113
+    static constexpr bool ROOT_USES_YP = false;
     __device__ __forceinline__ void root(double, const double (&y)[N], const double (&)[N], double (&g)[NR]) const {
         g[0] = y[0] - 0.0001;
         g[1] = y[2] - 0.01;
@@ -52,6 +53,7 @@ struct Lorenz63 {
     static constexpr int N = 3;
     static constexpr int NP = 3;
     static constexpr int NR = 0;  // no root functions
+    static constexpr bool ROOT_USES_YP = false;
     double p, r, b;
     __device__ __forceinline__ void load(const double* __restrict__ params, int64_t B, int64_t i) {
         p = params[i];
