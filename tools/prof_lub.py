@@ -1,6 +1,16 @@
 #!/usr/bin/env python3
-"""Per-phase clock64 profile of the blocked getrf (debug build: build/lib_lubprof.so, -DLUB_PROFILE).
-B200IDA_LIB=build/lib_lubprof.so python tools/prof_lub.py 100"""
+"""Per-phase clock64 profile of the blocked getrf (lu_blocked.cuh) on a debug build of the library:
+
+    cd rust_ida_b200/csrc && make
+    nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -std=c++17 -Xcompiler -fPIC -DLUB_PROFILE \
+         -c linalg_batched.cu -o ../../build/linalg_prof.o
+    nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../../build/lib_lubprof.so ida_engine.o ../../build/linalg_prof.o \
+         --cudart static
+    B200IDA_LIB=build/lib_lubprof.so python tools/prof_lub.py 100        # n = 100, benchmark batch
+
+Prints, for CTA 0, the cycles warp 0 and warp 1 spent in each phase of lub_factor (panel, [S], strip, panel || rest,
+barrier waits, staging) and the breakdown of a panel column step (load+keys, reduction, pivot+reciprocal, scale,
+update of the remaining panel columns, syncwarp, permutation).  The production build contains none of this."""
 import ctypes
 import math
 import os
