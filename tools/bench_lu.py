@@ -32,6 +32,8 @@ def main():
     ap.add_argument("--sizes", default="3,4,8,16,32,64,100,128,256")
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--min-mb", type=float, default=512.0)
+    ap.add_argument("--batch-scale", type=int, default=1,
+                    help="multiply the config's batch (throughput regime: many systems per resident CTA / warp)")
     args = ap.parse_args()
     peaks = {}
     try:
@@ -42,7 +44,7 @@ def main():
     dev = torch.device("cuda", 0)
     L = _lib.lib()
     for n in [int(x) for x in args.sizes.split(",")]:
-        batch = math.ceil(9 * (1 << 20) / (n * n))
+        batch = math.ceil(9 * (1 << 20) / (n * n)) * args.batch_scale
         layout = "soa" if n <= 8 else "aos"
         lay = _lib.LAYOUT_SOA if layout == "soa" else _lib.LAYOUT_AOS
         bytes_mat = 8 * n * n * batch
