@@ -55,6 +55,7 @@ extern "C" {
                                 netf: *mut i64, ncfn: *mut i64, nsetups: *mut i64, nattempts: *mut i64, mem: c_int) -> c_int;
     pub fn b200ida_get_step_info(e: *mut RawEnsemble, kused: *mut i32, kcur: *mut i32, hused: *mut f64, hcur: *mut f64,
                                  tcur: *mut f64, h0u: *mut f64, mem: c_int) -> c_int;
+    pub fn b200ida_get_dky(e: *mut RawEnsemble, t: f64, k: c_int, dky: *mut f64, status: *mut i32, mem: c_int) -> c_int;
     pub fn b200ida_sync(e: *mut RawEnsemble) -> c_int;
 }
 

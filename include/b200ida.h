@@ -118,6 +118,7 @@ int b200ida_wrms_masked_batched(const double* x, const double* w, const unsigned
 #define B200IDA_ST_ILL_INPUT (-7)     /* tout too close to t0, src/impl_solve.rs:97-109 */
 #define B200IDA_ST_BAD_T (-8)         /* IdaError::BadTimeValue from get_solution, src/lib.rs:1286-1292 */
 #define B200IDA_ST_CLOSE_ROOTS (-9)   /* IdaError::CloseRoots, src/impl_r_check.rs:199-203 */
+#define B200IDA_ST_BAD_K (-10)       /* IdaError::BadK from get_dky, src/lib.rs:443-447 */
 #define B200IDA_ST_ROOT 2             /* IdaSolveStatus::Root (src/lib.rs:57-63): internal to a ladder launch, see b200ida_set_roots */
 
 typedef struct b200ida_ensemble b200ida_ensemble; /* opaque */
@@ -210,6 +211,13 @@ int b200ida_set_roots(b200ida_ensemble* e, int max_events, double* ev_t, double*
 
 /* get_yy / get_yp (src/ida_io.rs:11-19) and the tret of the last solve; SoA [n][batch] / [batch]; NULL skips. */
 int b200ida_get_state(b200ida_ensemble* e, double* yy, double* yp, double* tret, int mem);
+
+/* Ida::get_dky (src/lib.rs:424-529) on every instance: dky[i][b] = k-th derivative at time t of instance b's
+ * interpolating polynomial over its last step (k = 0: the solution itself, 1: y', ... up to the order last used).
+ * dky [out] [n][batch] SoA; status [out, may be NULL] [batch]: 0, B200IDA_ST_BAD_K (k > order last used by that
+ * instance, IdaError::BadK :443-447) or B200IDA_ST_BAD_T (t before the instance's last step, IdaError::BadTimeValue
+ * :456-466); the dky column of a failed instance is left as it was.  Reads the persistent state only -- no stepping. */
+int b200ida_get_dky(b200ida_ensemble* e, double t, int k, double* dky, int32_t* status, int mem);
 
 /* Statistics, [batch] each, NULL skips.  Names follow src/ida_io.rs:
  *   nst get_num_steps :58   nre get_num_res_evals :64   nje get_num_jac_evals :79

@@ -64,6 +64,12 @@ def lib():
         L.oracle_unit_complete_step.argtypes = [C.c_void_p, C.c_double, C.c_double]
         L.oracle_unit_get_solution.restype = C.c_int
         L.oracle_unit_get_solution.argtypes = [C.c_void_p, C.c_double]
+        L.oracle_unit_get_dky.restype = C.c_int
+        L.oracle_unit_get_dky.argtypes = [C.c_void_p, C.c_double, C.c_int, _dp]
+        L.oracle_ensemble_dky.restype = C.c_int
+        L.oracle_ensemble_dky.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int, _dp, _dp, _dp, C.c_double, _dp, _dp, C.c_int,
+                                          C.c_int, C.c_int, _dp, np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS"),
+                                          _dp, np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")]
         L.oracle_newton_quad3.restype = C.c_int
         L.oracle_newton_quad3.argtypes = [_dp, _dp, C.c_double, C.c_int, _dp, C.POINTER(C.c_long),
                                           C.POINTER(C.c_long)]
@@ -183,6 +189,12 @@ class Unit:
     def get_solution(self, t):
         return lib().oracle_unit_get_solution(self.h, t)
 
+    def get_dky(self, t, k):
+        """Ida::get_dky (src/lib.rs:424-529): (status, dky[n])"""
+        out = np.zeros(self.n)
+        r = lib().oracle_unit_get_dky(self.h, t, k, out)
+        return r, out
+
 
 def newton_quad3(y0, w, tol, maxiters):
     y = np.zeros(3)
@@ -220,6 +232,20 @@ def ensemble_solve(kind, n, params, yy0, yp0, rtol, atol, touts, nthreads=1, wan
     if want_traj:
         out["yy_traj"] = traj
     return out
+
+
+def ensemble_dky(kind, n, params, yy0, yp0, rtol, atol, touts, tq, kq, nthreads=1):
+    """Integrate over `touts`, then get_dky(tq[q], kq[q]) on every instance's final state: (dky (nq,n,B), status (nq,B));
+    rows of failed queries stay NaN."""
+    params, yy0, yp0 = (np.ascontiguousarray(a, dtype=np.float64) for a in (params, yy0, yp0))
+    B = yy0.shape[1]
+    tq = np.ascontiguousarray(tq, dtype=np.float64)
+    kq = np.ascontiguousarray(kq, dtype=np.int32)
+    dky = np.full((len(tq), n, B), np.nan)
+    st = np.zeros((len(tq), B), dtype=np.int32)
+    lib().oracle_ensemble_dky(kind, n, B, params.shape[0], params, yy0, yp0, rtol, np.ascontiguousarray(atol, dtype=np.float64),
+                              np.ascontiguousarray(touts, dtype=np.float64), len(touts), nthreads, len(tq), tq, kq, dky, st)
+    return dky, st
 
 
 def attempt_trace(kind, params, yy0, yp0, rtol, atol, touts, max_rows=4096):

@@ -70,6 +70,7 @@ enum Status : int {
     ST_LSETUP_FAIL = -5,     // singular Jacobian (reference: panic)
     ST_BAD_EWT = -6,         // some ewt component <= 0
     ST_ILL_INPUT = -7,       // tout too close to t0
+    ST_BAD_K = -10,          // IdaError::BadK from get_dky (src/lib.rs:443-447)
     ST_BAD_T = -8,           // get_solution BadTimeValue (propagated from stop_test1)
 };
 
@@ -968,6 +969,45 @@ struct Ida {
         return 0;
     }
 
+    // get_dky -- src/lib.rs:424-529 ; returns 0, ST_BAD_K or ST_BAD_T.  k-th derivative of the interpolating polynomial
+    // at t, from phi / psi of the last step.  Followed as written, including where it departs from SUNDIALS' IDAGetDky:
+    // the inner recurrences run to j = kused - k + 1 for EVERY i (SUNDIALS: kused - k + i), so for k >= 2 the higher
+    // c_j^(k) are never formed and stay 0 (src/lib.rs:496-506); psij_1 is not reset between passes.  The one place
+    // the reference cannot be followed: k = 0 with kused = 5 indexes cjk[6] of a 6-array and panics (:497); here the
+    // recurrence stops at j = 5 -- entry 6 would not be used by the sum (:512-526) anyway.
+    // Sum: ndarray sum_axis(Axis(0)) over rows j = k..=kused of phi_j * c_j, folded from zeros in row order.
+    int get_dky(double t, int k, double* dky) const {
+        if (k < 0 || k > kused) return ST_BAD_K;
+        const double sgn = (hh > 0.0 || (hh == 0.0 && !std::signbit(hh))) ? 1.0 : -1.0;  // f64::signum
+        const double tfuzz = 100.0 * DBL_EPS * (std::fabs(tn) + std::fabs(hh)) * sgn;
+        const double tp = tn - hused - tfuzz;
+        if ((t - tp) * hh < 0.0) return ST_BAD_T;
+        double cjk[MXORDP1] = {0, 0, 0, 0, 0, 0}, cjk_1[MXORDP1] = {0, 0, 0, 0, 0, 0};
+        const double delt = t - tn;
+        double psij_1 = 0.0;
+        const int jtop = std::min(kused - k + 1, MXORDP1 - 1);
+        for (int i = 0; i <= k; ++i) {
+            const double si = (double)i;
+            if (i == 0) {
+                cjk[i] = 1.0;
+            } else {
+                cjk[i] = cjk[i - 1] * si / psi[i - 1];
+                psij_1 = psi[i - 1];
+            }
+            for (int j = i + 1; j <= jtop; ++j) {
+                cjk[j] = (si * cjk_1[j - 1] + cjk[j - 1] * (delt + psij_1)) / psi[j - 1];
+                psij_1 = psi[j - 1];
+            }
+            for (int j = i + 1; j <= jtop; ++j) cjk_1[j] = cjk[j];
+        }
+        for (int i = 0; i < n; ++i) dky[i] = 0.0;
+        for (int j = k; j <= kused; ++j) {
+            const double* ph = &phi[(size_t)j * n];
+            for (int i = 0; i < n; ++i) dky[i] = dky[i] + ph[i] * cjk[j];
+        }
+        return 0;
+    }
+
     // solve (IdaTask::Normal, optional rootfinding, no tstop) -- src/impl_solve.rs:69-376 with
     // stop_test1/2 NORMAL branches src/impl_stop_test.rs:53-65,152-161
     int solve(double tout, double& tret) {
@@ -1202,6 +1242,7 @@ void oracle_unit_complete_step(void* h, double err_k, double err_km1) {
     static_cast<OracleUnit*>(h)->ida.complete_step(err_k, err_km1);
 }
 int oracle_unit_get_solution(void* h, double t) { return static_cast<OracleUnit*>(h)->ida.get_solution(t); }
+int oracle_unit_get_dky(void* h, double t, int k, double* dky) { return static_cast<OracleUnit*>(h)->ida.get_dky(t, k, dky); }
 
 // ---- Newton known-answer problem: the data of crates/nonlinear/src/newton.rs:192-343 -----------
 // f1 = x^2+y^2+z^2-1, f2 = 2x^2+y^2-4z, f3 = 3x^2-4y+z^2 ; J analytic; ctest = (wrms(del) <= tol)
@@ -1303,6 +1344,43 @@ int oracle_ensemble_solve(int kind, int n, int64_t B, int nparams, const double*
         for (int t = 0; t < nthreads; ++t) th.emplace_back(worker);
         for (auto& t : th) t.join();
     }
+    return 0;
+}
+
+// Integrate every instance over the ladder, then evaluate get_dky(tq[q], kq[q]) for each query q on the final state:
+// dky [nq][n][B] (rows of a failed query are left untouched), st [nq][B].
+int oracle_ensemble_dky(int kind, int n, int64_t B, int nparams, const double* params, const double* yy0, const double* yp0,
+                        double rtol, const double* atol, const double* touts, int ntout, int nthreads, int nq,
+                        const double* tq, const int32_t* kq, double* dky, int32_t* st) {
+    if (nthreads < 1) nthreads = 1;
+    std::atomic<int64_t> next(0);
+    auto worker = [&]() {
+        std::vector<double> par(nparams), y0(n), yp0v(n), out(n);
+        for (;;) {
+            const int64_t b = next.fetch_add(1);
+            if (b >= B) break;
+            for (int k = 0; k < nparams; ++k) par[k] = params[(size_t)k * B + b];
+            for (int i = 0; i < n; ++i) {
+                y0[i] = yy0[(size_t)i * B + b];
+                yp0v[i] = yp0[(size_t)i * B + b];
+            }
+            Ida ida;
+            Problem p{kind, n, par.data()};
+            ida.init(p, y0.data(), yp0v.data(), rtol, atol);
+            double tret = 0.0;
+            for (int it = 0; it < ntout; ++it) ida.solve(touts[it], tret);
+            for (int q = 0; q < nq; ++q) {
+                const int r = ida.get_dky(tq[q], kq[q], out.data());
+                st[(size_t)q * B + b] = r;
+                if (r == 0)
+                    for (int i = 0; i < n; ++i) dky[((size_t)q * n + i) * B + b] = out[i];
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nthreads; ++t) th.emplace_back(worker);
+    worker();
+    for (auto& t : th) t.join();
     return 0;
 }
 

@@ -111,6 +111,76 @@ __global__ void permute_rows_kernel(const double* __restrict__ src, double* __re
     const int64_t o = perm ? (int64_t)perm[s] : s;
     for (int r = 0; r < rows; ++r) dst[(int64_t)r * B + s] = src[(int64_t)r * B + o];
 }
+// Ida::get_dky (src/lib.rs:424-529) for every instance of the ensemble at one (t, k): k-th derivative of the
+// interpolating polynomial of the last step, from the persistent phi / psi / tn / hh / hused / kused.  One thread per
+// instance over the SoA state (coalesced rows), written straight to caller order.  HBM-bound: reads (kused-k+1) n + ~10
+// doubles, writes n.  The recurrences are followed as the reference has them (inner loops to kused-k+1 for every i, so
+// for k >= 2 the higher coefficients stay 0; psij_1 carried across passes); k = 0 with kused = 5 would index past the
+// reference's 6-entry array (it panics), here the recurrence stops at j = 5, which the sum does not use anyway.
+// Per-instance status: 0, B200IDA_ST_BAD_K, B200IDA_ST_BAD_T (dky of that instance is left untouched).
+__global__ void __launch_bounds__(256) ida_dky_kernel(const double* __restrict__ ds, const int* __restrict__ is, int n, int64_t B,
+                                                      double t, int k, double* __restrict__ dky, int* __restrict__ status,
+                                                      const int* __restrict__ perm) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= B) return;
+    const int64_t o = perm ? (int64_t)perm[s] : s;
+    const Layout lay(n);
+    const int kused = is[(int64_t)Layout::KUSED * B + s];
+    if (k < 0 || k > kused) {
+        if (status) status[o] = B200IDA_ST_BAD_K;
+        return;
+    }
+    const double tn = ds[(int64_t)lay.scal(Layout::TN) * B + s], hh = ds[(int64_t)lay.scal(Layout::HH) * B + s],
+                 hused = ds[(int64_t)lay.scal(Layout::HUSED) * B + s];
+    const double sgn = (hh > 0.0 || (hh == 0.0 && !signbit(hh))) ? 1.0 : -1.0;
+    const double tfuzz = 100.0 * DBL_EPS * (fabs(tn) + fabs(hh)) * sgn;
+    const double tp = tn - hused - tfuzz;
+    if ((t - tp) * hh < 0.0) {
+        if (status) status[o] = B200IDA_ST_BAD_T;
+        return;
+    }
+    double psi[MXORDP1], cjk[MXORDP1], cjk_1[MXORDP1];
+#pragma unroll
+    for (int j = 0; j < MXORDP1; ++j) {
+        psi[j] = ds[(int64_t)lay.psi(j) * B + s];
+        cjk[j] = 0.0;
+        cjk_1[j] = 0.0;
+    }
+    const double delt = t - tn;
+    double psij_1 = 0.0;
+    const int jtop = min(kused - k + 1, MXORDP1 - 1);
+    // fully unrolled with predicates so that psi / cjk stay in registers
+#pragma unroll
+    for (int i = 0; i < MXORDP1; ++i) {
+        if (i <= k) {
+            const double si = (double)i;
+            if (i == 0) {
+                cjk[0] = 1.0;
+            } else {
+                cjk[i] = cjk[i - 1] * si / psi[i - 1];
+                psij_1 = psi[i - 1];
+            }
+#pragma unroll
+            for (int j = i + 1; j < MXORDP1; ++j) {
+                if (j <= jtop) {
+                    cjk[j] = (si * cjk_1[j - 1] + cjk[j - 1] * (delt + psij_1)) / psi[j - 1];
+                    psij_1 = psi[j - 1];
+                }
+            }
+#pragma unroll
+            for (int j = i + 1; j < MXORDP1; ++j)
+                if (j <= jtop) cjk_1[j] = cjk[j];
+        }
+    }
+    for (int i = 0; i < n; ++i) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < MXORDP1; ++j)
+            if (j >= k && j <= kused) acc = acc + ds[(int64_t)lay.phi(j, i) * B + s] * cjk[j];
+        dky[(int64_t)i * B + o] = acc;
+    }
+    if (status) status[o] = 0;
+}
 // Morton key of the (min/max-normalised) parameter vector of each instance: instances that are close in
 // parameter space get adjacent slots, so the lanes of a warp take similar step/Newton/retry decisions.
 __global__ void order_key_kernel(const double* __restrict__ params, const double* __restrict__ lo, const double* __restrict__ hi,
@@ -614,6 +684,32 @@ int b200ida_get_step_info(b200ida_ensemble* e, int32_t* kused, int32_t* kcur, do
     if ((rc = rows_out<double, double>(e, hcur, e->dstate + (size_t)lay.scal(Layout::HH) * B, 1, mem))) return rc;
     if ((rc = rows_out<double, double>(e, tcur, e->dstate + (size_t)lay.scal(Layout::TN) * B, 1, mem))) return rc;
     if ((rc = rows_out<double, double>(e, h0u, e->dstate + (size_t)lay.scal(Layout::H0U) * B, 1, mem))) return rc;
+    return B200IDA_OK;
+}
+
+int b200ida_get_dky(b200ida_ensemble* e, double t, int k, double* dky, int32_t* status, int mem) {
+    if (!e || !dky || check_mem(mem)) return set_error(B200IDA_ERR_ARG, "b200ida_get_dky: bad argument");
+    B200_CUDA_TRY(cudaSetDevice(e->device));
+    const int64_t B = e->B;
+    const unsigned grid = (unsigned)((B + 255) / 256);
+    if (mem == B200IDA_MEM_DEVICE) {
+        ida_dky_kernel<<<grid, 256, 0, e->stream>>>(e->dstate, e->istate, e->n, B, t, k, dky, status, e->perm);
+        B200_CUDA_TRY(cudaGetLastError());
+        return B200IDA_OK;
+    }
+    // host buffers: compute into scratch (pre-filled from the caller's dky so that failed instances stay untouched)
+    const size_t dbytes = (size_t)e->n * B * sizeof(double), sbytes = (size_t)B * sizeof(int32_t);
+    void *d_dky, *d_st;
+    e->scratch_reset();
+    B200_CUDA_TRY(e->scratch_take(dbytes, &d_dky));
+    B200_CUDA_TRY(e->scratch_take(sbytes, &d_st));
+    B200_CUDA_TRY(cudaMemcpyAsync(d_dky, dky, dbytes, cudaMemcpyHostToDevice, e->stream));
+    ida_dky_kernel<<<grid, 256, 0, e->stream>>>(e->dstate, e->istate, e->n, B, t, k, static_cast<double*>(d_dky),
+                                                static_cast<int*>(d_st), e->perm);
+    B200_CUDA_TRY(cudaGetLastError());
+    B200_CUDA_TRY(cudaMemcpyAsync(dky, d_dky, dbytes, cudaMemcpyDeviceToHost, e->stream));
+    if (status) B200_CUDA_TRY(cudaMemcpyAsync(status, d_st, sbytes, cudaMemcpyDeviceToHost, e->stream));
+    B200_CUDA_TRY(cudaStreamSynchronize(e->stream));
     return B200IDA_OK;
 }
 

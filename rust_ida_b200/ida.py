@@ -30,6 +30,7 @@ class IdaSolveStatus(enum.IntEnum):
     BadErrorWeight = -6   # src/impl_solve.rs:272-285
     IllegalInput = -7     # src/impl_solve.rs:97-109
     BadTimeValue = -8     # src/lib.rs:1286-1292
+    BadK = -10            # IdaError::BadK from get_dky, src/lib.rs:443-447
     CloseRoots = -9       # IdaError::CloseRoots, src/impl_r_check.rs:199-203
     Root = 2              # IdaSolveStatus::Root (src/lib.rs:57-63); consumed inside a ladder launch (enable_roots)
 
@@ -234,6 +235,19 @@ class Ida:
 
     def get_num_lin_res_evals(self):  # :92 (always 0: no DQ Jacobian)
         return B.empty_like_space(self._ref, (self.batch,), np.int64) * 0
+
+    def get_dky(self, t, k, out=None):
+        """Ida::get_dky (src/lib.rs:424-529) on every instance: the k-th derivative at time `t` of each instance's
+        interpolating polynomial over its last step.  Returns (dky (n, batch), status (batch,) int32: 0 / BadK /
+        BadTimeValue); columns of failed instances keep what `out` held (NaN when `out` is not given)."""
+        if out is None:
+            out = B.empty_like_space(self._ref, (self.n, self.batch), np.float64)
+            out[...] = float("nan")
+        st = B.empty_like_space(self._ref, (self.batch,), np.int32)
+        po, _ = B.describe(out, np.float64, "out")
+        ps, _ = B.describe(st, np.int32, "status")
+        _lib.check(_lib.lib().b200ida_get_dky(self._h, float(t), int(k), po, ps, self._mem))
+        return out, st
 
     def _stepinfo(self, idx):
         dt = np.int32 if idx < 2 else np.float64

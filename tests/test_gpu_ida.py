@@ -420,3 +420,57 @@ def test_root_state_survives_between_launches():
         ida.close()
     assert np.array_equal(out[0]["count"], out[1]["count"]) and np.array_equal(out[0]["nge"], out[1]["nge"])
     assert_bit_equal(out[0]["t"], out[1]["t"], "root times, ladder vs call by call")
+
+
+@pytest.mark.parametrize("problem,device_buffers", [("roberts", True), ("roberts", False), ("heat", True)])
+def test_get_dky_matches_the_oracle(problem, device_buffers):
+    """Dense output (SURVEY 8 f2): Ida::get_dky (src/lib.rs:424-529) evaluated by the device for every instance equals
+    the oracle's bit for bit, for every derivative order, inside and outside each instance's last step."""
+    import torch
+    import rust_ida_b200 as r
+    from rust_ida_b200.problems import heat_ensemble_params, roberts_ensemble_params
+    ob, _ = oracle_with_detpow()
+    if problem == "roberts":
+        B, n = 777, 3
+        p = roberts_ensemble_params(B, seed=99)
+        yy0, yp0 = r.Roberts.consistent_ic(p)
+        rtol, atol, touts, kind = ROBERTS_RTOL, ROBERTS_ATOL, ROBERTS_TOUTS[:6], ob.PK_ROBERTS
+        mk = lambda pp: r.Roberts(pp)
+    else:
+        M, B = 10, 37
+        n = M * M
+        p = heat_ensemble_params(B, M=M, seed=5)
+        yy0, yp0 = r.Heat2D.consistent_ic(p, M)
+        rtol, atol, touts, kind = 1e-6, np.full(n, 1e-8), 0.01 * 2.0 ** np.arange(6), ob.PK_HEAT2D
+        mk = lambda pp: r.Heat2D(pp, M=M)
+    tend = float(touts[-1])
+    # query times: the output time itself (inside every instance's last step), slightly before, far before (BadTimeValue
+    # for most), beyond t_n (extrapolation is legal); orders 0..5 (BadK where k > kused of that instance)
+    tq = np.array([tend] * 6 + [tend * (1 - 1e-3)] * 3 + [tend * 0.5, tend * 1.01, tend * 1.01])
+    kq = np.array([0, 1, 2, 3, 4, 5, 0, 1, 2, 0, 0, 1], dtype=np.int32)
+    ref, rst = ob.ensemble_dky(kind, n, p, yy0, yp0, rtol, atol, touts, tq, kq, nthreads=8)
+    if device_buffers:
+        ida = r.Ida(mk(torch.from_numpy(p).cuda()), torch.from_numpy(yy0).cuda(), torch.from_numpy(yp0).cuda(),
+                    r.TolControlSV(rtol, atol))
+    else:
+        ida = r.Ida(mk(p), yy0, yp0, r.TolControlSV(rtol, atol))
+    status, _ = ida.solve_ladder(touts, want_traj=False)
+    seen = set()
+    for q in range(len(tq)):
+        dky, st = ida.get_dky(tq[q], int(kq[q]))
+        if device_buffers:
+            dky, st = dky.cpu().numpy(), st.cpu().numpy()
+        assert np.array_equal(st, rst[q]), (q, np.flatnonzero(st != rst[q])[:5])
+        ok = st == 0
+        assert_bit_equal(dky[:, ok], ref[q][:, ok], "dky of query %d" % q)
+        assert np.isnan(dky[:, ~ok]).all()  # untouched
+        seen |= set(np.unique(st).tolist())
+    # (the heat instances all end at order 5, so no k is too large for them -- and k = 0 runs the clamped recurrence)
+    assert seen == ({0, -8, -10} if problem == "roberts" else {0, -8})
+    # k = 0 at the output time is the solution the solver returned there, to rounding (a different recurrence)
+    y_at, _ = ida.get_dky(tend, 0)
+    yy = ida.get_yy()
+    if device_buffers:
+        y_at, yy = y_at.cpu().numpy(), yy.cpu().numpy()
+    np.testing.assert_allclose(y_at, yy, rtol=1e-9, atol=1e-14)
+    ida.close()

@@ -70,4 +70,5 @@ def test_status_enum_matches_header():
     assert int(codes["LSETUP_FAIL"]) == r.IdaSolveStatus.LinearSetupFail
     assert int(codes["BAD_T"]) == r.IdaSolveStatus.BadTimeValue
     assert int(codes["CLOSE_ROOTS"]) == r.IdaSolveStatus.CloseRoots and int(codes["ROOT"]) == r.IdaSolveStatus.Root
+    assert int(codes["BAD_K"]) == r.IdaSolveStatus.BadK
     assert len(codes) == len(r.IdaSolveStatus)

@@ -205,6 +205,43 @@ def test_get_solution_golden(golden_dir):
     np.testing.assert_allclose(u.get("yp"), it["ypret_expect"], rtol=1e-15)
 
 
+def test_get_dky_properties(golden_dir):
+    """get_dky (src/lib.rs:424-529) has no test or caller in the reference, so the restatement is pinned by what the
+    function must satisfy on the state of the reference's own get_solution fixture: k = 0 at t_n is phi[0] exactly
+    (every other coefficient is a product with delt + psi_{-1} = 0); k = 0 and k = 1 are the same polynomial and its
+    derivative that get_solution evaluates (different recurrence, so equal to rounding, and get_solution IS pinned to
+    the reference's expected values above); the k-th coefficient is k! / (psi_0 .. psi_{k-1}); BadK / BadTimeValue."""
+    it = {norm_name(i["name"]): i["value"] for i in load(golden_dir, "get_solution")["test_get_solution"]}
+    u = ob.Unit(3)
+    kused = int(it["kused"])
+    u.set("kused", kused)
+    for k in ("hh", "tn", "hused", "phi", "psi"):
+        u.set(k, it[k])
+    phi, psi, tn = np.array(it["phi"], dtype=np.float64).reshape(6, 3), np.array(it["psi"], dtype=np.float64), float(it["tn"])
+    r, d0 = u.get_dky(tn, 0)
+    assert r == 0 and np.array_equal(d0, phi[0] + 0.0)
+    t = float(it["t"])
+    assert u.get_solution(t) == 0
+    r0, d0 = u.get_dky(t, 0)
+    r1, d1 = u.get_dky(t, 1)
+    assert r0 == 0 and r1 == 0
+    np.testing.assert_allclose(d0, u.get("yy"), rtol=1e-13)
+    np.testing.assert_allclose(d1, u.get("yp"), rtol=1e-12)
+    np.testing.assert_allclose(d0, it["yret_expect"], rtol=1e-13)
+    np.testing.assert_allclose(d1, it["ypret_expect"], rtol=1e-12)
+    # highest derivative: only c_k^(k) = k!/(psi_0...psi_{k-1}) survives, times phi[k]
+    rk, dk = u.get_dky(t, kused)
+    import math
+    assert rk == 0
+    np.testing.assert_allclose(dk, phi[kused] * (math.factorial(kused) / np.prod(psi[:kused])), rtol=1e-14)
+    assert u.get_dky(t, kused + 1)[0] == -10 and u.get_dky(t, -1)[0] == -10       # BadK
+    assert u.get_dky(tn - 10.0 * float(it["hused"]), 0)[0] == -8                    # BadTimeValue
+    # kused = 5, k = 0: the reference indexes past its 6-entry coefficient array; the restatement stops at j = 5
+    u.set("kused", 5)
+    r5, d5 = u.get_dky(t, 0)
+    assert r5 == 0 and np.isfinite(d5).all()
+
+
 # ---- end to end: examples/roberts.rs (config 1) ------------------------------------------------------
 ROBERTS_TABLE = [  # (nst, kused, hused) at tout = 0.4*10^i -- SURVEY.md section 6 / BASELINE.md section 2
     (29, 3, 8.80238e-02), (43, 4, 6.33772e-01), (68, 4, 3.19323e+00), (95, 4, 3.32007e+01),

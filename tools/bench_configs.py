@@ -99,6 +99,37 @@ def main():
                               "ms": ms, "instances_per_s": B / (ms * 1e-3), "bit_identical_to_thread_kernel": same}), flush=True)
             ida.close()
 
+    if "dky" in args.which:
+        # dense output: get_dky on the persistent state of 2^20 Roberts instances (HBM-bound elementwise kernel)
+        import torch
+        B = 1 << 20
+        p = roberts_ensemble_params(B, seed=1234)
+        yy0, yp0 = Roberts.consistent_ic(p)
+        pd, y0, yp = to_dev(p, yy0, yp0)
+        touts = 0.4 * 10.0 ** np.arange(4)
+        ida = r.Ida(Roberts(pd), y0, yp, r.TolControlSV(1e-4, [1e-8, 1e-6, 1e-6]))
+        ida.solve_ladder(touts, want_traj=False)
+        kused = ida.get_last_order().double().mean().item()
+        out = torch.empty((3, B), dtype=torch.float64, device="cuda")
+        for k in (0, 1):
+            for _ in range(3):
+                ida.get_dky(float(touts[-1]), k, out=out)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 20
+            e0.record()
+            for _ in range(reps):
+                ida.get_dky(float(touts[-1]), k, out=out)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            # algorithmic bytes per instance: (kused - k + 1) phi rows of 3, 6 psi, tn/hh/hused, kused, 3 out, status
+            byt = ((kused - k + 1) * 3 + 6 + 3 + 3) * 8 + 8
+            print(json.dumps({"config": "get_dky on 2^20 Roberts instances", "k": k, "ms": ms, "kused_mean": kused,
+                              "alg_bytes_per_instance": byt, "gbs": byt * B / (ms * 1e-3) * 1e-9,
+                              "note": "includes the status write and the ctypes call; 168 MB working set is near L2 size"}), flush=True)
+        ida.close()
+
 
 if __name__ == "__main__":
     main()
