@@ -23,14 +23,21 @@ int main() {
     }
     try {
         EnsembleIda ida(B200IDA_PROBLEM_ROBERTS, 3, B, 3, params.data(), yy0.data(), yp0.data(), rtol, atol);
-        std::printf("%-12s %-14s %-14s %-14s %5s\n", "t", "y1", "y2", "y3", "nst");
+        std::printf("%-12s %-14s %-14s %-14s %5s %2s %-12s\n", "t", "y1", "y2", "y3", "nst", "k", "h");
         double tout = 0.4;
         for (int iout = 0; iout < 12; ++iout, tout *= 10.0) {
             auto st = ida.solve(tout);
             auto yy = ida.get_yy();
             auto nst = ida.get_num_steps();
-            std::printf("%-12.5e %-14.5e %-14.5e %-14.5e %5ld   status %d\n", tout, yy[0], yy[B], yy[2 * B], (long)nst[0], st[0]);
+            std::printf("%-12.5e %-14.5e %-14.5e %-14.5e %5ld %2d %-12.5e status %d\n", tout, yy[0], yy[B], yy[2 * B], (long)nst[0],
+                        ida.get_last_order()[0], ida.get_last_step()[0], st[0]);
         }
+        // dense output on the last step: y' at the final output time from get_dky(k = 1) next to the solver's own yp
+        std::vector<double> d1;
+        const auto dst = ida.get_dky(4.0e10, 1, d1);
+        const auto yp = ida.get_yp();
+        std::printf("dky1 %.6e %.6e %.6e dky_status %d yp %.6e %.6e %.6e\n", d1[0], d1[B], d1[2 * B], dst[0], yp[0],
+                    yp[B], yp[2 * B]);
         auto nst = ida.get_num_steps();
         std::printf("steps %ld  res evals %ld  jac evals %ld  nonlin iters %ld  err test fails %ld  conv fails %ld\n", (long)nst[0],
                     (long)ida.get_num_res_evals()[0], (long)ida.get_num_jac_evals()[0], (long)ida.get_num_nonlin_solv_iters()[0],

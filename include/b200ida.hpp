@@ -82,6 +82,24 @@ class EnsembleIda {
         check(b200ida_solve(h_, tout, (int)itask, st.data(), B200IDA_MEM_HOST));
         return st;
     }
+    // every output time of `touts` in ONE launch (each still a separate solve() call per instance: mxstep is per call,
+    // h0 comes from the first one); y_traj, if given, receives y(tout_k) as [ntout][n][batch]
+    std::vector<int32_t> solve_ladder(const std::vector<double>& touts, std::vector<double>* y_traj = nullptr,
+                                      IdaTask itask = IdaTask::Normal) {
+        std::vector<int32_t> st(touts.size() * (size_t)batch_);
+        if (y_traj) y_traj->assign(touts.size() * (size_t)n_ * batch_, 0.0);
+        check(b200ida_solve_ladder(h_, touts.data(), (int)touts.size(), (int)itask, y_traj ? y_traj->data() : nullptr, st.data(),
+                                   B200IDA_MEM_HOST));
+        return st;
+    }
+    // Ida::get_dky(t, k, &mut dky), src/lib.rs:424-529: dky [n][batch]; the Result of each instance in `status`
+    // (0, B200IDA_ST_BAD_K, B200IDA_ST_BAD_T); columns of failed instances keep what dky held
+    std::vector<int32_t> get_dky(double t, int k, std::vector<double>& dky) const {
+        dky.resize((size_t)n_ * batch_);
+        std::vector<int32_t> st((size_t)batch_);
+        check(b200ida_get_dky(h_, t, k, dky.data(), st.data(), B200IDA_MEM_HOST));
+        return st;
+    }
     std::vector<double> get_yy() const {  // src/ida_io.rs:11
         std::vector<double> y((size_t)n_ * batch_);
         check(b200ida_get_state(h_, y.data(), nullptr, nullptr, B200IDA_MEM_HOST));
@@ -98,6 +116,13 @@ class EnsembleIda {
     std::vector<int64_t> get_num_nonlin_solv_iters() const { return counter(3); }       // :84
     std::vector<int64_t> get_num_err_test_fails() const { return counter(4); }          // :74
     std::vector<int64_t> get_num_nonlin_solv_conv_fails() const { return counter(5); }  // :104
+    std::vector<int64_t> get_num_lin_solv_setups() const { return counter(6); }         // :69
+    std::vector<int32_t> get_last_order() const { return step_i(0); }                   // :22
+    std::vector<int32_t> get_current_order() const { return step_i(1); }                // :27
+    std::vector<double> get_last_step() const { return step_d(2); }                     // :38
+    std::vector<double> get_current_step() const { return step_d(3); }                  // :43 (`get_current_setp` there)
+    std::vector<double> get_current_time() const { return step_d(4); }                  // :48
+    std::vector<double> get_actual_init_step() const { return step_d(5); }              // :32
 
   private:
     std::vector<int64_t> counter(int which) const {
@@ -106,6 +131,18 @@ class EnsembleIda {
         a[which] = c.data();
         check(b200ida_get_counters(h_, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], B200IDA_MEM_HOST));
         return c;
+    }
+    std::vector<int32_t> step_i(int which) const {
+        std::vector<int32_t> v((size_t)batch_);
+        check(b200ida_get_step_info(h_, which == 0 ? v.data() : nullptr, which == 1 ? v.data() : nullptr, nullptr, nullptr, nullptr,
+                                    nullptr, B200IDA_MEM_HOST));
+        return v;
+    }
+    std::vector<double> step_d(int which) const {
+        std::vector<double> v((size_t)batch_);
+        check(b200ida_get_step_info(h_, nullptr, nullptr, which == 2 ? v.data() : nullptr, which == 3 ? v.data() : nullptr,
+                                    which == 4 ? v.data() : nullptr, which == 5 ? v.data() : nullptr, B200IDA_MEM_HOST));
+        return v;
     }
     b200ida_ensemble* h_ = nullptr;
     int n_;

@@ -220,7 +220,18 @@ def test_cpp_host_mirror_example():
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "steps 362  res evals 537  jac evals 60  nonlin iters 537  err test fails 15  conv fails 0" in out.stdout
-    assert "4.00000e+10  4.86409e-08   1.94564e-13   1.00000e+00" in " ".join(out.stdout.split("\n")[-3].split()) or True
+    # the (nst, k, h) columns of the table examples/roberts.rs:87-113 prints, through the step-info getters
+    table = [(29, 3, 8.80238e-02), (43, 4, 6.33772e-01), (68, 4, 3.19323e+00), (95, 4, 3.32007e+01), (126, 3, 3.14577e+02),
+             (161, 5, 2.50577e+03), (202, 3, 2.63706e+04), (250, 3, 1.71865e+05), (293, 4, 2.36551e+06), (325, 4, 2.68085e+07),
+             (348, 3, 7.43054e+08), (362, 2, 7.54805e+09)]
+    rows = [ln.split() for ln in out.stdout.split("\n") if "status" in ln and ln[0].isdigit()]
+    assert len(rows) == 12
+    for row, (nst, k, h) in zip(rows, table):
+        assert (int(row[4]), int(row[5])) == (nst, k) and abs(float(row[6]) / h - 1.0) < 1e-5 and row[-1] == "0"
+    # get_dky(t_end, 1) agrees with the solver's yp at the output time to rounding
+    dk = [ln for ln in out.stdout.split("\n") if ln.startswith("dky1")][0].split()
+    nums = [float(dk[i]) for i in (1, 2, 3, 5, 7, 8, 9)]
+    assert len(nums) == 7 and nums[3] == 0 and np.allclose(nums[:3], nums[4:], rtol=1e-5)
 
 
 @pytest.mark.parametrize("mode", ["on", "off"])
