@@ -358,6 +358,17 @@ static int rows_out(b200ida_ensemble* e, TD* dst, const TS* src, int rows, int m
 
 extern "C" {
 
+#ifdef ROOT_PROF
+int b200ida_debug_root_prof(unsigned long long* out8, int reset) {
+    if (out8) cudaMemcpyFromSymbol(out8, b200ida::root_prof, 8 * sizeof(unsigned long long));
+    if (reset) {
+        unsigned long long z[8] = {0};
+        cudaMemcpyToSymbol(b200ida::root_prof, z, sizeof(z));
+    }
+    return 0;
+}
+#endif
+
 const char* b200ida_last_error(void) { return last_error_buf(); }
 int b200ida_version(void) { return B200IDA_VERSION; }
 int b200ida_device_count(void) {

@@ -27,6 +27,18 @@
 #include "ida_common.cuh"
 
 namespace b200ida {
+// -DROOT_PROF: clock64 phase profile of solve_ladder (tools/prof_roots.py); compiled out otherwise
+#ifdef ROOT_PROF
+__device__ unsigned long long root_prof[8];
+#define RP_LEAD() ((__ffs(__activemask()) - 1) == (int)(threadIdx.x & 31))
+#define RP_T(v) long long v = clock64()
+#define RP_ACC(slot, v) do { if (RP_LEAD()) atomicAdd(&root_prof[slot], (unsigned long long)(clock64() - (v))); } while (0)
+#define RP_COUNT(slot) do { if (RP_LEAD()) atomicAdd(&root_prof[slot], 1ull); } while (0)
+#else
+#define RP_T(v)
+#define RP_ACC(slot, v)
+#define RP_COUNT(slot)
+#endif
 
 #ifndef IDA_THREAD_BLOCK
 #define IDA_THREAD_BLOCK 128
@@ -1096,6 +1108,7 @@ struct IdaThread {
 
 #pragma unroll 1
         while (it < lad.ntout) {
+            RP_T(ti0);
             if (need_prologue) {
                 need_prologue = false;
                 tout = lad.touts[it];
@@ -1112,6 +1125,7 @@ struct IdaThread {
                     }
                 } else {
                     if constexpr (ROOTS) {  // root stop checks: src/impl_solve.rs:186-227
+                        RP_T(tp0);
                         const int ier2 = r_check2();
                         if (ier2 != 0) {
                             if (ier2 == 1) {
@@ -1134,6 +1148,7 @@ struct IdaThread {
                                 }
                             }
                         }
+                        RP_ACC(0, tp0);
                     }
                     // stop_test1, NORMAL: src/impl_stop_test.rs:53-65
                     if (call_done) {
@@ -1234,7 +1249,10 @@ struct IdaThread {
                     nstloc += 1;
                     bool root_ret = false;
                     if constexpr (ROOTS) {  // root in the last step taken: src/impl_solve.rs:335-344
-                        if (r_check3() == 1) {
+                        RP_T(td0);
+                        const int rc3 = r_check3();
+                        RP_ACC(rc3 == 1 ? 2 : 1, td0);
+                        if (rc3 == 1) {
                             irfnd = true;
                             tretlast = rsm(4 * NR + 0);
                             tret = rsm(4 * NR + 0);
@@ -1284,9 +1302,8 @@ struct IdaThread {
                         for (int i = 0; i < NR; ++i) rp.ev_iroots[((int64_t)c * NR + i) * B + b] = rsm(3 * NR + i);
                     }
                     rp.ev_count[b] = c + 1;
-                    call_done = false;
+                    call_done = false;  // falls through to the loop end (no `continue`: a second back edge splits the warp)
                     need_prologue = true;
-                    continue;
                 }
             }
             if (call_done) {
@@ -1298,6 +1315,8 @@ struct IdaThread {
                 it += 1;
                 need_prologue = true;
             }
+            RP_ACC(3, ti0);
+            RP_COUNT(4);
         }
     }
 };
