@@ -179,6 +179,44 @@ impl EnsembleIda {
         Ok(y)
     }
 
+    /// every output time of `touts` in one launch; `y_traj`, if wanted, is `[ntout][n][batch]`
+    pub fn solve_ladder(&mut self, touts: &[f64], want_traj: bool) -> Result<(Vec<i32>, Option<Vec<f64>>), EngineError> {
+        let mut st = vec![0i32; touts.len() * self.batch];
+        let mut traj = if want_traj { Some(vec![0f64; touts.len() * self.n * self.batch]) } else { None };
+        let tp = traj.as_mut().map_or(std::ptr::null_mut(), |v| v.as_mut_ptr());
+        check(unsafe { b200ida_solve_ladder(self.h, touts.as_ptr(), touts.len() as c_int, TASK_NORMAL, tp, st.as_mut_ptr(), MEM_HOST) })?;
+        Ok((st, traj))
+    }
+
+    /// `Ida::get_dky(t, k, &mut dky)` (src/lib.rs:424-529) on every instance: `dky` is `[n][batch]`, the returned
+    /// vector holds each instance's outcome (0, BadK = -10, BadTimeValue = -8); failed columns keep their contents
+    pub fn get_dky(&self, t: f64, k: usize, dky: &mut [f64]) -> Result<Vec<i32>, EngineError> {
+        assert_eq!(dky.len(), self.n * self.batch);
+        let mut st = vec![0i32; self.batch];
+        check(unsafe { b200ida_get_dky(self.h, t, k as c_int, dky.as_mut_ptr(), st.as_mut_ptr(), MEM_HOST) })?;
+        Ok(st)
+    }
+
+    pub fn get_yp(&self) -> Result<Vec<f64>, EngineError> {
+        let mut y = vec![0f64; self.n * self.batch];
+        check(unsafe { b200ida_get_state(self.h, std::ptr::null_mut(), y.as_mut_ptr(), std::ptr::null_mut(), MEM_HOST) })?;
+        Ok(y)
+    }
+
+    /// `get_last_order` / `get_last_step` (src/ida_io.rs:22, 38)
+    pub fn get_last_order(&self) -> Result<Vec<i32>, EngineError> {
+        let mut v = vec![0i32; self.batch];
+        let (zi, zd) = (std::ptr::null_mut::<i32>(), std::ptr::null_mut::<f64>());
+        check(unsafe { b200ida_get_step_info(self.h, v.as_mut_ptr(), zi, zd, zd, zd, zd, MEM_HOST) })?;
+        Ok(v)
+    }
+    pub fn get_last_step(&self) -> Result<Vec<f64>, EngineError> {
+        let mut v = vec![0f64; self.batch];
+        let (zi, zd) = (std::ptr::null_mut::<i32>(), std::ptr::null_mut::<f64>());
+        check(unsafe { b200ida_get_step_info(self.h, zi, zi, v.as_mut_ptr(), zd, zd, zd, MEM_HOST) })?;
+        Ok(v)
+    }
+
     pub fn get_num_steps(&self) -> Result<Vec<i64>, EngineError> {
         let mut c = vec![0i64; self.batch];
         let z = std::ptr::null_mut();
