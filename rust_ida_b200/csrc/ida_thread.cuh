@@ -1047,6 +1047,43 @@ struct IdaThread {
 
     // IDARcheck3 -- src/impl_r_check.rs:211-267 ; 0 continue, 1 root found (body: root_check3 above, out of line)
     __device__ __forceinline__ int r_check3() {
+        // Fast path, inline: the check after an ordinary step (thi = t_n, g(t_n) from phi[0], see root_check3) when no
+        // active g_i changes sign or vanishes -- all but ~2 of the ~370 checks of a Roberts instance.  It performs
+        // exactly the state updates of root_check3's no-root path; anything else (sign change, zero, NaN, output time
+        // inside the step) takes the out-of-line function, which starts over from the unmodified state.
+        if constexpr (!P::ROOT_USES_YP) {
+            if ((rsm(4 * NR + 4) - tn) * hh >= 0.0) {
+                double y[N], ypz[N], g[NR];
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    y[i] = 0.0 + phi(0, i);
+                    ypz[i] = 0.0;
+                }
+                if constexpr (P::NR > 0) prob.root(tn, y, ypz, g);
+                bool quiet = true;
+#pragma unroll
+                for (int i = 0; i < NR; ++i) {
+                    const double glo_i = rsm(0 * NR + i);
+                    const bool live = gactive[i] && (0.0 * glo_i <= 0.0);
+                    if (live && (fabs(g[i]) == 0.0 || glo_i * g[i] < 0.0)) quiet = false;
+                }
+                if (quiet) {
+                    rsm(4 * NR + 1) = tn;                                    // thi
+                    rsm(4 * NR + 3) = (fabs(tn) + fabs(hh)) * DBL_EPS * 100.0;  // ttol
+                    rsm(4 * NR + 2) = tn;                                    // trout
+                    rsm(4 * NR + 0) = tn;                                    // tlo
+#pragma unroll
+                    for (int i = 0; i < NR; ++i) {
+                        rsm(1 * NR + i) = g[i];  // ghi
+                        rsm(2 * NR + i) = g[i];  // grout
+                        rsm(0 * NR + i) = g[i];  // glo
+                        if (!gactive[i] && g[i] != 0.0) gactive[i] = true;
+                    }
+                    nge += 1;
+                    return 0;
+                }
+            }
+        }
         unsigned gmask = 0;
 #pragma unroll
         for (int i = 0; i < NR; ++i) gmask |= gactive[i] ? (1u << i) : 0u;
