@@ -72,3 +72,22 @@ def test_status_enum_matches_header():
     assert int(codes["CLOSE_ROOTS"]) == r.IdaSolveStatus.CloseRoots and int(codes["ROOT"]) == r.IdaSolveStatus.Root
     assert int(codes["BAD_K"]) == r.IdaSolveStatus.BadK
     assert len(codes) == len(r.IdaSolveStatus)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` needs no GPU: one JSON line, the same metric / unit / config keys as the CUDA arm,
+    the reference-arm extras, and a positive instances/s figure from the oracle port."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["unit"] == "instances/s" and j["higher_is_better"] is True
+    assert j["n_gpus"] == 1 and j["steps"] == 1 and j["warmup"] == 0 and j["dtype"] == "f64"
+    assert j["value"] > 0 and j["ms_per_step"] > 0 and "workload" in j["config"]
+    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1
+    assert j["cpu_baseline"]["value"] == j["value"]
+    assert j["e2e"] == {"value": j["value"], "unit": j["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
