@@ -163,7 +163,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": val, "unit": "instances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---- GPU arm -----------------------------------------------------------------------------------------------------
@@ -330,12 +330,26 @@ def run_ours(args, rank, world, local_rank):
         "cpu_baseline": cpu,
         "clocks": clk.summary(),
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_FD = 1
+
+
+def emit(line):
+    """The one JSON line of the contract, written to the process's ORIGINAL stdout (see main)."""
+    os.write(_JSON_FD, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    # Libraries may write to fd 1 behind Python's back (NCCL prints "NCCL version ..." to stdout when the box sets
+    # NCCL_DEBUG=VERSION): keep the real stdout for the JSON line only and send everything else to stderr.
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
