@@ -311,18 +311,18 @@ def run_ours(args, rank, world, local_rank):
         "roofline": {"bound": "fp64", "achieved": achieved_gops, "peak": peak_gops, "unit": "GFLOP/s (un-fused FP64 ops)",
                      "frac": achieved_gops / peak_gops,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch at batch 2^20 (ncu --set full,
-                     # profiles/r1e_ida_solve_thread_final_ncu_summary.csv), scaled to this batch
-                     "traffic": int(2181624000 * (B / float(1 << 20))),
+                     # profiles/r1g_ida_solve_thread_ncu_summary.csv), scaled to this batch
+                     "traffic": int(2185871000 * (B / float(1 << 20))),
                      "hbm_view": {"algorithmic_bytes_per_launch": B * ALG_BYTES_PER_INSTANCE,
                                   "achieved_gbs": B * ALG_BYTES_PER_INSTANCE / (kernel_ms * 1e-3) * 1e-9, "peak_gbs": hbm_peak,
                                   "frac": B * ALG_BYTES_PER_INSTANCE / (kernel_ms * 1e-3) * 1e-9 / hbm_peak,
                                   "note": "state read once + written once per launch; three orders of magnitude below the "
                                           "FP64 bound, which is why the roofline above is the FP64 issue rate"},
-                     # hardware-side view of the same kernel from ncu (profiles/r1e_ida_solve_thread_final_ncu_summary.csv):
+                     # hardware-side view of the same kernel from ncu (profiles/r1g_ida_solve_thread_ncu_summary.csv):
                      # the FP64 pipe is busy 29 % of the cycles, the schedulers issue on 43 % -- division, sqrt and pow
                      # expand to 10-60 FP64-pipe instructions per algorithmic op, which is the gap to `frac`
-                     "ncu": {"sm__pipe_fp64_cycles_active_pct": 28.96, "smsp__issue_active_pct": 43.32,
-                             "active_lanes_per_instruction": 20.21, "source": "profiles/r1e_ida_solve_thread_final_ncu_summary.csv"},
+                     "ncu": {"sm__pipe_fp64_cycles_active_pct": 28.95, "smsp__issue_active_pct": 43.47,
+                             "active_lanes_per_instruction": 20.63, "source": "profiles/r1g_ida_solve_thread_ncu_summary.csv"},
                      "kernel": "ida_solve_thread_kernel<Roberts>", "kernel_ms": kernel_ms,
                      "ops_per_launch": tot_attempts * OPS_PER_ATTEMPT, "attempts_per_launch": tot_attempts,
                      "peak_source": "measured on this GPU by b200ida_fp64_issue_rate (MEASURED_PEAKS.json has no FP64 entry): "
