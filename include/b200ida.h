@@ -247,6 +247,11 @@ int b200ida_fp64_issue_rate(int kind, int device, double* ginstr_per_s);
  * Exposed so tests can prove device pow == host libm pow bit-for-bit. */
 int b200ida_detpow_batched(const double* x, const double* y, double* out, int64_t n, int mem, void* stream);
 
+/* q[i] = a[i] / b[i] and r[i] = 1.0 / b[i] through the straight-line division fast paths of csrc/fastdiv.cuh (what the
+ * thread-per-instance kernel uses for ewt_set src/tol_control.rs:80, set_coeffs src/lib.rs:744-750 and dense_get_rs
+ * crates/linear/src/dense.rs:196-205).  Exposed so tests can prove them bit-identical to IEEE division.  HOST buffers. */
+int b200ida_fastdiv_batched(const double* a, const double* b, double* q, double* r, int64_t n);
+
 #ifdef __cplusplus
 }
 #endif

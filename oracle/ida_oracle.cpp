@@ -338,6 +338,14 @@ struct Ida {
     int32_t* trace_i = nullptr;
     long trace_max = 0, trace_count = 0;
     double trace_tret = 0.0;  // the caller's tret (a local of Ida::solve's caller in the reference)
+    // ---- per-attempt event log (lane-divergence analysis, tests/analysis/sim_lanes.py): one word per attempt --------
+    // bits 0-2 kk at the top, 3 coefficients recomputed (kk+1 >= ns), 4-6 ns after its update, 7-8 Jacobian setups,
+    // 9-12 Newton iterations, 13-14 wrms calls of test_error (0 = not run), 15 converged, 16 pow in complete_step /
+    // handle_n_flag, 17 err_kp1 norm formed, 18-20 kk after, 21 phase after, 22 output time reached by this step
+    uint32_t* ev = nullptr;
+    float* ev_h = nullptr;  // |hh| after the attempt (sort-key experiments)
+    long ev_max = 0, ev_count = 0;
+    uint32_t ev_word = 0;
     void dump_frame() {
         const long c = trace_count++;
         if (c >= trace_max) return;
@@ -699,7 +707,11 @@ struct Ida {
         for (;;) {
             if (trace_d) dump_frame();  // data_trace frame: state at the top of the attempt (src/lib.rs:635-639)
             nattempts += 1;
+            uint32_t evw = 0;
+            const long ev_nje0 = nje, ev_nni0 = nls.niters;
+            if (ev) evw = (uint32_t)kk;
             ck = set_coeffs();
+            if (ev) evw |= (uint32_t)(kk + 1 >= ns) << 3 | (uint32_t)std::min(ns, 7) << 4;
             tn += hh;
             predict();
             int nflag = nonlinear_solve();
@@ -708,20 +720,45 @@ struct Ida {
             err_km1 = 0.0;
             if (nflag == 0) {
                 converged = test_error(ck, err_k, err_km1);
+                if (ev) evw |= (uint32_t)(1 + (kk > 1) + (kk > 2)) << 13;
                 if (!converged) nflag = 2;
             }
-            if (converged) break;
+            if (ev) evw |= (uint32_t)std::min(nje - ev_nje0, 3L) << 7 | (uint32_t)std::min(nls.niters - ev_nni0, 15L) << 9;
+            if (converged) {
+                ev_word = evw | 1u << 15;
+                break;
+            }
             restore(saved_t);
             if (nflag < 0) {  // singular Jacobian: fatal (reference panics)
                 ncfn += 1;
                 return nflag;
             }
             const int kflag = handle_n_flag(nflag, err_k, err_km1, ncf, nef);
+            if (ev) {
+                evw |= (uint32_t)(nflag == 2 && nef == 1) << 16 | (uint32_t)kk << 18 | (uint32_t)phase << 21;
+                if (ev_count < ev_max) {
+                    ev[ev_count] = evw;
+                    ev_h[ev_count] = (float)std::fabs(hh);
+                }
+                ev_count += 1;
+            }
             if (kflag != 0) return kflag;
             if (nst == 0) reset();
         }
+        const int ev_ph0 = phase, ev_kk0 = kk, ev_ns = ns, ev_kdiff = kk - kused;
         complete_step(err_k, err_km1);
         for (int i = 0; i < n; ++i) ee[i] *= ck;
+        if (ev) {
+            // which branches complete_step took (restated from its conditions on the state before the call)
+            const bool ph1 = ev_ph0 == 1 || knew == ev_kk0 - 1 || ev_kk0 == maxord;
+            const bool kp1 = ph1 && !(knew == ev_kk0 - 1) && ev_kk0 != maxord && !(ev_kk0 + 1 >= ev_ns || ev_kdiff == 1);
+            ev_word |= (uint32_t)ph1 << 16 | (uint32_t)kp1 << 17 | (uint32_t)kk << 18 | (uint32_t)phase << 21;
+            if (ev_count < ev_max) {
+                ev[ev_count] = ev_word;
+                ev_h[ev_count] = (float)std::fabs(hh);
+            }
+            ev_count += 1;
+        }
         return 0;
     }
 
@@ -1125,6 +1162,7 @@ struct Ida {
                 tret = tout;
                 tretlast = tout;
                 get_solution(tout);
+                if (ev && ev_count >= 1 && ev_count <= ev_max) ev[ev_count - 1] |= 1u << 22;
                 return ST_SUCCESS;
             }
         }
@@ -1375,6 +1413,40 @@ int oracle_ensemble_dky(int kind, int n, int64_t B, int nparams, const double* p
                 if (r == 0)
                     for (int i = 0; i < n; ++i) dky[((size_t)q * n + i) * B + b] = out[i];
             }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nthreads; ++t) th.emplace_back(worker);
+    worker();
+    for (auto& t : th) t.join();
+    return 0;
+}
+
+// per-attempt event words of every instance (see Ida::ev): ev [B][max_att] uint32, ev_h [B][max_att] float, natt [B].
+int oracle_ensemble_events(int kind, int n, int64_t B, int nparams, const double* params, const double* yy0, const double* yp0,
+                           double rtol, const double* atol, const double* touts, int ntout, int nthreads, long max_att,
+                           uint32_t* ev, float* ev_h, int32_t* natt) {
+    if (nthreads < 1) nthreads = 1;
+    std::atomic<int64_t> next(0);
+    auto worker = [&]() {
+        std::vector<double> par(nparams), y0(n), yp0v(n);
+        for (;;) {
+            const int64_t b = next.fetch_add(1);
+            if (b >= B) break;
+            for (int k = 0; k < nparams; ++k) par[k] = params[(size_t)k * B + b];
+            for (int i = 0; i < n; ++i) {
+                y0[i] = yy0[(size_t)i * B + b];
+                yp0v[i] = yp0[(size_t)i * B + b];
+            }
+            Ida ida;
+            Problem p{kind, n, par.data()};
+            ida.init(p, y0.data(), yp0v.data(), rtol, atol);
+            ida.ev = ev + (size_t)b * max_att;
+            ida.ev_h = ev_h + (size_t)b * max_att;
+            ida.ev_max = max_att;
+            double tret = 0.0;
+            for (int it = 0; it < ntout; ++it) ida.solve(touts[it], tret);
+            natt[b] = (int32_t)ida.ev_count;
         }
     };
     std::vector<std::thread> th;

@@ -30,6 +30,10 @@ inline int set_error(int code, const char* fmt, ...) {
 struct DevBuf {
     void* p = nullptr;
     cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+    }
     ~DevBuf() {
         if (p) cudaFree(p);
     }

@@ -84,6 +84,20 @@ struct RootParams {
     int max_ev;
 };
 
+// deferred output interpolation (production thread kernels): a lane that passes an output time only SNAPSHOTS what
+// get_solution (src/lib.rs:1274-1343) reads -- phi[0..kord], psi[0..kord-1], kused, tn, hh, hused -- and a second,
+// lane-coherent kernel (ida_interp_kernel) evaluates y(tout), y'(tout) for every (instance, output time) afterwards:
+// same operations on the same operands, so the values are bit-identical, but the ~400-instruction interpolation is no
+// longer issued once per lane per output time by a warp whose lanes reach their output times on different attempts.
+// snap: [batch][ntout][SNAP_DOUBLES] by caller-visible instance id, AoS so that the lone lane writes whole sectors;
+// fields 0..6n+5 are phi / psi at their Layout offsets, then kused, tn, hh, hused.  valid: [ntout][batch] bytes, written
+// for every call of every instance (1 = snapshot taken, 0 = the call returned some other way and interpolated inline).
+struct DeferParams {
+    double* snap;
+    unsigned char* valid;
+};
+__host__ __device__ constexpr int snap_doubles(int n) { return 6 * n + 6 + 4; }
+
 // select a[k] from a 6-entry register array without dynamic indexing
 __device__ __forceinline__ double pick6(const double (&a)[MXORDP1], int k) {
     double v = a[0];

@@ -28,11 +28,15 @@ char* last_error_buf() {
 #ifndef IDA_MIN_BLOCKS
 #define IDA_MIN_BLOCKS 3  // 168 regs, 12 warps/SM: measured faster than 4 (128 regs + spills) and 2
 #endif
+#ifndef IDA_DEFER
+#define IDA_DEFER 1  // deferred output interpolation (DeferParams, ida_common.cuh); 0: interpolate in the solve kernel
+#endif
 template <class P, bool TRACE = false, bool ROOTS = false>
 __global__ void __launch_bounds__(THREAD_BLOCK, IDA_MIN_BLOCKS)
 ida_solve_thread_kernel(double* __restrict__ ds, int* __restrict__ is, const double* __restrict__ params, int64_t B,
                         TolN<P::N> tol, LadderParams lad, double* __restrict__ yy_traj, int32_t* __restrict__ status,
-                        const int* __restrict__ perm, TraceParams tr = TraceParams(), RootParams rp = RootParams()) {
+                        const int* __restrict__ perm, TraceParams tr = TraceParams(), RootParams rp = RootParams(),
+                        DeferParams df = DeferParams()) {
     extern __shared__ double smem[];
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // slot
     if (b >= B) return;
@@ -42,11 +46,47 @@ ida_solve_thread_kernel(double* __restrict__ ds, int* __restrict__ is, const dou
     s.prob.load(params, B, b);
     s.load(ds, is, B, b);
     if constexpr (ROOTS) s.load_roots(rp, B, b);
-    s.template solve_ladder<TRACE, ROOTS>(lad, tol, yy_traj, status, B, ob, tr, rp);
+    // the production instantiation defers the output interpolation to ida_interp_kernel; the TRACE and ROOTS
+    // instantiations read yy / yp right after get_solution (trace frames, g(t, y)) and keep it in line
+    s.template solve_ladder<TRACE, ROOTS, !TRACE && !ROOTS && IDA_DEFER>(lad, tol, yy_traj, status, B, ob, tr, rp, df);
     s.store(ds, is, B, b);
     if constexpr (ROOTS) {
         s.store_roots(rp, B, b);
         if (rp.nge_out) rp.nge_out[ob] = s.nge;
+    }
+}
+
+// Second pass of the deferred output interpolation (DeferParams, ida_common.cuh): get_solution (src/lib.rs:1274-1343)
+// for every (instance, output time) whose call returned through stop_test2, from the snapshot the solve kernel took.
+// One thread per slot, all lanes walk the output times together.  y(tout) goes to yy_traj (caller order) when one was
+// asked for; y, y' of the LAST call go to the persistent state, where the reference's solve() leaves them.
+template <int N>
+__global__ void __launch_bounds__(128)
+ida_interp_kernel(double* __restrict__ ds, int64_t B, LadderParams lad, DeferParams df, double* __restrict__ yy_traj,
+                  const int* __restrict__ perm) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int64_t ob = perm ? (int64_t)perm[b] : b;
+    constexpr Layout lay(N);
+    constexpr int SD = snap_doubles(N);
+#pragma unroll 1
+    for (int it = 0; it < lad.ntout; ++it) {
+        if (!df.valid[(int64_t)it * B + ob]) continue;
+        const double* sp = df.snap + ((size_t)ob * lad.ntout + it) * SD;
+        double out[2 * N];
+        const int r = get_solution_fn<N, 1>(sp, sp[6 * N + 8], sp[6 * N + 9], sp[6 * N + 7], (int)sp[6 * N + 6], lad.touts[it], out);
+        if (r != 0) continue;  // unreachable after stop_test2 (tout lies inside the last step); yy / yp stay as they are
+        if (yy_traj) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) yy_traj[((int64_t)it * N + i) * B + ob] = out[i];
+        }
+        if (it == lad.ntout - 1) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                ds[(int64_t)lay.yy(i) * B + b] = out[i];
+                ds[(int64_t)lay.yp(i) * B + b] = out[N + i];
+            }
+        }
     }
 }
 
@@ -206,6 +246,28 @@ __global__ void detpow_kernel(const double* __restrict__ x, const double* __rest
     if (i < n) out[i] = detpow::det_pow(x[i], y[i]);
 }
 
+// q = a / b and r = 1 / b through fastdiv.cuh: three quotients per thread in one batch, like the solver's call sites
+__global__ void fastdiv_kernel(const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ q,
+                               double* __restrict__ r, int64_t n) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t i0 = 3 * t;
+    if (i0 + 2 < n) {
+        const double aa[3] = {a[i0], a[i0 + 1], a[i0 + 2]}, bb[3] = {b[i0], b[i0 + 1], b[i0 + 2]};
+        double qq[3], rr[3];
+        div_batch<3>(aa, bb, qq);
+        rcp_batch<3>(bb, rr);
+        for (int k = 0; k < 3; ++k) {
+            q[i0 + k] = qq[k];
+            r[i0 + k] = rr[k];
+        }
+    } else {
+        for (int64_t i = i0; i < n; ++i) {
+            q[i] = div1(a[i], b[i]);
+            r[i] = rcp1(b[i]);
+        }
+    }
+}
+
 // FP64 issue-rate microbenchmark: 8 independent dependency chains per thread, register resident.
 template <int KIND>
 __global__ void __launch_bounds__(256) fp64_rate_kernel(double* out, int iters, double seed) {
@@ -247,6 +309,8 @@ struct b200ida_ensemble {
     TraceParams trace = {nullptr, nullptr, nullptr, 0, -1};  // b200ida_set_trace; id < 0: off
     RootParams roots = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0};  // b200ida_set_roots; max_ev == 0: off
     DevBuf root_d, root_i;  // the per-instance root state (engine-owned)
+    DevBuf snap, snap_valid;  // deferred output interpolation (DeferParams), grown to the longest ladder seen
+    size_t snap_cap = 0, valid_cap = 0;
     // persistent device scratch for the host-buffer (end-to-end) entry points and the order builder: a few blocks
     // grown on demand, sub-allocated per API call (scratch_reset() rewinds), freed only by destroy -- so there is no
     // cudaMalloc / cudaFree (and no implicit device synchronisation) on the per-step path once warmed up
@@ -598,14 +662,34 @@ int b200ida_solve_ladder(b200ida_ensemble* e, const double* touts, int ntout, in
                 ida_solve_thread_kernel<Lorenz63, true><<<grid, tb, smem, e->stream>>>(e->dstate, e->istate, e->params, e->B, tol, lad,
                                                                                        d_traj, d_stat, e->perm, e->trace);
             }
-        } else if (e->problem == B200IDA_PROBLEM_ROBERTS) {
-            B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_thread_kernel<Roberts>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            ida_solve_thread_kernel<Roberts><<<grid, tb, smem, e->stream>>>(e->dstate, e->istate, e->params, e->B, tol, lad,
-                                                                            d_traj, d_stat, e->perm);
         } else {
-            B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_thread_kernel<Lorenz63>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            ida_solve_thread_kernel<Lorenz63><<<grid, tb, smem, e->stream>>>(e->dstate, e->istate, e->params, e->B, tol, lad,
-                                                                             d_traj, d_stat, e->perm);
+            // production path: solve kernel (snapshots at the output times) + the coherent interpolation pass
+            const size_t need_snap = (size_t)e->B * ntout * snap_doubles(3) * sizeof(double), need_valid = (size_t)e->B * ntout;
+            if (need_snap > e->snap_cap) {
+                e->snap.release();
+                e->snap_cap = 0;
+                B200_CUDA_TRY(e->snap.alloc(need_snap));
+                e->snap_cap = need_snap;
+            }
+            if (need_valid > e->valid_cap) {
+                e->snap_valid.release();
+                e->valid_cap = 0;
+                B200_CUDA_TRY(e->snap_valid.alloc(need_valid));
+                e->valid_cap = need_valid;
+            }
+            const DeferParams df = {e->snap.as<double>(), e->snap_valid.as<unsigned char>()};
+            if (e->problem == B200IDA_PROBLEM_ROBERTS) {
+                B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_thread_kernel<Roberts>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                ida_solve_thread_kernel<Roberts><<<grid, tb, smem, e->stream>>>(e->dstate, e->istate, e->params, e->B, tol, lad,
+                                                                                d_traj, d_stat, e->perm, TraceParams(), RootParams(), df);
+            } else {
+                B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_thread_kernel<Lorenz63>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                ida_solve_thread_kernel<Lorenz63><<<grid, tb, smem, e->stream>>>(e->dstate, e->istate, e->params, e->B, tol, lad,
+                                                                                 d_traj, d_stat, e->perm, TraceParams(), RootParams(), df);
+            }
+            B200_CUDA_TRY(cudaGetLastError());
+            if (IDA_DEFER)
+                ida_interp_kernel<3><<<(unsigned)((e->B + 127) / 128), 128, 0, e->stream>>>(e->dstate, e->B, lad, df, d_traj, e->perm);
         }
     } else {
         const bool warp = kernel == B200IDA_KERNEL_WARP;
@@ -758,6 +842,25 @@ int b200ida_detpow_batched(const double* x, const double* y, double* out, int64_
     B200_CUDA_TRY(cudaGetLastError());
     B200_CUDA_TRY(cudaMemcpyAsync(out, dout.p, bytes, cudaMemcpyDeviceToHost, st));
     B200_CUDA_TRY(cudaStreamSynchronize(st));
+    return B200IDA_OK;
+}
+
+int b200ida_fastdiv_batched(const double* a, const double* b, double* q, double* r, int64_t n) {
+    if (!a || !b || !q || !r || n < 1) return set_error(B200IDA_ERR_ARG, "b200ida_fastdiv_batched: bad argument");
+    if (b200ida_device_count() < 1) return set_error(B200IDA_ERR_NO_DEVICE, "b200ida_fastdiv_batched: no CUDA device");
+    DevBuf da, db, dq, dr;
+    const size_t bytes = (size_t)n * sizeof(double);
+    B200_CUDA_TRY(da.alloc(bytes));
+    B200_CUDA_TRY(db.alloc(bytes));
+    B200_CUDA_TRY(dq.alloc(bytes));
+    B200_CUDA_TRY(dr.alloc(bytes));
+    B200_CUDA_TRY(cudaMemcpy(da.p, a, bytes, cudaMemcpyHostToDevice));
+    B200_CUDA_TRY(cudaMemcpy(db.p, b, bytes, cudaMemcpyHostToDevice));
+    const int64_t threads = (n + 2) / 3;
+    fastdiv_kernel<<<(unsigned)((threads + 255) / 256), 256>>>(da.as<double>(), db.as<double>(), dq.as<double>(), dr.as<double>(), n);
+    B200_CUDA_TRY(cudaGetLastError());
+    B200_CUDA_TRY(cudaMemcpy(q, dq.p, bytes, cudaMemcpyDeviceToHost));
+    B200_CUDA_TRY(cudaMemcpy(r, dr.p, bytes, cudaMemcpyDeviceToHost));
     return B200IDA_OK;
 }
 

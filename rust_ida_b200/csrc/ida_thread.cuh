@@ -24,6 +24,7 @@
 // with -fmad=false: + - * / sqrt are IEEE correctly rounded and un-fused, pow is detpow.h.
 #pragma once
 #include "detpow.h"
+#include "fastdiv.cuh"
 #include "ida_common.cuh"
 
 namespace b200ida {
@@ -60,10 +61,22 @@ struct TolN {
 #ifndef IDA_DIV_NOINLINE
 #define IDA_DIV_NOINLINE 0
 #endif
+// IDA_FASTDIV: divisions through fastdiv.cuh (straight-line fast paths, independent quotients batched under one range
+// test) instead of nvcc's inline expansion (one taken branch per quotient, chains not interleaved); bit-identical
+#ifndef IDA_FASTDIV
+#define IDA_FASTDIV 1
+#endif
 #if IDA_DIV_NOINLINE
 __device__ __noinline__ double ddiv(double a, double b) { return a / b; }
+#elif IDA_FASTDIV
+__device__ __forceinline__ double ddiv(double a, double b) { return div1(a, b); }
 #else
 __device__ __forceinline__ double ddiv(double a, double b) { return a / b; }
+#endif
+#if IDA_FASTDIV
+__device__ __forceinline__ double drcp(double b) { return rcp1(b); }
+#else
+__device__ __forceinline__ double drcp(double b) { return 1.0 / b; }
 #endif
 #if IDA_POW_INLINE
 __device__ __forceinline__ double pow_noinline(double x, double y) { return detpow::det_pow(x, y); }
@@ -112,7 +125,7 @@ __device__ __forceinline__ double wrms(const double (&x)[N], const double (&w)[N
 
 // ---- get_solution: src/lib.rs:1274-1343 ; returns 0 or B200IDA_ST_BAD_T.  Out of line (called ~12 times per
 // instance); reads phi / psi from the thread's shared-memory column, writes yret to out[0..N), ypret to out[N..2N).
-template <int N>
+template <int N, int STRIDE = THREAD_BLOCK>
 __device__ __noinline__ int get_solution_fn(const double* sm, double hh, double hused, double tn, int kused, double t,
                                             double* out) {
     const double sgn = (hh > 0.0 || (hh == 0.0 && !signbit(hh))) ? 1.0 : -1.0;
@@ -130,19 +143,19 @@ __device__ __noinline__ int get_solution_fn(const double* sm, double hh, double 
     double y[N], yp[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-        y[i] = 0.0 + c * sm[i * THREAD_BLOCK];
+        y[i] = 0.0 + c * sm[i * STRIDE];
         yp[i] = 0.0;
     }
 #pragma unroll 1
     for (int j = 1; j <= kord; ++j) {
-        const double psi_jm1 = sm[(6 * N + j - 1) * THREAD_BLOCK];
+        const double psi_jm1 = sm[(6 * N + j - 1) * STRIDE];
         const double gam = num / psi_jm1;
         d = d * gam + c / psi_jm1;
         c = c * gam;
         num = delt + psi_jm1;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            const double p = sm[(j * N + i) * THREAD_BLOCK];
+            const double p = sm[(j * N + i) * STRIDE];
             y[i] += c * p;
             yp[i] += d * p;
         }
@@ -169,6 +182,18 @@ __device__ __forceinline__ double alphas_of(int kk) {
     v = (kk == 3) ? t3 : v;
     v = (kk == 4) ? t4 : v;
     v = (kk == 5) ? t5 : v;
+    return v;
+}
+
+// 1.0 / (double)k for k = 1..6, the exponents of the step-size formulas (src/impl_complete_step.rs:128-132,
+// src/lib.rs:1155-1160): correctly rounded constants, selected instead of divided
+__device__ __forceinline__ double inv_small(int k) {
+    double v = 1.0;
+    v = (k == 2) ? 1.0 / 2.0 : v;
+    v = (k == 3) ? 1.0 / 3.0 : v;
+    v = (k == 4) ? 1.0 / 4.0 : v;
+    v = (k == 5) ? 1.0 / 5.0 : v;
+    v = (k == 6) ? 1.0 / 6.0 : v;
     return v;
 }
 
@@ -433,8 +458,15 @@ struct IdaThread {
 
     // ---- TolControlSV::ewt_set: src/tol_control.rs:71-82 -------------------------------------------------
     __device__ __forceinline__ void ewt_set(const TolN<N>& tol) {
+#if IDA_FASTDIV
+        double den[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) den[i] = tol.rtol * fabs(phi(0, i)) + tol.atol[i];
+        rcp_batch<N>(den, ewt);
+#else
 #pragma unroll
         for (int i = 0; i < N; ++i) ewt[i] = ddiv(1.0, tol.rtol * fabs(phi(0, i)) + tol.atol[i]);
+#endif
     }
 
     // ---- set_coeffs: src/lib.rs:722-782 ----------------------------------------------------------------
@@ -452,11 +484,23 @@ struct IdaThread {
             for (int i = 1; i <= kk; ++i) {
                 const double temp2 = psi(i - 1);
                 psi(i - 1) = temp1;
+#if IDA_FASTDIV
+                // the three quotients of one pass are independent of each other: one basic block, one range test
+                const double num[3] = {beta_prev * temp1, hh, alpha_prev};
+                temp1 = temp2 + hh;
+                const double den[3] = {temp2, temp1, hh};
+                double quo[3];
+                div_batch<3>(num, den, quo);
+                const double b_i = quo[0], a_i = quo[1];
+                const double s_i = (double)i * sigma_prev * a_i;
+                const double g_i = gamma_prev + quo[2];
+#else
                 const double b_i = ddiv(beta_prev * temp1, temp2);
                 temp1 = temp2 + hh;
                 const double a_i = ddiv(hh, temp1);
                 const double s_i = (double)i * sigma_prev * a_i;
                 const double g_i = gamma_prev + ddiv(alpha_prev, hh);
+#endif
                 beta(i) = b_i;
                 alpha(i) = a_i;
                 sigma(i) = s_i;
@@ -534,7 +578,7 @@ struct IdaThread {
                     }
                 }
             }
-            const double mult = ddiv(1.0, J[k][k]);
+            const double mult = drcp(J[k][k]);
 #pragma unroll
             for (int i = k + 1; i < N; ++i) J[i][k] *= mult;
 #pragma unroll
@@ -568,6 +612,41 @@ struct IdaThread {
 #pragma unroll
             for (int i = k + 1; i < N; ++i) b[i] -= J[i][k] * bk;
         }
+#if IDA_FASTDIV
+        // back substitution with the N quotients on their fast paths in one basic block: the reciprocal refinement of
+        // every u_kk is independent of b and is scheduled ahead of the chain; one range test for all of them, and a
+        // cold redo from the saved right-hand side
+        double save[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) save[i] = b[i];
+        bool all = true;
+#pragma unroll
+        for (int k = N - 1; k >= 1; --k) {
+            bool ok;
+            b[k] = div_fast(b[k], J[k][k], ok);
+            all = all && ok;
+            const double bk = b[k];
+#pragma unroll
+            for (int i = 0; i < k; ++i) b[i] -= J[i][k] * bk;
+        }
+        {
+            bool ok;
+            b[0] = div_fast(b[0], J[0][0], ok);
+            all = all && ok;
+        }
+        if (__builtin_expect(!all, 0)) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) b[i] = save[i];
+#pragma unroll
+            for (int k = N - 1; k >= 1; --k) {
+                b[k] = div_slow(b[k], J[k][k]);
+                const double bk = b[k];
+#pragma unroll
+                for (int i = 0; i < k; ++i) b[i] -= J[i][k] * bk;
+            }
+            b[0] = div_slow(b[0], J[0][0]);
+        }
+#else
 #pragma unroll
         for (int k = N - 1; k >= 1; --k) {
             b[k] = ddiv(b[k], J[k][k]);
@@ -576,6 +655,7 @@ struct IdaThread {
             for (int i = 0; i < k; ++i) b[i] -= J[i][k] * bk;
         }
         b[0] = ddiv(b[0], J[0][0]);
+#endif
     }
 
     // ---- IdaNLProblem::sys: src/ida_nls.rs:118-153 ------------------------------------------------------
@@ -746,7 +826,7 @@ struct IdaThread {
         for (int j = 1; j <= kk; ++j) psi(j - 1) = psi(j) - hh;
 #pragma unroll 1
         for (int j = ns; j <= kk; ++j) {
-            const double c = ddiv(1.0, beta(j));
+            const double c = drcp(beta(j));
 #pragma unroll
             for (int i = 0; i < N; ++i) phi(j, i) *= c;
         }
@@ -762,7 +842,7 @@ struct IdaThread {
                 const double err_knew = (kk == knew) ? err_k : err_km1;
                 kk = knew;
                 const double base = 2.0 * err_knew + 0.0001;
-                const double arg = 1.0 / (double)(kk + 1);
+                const double arg = inv_small(kk + 1);
                 rr = 0.9 * pow_noinline(base, -arg);
                 rr = fmax(0.25, fmin(0.9, rr));
                 hh *= rr;
@@ -849,7 +929,7 @@ struct IdaThread {
             double hnew = hh;
             {
                 const double base = 2.0 * err_knew + 0.0001;
-                const double arg = -(1.0 / (double)(kk + 1));
+                const double arg = -inv_small(kk + 1);
                 rr = pow_noinline(base, arg);
             }
             if (rr >= 2.0) {
@@ -1134,11 +1214,14 @@ struct IdaThread {
     // Equivalent to calling Ida::solve(touts[k], .., Normal) for k = 0..ntout-1 (src/impl_solve.rs:69-376 with the
     // NORMAL branches of stop_test1/2, src/impl_stop_test.rs:53-65,152-161).  After call k, yy is written to
     // yy_traj[k][.][b] and the call's status to status[k][b] when those pointers are non-null.
-    template <bool TRACE, bool ROOTS = false>
+    // DEFER: y(tout) of a call that returns through stop_test2 is not interpolated here but snapshotted for
+    // ida_interp_kernel (DeferParams in ida_common.cuh); every other return path interpolates in line.
+    template <bool TRACE, bool ROOTS = false, bool DEFER = false>
     __device__ __forceinline__ void solve_ladder(const LadderParams& lad, const TolN<N>& tol, double* __restrict__ yy_traj,
                                                  int32_t* __restrict__ status, int64_t B, int64_t b, const TraceParams& tr,
-                                                 const RootParams& rp = RootParams()) {
+                                                 const RootParams& rp = RootParams(), const DeferParams& df = DeferParams()) {
         int it = 0;
+        bool deferred = false;
         bool need_prologue = true;
         bool in_step = false;
         bool call_done = false;
@@ -1157,6 +1240,7 @@ struct IdaThread {
                 in_step = false;
                 call_done = false;
                 call_status = 0;
+                deferred = false;
                 if constexpr (ROOTS) rsm(4 * NR + 4) = tout;  // src/impl_solve.rs:78-82
                 if (nst == 0) {
                     const int r = first_call<ROOTS>(tout, tol);
@@ -1306,7 +1390,25 @@ struct IdaThread {
                     if (!root_ret && (tn - tout) * hh >= 0.0) {
                         tret = tout;
                         tretlast = tout;
-                        get_solution(tout);
+                        if constexpr (DEFER) {
+                            // what get_solution(tout) reads, to row (b, it) of the snapshot buffer
+                            double* sp = df.snap + ((size_t)b * lad.ntout + it) * snap_doubles(N);
+                            const int kord = (kused == 0) ? 1 : kused;
+#pragma unroll 1
+                            for (int j = 0; j <= kord; ++j) {
+#pragma unroll
+                                for (int i = 0; i < N; ++i) sp[j * N + i] = phi(j, i);
+                            }
+#pragma unroll 1
+                            for (int j = 0; j < kord; ++j) sp[6 * N + j] = psi(j);
+                            sp[6 * N + 6] = (double)kused;
+                            sp[6 * N + 7] = tn;
+                            sp[6 * N + 8] = hh;
+                            sp[6 * N + 9] = hused;
+                            deferred = true;
+                        } else {
+                            get_solution(tout);
+                        }
                         call_status = B200IDA_ST_SUCCESS;
                         call_done = true;
                     }
@@ -1348,7 +1450,8 @@ struct IdaThread {
                 }
             }
             if (call_done) {
-                if (yy_traj) {
+                if constexpr (DEFER) df.valid[(int64_t)it * B + b] = deferred ? 1 : 0;
+                if (yy_traj && !(DEFER && deferred)) {
 #pragma unroll
                     for (int i = 0; i < N; ++i) yy_traj[((int64_t)it * N + i) * B + b] = yy[i];
                 }

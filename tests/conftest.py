@@ -16,3 +16,15 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(autouse=True)
+def _oracle_pow_is_libm_again():
+    """the oracle's pow is a process-global: whatever a test swapped in, the next test starts from the libm pow"""
+    yield
+    try:
+        from oracle import binding as ob
+        if ob._lib is not None:
+            ob.set_pow(None)
+    except Exception:
+        pass

@@ -25,9 +25,19 @@ def detpow_host_lib():
     return L
 
 
+def parity_oracle():
+    """oracle.binding with its DEFAULT pow: the platform libm `pow`, i.e. what the reference's f64::powf calls.  Every
+    GPU parity test compares the device results with this oracle, so a det_pow / libm mismatch on a real trajectory
+    fails a test instead of hiding behind a shared pow."""
+    from oracle import binding as ob
+    ob.set_pow(None)
+    return ob, None
+
+
 def oracle_with_detpow():
-    """oracle.binding with pow switched to the engine's det_pow (bit-identical to glibc pow on the main
-    path, proven by tests/test_detpow.py; this only removes any dependence on the box's libm)."""
+    """oracle.binding with pow switched to the engine's det_pow (csrc/detpow.h built for the host).  Only used by
+    tests/test_detpow.py to show that the two oracles agree on whole trajectories; tests/conftest.py restores the libm
+    pow after every test, so the swap never leaks into another test."""
     from oracle import binding as ob
     L = detpow_host_lib()
     ob.set_pow(C.cast(L.detpow_host, C.c_void_p))

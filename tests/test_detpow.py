@@ -59,3 +59,23 @@ def test_pow_with_exponent_one_is_the_identity():
     ref = np.array([libm.pow(float(v), 1.0) for v in sample])
     assert np.array_equal(ref.view(np.uint64), sample.view(np.uint64)), "libm pow(x, 1.0) != x"
     assert np.isnan(libm.pow(float("nan"), 1.0))
+
+
+def test_detpow_oracle_and_libm_oracle_agree_on_whole_trajectories():
+    """The GPU parity tests compare with the libm-pow oracle (helpers.parity_oracle).  This closes the loop on the CPU:
+    the same oracle with the engine's det_pow swapped in gives bit-identical states and counters on perturbed Roberts
+    and Lorenz ensembles, i.e. det_pow == libm pow on every argument real trajectories produce."""
+    from helpers import (LORENZ_ATOL, LORENZ_RTOL, LORENZ_TOUTS, ROBERTS_ATOL, ROBERTS_RTOL, ROBERTS_TOUTS, oracle_with_detpow,
+                         parity_oracle)
+    from rust_ida_b200.problems import Lorenz63, Roberts, lorenz_ensemble_params, roberts_ensemble_params
+    for kind, P, params, rtol, atol, touts in (
+            (0, Roberts, roberts_ensemble_params(3000, seed=99), ROBERTS_RTOL, ROBERTS_ATOL, ROBERTS_TOUTS),
+            (1, Lorenz63, lorenz_ensemble_params(1500, seed=99), LORENZ_RTOL, LORENZ_ATOL, LORENZ_TOUTS)):
+        yy0, yp0 = P.consistent_ic(params)
+        ob, _ = parity_oracle()
+        a = ob.ensemble_solve(kind, 3, params, yy0, yp0, rtol, atol, touts, nthreads=8)
+        ob, _ = oracle_with_detpow()
+        b = ob.ensemble_solve(kind, 3, params, yy0, yp0, rtol, atol, touts, nthreads=8)
+        assert np.array_equal(a["yy"].view(np.uint64), b["yy"].view(np.uint64))
+        for k in ("nst", "nni", "nje", "netf", "ncfn"):
+            assert np.array_equal(a["counters"][k], b["counters"][k]), k

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from helpers import (LORENZ_ATOL, LORENZ_RTOL, LORENZ_TOUTS, ROBERTS_ATOL, ROBERTS_RTOL, ROBERTS_TOUTS, assert_bit_equal,
-                     oracle_with_detpow)
+                     parity_oracle)
 
 pytestmark = pytest.mark.gpu
 
@@ -30,7 +30,7 @@ def test_roberts_one_million_instances():
     import torch
     import rust_ida_b200 as r
     from rust_ida_b200.problems import roberts_ensemble_params
-    ob, _ = oracle_with_detpow()
+    ob, _ = parity_oracle()
     B = 1 << 20
     p = roberts_ensemble_params(B, seed=1234)
     yy0, yp0 = r.Roberts.consistent_ic(p)
@@ -66,7 +66,7 @@ def test_lorenz_four_million_instances():
     import torch
     import rust_ida_b200 as r
     from rust_ida_b200.problems import lorenz_ensemble_params
-    ob, _ = oracle_with_detpow()
+    ob, _ = parity_oracle()
     B = 4 << 20
     p = lorenz_ensemble_params(B, seed=1234)
     yy0, yp0 = r.Lorenz63.consistent_ic(p)
@@ -86,7 +86,7 @@ def test_heat_sixty_four_thousand_instances():
     import torch
     import rust_ida_b200 as r
     from rust_ida_b200.problems import heat_ensemble_params
-    ob, _ = oracle_with_detpow()
+    ob, _ = parity_oracle()
     B, M = 65536, 10
     n = M * M
     p = heat_ensemble_params(B, M=M, seed=1234)

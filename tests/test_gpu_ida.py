@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from helpers import (LORENZ_ATOL, LORENZ_RTOL, LORENZ_TOUTS, ROBERTS_ATOL, ROBERTS_RTOL, ROBERTS_TOUTS,
-                     assert_bit_equal, oracle_with_detpow)
+                     assert_bit_equal, parity_oracle)
 
 pytestmark = pytest.mark.gpu
 
@@ -81,7 +81,7 @@ def test_roberts_ensemble_parity(ladder, device_buffers):
     """config 2 at test size: 4,224 rate-perturbed instances (33 CTAs incl. a ragged tail)"""
     from rust_ida_b200 import Roberts
     from rust_ida_b200.problems import roberts_ensemble_params
-    ob, _ = oracle_with_detpow()
+    ob, _ = parity_oracle()
     B = 4224 - 37
     p = roberts_ensemble_params(B, seed=1234)
     yy0, yp0 = Roberts.consistent_ic(p)
@@ -98,7 +98,7 @@ def test_lorenz_ensemble_parity():
     """config 3 at test size"""
     from rust_ida_b200 import Lorenz63
     from rust_ida_b200.problems import lorenz_ensemble_params
-    ob, _ = oracle_with_detpow()
+    ob, _ = parity_oracle()
     B = 2048 + 5
     p = lorenz_ensemble_params(B, seed=1234)
     yy0, yp0 = Lorenz63.consistent_ic(p)
@@ -114,7 +114,7 @@ def test_mxstep_is_per_call_and_resumable():
     solve(5.0) returns TooMuchWork after exactly 500 steps, and calling again continues from there -- same as
     the oracle."""
     from rust_ida_b200 import IdaSolveStatus, Lorenz63
-    ob, _ = oracle_with_detpow()
+    ob, _ = parity_oracle()
     p = np.array(Lorenz63.DEFAULT).reshape(3, 1).repeat(3, axis=1).copy()
     yy0, yp0 = Lorenz63.consistent_ic(p)
     touts = np.array([5.0, 5.0, 6.0])
@@ -131,7 +131,7 @@ def test_error_statuses_match_oracle():
     """ill-posed inputs: tout == t0 (IllegalInput), absurd tolerance (TooMuchAccuracy), singular
     Jacobian (k = 0 Roberts => the reference panics; engine and oracle report LinearSetupFail)."""
     from rust_ida_b200 import IdaSolveStatus, Roberts
-    ob, _ = oracle_with_detpow()
+    ob, _ = parity_oracle()
     p = np.array(Roberts.DEFAULT).reshape(3, 1).repeat(2, axis=1).copy()
     yy0, yp0 = Roberts.consistent_ic(p)
     for rtol, atol, touts in ((1e-4, ROBERTS_ATOL, np.array([0.0, 0.4])), (1e-20, np.full(3, 1e-30), np.array([0.4]))):
@@ -168,7 +168,7 @@ def test_team_kernels_match_oracle_on_roberts(kernel):
     oracle (and therefore to the thread-per-instance kernel)."""
     from rust_ida_b200 import Roberts
     from rust_ida_b200.problems import roberts_ensemble_params
-    ob, _ = oracle_with_detpow()
+    ob, _ = parity_oracle()
     B = 777
     p = roberts_ensemble_params(B, seed=4321)
     yy0, yp0 = Roberts.consistent_ic(p)
@@ -184,7 +184,7 @@ def test_heat2d_parity(M, kernel, B):
     resident in shared memory), coefficient perturbed +-10 % per instance."""
     from rust_ida_b200 import Heat2D
     from rust_ida_b200.problems import heat_ensemble_params
-    ob, _ = oracle_with_detpow()
+    ob, _ = parity_oracle()
     n = M * M
     p = heat_ensemble_params(B, M=M, seed=1234)
     yy0, yp0 = Heat2D.consistent_ic(p, M)
@@ -242,7 +242,7 @@ def test_internal_reordering_is_invisible(mode, device_buffers):
     import rust_ida_b200 as r
     from rust_ida_b200 import Roberts
     from rust_ida_b200.problems import roberts_ensemble_params
-    ob, _ = oracle_with_detpow()
+    ob, _ = parity_oracle()
     B = 1531
     p = roberts_ensemble_params(B, seed=77)
     yy0, yp0 = Roberts.consistent_ic(p)
@@ -261,7 +261,7 @@ def test_reinit_with_new_parameters_rebuilds_order():
     import rust_ida_b200 as r
     from rust_ida_b200 import Roberts
     from rust_ida_b200.problems import roberts_ensemble_params
-    ob, _ = oracle_with_detpow()
+    ob, _ = parity_oracle()
     B = 5000  # >= 4096: AUTO reorders
     p1 = roberts_ensemble_params(B, seed=1)
     p2 = roberts_ensemble_params(B, seed=2)
@@ -305,7 +305,7 @@ def test_every_attempt_of_a_traced_instance_is_bit_identical(problem, picks):
     import torch
     import rust_ida_b200 as r
     from rust_ida_b200.problems import lorenz_ensemble_params, roberts_ensemble_params
-    ob, _ = oracle_with_detpow()
+    ob, _ = parity_oracle()
     B = 300
     if problem == "roberts":
         cls, kind, rtol, atol, touts = r.Roberts, ob.PK_ROBERTS, ROBERTS_RTOL, ROBERTS_ATOL, ROBERTS_TOUTS
@@ -347,7 +347,7 @@ def test_every_attempt_of_a_traced_heat_instance_is_bit_identical(M, kernel):
     n = 16) equals the oracle's bit for bit"""
     import rust_ida_b200 as r
     from rust_ida_b200.problems import heat_ensemble_params
-    ob, _ = oracle_with_detpow()
+    ob, _ = parity_oracle()
     n, B = M * M, 24
     p = heat_ensemble_params(B, M=M, seed=1234)
     yy0, yp0 = r.Heat2D.consistent_ic(p, M)
@@ -378,7 +378,7 @@ def test_roberts_root_events_match_the_oracle():
     import torch
     import rust_ida_b200 as r
     from rust_ida_b200.problems import roberts_ensemble_params
-    ob, _ = oracle_with_detpow()
+    ob, _ = parity_oracle()
     B = 700
     p = roberts_ensemble_params(B, seed=1234)
     p[:, 11] = r.Roberts.DEFAULT
@@ -440,7 +440,7 @@ def test_get_dky_matches_the_oracle(problem, device_buffers):
     import torch
     import rust_ida_b200 as r
     from rust_ida_b200.problems import heat_ensemble_params, roberts_ensemble_params
-    ob, _ = oracle_with_detpow()
+    ob, _ = parity_oracle()
     if problem == "roberts":
         B, n = 777, 3
         p = roberts_ensemble_params(B, seed=99)
