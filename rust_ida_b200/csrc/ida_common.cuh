@@ -89,9 +89,10 @@ struct RootParams {
 // lane-coherent kernel (ida_interp_kernel) evaluates y(tout), y'(tout) for every (instance, output time) afterwards:
 // same operations on the same operands, so the values are bit-identical, but the ~400-instruction interpolation is no
 // longer issued once per lane per output time by a warp whose lanes reach their output times on different attempts.
-// snap: [batch][ntout][SNAP_DOUBLES] by caller-visible instance id, AoS so that the lone lane writes whole sectors;
-// fields 0..6n+5 are phi / psi at their Layout offsets, then kused, tn, hh, hused.  valid: [ntout][batch] bytes, written
-// for every call of every instance (1 = snapshot taken, 0 = the call returned some other way and interpolated inline).
+// snap: [batch][ntout][snap_doubles(n)] by slot, AoS so that the lone lane writes whole sectors and the second pass
+// streams; fields 0..6n+5 are phi / psi at their Layout offsets, then kused, tn, hh, hused.  valid: [batch][ntout] bytes,
+// written for every call of every instance (1 = snapshot taken, 0 = the call returned some other way and interpolated
+// in line).
 struct DeferParams {
     double* snap;
     unsigned char* valid;

@@ -48,7 +48,7 @@ ida_solve_thread_kernel(double* __restrict__ ds, int* __restrict__ is, const dou
     if constexpr (ROOTS) s.load_roots(rp, B, b);
     // the production instantiation defers the output interpolation to ida_interp_kernel; the TRACE and ROOTS
     // instantiations read yy / yp right after get_solution (trace frames, g(t, y)) and keep it in line
-    s.template solve_ladder<TRACE, ROOTS, !TRACE && !ROOTS && IDA_DEFER>(lad, tol, yy_traj, status, B, ob, tr, rp, df);
+    s.template solve_ladder<TRACE, ROOTS, !TRACE && !ROOTS && IDA_DEFER>(lad, tol, yy_traj, status, B, ob, tr, rp, df, b);
     s.store(ds, is, B, b);
     if constexpr (ROOTS) {
         s.store_roots(rp, B, b);
@@ -58,34 +58,72 @@ ida_solve_thread_kernel(double* __restrict__ ds, int* __restrict__ is, const dou
 
 // Second pass of the deferred output interpolation (DeferParams, ida_common.cuh): get_solution (src/lib.rs:1274-1343)
 // for every (instance, output time) whose call returned through stop_test2, from the snapshot the solve kernel took.
-// One thread per slot, all lanes walk the output times together.  y(tout) goes to yy_traj (caller order) when one was
-// asked for; y, y' of the LAST call go to the persistent state, where the reference's solve() leaves them.
+// One thread per (slot, output time); the snapshot rows of consecutive threads are consecutive in HBM, each thread
+// pulls its 224-byte row with 16-byte loads issued back to back and interpolates from registers -- an HBM-streaming
+// kernel (algorithmic bytes: one row read, n doubles written).  y(tout) goes to yy_traj (caller order) when one was
+// asked for; y, y' of the LAST call go to the persistent state, where the reference's solve() leaves them.  The
+// arithmetic is get_solution_fn's (ida_thread.cuh) operation for operation, with the order loop unrolled and guarded.
 template <int N>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 ida_interp_kernel(double* __restrict__ ds, int64_t B, LadderParams lad, DeferParams df, double* __restrict__ yy_traj,
                   const int* __restrict__ perm) {
-    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    const int64_t ob = perm ? (int64_t)perm[b] : b;
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // slot * ntout + it
+    if (g >= B * lad.ntout) return;
+    if (!df.valid[g]) return;
+    const int64_t b = g / lad.ntout;
+    const int it = (int)(g - b * lad.ntout);
     constexpr Layout lay(N);
     constexpr int SD = snap_doubles(N);
-#pragma unroll 1
-    for (int it = 0; it < lad.ntout; ++it) {
-        if (!df.valid[(int64_t)it * B + ob]) continue;
-        const double* sp = df.snap + ((size_t)ob * lad.ntout + it) * SD;
-        double out[2 * N];
-        const int r = get_solution_fn<N, 1>(sp, sp[6 * N + 8], sp[6 * N + 9], sp[6 * N + 7], (int)sp[6 * N + 6], lad.touts[it], out);
-        if (r != 0) continue;  // unreachable after stop_test2 (tout lies inside the last step); yy / yp stay as they are
-        if (yy_traj) {
+    static_assert(SD % 2 == 0, "rows are read as 16-byte pairs");
+    double v[SD];
+    const double2* row = reinterpret_cast<const double2*>(df.snap + (size_t)g * SD);
 #pragma unroll
-            for (int i = 0; i < N; ++i) yy_traj[((int64_t)it * N + i) * B + ob] = out[i];
-        }
-        if (it == lad.ntout - 1) {
+    for (int k = 0; k < SD / 2; ++k) {
+        const double2 t = row[k];
+        v[2 * k] = t.x;
+        v[2 * k + 1] = t.y;
+    }
+    const int kused = (int)v[6 * N + 6];
+    const double tn = v[6 * N + 7], hh = v[6 * N + 8], hused = v[6 * N + 9], t = lad.touts[it];
+    const double sgn = (hh > 0.0 || (hh == 0.0 && !signbit(hh))) ? 1.0 : -1.0;
+    const double tfuzz = 100.0 * DBL_EPS * (fabs(tn) + fabs(hh)) * sgn;
+    const double tp = tn - hused - tfuzz;
+    if ((t - tp) * hh < 0.0) return;  // unreachable after stop_test2 (tout lies inside the last step)
+    const int kord = (kused == 0) ? 1 : kused;
+    const double delt = t - tn;
+    double c = 1.0, d = 0.0, num = delt;
+    double y[N], yp[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        y[i] = 0.0 + c * v[i];
+        yp[i] = 0.0;
+    }
+#pragma unroll
+    for (int j = 1; j <= MAXORD; ++j) {
+        if (j <= kord) {
+            const double psi_jm1 = v[6 * N + j - 1];
+            const double gam = num / psi_jm1;
+            d = d * gam + c / psi_jm1;
+            c = c * gam;
+            num = delt + psi_jm1;
 #pragma unroll
             for (int i = 0; i < N; ++i) {
-                ds[(int64_t)lay.yy(i) * B + b] = out[i];
-                ds[(int64_t)lay.yp(i) * B + b] = out[N + i];
+                const double p = v[j * N + i];
+                y[i] += c * p;
+                yp[i] += d * p;
             }
+        }
+    }
+    if (yy_traj) {
+        const int64_t ob = perm ? (int64_t)perm[b] : b;
+#pragma unroll
+        for (int i = 0; i < N; ++i) yy_traj[((int64_t)it * N + i) * B + ob] = y[i];
+    }
+    if (it == lad.ntout - 1) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            ds[(int64_t)lay.yy(i) * B + b] = y[i];
+            ds[(int64_t)lay.yp(i) * B + b] = yp[i];
         }
     }
 }
@@ -689,7 +727,7 @@ int b200ida_solve_ladder(b200ida_ensemble* e, const double* touts, int ntout, in
             }
             B200_CUDA_TRY(cudaGetLastError());
             if (IDA_DEFER)
-                ida_interp_kernel<3><<<(unsigned)((e->B + 127) / 128), 128, 0, e->stream>>>(e->dstate, e->B, lad, df, d_traj, e->perm);
+                ida_interp_kernel<3><<<(unsigned)((e->B * ntout + 255) / 256), 256, 0, e->stream>>>(e->dstate, e->B, lad, df, d_traj, e->perm);
         }
     } else {
         const bool warp = kernel == B200IDA_KERNEL_WARP;

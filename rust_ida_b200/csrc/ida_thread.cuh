@@ -45,7 +45,7 @@ __device__ unsigned long long root_prof[8];
 #define IDA_THREAD_BLOCK 128
 #endif
 #ifndef IDA_WRMS_INLINE
-#define IDA_WRMS_INLINE 0
+#define IDA_WRMS_INLINE 1
 #endif
 #ifndef IDA_POW_INLINE
 #define IDA_POW_INLINE 0
@@ -102,25 +102,42 @@ __device__ __forceinline__ double div_const(double x) {
 }
 
 // ---- WRMS norm: src/norm_rms.rs:31-38 (ordered fold from 0) -------------------------------------------
+// sqrt(acc / n) is the expensive, shareable part (~35 instructions with the division and the square root); the fold
+// itself is 8 FP64 instructions on values the caller already holds in registers.  So the fold is inlined at every call
+// site and only the tail is an out-of-line function -- one double in, one out -- instead of marshalling six doubles
+// through the call (the round-1 profile: 9 % of all executed instructions were register moves around wrms3).
 template <int N>
-__device__ __forceinline__ double wrms_inline(const double (&x)[N], const double (&w)[N]) {
+__device__ __forceinline__ double wrms_acc(const double (&x)[N], const double (&w)[N]) {
     double acc = 0.0;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         const double p = x[i] * w[i];
         acc = acc + p * p;
     }
+    return acc;
+}
+template <int N>
+__device__ __forceinline__ double wrms_tail_inline(double acc) {
     if constexpr (N >= 2 && N <= 7) return sqrt(div_const<N>(acc));
     else return sqrt(acc / (double)N);
 }
-__device__ __noinline__ double wrms3(double x0, double x1, double x2, double w0, double w1, double w2) {
-    const double x[3] = {x0, x1, x2}, w[3] = {w0, w1, w2};
-    return wrms_inline<3>(x, w);
+template <int N>
+__device__ __noinline__ double wrms_tail(double acc) { return wrms_tail_inline<N>(acc); }
+// the three norms of test_error (src/lib.rs:980-1012) are independent: one call, three interleaved chains
+template <int N>
+__device__ __noinline__ void wrms_tail3(double a0, double a1, double a2, double& r0, double& r1, double& r2) {
+    r0 = wrms_tail_inline<N>(a0);
+    r1 = wrms_tail_inline<N>(a1);
+    r2 = wrms_tail_inline<N>(a2);
+}
+template <int N>
+__device__ __forceinline__ double wrms_inline(const double (&x)[N], const double (&w)[N]) {
+    return wrms_tail_inline<N>(wrms_acc<N>(x, w));
 }
 template <int N>
 __device__ __forceinline__ double wrms(const double (&x)[N], const double (&w)[N]) {
-    if constexpr (N == 3 && !IDA_WRMS_INLINE) return wrms3(x[0], x[1], x[2], w[0], w[1], w[2]);
-    else return wrms_inline<N>(x, w);
+    if constexpr (IDA_WRMS_INLINE) return wrms_inline<N>(x, w);
+    else return wrms_tail<N>(wrms_acc<N>(x, w));
 }
 
 // ---- get_solution: src/lib.rs:1274-1343 ; returns 0 or B200IDA_ST_BAD_T.  Out of line (called ~12 times per
@@ -470,9 +487,11 @@ struct IdaThread {
     }
 
     // ---- set_coeffs: src/lib.rs:722-782 ----------------------------------------------------------------
+    // (the scaling of phi[ns..=kk] by beta, :772-779, is done by predict() below in the same pass that sums phi)
     __device__ __forceinline__ double set_coeffs() {
         if (hh != hused || kk != kused) ns = 0;
         ns = min(ns + 1, kused + 2);
+        double alpha0 = 0.0;  // -(alpha[0] + ... + alpha[kk-1]) accumulated in index order, src/lib.rs:757-763
         if (kk + 1 >= ns) {
             beta(0) = 1.0;
             alpha(0) = 1.0;
@@ -484,6 +503,7 @@ struct IdaThread {
             for (int i = 1; i <= kk; ++i) {
                 const double temp2 = psi(i - 1);
                 psi(i - 1) = temp1;
+                alpha0 -= alpha_prev;  // the alpha[i-1] this pass has in a register
 #if IDA_FASTDIV
                 // the three quotients of one pass are independent of each other: one basic block, one range test
                 const double num[3] = {beta_prev * temp1, hh, alpha_prev};
@@ -511,28 +531,23 @@ struct IdaThread {
                 gamma_prev = g_i;
             }
             psi(kk) = temp1;
+        } else {
+#pragma unroll 1
+            for (int i = 0; i < kk; ++i) alpha0 -= alpha(i);
         }
         // alphas = -(1 + 1/2 + ... + 1/kk) accumulated in that order (src/lib.rs:757-763): a constant per kk,
         // so it comes from a table built with the same sequential IEEE operations at compile time.
         const double alphas = alphas_of(kk);
-        double alpha0 = 0.0;
-#pragma unroll 1
-        for (int i = 0; i < kk; ++i) alpha0 -= alpha(i);
         cjlast = cj;
         cj = ddiv(-alphas, hh);
         const double akk = alpha(kk);
         double ck = fabs(akk + alphas - alpha0);
         ck = fmax(ck, akk);
-#pragma unroll 1
-        for (int j = ns; j <= kk; ++j) {
-            const double bj = beta(j);
-#pragma unroll
-            for (int i = 0; i < N; ++i) phi(j, i) *= bj;
-        }
         return ck;
     }
 
-    // ---- predict: src/lib.rs:894-959 -------------------------------------------------------------------
+    // ---- predict: src/lib.rs:894-959, fused with the tail of set_coeffs (src/lib.rs:772-779): phi[j] *= beta[j] for
+    // j = ns..kk happens in the pass that reads phi[j] anyway (phi[0] is never scaled: ns >= 1) ---------------------------
     __device__ __forceinline__ void predict() {
 #pragma unroll
         for (int i = 0; i < N; ++i) {
@@ -541,10 +556,15 @@ struct IdaThread {
         }
 #pragma unroll 1
         for (int j = 1; j <= kk; ++j) {
-            const double gj = gamma(j);
+            const double gj = gamma(j), bj = beta(j);
+            const bool scale = j >= ns;
 #pragma unroll
             for (int i = 0; i < N; ++i) {
-                const double p = phi(j, i);
+                double p = phi(j, i);
+                if (scale) {
+                    p *= bj;
+                    phi(j, i) = p;
+                }
                 yypredict[i] += p;
                 yppredict[i] += gj * p;
             }
@@ -791,24 +811,34 @@ struct IdaThread {
     }
 
     // ---- test_error: src/lib.rs:967-1039 -------------------------------------------------------------------
+    // The up-to-three norms (of ee, ee + phi[kk], ee + phi[kk] + phi[kk-1]) are formed for every lane and finished by ONE
+    // out-of-line call whose three division / square-root chains interleave; a lane whose order does not use the
+    // second or third norm ignores it (same operands and operations wherever a value is used: bit-identical).
     __device__ __forceinline__ bool test_error(double ck, double& err_k, double& err_km1) {
         const double scalar_kk = (double)kk;
-        const double enorm_k = wrms<N>(ee, ewt);
+        const int km1 = max(kk - 1, 0), km2 = max(kk - 2, 0);
+        double d2[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) delta[i] = phi(kk, i) + ee[i];
+#pragma unroll
+        for (int i = 0; i < N; ++i) d2[i] = delta[i] + phi(km1, i);
+        double enorm_k, enorm_km1, enorm_km2;
+        if constexpr (IDA_WRMS_INLINE) {
+            enorm_k = wrms_inline<N>(ee, ewt);
+            enorm_km1 = wrms_inline<N>(delta, ewt);
+            enorm_km2 = wrms_inline<N>(d2, ewt);
+        } else {
+            wrms_tail3<N>(wrms_acc<N>(ee, ewt), wrms_acc<N>(delta, ewt), wrms_acc<N>(d2, ewt), enorm_k, enorm_km1, enorm_km2);
+        }
         err_k = sigma(kk) * enorm_k;
         const double terr_k = err_k * (scalar_kk + 1.0);
         err_km1 = 0.0;
         int knew_ = kk;
         if (kk > 1) {
-#pragma unroll
-            for (int i = 0; i < N; ++i) delta[i] = phi(kk, i) + ee[i];
-            const double enorm_km1 = wrms<N>(delta, ewt);
-            err_km1 = sigma(kk - 1) * enorm_km1;
+            err_km1 = sigma(km1) * enorm_km1;
             const double terr_km1 = scalar_kk * err_km1;
             if (kk > 2) {
-#pragma unroll
-                for (int i = 0; i < N; ++i) delta[i] += phi(kk - 1, i);
-                const double enorm_km2 = wrms<N>(delta, ewt);
-                const double err_km2 = sigma(kk - 2) * enorm_km2;
+                const double err_km2 = sigma(km2) * enorm_km2;
                 const double terr_km2 = (scalar_kk - 1.0) * err_km2;
                 if (fmax(terr_km1, terr_km2) <= terr_k) knew_ = kk - 1;
             } else {
@@ -886,8 +916,10 @@ struct IdaThread {
             if (nst > 1) {
                 kk += 1;
                 double hnew = 2.0 * hh;
-                const double t = fabs(hnew) * HMAX_INV;
-                if (t > 1.0) hnew /= t;
+                if constexpr (HMAX_INV != 0.0) {  // no hmax setter exists: |h| * 0 > 1 is never true, and nvcc would
+                    const double t = fabs(hnew) * HMAX_INV;  // otherwise evaluate the division speculatively (by zero:
+                    if (t > 1.0) hnew /= t;                  // the slow path, 4 % of the round-1 kernel's samples)
+                }
                 hh = hnew;
             }
         } else {
@@ -934,8 +966,10 @@ struct IdaThread {
             }
             if (rr >= 2.0) {
                 hnew = 2.0 * hh;
-                const double t = fabs(hnew) * HMAX_INV;
-                if (t > 1.0) hnew /= t;
+                if constexpr (HMAX_INV != 0.0) {
+                    const double t = fabs(hnew) * HMAX_INV;
+                    if (t > 1.0) hnew /= t;
+                }
             } else if (rr <= 1.0) {
                 rr = fmax(0.5, fmin(rr, 0.9));
                 hnew = hh * rr;
@@ -1197,8 +1231,10 @@ struct IdaThread {
         const double ypnorm = wrms<N>(p1, ewt);
         if (ypnorm > 2.0 / hh) hh = 0.5 / ypnorm;
         if (tout < tn) hh = -hh;
-        const double rh = fabs(hh) * HMAX_INV;
-        if (rh > 1.0) hh /= rh;
+        if constexpr (HMAX_INV != 0.0) {
+            const double rh = fabs(hh) * HMAX_INV;
+            if (rh > 1.0) hh /= rh;
+        }
         h0u = hh;
         kk = 0;
         kused = 0;
@@ -1219,7 +1255,7 @@ struct IdaThread {
     template <bool TRACE, bool ROOTS = false, bool DEFER = false>
     __device__ __forceinline__ void solve_ladder(const LadderParams& lad, const TolN<N>& tol, double* __restrict__ yy_traj,
                                                  int32_t* __restrict__ status, int64_t B, int64_t b, const TraceParams& tr,
-                                                 const RootParams& rp = RootParams(), const DeferParams& df = DeferParams()) {
+                                                 const RootParams& rp = RootParams(), const DeferParams& df = DeferParams(), int64_t slot = 0) {
         int it = 0;
         bool deferred = false;
         bool need_prologue = true;
@@ -1391,8 +1427,8 @@ struct IdaThread {
                         tret = tout;
                         tretlast = tout;
                         if constexpr (DEFER) {
-                            // what get_solution(tout) reads, to row (b, it) of the snapshot buffer
-                            double* sp = df.snap + ((size_t)b * lad.ntout + it) * snap_doubles(N);
+                            // what get_solution(tout) reads, to row (slot, it) of the snapshot buffer
+                            double* sp = df.snap + ((size_t)slot * lad.ntout + it) * snap_doubles(N);
                             const int kord = (kused == 0) ? 1 : kused;
 #pragma unroll 1
                             for (int j = 0; j <= kord; ++j) {
@@ -1450,7 +1486,7 @@ struct IdaThread {
                 }
             }
             if (call_done) {
-                if constexpr (DEFER) df.valid[(int64_t)it * B + b] = deferred ? 1 : 0;
+                if constexpr (DEFER) df.valid[slot * lad.ntout + it] = deferred ? 1 : 0;
                 if (yy_traj && !(DEFER && deferred)) {
 #pragma unroll
                     for (int i = 0; i < N; ++i) yy_traj[((int64_t)it * N + i) * B + b] = yy[i];
