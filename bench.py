@@ -8,7 +8,7 @@ instance, each instance integrated from t = 0 to t = 4e10 through the reference'
 A "step" is one pass of the hot path over one batch: re-initialise the ensemble state (Ida::new) and
 integrate every instance to t = 4e10 (one solve-ladder kernel launch).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--scaling weak|strong] [--impl ours|reference]
 
     value      instances/s with params / yy0 / yp0 already resident in HBM
     e2e        the same through the C-ABI host-buffer path: H2D of the inputs from pinned memory, the
@@ -18,9 +18,14 @@ integrate every instance to t = 4e10 (one solve-ladder kernel launch).
     cpu_baseline  the CPU oracle (a C++ restatement of rust-ida, NOT rust-ida itself: there is no Rust
                toolchain here) on a bounded sample, one instance per thread on all host cores
 
-N > 1 (torchrun): one process per GPU, instances sharded by contiguous id range (weak scaling: --batch
-instances per GPU), no collective inside the step; one NCCL all_gather of the per-instance step counts at
-the end of every step.
+    parity     the CPU leg integrates EVERY instance of the (rank-0) batch with the libm-pow oracle and the device
+               results (final states and step counts) are compared with it bit for bit
+    extra      the rest of BASELINE.json's metric on the same GPU: the config-4 batched LU table, Lorenz-63 (config 3)
+               and heat 2-D (config 5), each with its own roofline fraction (N = 1 only; --no-extra skips it)
+
+N > 1 (torchrun): one process per GPU, instances sharded by contiguous id range, no collective inside the step; one
+NCCL all_gather of the per-instance statistics block {nst, nre, nje, nni, netf, ncfn, status, kused} at the end of
+every step.  --scaling weak (default): --batch instances per GPU; --scaling strong: --batch instances in total.
 """
 import argparse
 import json
@@ -38,9 +43,12 @@ RTOL = 1e-4
 ATOL = np.array([1e-8, 1e-6, 1e-6])
 TOUTS = 0.4 * 10.0 ** np.arange(12)
 SEED = 1234
-# FP64 arithmetic per step attempt of the reference algorithm at n = 3 (each add, mul, div, sqrt, pow counted
-# as ONE op): 98,244 ops / 377 attempts for the default Roberts instance (SURVEY.md 6 / BASELINE.md 2).
-OPS_PER_ATTEMPT = 98244.0 / 377.0
+# FP64 arithmetic per step attempt of the reference algorithm at n = 3 (each add, mul, div, sqrt, pow counted as ONE
+# op).  Measured at run time by the operation counter of the oracle (oracle/ida_oracle.cpp built with
+# -DORACLE_COUNT_OPS) on a sample of this workload; this constant is only the fallback when the CPU leg is switched
+# off: 274.7 = the counter's figure for the first 20,000 instances of the workload (default Roberts instance: 103,604
+# ops / 377 attempts = 274.8, with the 2,030 sqrt and 528 pow of SURVEY.md section 6).
+OPS_PER_ATTEMPT_FALLBACK = 274.7
 # algorithmic HBM bytes per instance and launch: the SoA state (10n + 45 + n^2 doubles + 16 + n int32, n = 3) is read
 # once and written once
 ALG_BYTES_PER_INSTANCE = 2 * ((10 * 3 + 45 + 9) * 8 + (16 + 3) * 4)
@@ -53,6 +61,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=1 << 20, help="instances per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch instances per GPU; strong: --batch instances in total, split over the GPUs")
+    ap.add_argument("--no-extra", action="store_true", help="skip the config 3 / 4 / 5 measurements of `extra`")
     ap.add_argument("--cpu-sample", type=int, default=0, help="instances in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -108,28 +119,37 @@ class ClockSampler:
 
 
 # ---- CPU arm: the oracle port on the host cores --------------------------------------------------------------
-def cpu_run(sample, first_id=0):
-    """integrate `sample` perturbed Roberts instances to t=4e10 with the CPU oracle on all cores -> (inst/s, cores)"""
+def cpu_run(sample, first_id=0, keep=False):
+    """integrate `sample` perturbed Roberts instances to t=4e10 with the CPU oracle (libm pow, the reference's
+    f64::powf) on all cores -> (inst/s, cores, seconds[, oracle outputs])"""
     from oracle import binding as ob
     from rust_ida_b200.problems import Roberts, roberts_ensemble_params
     cores = os.cpu_count() or 1
     p = roberts_ensemble_params(sample, seed=SEED, first_id=first_id)
     yy0, yp0 = Roberts.consistent_ic(p)
+    ob.set_pow(None)
     t0 = time.perf_counter()
     out = ob.ensemble_solve(ob.PK_ROBERTS, 3, p, yy0, yp0, RTOL, ATOL, TOUTS, nthreads=cores)
     dt = time.perf_counter() - t0
     assert (out["status"] == 0).all()
+    if keep:
+        return sample / dt, cores, dt, out
     return sample / dt, cores, dt
 
 
-def auto_cpu_sample(target_s=12.0):
-    rate, cores, _ = cpu_run(256 * (os.cpu_count() or 1))
-    n = int(rate * target_s)
-    return max(1024, min(n, 1 << 20))
+def ops_per_attempt(sample=8192, first_id=0):
+    """algorithmic FP64 ops per step attempt of this workload, counted by the instrumented oracle on a sample"""
+    from oracle import binding as ob
+    from rust_ida_b200.problems import Roberts, roberts_ensemble_params
+    p = roberts_ensemble_params(sample, seed=SEED, first_id=first_id)
+    yy0, yp0 = Roberts.consistent_ic(p)
+    ops, natt = ob.ensemble_ops(ob.PK_ROBERTS, 3, p, yy0, yp0, RTOL, ATOL, TOUTS, nthreads=os.cpu_count() or 1)
+    tot = ops.sum(axis=0)
+    return float(tot.sum()) / float(natt.sum()), {k: int(v) for k, v in zip(("add", "mul", "div", "sqrt", "pow"), tot)}, sample
 
 
-def workload_config(B):
-    """the `config` object both arms print (the reference arm must run on our arm's config)"""
+def workload_config(B, world=1, scaling="weak"):
+    """the `config` object both arms print (the reference arm runs on our arm's config)"""
     return {"workload": "Roberts ensemble, n=3, %d instances per GPU, rate constants +-10%% (splitmix64 seed 1234 "
                         "keyed by instance id), rtol 1e-4, atol [1e-8,1e-6,1e-6], tout = 0.4*10^i i=0..11 "
                         "(BASELINE.json configs[1])" % B,
@@ -137,28 +157,36 @@ def workload_config(B):
             "l2": "per-step state (%.0f MB/GPU) is larger than the 126 MB L2" % (B * 0.78e-3)}
 
 
+def batch_per_gpu(args, world):
+    return args.batch if args.scaling == "weak" else max(1, args.batch // world)
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU path for the same metric/config.  rust-ida cannot be built here
     (no Rust toolchain, tree mid-refactor), so this is the oracle port, all host threads, bounded sample."""
     if rank != 0:
         return
-    sample = args.cpu_sample or auto_cpu_sample(6.0)
-    for _ in range(args.warmup):
-        cpu_run(max(256, sample // 8))
+    B = batch_per_gpu(args, world)
+    # one step = the whole per-GPU batch of our arm (the same instances: ids 0..B-1), all host threads; --cpu-sample
+    # bounds the step for slow hosts (then `sample` says so)
+    sample = args.cpu_sample or B
+    for _ in range(min(args.warmup, 1)):
+        cpu_run(max(256, sample // 16))
     t0 = time.perf_counter()
     tot = 0
     for k in range(args.steps):
-        cpu_run(sample, first_id=k * sample)
+        cpu_run(sample, first_id=0)
         tot += sample
     dt = time.perf_counter() - t0
     cores = os.cpu_count() or 1
     val = tot / dt
-    desc = "%d perturbed Roberts instances per step (of the %d-per-GPU workload), to t=4e10" % (sample, args.batch)
+    desc = "%d perturbed Roberts instances per step (%s the %d-per-GPU workload), to t=4e10" % (
+        sample, "all of" if sample == B else "a sample of", B)
     line = {
         "impl": "reference", "metric": "ensemble DAE solves/sec (Roberts, t=4e10)", "value": val, "unit": "instances/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args.batch),
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(B, world, args.scaling),
         "cpu_baseline": {"value": val, "unit": "instances/s", "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": val, "unit": "instances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -181,7 +209,7 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    B = args.batch
+    B = batch_per_gpu(args, world)
     first_id = rank * B  # contiguous id range per rank; parameters are keyed by instance id
     p_h = roberts_ensemble_params(B, seed=SEED, first_id=first_id)
     yy0_h, yp0_h = Roberts.consistent_ic(p_h)
@@ -200,8 +228,10 @@ def run_ours(args, rank, world, local_rank):
     tol = r.TolControlSV(RTOL, ATOL)
     ida = r.Ida(Roberts(p_d), yy0_d, yp0_d, tol, device=local_rank)
     status_d = torch.empty((len(TOUTS), B), dtype=torch.int32, device=dev)
-    nst_d = torch.empty((B,), dtype=torch.int64, device=dev)
-    gathered = torch.empty((world * B,), dtype=torch.int64, device=dev) if world > 1 else None
+    # the per-instance statistics block of the final gather: nst, nre, nje, nni, netf, ncfn, status, kused
+    stats_d = torch.empty((8, B), dtype=torch.int64, device=dev)
+    kused_d = torch.empty((B,), dtype=torch.int32, device=dev)
+    gathered = torch.empty((world, 8, B), dtype=torch.int64, device=dev) if world > 1 else None
     L = _lib.lib()
     h = ida._h
     touts = np.ascontiguousarray(TOUTS)
@@ -217,9 +247,13 @@ def run_ours(args, rank, world, local_rank):
         _lib.check(L.b200ida_solve_ladder(h, touts.ctypes.data, len(touts), 0, null, status_d.data_ptr(), _lib.MEM_DEVICE))
         if k is not None:
             ev_k1[k].record()
-        _lib.check(L.b200ida_get_counters(h, nst_d.data_ptr(), null, null, null, null, null, null, null, _lib.MEM_DEVICE))
-        if world > 1:  # the only collective: final gather of per-instance statistics
-            dist.all_gather_into_tensor(gathered, nst_d)
+        row = lambda i: stats_d[i].data_ptr()
+        _lib.check(L.b200ida_get_counters(h, row(0), row(1), row(2), row(3), row(4), row(5), null, null, _lib.MEM_DEVICE))
+        _lib.check(L.b200ida_get_step_info(h, kused_d.data_ptr(), null, null, null, null, null, _lib.MEM_DEVICE))
+        stats_d[6].copy_(status_d[-1])
+        stats_d[7].copy_(kused_d)
+        if world > 1:  # the only collective: final gather of the per-instance statistics
+            dist.all_gather_into_tensor(gathered, stats_d)
 
     def barrier():
         if world > 1:
@@ -230,12 +264,14 @@ def run_ours(args, rank, world, local_rank):
         step_device()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = L.b200ida_kernel_launches()
     with ClockSampler(local_rank) as clk:
         e0.record()
         for k in range(args.steps):
             step_device(k)
         e1.record()
         barrier()
+    launches = int(L.b200ida_kernel_launches() - launches0)
     ms = e0.elapsed_time(e1)
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(ev_k0, ev_k1)]))
     if world > 1:
@@ -245,8 +281,10 @@ def run_ours(args, rank, world, local_rank):
     ok = bool((status_d == 0).all().item())
     attempts = ida.get_num_step_attempts()
     tot_attempts = float(attempts.sum().item())
-    nst = nst_d
+    nst = stats_d[0]
     nst_minmax = (int(nst.min().item()), int(nst.max().item()), float(nst.double().mean().item()))
+    yy_dev = ida.get_yy().cpu().numpy()
+    nst_dev = nst.cpu().numpy()
 
     # ---- end to end through the host-buffer C-ABI path: H2D inputs (pinned), solve, D2H results --------------
     def step_e2e():
@@ -267,7 +305,8 @@ def run_ours(args, rank, world, local_rank):
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t[0])
-    e2e_ok = bool(np.array_equal(nst_out_pin.numpy(), nst_d.cpu().numpy()))
+    e2e_ok = bool(np.array_equal(nst_out_pin.numpy(), nst_dev) and
+                  np.array_equal(yy_out_pin.numpy().view(np.uint64), yy_dev.view(np.uint64)))
     h2d = int(p_pin.numel() + yy0_pin.numel() + yp0_pin.numel()) * 8
     d2h = int(yy_out_pin.numel() + nst_out_pin.numel()) * 8
 
@@ -279,60 +318,157 @@ def run_ours(args, rank, world, local_rank):
         _lib.check(L.b200ida_fp64_issue_rate(kind, local_rank, C.byref(v)))
         rate[name] = v.value
     peak_gops = min(rate["dadd"], rate["dmul"])  # un-fused: one instruction per algorithmic op
-    achieved_gops = tot_attempts * OPS_PER_ATTEMPT / (kernel_ms * 1e-3) * 1e-9
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
+    # ---- CPU leg (rank 0, N = 1): every instance of the batch through the libm-pow oracle; it is the cpu_baseline AND
+    # the parity check of the device results; the instrumented oracle gives the roofline's work unit ---------------------
     cpu = None
-    if not args.no_cpu_baseline and world >= 1:
-        sample = args.cpu_sample or auto_cpu_sample(12.0)
-        val, cores, dt = cpu_run(sample)
+    parity = None
+    opa, opa_src = OPS_PER_ATTEMPT_FALLBACK, "fallback constant (CPU leg off)"
+    if not args.no_cpu_baseline and world == 1:
+        sample = args.cpu_sample or B
+        val, cores, dt, ref = cpu_run(sample, first_id=first_id, keep=True)
         cpu = {"value": val, "unit": "instances/s", "cores": cores, "kind": "port",
-               "sample": "%d perturbed Roberts instances of the same workload to t=4e10 (%.1f s), C++ restatement of "
-                         "rust-ida (oracle/), one instance per thread" % (sample, dt)}
+               "sample": "%s %d perturbed Roberts instances of the workload to t=4e10 (%.1f s), C++ restatement of "
+                         "rust-ida (oracle/) with libm pow, one instance per thread" % ("all" if sample == B else "the first", sample, dt)}
+        bad_nst = int(np.count_nonzero(ref["counters"]["nst"] != nst_dev[:sample]))
+        bad_yy = int(np.count_nonzero((ref["yy"].view(np.uint64) != yy_dev[:, :sample].view(np.uint64)).any(axis=0)))
+        parity = {"checked": int(sample), "mismatch": int(max(bad_nst, bad_yy)), "mismatch_nst": bad_nst, "mismatch_yy": bad_yy,
+                  "pow": "libm", "compared": "final yy (3 doubles, bit-exact) and nst of every checked instance, device run vs CPU oracle",
+                  "all_status_zero": ok, "nst_min_max_mean": list(nst_minmax)}
+        opa_v, opa_mix, opa_n = ops_per_attempt(min(8192, B), first_id=first_id)
+        opa, opa_src = opa_v, "oracle op counter (-DORACLE_COUNT_OPS) on the first %d instances: %s" % (opa_n, json.dumps(opa_mix))
+    achieved_gops = tot_attempts * opa / (kernel_ms * 1e-3) * 1e-9
 
+    # ---- the rest of BASELINE.json's metric on this GPU (N = 1 only) -------------------------------------------------------
+    extra = None
+    if world == 1 and not args.no_extra:
+        extra = run_extra(peak_gops)
+
+    quoted = quoted_profile()
     total = world * B * args.steps
     try:
         hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+        hbm_src = "MEASURED_PEAKS.json"
     except Exception:
         hbm_peak = 6650.0  # fallback stated in /opt/skills/guides/B200_PROFILING.md
+        hbm_src = "fallback of B200_PROFILING.md"
+    alg_bytes = B * ALG_BYTES_PER_INSTANCE
     line = {
         "metric": "ensemble DAE solves/sec (Roberts, t=4e10)",
         "value": total / (ms * 1e-3), "unit": "instances/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": dict(workload_config(B), parity="all status==0: %s; nst min/max/mean %d/%d/%.1f" % ((ok,) + nst_minmax)),
+        "config": workload_config(B, world, args.scaling),
+        "parity": parity,
         "e2e": {"value": world * B * e2e_steps / e2e_s, "unit": "instances/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "results_match_device_run": e2e_ok},
-        "gpu_launches": args.steps * 3,  # per step: ida_init_kernel, ida_solve_thread_kernel, widen_i32_kernel
+        "gpu_launches": launches,  # counted by the library (b200ida_kernel_launches) over the timed region
         "roofline": {"bound": "fp64", "achieved": achieved_gops, "peak": peak_gops, "unit": "GFLOP/s (un-fused FP64 ops)",
                      "frac": achieved_gops / peak_gops,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch at batch 2^20 (ncu --set full,
-                     # profiles/r1g_ida_solve_thread_ncu_summary.csv), scaled to this batch
-                     "traffic": int(2185871000 * (B / float(1 << 20))),
-                     "hbm_view": {"algorithmic_bytes_per_launch": B * ALG_BYTES_PER_INSTANCE,
-                                  "achieved_gbs": B * ALG_BYTES_PER_INSTANCE / (kernel_ms * 1e-3) * 1e-9, "peak_gbs": hbm_peak,
-                                  "frac": B * ALG_BYTES_PER_INSTANCE / (kernel_ms * 1e-3) * 1e-9 / hbm_peak,
+                     "traffic": quoted.get("traffic_bytes_per_launch"),
+                     "hbm_view": {"algorithmic_bytes_per_launch": alg_bytes,
+                                  "achieved_gbs": alg_bytes / (kernel_ms * 1e-3) * 1e-9, "peak_gbs": hbm_peak, "peak_source": hbm_src,
+                                  "frac": alg_bytes / (kernel_ms * 1e-3) * 1e-9 / hbm_peak,
                                   "note": "state read once + written once per launch; three orders of magnitude below the "
                                           "FP64 bound, which is why the roofline above is the FP64 issue rate"},
-                     # hardware-side view of the same kernel from ncu (profiles/r1g_ida_solve_thread_ncu_summary.csv):
-                     # the FP64 pipe is busy 29 % of the cycles, the schedulers issue on 43 % -- division, sqrt and pow
-                     # expand to 10-60 FP64-pipe instructions per algorithmic op, which is the gap to `frac`
-                     "ncu": {"sm__pipe_fp64_cycles_active_pct": 28.95, "smsp__issue_active_pct": 43.47,
-                             "active_lanes_per_instruction": 20.63, "source": "profiles/r1g_ida_solve_thread_ncu_summary.csv"},
-                     "kernel": "ida_solve_thread_kernel<Roberts>", "kernel_ms": kernel_ms,
-                     "ops_per_launch": tot_attempts * OPS_PER_ATTEMPT, "attempts_per_launch": tot_attempts,
+                     "quoted_from_profile": quoted,
+                     "kernel": "ida_solve_thread_kernel<Roberts> (+ ida_interp_kernel<3>, the deferred output interpolation, "
+                               "inside the same CUDA-event bracket)",
+                     "kernel_ms": kernel_ms, "ops_per_attempt": opa, "ops_per_attempt_source": opa_src,
+                     "ops_per_launch": tot_attempts * opa, "attempts_per_launch": tot_attempts,
                      "peak_source": "measured on this GPU by b200ida_fp64_issue_rate (MEASURED_PEAKS.json has no FP64 entry): "
                                     "dfma %.0f, dadd %.0f, dmul %.0f Ginstr/s" % (rate["dfma"], rate["dadd"], rate["dmul"])},
         "cpu_baseline": cpu,
+        "extra": extra,
         "clocks": clk.summary(),
     }
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def quoted_profile():
+    """ncu figures of the solve kernel, READ from the newest committed summary under profiles/ (never typed in here):
+    they describe the build that summary was taken from, which the entry names."""
+    import csv
+    import glob
+    cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ida_solve_thread*_ncu_summary.csv")))
+    if not cands:
+        return {}
+    path = cands[-1]
+    vals = {}
+    note = ""
+    try:
+        for row in csv.reader(open(path)):
+            if row and row[0].startswith("#"):
+                note = ",".join(row).lstrip("# ").strip()
+            if len(row) >= 4 and row[1] in ("dram__bytes_read.sum", "dram__bytes_write.sum",
+                                            "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+                                            "smsp__issue_active.avg.pct_of_peak_sustained_active",
+                                            "smsp__thread_inst_executed_per_inst_executed.ratio", "gpu__time_duration.sum",
+                                            "smsp__inst_executed.sum"):
+                vals[row[1]] = (float(row[3]), row[2])
+    except Exception:
+        return {}
+    out = {"source": os.path.relpath(path, ROOT), "source_note": note,
+           "applies_to": "the build and batch (2^20) that file was captured from, not necessarily this run"}
+    if "dram__bytes_read.sum" in vals and "dram__bytes_write.sum" in vals:
+        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+        out["traffic_bytes_per_launch"] = int(sum(vals[k][0] * scale.get(vals[k][1], 1.0)
+                                                  for k in ("dram__bytes_read.sum", "dram__bytes_write.sum")))
+    for k, name in (("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_fp64_cycles_active_pct"),
+                    ("smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__issue_active_pct"),
+                    ("smsp__thread_inst_executed_per_inst_executed.ratio", "active_lanes_per_instruction"),
+                    ("gpu__time_duration.sum", "kernel_ms_under_ncu"), ("smsp__inst_executed.sum", "warp_instructions")):
+        if k in vals:
+            out[name] = vals[k][0]
+    return out
+
+
+def run_extra(fp64_peak_gops):
+    """the other halves of BASELINE.json's metric, measured in the same process on the same GPU: batched LU (config 4),
+    Lorenz-63 (config 3, 4 * 2^20 instances) and heat 2-D (config 5, 65,536 instances).  Failures are reported, not fatal."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    out = {}
+    try:
+        import bench_lu
+        rows = bench_lu.run_lu(reps=2, fp64_peak_gops=fp64_peak_gops)
+        out["lu_config4"] = [{k: (round(v, 6) if isinstance(v, float) else v) for k, v in row.items()
+                              if k in ("op", "n", "batch", "layout", "ms", "matrices_per_s", "gflops", "algorithmic_gbs",
+                                       "hbm_frac_of_measured", "fp64_frac", "pivots_bit_exact_vs_oracle")} for row in rows]
+    except Exception as exc:  # noqa: BLE001
+        out["lu_config4"] = {"error": repr(exc)}
+    try:
+        import bench_configs
+        from oracle import binding as ob
+        from rust_ida_b200.problems import Lorenz63, lorenz_ensemble_params
+        lo = bench_configs.run_lorenz(4 << 20, reps=2)
+        p = lorenz_ensemble_params(4096, seed=1234)
+        yy0, yp0 = Lorenz63.consistent_ic(p)
+        ops, natt = ob.ensemble_ops(ob.PK_LORENZ63, 3, p, yy0, yp0, 1e-6, np.full(3, 1e-8), 0.5 * np.arange(1, 11),
+                                    nthreads=os.cpu_count() or 1)
+        opa = float(ops.sum()) / float(natt.sum())
+        g = lo["attempts"] * opa / (lo["ms"] * 1e-3) * 1e-9
+        lo["roofline"] = {"bound": "fp64", "ops_per_attempt": opa, "achieved_gflops": g, "peak_gflops": fp64_peak_gops,
+                          "frac": g / fp64_peak_gops}
+        out["lorenz_config3"] = lo
+    except Exception as exc:  # noqa: BLE001
+        out["lorenz_config3"] = {"error": repr(exc)}
+    try:
+        import bench_configs
+        he = bench_configs.run_heat(65536, reps=1)
+        he["roofline"] = {"bound": "fp64", "achieved_gflops": he["lu_plus_solve_gflops"], "peak_gflops": fp64_peak_gops,
+                          "frac": he["lu_plus_solve_gflops"] / fp64_peak_gops,
+                          "note": "LU + triangular-solve flops only (the iteration matrix stays in shared memory)"}
+        out["heat_config5"] = he
+    except Exception as exc:  # noqa: BLE001
+        out["heat_config5"] = {"error": repr(exc)}
+    return out
 
 
 _JSON_FD = 1

@@ -242,6 +242,11 @@ int b200ida_sync(b200ida_ensemble* e);
  * G instructions/s per GPU (thread-level operations: one DFMA counts 1). */
 int b200ida_fp64_issue_rate(int kind, int device, double* ginstr_per_s);
 
+/* Number of the engine's own CUDA kernels launched by Level-2 calls (create / reinit / solve / getters) of this process
+ * so far (library kernels such as CUB's sort are not counted).  bench.py reports the difference over its timed region
+ * as `gpu_launches`. */
+long long b200ida_kernel_launches(void);
+
 /* out[i] = det_pow(x[i], y[i]) on the device: the glibc-2.39-compatible pow the engine uses wherever the
  * reference calls f64::powf (src/impl_complete_step.rs:128-132, src/lib.rs:1163-1169, src/ida_nls.rs:249-253).
  * Exposed so tests can prove device pow == host libm pow bit-for-bit. */

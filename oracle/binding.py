@@ -22,7 +22,7 @@ POW_FN = C.CFUNCTYPE(C.c_double, C.c_double, C.c_double)
 
 def build(force=False):
     src = os.path.join(_HERE, "ida_oracle.cpp")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src) or not os.path.exists(os.path.join(_HERE, "libida_oracle_ops.so")):
         subprocess.check_call(["make", "-C", _HERE, "-s", "-B"])
     return _SO
 
@@ -306,3 +306,26 @@ def single_trace(kind, params, yy0, yp0, rtol, atol, touts):
                                    np.ascontiguousarray(yp0, dtype=np.float64), rtol,
                                    np.ascontiguousarray(atol, dtype=np.float64), touts, len(touts), rows, counters)
     return st, rows, dict(zip(COUNTER_NAMES, counters.tolist()))
+
+
+_ops_lib = None
+
+
+def ensemble_ops(kind, n, params, yy0, yp0, rtol, atol, touts, nthreads=1):
+    """Algorithmic FP64 operation counts of the reference algorithm (oracle built with -DORACLE_COUNT_OPS,
+    libida_oracle_ops.so): returns (ops (B, 5) int64 = add, mul, div, sqrt, pow per instance, attempts (B,) int64)."""
+    global _ops_lib
+    if _ops_lib is None:
+        build()
+        _ops_lib = C.CDLL(os.path.join(_HERE, "libida_oracle_ops.so"))
+        _ops_lib.oracle_ensemble_ops.restype = C.c_int
+        _ops_lib.oracle_ensemble_ops.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int, _dp, _dp, _dp, C.c_double, _dp, _dp, C.c_int,
+                                                 C.c_int, _i64p, _i64p]
+    params, yy0, yp0 = (np.ascontiguousarray(a, dtype=np.float64) for a in (params, yy0, yp0))
+    B = yy0.shape[1]
+    ops = np.zeros((B, 5), dtype=np.int64)
+    natt = np.zeros(B, dtype=np.int64)
+    touts = np.ascontiguousarray(touts, dtype=np.float64)
+    _ops_lib.oracle_ensemble_ops(kind, n, B, params.shape[0], params, yy0, yp0, rtol, np.ascontiguousarray(atol, dtype=np.float64),
+                                 touts, len(touts), int(nthreads), ops.reshape(-1), natt)
+    return ops, natt

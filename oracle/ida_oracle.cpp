@@ -55,6 +55,19 @@ constexpr double RATEMAX = 0.9;
 constexpr double HMAX_INV_DEFAULT = 0.0;
 constexpr double DBL_EPS = 2.220446049250313e-16;  // f64::EPSILON
 
+// ---- algorithmic operation counter (-DORACLE_COUNT_OPS build only: oracle/libida_oracle_ops.so) -----------------
+// One CNT per arithmetic block, placed where the block is: FP64 additions / subtractions, multiplications, divisions,
+// square roots and pow calls of the REFERENCE algorithm (negation, fabs, min / max, comparisons and integer -> double
+// conversions are not counted).  bench.py turns the per-instance totals into the work unit of its FP64 roofline
+// (ops per step attempt); the production build of the oracle compiles CNT away.
+#ifdef ORACLE_COUNT_OPS
+struct OpCount { long add = 0, mul = 0, div = 0, sqrt_ = 0, pow_ = 0; };
+thread_local OpCount g_ops;
+#define CNT(a, m, d, s, p) do { g_ops.add += (a); g_ops.mul += (m); g_ops.div += (d); g_ops.sqrt_ += (s); g_ops.pow_ += (p); } while (0)
+#else
+#define CNT(a, m, d, s, p) do { } while (0)
+#endif
+
 typedef double (*pow_fn_t)(double, double);
 pow_fn_t g_pow = static_cast<double (*)(double, double)>(std::pow);
 
@@ -101,6 +114,7 @@ struct Problem {
             r[1] = -r[0] - k3 * yy[1] * yy[1] - yp[1];
             r[0] -= yp[0];
             r[2] = yy[0] + yy[1] + yy[2] - 1.0;
+            CNT(7, 5, 0, 0, 0);
             break;
         }
         case PK_LORENZ63: {
@@ -109,6 +123,7 @@ struct Problem {
             r[0] = yp[0] - s * (yy[1] - yy[0]);
             r[1] = yp[1] - (yy[0] * (rr - yy[2]) - yy[1]);
             r[2] = yp[2] - (yy[0] * yy[1] - b * yy[2]);
+            CNT(7, 4, 0, 0, 0);
             break;
         }
         case PK_HEAT2D: {
@@ -122,6 +137,7 @@ struct Problem {
                     const double dif1 = yy[loc - 1] + yy[loc + 1] - 2.0 * yy[loc];
                     const double dif2 = yy[loc - M] + yy[loc + M] - 2.0 * yy[loc];
                     r[loc] = yp[loc] - coeff * (dif1 + dif2);
+                    CNT(6, 3, 0, 0, 0);
                 }
             break;
         }
@@ -145,6 +161,7 @@ struct Problem {
             A(2, 0) = 1.0;
             A(2, 1) = 1.0;
             A(2, 2) = 1.0;
+            CNT(3, 6, 0, 0, 0);
             break;
         }
         case PK_LORENZ63: {
@@ -158,6 +175,7 @@ struct Problem {
             A(2, 0) = -yy[1];
             A(2, 1) = -yy[0];
             A(2, 2) = cj + b;
+            CNT(4, 0, 0, 0, 0);
             break;
         }
         case PK_HEAT2D: {
@@ -167,6 +185,7 @@ struct Problem {
             for (int j = 1; j < M - 1; ++j)
                 for (int i = 1; i < M - 1; ++i) {
                     const int loc = j * M + i;
+                    CNT(1, 1, 0, 0, 0);
                     A(loc, loc) = cj + 4.0 * coeff;
                     A(loc, loc - 1) = -coeff;
                     A(loc, loc + 1) = -coeff;
@@ -196,13 +215,16 @@ int dense_get_rf(double* a, int64_t* pivot, int n) {
             for (int i = 0; i < n; ++i) std::swap(A(k, i), A(l, i));
         const double mult = 1.0 / A(k, k);
         for (int i = k + 1; i < n; ++i) A(i, k) *= mult;
+        CNT(0, n - k - 1, 1, 0, 0);
         for (int j = k + 1; j < n; ++j) {
             const double a_kj = A(k, j);
-            if (a_kj != 0.0)
+            if (a_kj != 0.0) {
+                CNT(n - k - 1, n - k - 1, 0, 0, 0);
                 for (int i = k + 1; i < n; ++i) {
                     const double a_ik = A(i, k);
                     A(i, j) -= a_kj * a_ik;
                 }
+            }
         }
     }
     return 0;
@@ -225,6 +247,7 @@ void dense_get_rs(const double* a, const int64_t* pivot, double* b, int n) {
         for (int i = 0; i < k; ++i) b[i] -= A(i, k) * bk;
     }
     b[0] /= A(0, 0);
+    CNT(n * (n - 1), n * (n - 1), n, 0, 0);
 }
 
 // ---- WRMS norm: src/norm_rms.rs:31-38 ; crates/nonlinear/src/norm_wrms.rs:24-33 -------------
@@ -234,6 +257,7 @@ double norm_wrms(const double* x, const double* w, int n) {
         const double p = x[i] * w[i];
         acc = acc + p * p;
     }
+    CNT(n, 2 * n, 1, 1, 0);
     return std::sqrt(acc / (double)n);
 }
 
@@ -281,6 +305,7 @@ struct Newton {
                 for (int i = 0; i < n; ++i) delta[i] = -delta[i];
                 problem.lsolve(y, delta.data());
                 for (int i = 0; i < n; ++i) y[i] += delta[i];
+                CNT(n, 0, 0, 0, 0);
                 const int c = problem.ctest(curiter, y, delta.data(), tol, w);
                 if (c == 1) {
                     jcur = false;
@@ -389,6 +414,7 @@ struct Ida {
     // TolControlSV::ewt_set -- src/tol_control.rs:71-82
     void ewt_set(const double* ycur) {
         for (int i = 0; i < n; ++i) ewt[i] = 1.0 / (rtol * std::fabs(ycur[i]) + atol[i]);
+        CNT(n, n, n, 0, 0);
     }
 
     // set_coeffs -- src/lib.rs:722-782
@@ -410,6 +436,7 @@ struct Ida {
                 alpha[i] = hh / temp1;
                 sigma[i] = scalar_i * sigma[i - 1] * alpha[i];
                 gamma[i] = gamma[i - 1] + alpha[i - 1] / hh;
+                CNT(2, 3, 3, 0, 0);
             }
             psi[kk] = temp1;
         }
@@ -418,15 +445,18 @@ struct Ida {
             const double scalar_i = (double)(i + 1);
             alphas -= 1.0 / scalar_i;
             alpha0 -= alpha[i];
+            CNT(2, 0, 1, 0, 0);
         }
         cjlast = cj;
         cj = -alphas / hh;
         double ck = std::fabs(alpha[kk] + alphas - alpha0);
+        CNT(2, 0, 1, 0, 0);
         ck = std::fmax(ck, alpha[kk]);
         if (ns <= kk)
             for (int j = ns; j <= kk; ++j) {
                 double* ph = PHI(j);
                 for (int i = 0; i < n; ++i) ph[i] *= beta[j];
+                CNT(0, n, 0, 0, 0);
             }
         return ck;
     }
@@ -443,6 +473,7 @@ struct Ida {
             const double* ph = PHI(j);
             for (int i = 0; i < n; ++i) yppredict[i] += gamma[j] * ph[i];
         }
+        CNT((kk + 1) * n + kk * n, kk * n, 0, 0, 0);
     }
 
     // IdaNLProblem::sys -- src/ida_nls.rs:118-153
@@ -450,6 +481,7 @@ struct Ida {
         for (int i = 0; i < n; ++i) yy[i] = yypredict[i] + ycor[i];
         for (int i = 0; i < n; ++i) yp[i] = yppredict[i];
         for (int i = 0; i < n; ++i) yp[i] += cj * ycor[i];
+        CNT(2 * n, n, 0, 0, 0);
         prob.res(tn, yy.data(), yp.data(), res);
         nre += 1;
         for (int i = 0; i < n; ++i) savres[i] = res[i];
@@ -479,6 +511,7 @@ struct Ida {
         if (cjratio != 1.0) {  // src/ida_ls.rs:406-410
             const double f = 2.0 / (1.0 + cjratio);
             for (int i = 0; i < n; ++i) b[i] *= f;
+            CNT(1, n, 1, 0, 0);
         }
     }
 
@@ -487,14 +520,18 @@ struct Ida {
         const double delnrm = norm_wrms(del, w, n);
         if (m == 0) {
             oldnrm = delnrm;
+            CNT(0, 1, 0, 0, 0);
             if (delnrm <= 0.0001 * toldel) return 1;
         } else {
             const double base = delnrm / oldnrm;
             const double arg = 1.0 / (double)m;
             const double rate = g_pow(base, arg);
+            CNT(0, 0, 2, 0, 1);
             if (rate > RATEMAX) return -1;
             ss = rate / (1.0 - rate);
+            CNT(1, 0, 1, 0, 0);
         }
+        CNT(0, 1, 0, 0, 0);
         if (ss * delnrm <= tol) return 1;
         return 0;
     }
@@ -521,6 +558,7 @@ struct Ida {
         cjratio = cj / cjold;
         const double temp1 = (1.0 - XRATE) / (1.0 + XRATE);
         const double temp2 = 1.0 / temp1;
+        CNT(0, 0, 1, 0, 0);  // cjratio only: temp1 / temp2 are compile-time constants in any optimised build
         if (cjratio < temp1 || cjratio > temp2) call_lsetup = true;
         if (cj != cjlast) ss = 100.0;
         for (int i = 0; i < n; ++i) delta[i] = 0.0;
@@ -530,6 +568,7 @@ struct Ida {
         for (int i = 0; i < n; ++i) yy[i] = yypredict[i] + ee[i];
         for (int i = 0; i < n; ++i) yp[i] = yppredict[i];
         for (int i = 0; i < n; ++i) yp[i] += cj * ee[i];
+        CNT(2 * n, n, 0, 0, 0);
         return ret;
     }
 
@@ -539,15 +578,18 @@ struct Ida {
         const double enorm_k = norm_wrms(ee.data(), ewt.data(), n);
         err_k = sigma[kk] * enorm_k;
         const double terr_k = err_k * (scalar_kk + 1.0);
+        CNT(1, 3, 0, 0, 0);  // incl. ck * enorm_k of the acceptance test
         err_km1 = 0.0;
         int knew_ = kk;
         if (kk > 1) {
+            CNT(n, 2, 0, 0, 0);
             const double* phk = PHI(kk);
             for (int i = 0; i < n; ++i) delta[i] = phk[i] + ee[i];
             const double enorm_km1 = norm_wrms(delta.data(), ewt.data(), n);
             err_km1 = sigma[kk - 1] * enorm_km1;
             const double terr_km1 = scalar_kk * err_km1;
             if (kk > 2) {
+                CNT(n + 1, 2, 0, 0, 0);
                 const double* phkm1 = PHI(kk - 1);
                 for (int i = 0; i < n; ++i) delta[i] += phkm1[i];
                 const double enorm_km2 = norm_wrms(delta.data(), ewt.data(), n);
@@ -555,6 +597,7 @@ struct Ida {
                 const double terr_km2 = (scalar_kk - 1.0) * err_km2;
                 if (std::fmax(terr_km1, terr_km2) <= terr_k) knew_ = kk - 1;
             } else {
+                CNT(0, 1, 0, 0, 0);
                 if (terr_km1 <= terr_k * 0.5) knew_ = kk - 1;
             }
         }
@@ -566,8 +609,10 @@ struct Ida {
     void restore(double saved_t) {
         tn = saved_t;
         for (int j = 1; j <= kk; ++j) psi[j - 1] = psi[j] - hh;
+        CNT(kk, 0, 0, 0, 0);
         if (ns <= kk)
             for (int j = ns; j <= kk; ++j) {
+                CNT(0, n, 1, 0, 0);
                 const double c = 1.0 / beta[j];
                 double* ph = PHI(j);
                 for (int i = 0; i < n; ++i) ph[i] *= c;
@@ -589,16 +634,19 @@ struct Ida {
                 rr = 0.9 * g_pow(base, -arg);
                 rr = std::fmax(0.25, std::fmin(0.9, rr));
                 hh *= rr;
+                CNT(1, 3, 1, 0, 1);
                 return 0;
             } else if (nef == 2) {
                 kk = knew;
                 rr = 0.25;
                 hh *= rr;
+                CNT(0, 1, 0, 0, 0);
                 return 0;
             } else if (nef < maxnef) {
                 kk = 1;
                 rr = 0.25;
                 hh *= rr;
+                CNT(0, 1, 0, 0, 0);
                 return 0;
             }
             return ST_ERR_FAIL;
@@ -608,6 +656,7 @@ struct Ida {
         ncfn += 1;
         rr = 0.25;
         hh *= rr;
+        CNT(0, 1, 0, 0, 0);
         if (ncf < maxncf) return 0;
         return ST_CONV_FAIL;
     }
@@ -616,6 +665,7 @@ struct Ida {
     void reset() {
         psi[0] = hh;
         for (auto& v : phi) v *= rr;
+        CNT(0, MXORDP1 * n, 0, 0, 0);
     }
 
     // complete_step -- src/impl_complete_step.rs:22-177
@@ -632,6 +682,7 @@ struct Ida {
                 const double t = std::fabs(hnew) * hmax_inv;
                 if (t > 1.0) hnew /= t;
                 hh = hnew;
+                CNT(0, 2, 0, 0, 0);
             }
         } else {
             enum { LOWER, MAINTAIN, RAISE } action;
@@ -649,6 +700,7 @@ struct Ida {
                 err_kp1 = enorm / (double)(kk + 2);
                 const double terr_k = (double)(kk + 1) * err_k;
                 const double terr_kp1 = (double)(kk + 2) * err_kp1;
+                CNT(n, 3, 1, 0, 0);  // incl. 0.5 * terr_k (kk == 1) or kk * err_km1 (kk > 1)
                 if (kk == 1) {
                     action = (terr_kp1 >= 0.5 * terr_k) ? MAINTAIN : RAISE;
                 } else {
@@ -668,19 +720,23 @@ struct Ida {
                 const double base = 2.0 * err_knew + 0.0001;
                 const double arg = -(1.0 / (double)(kk + 1));
                 rr = g_pow(base, arg);
+                CNT(1, 1, 1, 0, 1);
             }
             if (rr >= 2.0) {
                 hnew = 2.0 * hh;
                 const double t = std::fabs(hnew) * hmax_inv;
                 if (t > 1.0) hnew /= t;
+                CNT(0, 2, 0, 0, 0);
             } else if (rr <= 1.0) {
                 rr = std::fmax(0.5, std::fmin(rr, 0.9));
                 hnew = hh * rr;
+                CNT(0, 1, 0, 0, 0);
             }
             hh = hnew;
         }
         if (kused < maxord) std::copy(ee.begin(), ee.end(), PHI(kused + 1));
         for (int i = 0; i < n; ++i) tmp[i] = ee[i];
+        CNT((kused + 1) * n, 0, 0, 0, 0);
         for (int j = kused; j >= 0; --j) {
             double* ph = PHI(j);
             for (int i = 0; i < n; ++i) {
@@ -713,6 +769,7 @@ struct Ida {
             ck = set_coeffs();
             if (ev) evw |= (uint32_t)(kk + 1 >= ns) << 3 | (uint32_t)std::min(ns, 7) << 4;
             tn += hh;
+            CNT(1, 0, 0, 0, 0);
             predict();
             int nflag = nonlinear_solve();
             bool converged = false;
@@ -748,6 +805,7 @@ struct Ida {
         const int ev_ph0 = phase, ev_kk0 = kk, ev_ns = ns, ev_kdiff = kk - kused;
         complete_step(err_k, err_km1);
         for (int i = 0; i < n; ++i) ee[i] *= ck;
+        CNT(0, n, 0, 0, 0);
         if (ev) {
             // which branches complete_step took (restated from its conditions on the state before the call)
             const bool ph1 = ev_ph0 == 1 || knew == ev_kk0 - 1 || ev_kk0 == maxord;
@@ -979,11 +1037,13 @@ struct Ida {
         const double sgn = (hh > 0.0 || (hh == 0.0 && !std::signbit(hh))) ? 1.0 : -1.0;  // f64::signum
         const double tfuzz = 100.0 * DBL_EPS * (std::fabs(tn) + std::fabs(hh)) * sgn;
         const double tp = tn - hused - tfuzz;
+        CNT(5, 4, 0, 0, 0);  // tfuzz, tp, (t - tp) * hh, delt
         if ((t - tp) * hh < 0.0) return ST_BAD_T;
         const int kord = (kused == 0) ? 1 : kused;
         const double delt = t - tn;
         double c = 1.0, d = 0.0;
         double gam = delt / psi[0];
+        CNT(2 * kord + (2 * kord + 1) * n, 2 * kord + (2 * kord + 1) * n, 1 + 2 * kord, 0, 0);  // recurrence + both sums
         double cvals[MXORDP1], dvals[MXORDP1];
         cvals[0] = c;
         for (int j = 1; j <= kord; ++j) {
@@ -1063,7 +1123,11 @@ struct Ida {
             if (hh == 0.0) {
                 hh = 0.001 * tdist;
                 const double ypnorm = norm_wrms(PHI(1), ewt.data(), n);
-                if (ypnorm > 2.0 / hh) hh = 0.5 / ypnorm;
+                CNT(2, 5 + n, 1, 0, 0);  // tdist, troundoff, 0.001 tdist, 2/hh, rh, phi[1] *= hh, toldel
+                if (ypnorm > 2.0 / hh) {
+                    hh = 0.5 / ypnorm;
+                    CNT(0, 0, 1, 0, 0);
+                }
                 if (tout < tn) hh = -hh;
             }
             const double rh = std::fabs(hh) * hmax_inv;
@@ -1134,6 +1198,7 @@ struct Ida {
             }
             const double nrm = norm_wrms(PHI(0), ewt.data(), n);
             tolsf = DBL_EPS * nrm;
+            CNT(1, 2, 0, 0, 0);  // tolsf and the stop test (tn - tout) * hh after the step
             if (tolsf > 1.0) {
                 tolsf *= 10.0;
                 tret = tn;
@@ -1455,6 +1520,42 @@ int oracle_ensemble_events(int kind, int n, int64_t B, int nparams, const double
     for (auto& t : th) t.join();
     return 0;
 }
+
+#ifdef ORACLE_COUNT_OPS
+// algorithmic operation counts of every instance integrated over the ladder: ops [B][5] = add, mul, div, sqrt, pow;
+// natt [B] step attempts
+int oracle_ensemble_ops(int kind, int n, int64_t B, int nparams, const double* params, const double* yy0, const double* yp0,
+                        double rtol, const double* atol, const double* touts, int ntout, int nthreads, int64_t* ops, int64_t* natt) {
+    if (nthreads < 1) nthreads = 1;
+    std::atomic<int64_t> next(0);
+    auto worker = [&]() {
+        std::vector<double> par(nparams), y0(n), yp0v(n);
+        for (;;) {
+            const int64_t b = next.fetch_add(1);
+            if (b >= B) break;
+            for (int k = 0; k < nparams; ++k) par[k] = params[(size_t)k * B + b];
+            for (int i = 0; i < n; ++i) {
+                y0[i] = yy0[(size_t)i * B + b];
+                yp0v[i] = yp0[(size_t)i * B + b];
+            }
+            g_ops = OpCount();
+            Ida ida;
+            Problem p{kind, n, par.data()};
+            ida.init(p, y0.data(), yp0v.data(), rtol, atol);
+            double tret = 0.0;
+            for (int it = 0; it < ntout; ++it) ida.solve(touts[it], tret);
+            const long v[5] = {g_ops.add, g_ops.mul, g_ops.div, g_ops.sqrt_, g_ops.pow_};
+            for (int k = 0; k < 5; ++k) ops[b * 5 + k] = v[k];
+            natt[b] = ida.nattempts;
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nthreads; ++t) th.emplace_back(worker);
+    worker();
+    for (auto& t : th) t.join();
+    return 0;
+}
+#endif
 
 // single-instance trace: records (nst, kused, hused, y[0..n)) after every solve() call, used to
 // reproduce the table of examples/roberts.rs:87-113

@@ -40,10 +40,47 @@ def common_mem(*mems):
     return ms.pop()
 
 
-def current_stream(mem):
+def current_stream(mem, device=None):
+    """torch's current stream OF `device` (not of torch's current device) for device buffers"""
     if mem == _lib.MEM_DEVICE and torch is not None and torch.cuda.is_available():
-        return torch.cuda.current_stream().cuda_stream
+        return torch.cuda.current_stream(device).cuda_stream
     return None
+
+
+def device_of(*xs):
+    """CUDA device index shared by the torch tensors among xs (None if there are none); raises if they disagree"""
+    devs = {x.device.index for x in xs if is_torch(x) and x.is_cuda}
+    if len(devs) > 1:
+        raise ValueError("buffers live on different CUDA devices: %s" % sorted(devs))
+    return devs.pop() if devs else None
+
+
+def tensors_device(*xs):
+    """context manager making the CUDA device of the tensors among xs current for a Level-1 call (whose kernels run on
+    the current device), restoring the previous one afterwards; a no-op for host buffers"""
+    import contextlib
+    dev = device_of(*xs)
+    if dev is None or torch is None:
+        return contextlib.nullcontext(), None
+    return torch.cuda.device(dev), dev
+
+
+class on_device:
+    """Run C-ABI calls with `device` current and put the caller's current device back afterwards (every compute entry
+    point of the library calls cudaSetDevice on the handle's device)."""
+
+    def __init__(self, device):
+        self.device, self.prev = device, None
+
+    def __enter__(self):
+        if torch is not None and torch.cuda.is_available() and self.device is not None:
+            self.prev = torch.cuda.current_device()
+        return self
+
+    def __exit__(self, *a):
+        if self.prev is not None and self.prev != self.device:
+            torch.cuda.set_device(self.prev)
+        return False
 
 
 def empty_like_space(ref, shape, dtype):

@@ -26,6 +26,11 @@ inline int set_error(int code, const char* fmt, ...) {
                                         cudaGetErrorString(_e));                                         \
     } while (0)
 
+// launches of the engine's own kernels since the library was loaded (b200ida_kernel_launches): bench.py's `gpu_launches`
+// is the difference of this counter over the timed region, not a hand count
+long long& launch_counter();  // defined in ida_engine.cu
+inline void count_launch(int n = 1) { launch_counter() += n; }
+
 // RAII device scratch used by the host-memory (end-to-end) entry points
 struct DevBuf {
     void* p = nullptr;

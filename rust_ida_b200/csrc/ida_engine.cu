@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <new>
 
 #include <cub/cub.cuh>
@@ -16,6 +17,11 @@
 #include "problems.cuh"
 
 namespace b200ida {
+
+long long& launch_counter() {
+    static long long n = 0;
+    return n;
+}
 
 char* last_error_buf() {
     static thread_local char buf[512] = "";
@@ -343,6 +349,7 @@ struct b200ida_ensemble {
     double* params = nullptr;  // [nparams][B]
     double* d_atol = nullptr;  // [n]
     int kernel = B200IDA_KERNEL_AUTO;
+    int reorder = B200IDA_REORDER_AUTO;  // captured from the process default at create (b200ida_set_default_reorder)
     int* perm = nullptr;  // [B] slot -> caller-visible instance id, or null (identity)
     TraceParams trace = {nullptr, nullptr, nullptr, 0, -1};  // b200ida_set_trace; id < 0: off
     RootParams roots = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0};  // b200ida_set_roots; max_ev == 0: off
@@ -369,7 +376,31 @@ struct b200ida_ensemble {
                 return cudaSuccess;
             }
         }
-        if (nblk == MAX_BLOCKS) return cudaErrorMemoryAllocation;
+        if (nblk == MAX_BLOCKS) {
+            // every block is rewound between API calls (scratch_reset after a stream sync): drop the idle ones and
+            // replace them by one block that holds everything this call has asked for so far, twice over
+            size_t total = bytes, keep = 0;
+            for (int i = 0; i < nblk; ++i) total += blk_used[i];
+            for (int i = 0; i < nblk; ++i) {
+                if (blk_used[i] == 0) {
+                    cudaFree(blk[i]);
+                } else {
+                    blk[keep] = blk[i];
+                    blk_cap[keep] = blk_cap[i];
+                    blk_used[keep] = blk_used[i];
+                    ++keep;
+                }
+            }
+            nblk = keep;
+            if (nblk == MAX_BLOCKS) return cudaErrorMemoryAllocation;
+            cudaError_t err2 = cudaMalloc(&blk[nblk], 2 * total);
+            if (err2 != cudaSuccess) return err2;
+            blk_cap[nblk] = 2 * total;
+            blk_used[nblk] = bytes;
+            *out = blk[nblk];
+            ++nblk;
+            return cudaSuccess;
+        }
         const size_t cap = bytes > ((size_t)32 << 20) ? bytes : ((size_t)32 << 20);
         cudaError_t err = cudaMalloc(&blk[nblk], cap);
         if (err != cudaSuccess) return err;
@@ -385,12 +416,14 @@ struct b200ida_ensemble {
     }
 };
 
-static int g_reorder_mode = B200IDA_REORDER_AUTO;
+// process-wide DEFAULT for handles created afterwards (each handle keeps its own copy: changing the default never
+// re-orders a live ensemble); an atomic so that concurrent creators see a whole value
+static std::atomic<int> g_reorder_mode{B200IDA_REORDER_AUTO};
 
 // (re)build e->perm from parameters that are already on the device in CALLER order
 static int build_order(b200ida_ensemble* e, const double* d_params_caller_order) {
-    const bool want = g_reorder_mode == B200IDA_REORDER_ON ||
-                      (g_reorder_mode == B200IDA_REORDER_AUTO && e->problem != B200IDA_PROBLEM_HEAT2D && e->B >= 4096);
+    const bool want = e->reorder == B200IDA_REORDER_ON ||
+                      (e->reorder == B200IDA_REORDER_AUTO && e->problem != B200IDA_PROBLEM_HEAT2D && e->B >= 4096);
     if (!want || e->nparams < 1 || e->nparams > 8 || e->B >= (int64_t)1 << 31) {
         if (e->perm) cudaFree(e->perm);
         e->perm = nullptr;
@@ -400,6 +433,16 @@ static int build_order(b200ida_ensemble* e, const double* d_params_caller_order)
     const int P = e->nparams;
     cudaStream_t st = e->stream;
     if (!e->perm) B200_CUDA_TRY(cudaMalloc(&e->perm, (size_t)B * sizeof(int)));
+    struct PermGuard {  // an error return below must not leave an unfilled permutation attached to the handle
+        b200ida_ensemble* e;
+        bool done = false;
+        ~PermGuard() {
+            if (!done && e->perm) {
+                cudaFree(e->perm);
+                e->perm = nullptr;
+            }
+        }
+    } guard{e};
     size_t tb1 = 0, tb2 = 0, tb3 = 0;
     cub::DeviceReduce::Min(nullptr, tb1, d_params_caller_order, (double*)nullptr, (int)B, st);
     cub::DeviceReduce::Max(nullptr, tb2, d_params_caller_order, (double*)nullptr, (int)B, st);
@@ -422,8 +465,10 @@ static int build_order(b200ida_ensemble* e, const double* d_params_caller_order)
     }
     const int tb = 256;
     order_key_kernel<<<(unsigned)((B + tb - 1) / tb), tb, 0, st>>>(d_params_caller_order, lo, hi, P, B, keys, ids);
+    count_launch();
     B200_CUDA_TRY(cudaGetLastError());
     B200_CUDA_TRY(cub::DeviceRadixSort::SortPairs(p_tmp, tbytes, keys, keys2, ids, e->perm, (int)B, 0, 32, st));
+    guard.done = true;
     return B200IDA_OK;  // scratch is persistent and stream-ordered: no synchronisation needed
 }
 
@@ -438,6 +483,7 @@ static int rows_out(b200ida_ensemble* e, TD* dst, const TS* src, int rows, int m
     const unsigned grid = (unsigned)((B + tb - 1) / tb);
     if (mem == B200IDA_MEM_DEVICE) {
         unpermute_kernel<TS, TD><<<grid, tb, 0, e->stream>>>(src, dst, rows, B, e->perm);
+        count_launch();
         B200_CUDA_TRY(cudaGetLastError());
         return B200IDA_OK;
     }
@@ -451,6 +497,7 @@ static int rows_out(b200ida_ensemble* e, TD* dst, const TS* src, int rows, int m
     e->scratch_reset();
     B200_CUDA_TRY(e->scratch_take(bytes, &tmp));
     unpermute_kernel<TS, TD><<<grid, tb, 0, e->stream>>>(src, static_cast<TD*>(tmp), rows, B, e->perm);
+    count_launch();
     B200_CUDA_TRY(cudaGetLastError());
     B200_CUDA_TRY(cudaMemcpyAsync(dst, tmp, bytes, cudaMemcpyDeviceToHost, e->stream));
     B200_CUDA_TRY(cudaStreamSynchronize(e->stream));
@@ -473,6 +520,7 @@ int b200ida_debug_root_prof(unsigned long long* out8, int reset) {
 
 const char* b200ida_last_error(void) { return last_error_buf(); }
 int b200ida_version(void) { return B200IDA_VERSION; }
+long long b200ida_kernel_launches(void) { return launch_counter(); }
 int b200ida_device_count(void) {
     int c = 0;
     if (cudaGetDeviceCount(&c) != cudaSuccess) {
@@ -514,6 +562,7 @@ int b200ida_reinit(b200ida_ensemble* e, const double* params, const double* yy0,
         int rc = build_order(e, dp);
         if (rc != B200IDA_OK) return rc;
         permute_rows_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, st>>>(dp, e->params, e->nparams, batch, e->perm);
+        count_launch();
         B200_CUDA_TRY(cudaGetLastError());
     }
     if (mem == B200IDA_MEM_HOST) {
@@ -527,6 +576,7 @@ int b200ida_reinit(b200ida_ensemble* e, const double* params, const double* yy0,
     }
     const int tb = 256;
     ida_init_kernel<<<(unsigned)((batch + tb - 1) / tb), tb, 0, st>>>(e->dstate, dy0, dyp0, n, batch, e->perm);
+    count_launch();
     B200_CUDA_TRY(cudaGetLastError());
     // host buffers: the caller may reuse them as soon as we return, so wait for the H2D copies; the device scratch
     // itself is persistent and stream-ordered
@@ -564,6 +614,7 @@ int b200ida_create(b200ida_ensemble** out, int problem, int n, int64_t batch, in
     b200ida_ensemble* e = new (std::nothrow) b200ida_ensemble();
     if (!e) return set_error(B200IDA_ERR_ARG, "out of host memory");
     e->problem = problem;
+    e->reorder = g_reorder_mode.load();
     e->n = n;
     e->nparams = nparams;
     e->device = device;
@@ -673,6 +724,11 @@ int b200ida_solve_ladder(b200ida_ensemble* e, const double* touts, int ntout, in
     if (kernel == B200IDA_KERNEL_AUTO)
         kernel = (e->n == 3 && e->problem != B200IDA_PROBLEM_HEAT2D) ? B200IDA_KERNEL_THREAD
                  : (e->n <= 32 ? B200IDA_KERNEL_WARP : B200IDA_KERNEL_CTA);
+    if (e->roots.max_ev > 0 && kernel != B200IDA_KERNEL_THREAD)
+        return set_error(B200IDA_ERR_UNSUPPORTED, "rootfinding is implemented by the thread-per-instance kernel only "
+                                                  "(b200ida_set_kernel selected another one): no events would be reported");
+    if (e->roots.max_ev > 0 && e->trace.id >= 0)
+        return set_error(B200IDA_ERR_UNSUPPORTED, "rootfinding and the per-attempt trace cannot be active in the same launch");
     if (kernel == B200IDA_KERNEL_THREAD) {
         if (e->n != 3 || e->problem == B200IDA_PROBLEM_HEAT2D)
             return set_error(B200IDA_ERR_UNSUPPORTED, "thread-per-instance kernels exist for the n = 3 problems only");
@@ -689,16 +745,19 @@ int b200ida_solve_ladder(b200ida_ensemble* e, const double* touts, int ntout, in
             B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_thread_kernel<Roberts, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
             ida_solve_thread_kernel<Roberts, false, true><<<grid, tb, rsmem, e->stream>>>(e->dstate, e->istate, e->params, e->B, tol, lad,
                                                                                          d_traj, d_stat, e->perm, TraceParams(), e->roots);
+            count_launch();
         } else if (e->trace.id >= 0) {
             // traced run: the TRACE instantiation of the same kernel (the production instantiation carries no trace code)
             if (e->problem == B200IDA_PROBLEM_ROBERTS) {
                 B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_thread_kernel<Roberts, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 ida_solve_thread_kernel<Roberts, true><<<grid, tb, smem, e->stream>>>(e->dstate, e->istate, e->params, e->B, tol, lad,
                                                                                       d_traj, d_stat, e->perm, e->trace);
+                count_launch();
             } else {
                 B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_thread_kernel<Lorenz63, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 ida_solve_thread_kernel<Lorenz63, true><<<grid, tb, smem, e->stream>>>(e->dstate, e->istate, e->params, e->B, tol, lad,
                                                                                        d_traj, d_stat, e->perm, e->trace);
+                count_launch();
             }
         } else {
             // production path: solve kernel (snapshots at the output times) + the coherent interpolation pass
@@ -720,14 +779,18 @@ int b200ida_solve_ladder(b200ida_ensemble* e, const double* touts, int ntout, in
                 B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_thread_kernel<Roberts>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 ida_solve_thread_kernel<Roberts><<<grid, tb, smem, e->stream>>>(e->dstate, e->istate, e->params, e->B, tol, lad,
                                                                                 d_traj, d_stat, e->perm, TraceParams(), RootParams(), df);
+                count_launch();
             } else {
                 B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_thread_kernel<Lorenz63>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 ida_solve_thread_kernel<Lorenz63><<<grid, tb, smem, e->stream>>>(e->dstate, e->istate, e->params, e->B, tol, lad,
                                                                                  d_traj, d_stat, e->perm, TraceParams(), RootParams(), df);
+                count_launch();
             }
             B200_CUDA_TRY(cudaGetLastError());
-            if (IDA_DEFER)
+            if (IDA_DEFER) {
                 ida_interp_kernel<3><<<(unsigned)((e->B * ntout + 255) / 256), 256, 0, e->stream>>>(e->dstate, e->B, lad, df, d_traj, e->perm);
+                count_launch();
+            }
         }
     } else {
         const bool warp = kernel == B200IDA_KERNEL_WARP;
@@ -755,6 +818,7 @@ int b200ida_solve_ladder(b200ida_ensemble* e, const double* touts, int ntout, in
         else
             ida_solve_team_kernel<CtaTeam><<<grid, tb, smem, e->stream>>>(e->dstate, e->istate, e->params, e->B, e->n, e->problem,
                                                                           e->nparams, e->rtol, e->d_atol, lad, d_traj, d_stat, arena, e->perm, e->trace);
+        count_launch();
     }
     B200_CUDA_TRY(cudaGetLastError());
     if (mem == B200IDA_MEM_HOST) {
@@ -827,6 +891,7 @@ int b200ida_get_dky(b200ida_ensemble* e, double t, int k, double* dky, int32_t* 
     const unsigned grid = (unsigned)((B + 255) / 256);
     if (mem == B200IDA_MEM_DEVICE) {
         ida_dky_kernel<<<grid, 256, 0, e->stream>>>(e->dstate, e->istate, e->n, B, t, k, dky, status, e->perm);
+        count_launch();
         B200_CUDA_TRY(cudaGetLastError());
         return B200IDA_OK;
     }
@@ -839,6 +904,7 @@ int b200ida_get_dky(b200ida_ensemble* e, double t, int k, double* dky, int32_t* 
     B200_CUDA_TRY(cudaMemcpyAsync(d_dky, dky, dbytes, cudaMemcpyHostToDevice, e->stream));
     ida_dky_kernel<<<grid, 256, 0, e->stream>>>(e->dstate, e->istate, e->n, B, t, k, static_cast<double*>(d_dky),
                                                 static_cast<int*>(d_st), e->perm);
+    count_launch();
     B200_CUDA_TRY(cudaGetLastError());
     B200_CUDA_TRY(cudaMemcpyAsync(dky, d_dky, dbytes, cudaMemcpyDeviceToHost, e->stream));
     if (status) B200_CUDA_TRY(cudaMemcpyAsync(status, d_st, sbytes, cudaMemcpyDeviceToHost, e->stream));
@@ -848,7 +914,7 @@ int b200ida_get_dky(b200ida_ensemble* e, double t, int k, double* dky, int32_t* 
 
 int b200ida_set_default_reorder(int mode) {
     if (mode < B200IDA_REORDER_OFF || mode > B200IDA_REORDER_AUTO) return set_error(B200IDA_ERR_ARG, "b200ida_set_default_reorder: bad mode");
-    g_reorder_mode = mode;
+    g_reorder_mode.store(mode);
     return B200IDA_OK;
 }
 

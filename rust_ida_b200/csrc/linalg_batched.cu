@@ -23,6 +23,17 @@
 #include "lu_team.cuh"
 #include "lu_blocked.cuh"
 
+// Kernel-selection overrides used by tools/ while tuning (B200IDA_LUBG_THREADS, B200IDA_GETRS_NO_TMA): compiled in only
+// with -DB200IDA_EXPERIMENTS, so that the shipped library's kernel choice never depends on the environment.
+static inline const char* experiment_env(const char* name) {
+#ifdef B200IDA_EXPERIMENTS
+    return getenv(name);
+#else
+    (void)name;
+    return nullptr;
+#endif
+}
+
 namespace b200ida {
 
 // element (i, j) of system b
@@ -761,7 +772,7 @@ static int launch_getrf_blocked_global(double* A, int64_t* piv, int32_t* info, i
     unsigned grid = 1;
     int rc;
     // few, large systems (one per SM): the trailing update, not the pivot chain, is the long pole -> 16 warps
-    const char* force = getenv("B200IDA_LUBG_THREADS");  // kernel experiments only
+    const char* force = experiment_env("B200IDA_LUBG_THREADS");
     if (force && atoi(force) == 128) {
         if ((rc = launch_cfg(getrf_blocked_global<128>, 128, smem, B, 1, &grid))) return rc;
         getrf_blocked_global<128><<<grid, 128, smem, st>>>(A, piv, info, n, B);
@@ -1112,7 +1123,7 @@ static int getrf_dev(double* A, int64_t* piv, int32_t* info, int n, int64_t B, i
         B200_CUDA_TRY(cudaGetLastError());
         return B200IDA_OK;
     }
-    if (!soa && n > 32 && (n >= 115 || getenv("B200IDA_LUBG_THREADS"))) return launch_getrf_blocked_global(A, piv, info, n, B, st);
+    if (!soa && n > 32 && (n >= 115 || experiment_env("B200IDA_LUBG_THREADS"))) return launch_getrf_blocked_global(A, piv, info, n, B, st);
     if (n > 32 && n <= SMEM_MAX_N)
         return soa ? launch_getrf_blocked_n<true>(A, piv, info, n, B, st) : launch_getrf_blocked_n<false>(A, piv, info, n, B, st);
     return launch_group<true>(A, piv, info, nullptr, n, B, soa, st);
@@ -1134,7 +1145,7 @@ static int getrs_dev(const double* LU, const int64_t* piv, double* bx, int n, in
         B200_CUDA_TRY(cudaGetLastError());
         return B200IDA_OK;
     }
-    if (!soa && n > 32 && (n & 1) == 0 && (reinterpret_cast<uintptr_t>(LU) & 15) == 0 && !getenv("B200IDA_GETRS_NO_TMA")) {
+    if (!soa && n > 32 && (n & 1) == 0 && (reinterpret_cast<uintptr_t>(LU) & 15) == 0 && !experiment_env("B200IDA_GETRS_NO_TMA")) {
         if (n <= 64) return launch_getrs_tma<2>(LU, piv, bx, n, B, st);
         if (n <= 128) return launch_getrs_tma<4>(LU, piv, bx, n, B, st);
         return launch_getrs_tma<8>(LU, piv, bx, n, B, st);

@@ -38,7 +38,7 @@ class IdaSolveStatus(enum.IntEnum):
 def set_default_reorder(mode):
     """"off" | "on" | "auto": internal warp-coherence ordering of instances (include/b200ida.h); results and
     the caller-visible instance order are unaffected."""
-    _lib.check(_lib.lib().b200ida_set_default_reorder({"off": 0, "on": 1, "auto": 2}[mode]))
+    self._call("b200ida_set_default_reorder", {"off": 0, "on": 1, "auto": 2}[mode])
 
 
 class AttemptTrace:
@@ -71,10 +71,18 @@ class RootEvents:
 class Ida:
     """Ida<P, Dense, Newton, TolControlSV> for a whole ensemble."""
 
-    def __init__(self, problem, yy0, yp0, tol_control, device=0):
+    def __init__(self, problem, yy0, yp0, tol_control, device=None):
         """Ida::new(problem, yy0, yp0, tol_control) (src/lib.rs:278-283).  yy0, yp0: (n, batch) SoA,
-        numpy (host; copied in) or torch CUDA tensors (device), same space as problem.params."""
+        numpy (host; copied in) or torch CUDA tensors (device), same space as problem.params.
+        device: CUDA device of the ensemble.  For CUDA tensors it is taken from the tensors (which must all live on one
+        device; an explicit `device` that disagrees is an error); for host buffers it defaults to 0."""
         _lib.require_device()
+        tdev = B.device_of(problem.params, yy0, yp0)
+        if tdev is not None:
+            if device is not None and int(device) != tdev:
+                raise ValueError("device=%r but params / yy0 / yp0 live on cuda:%d" % (device, tdev))
+            device = tdev
+        device = 0 if device is None else int(device)
         n, batch = problem.model_size(), problem.batch
         if tuple(yy0.shape) != (n, batch) or tuple(yp0.shape) != (n, batch):
             raise ValueError("yy0 / yp0 must have shape (%d, %d)" % (n, batch))  # assert_eq!, src/lib.rs:284
@@ -88,12 +96,18 @@ class Ida:
         self._mem = B.common_mem(m1, m2, m3)
         self._ref = yy0  # which space outputs are allocated in
         h = C.c_void_p()
-        _lib.check(_lib.lib().b200ida_create(C.byref(h), problem.kind, n, batch, problem.nparams, pp, py, pyp,
-                                             tol_control.ida_rtol, self._atol.ctypes.data, self._mem, device,
-                                             B.current_stream(self._mem)))
+        with B.on_device(device):
+            _lib.check(_lib.lib().b200ida_create(C.byref(h), problem.kind, n, batch, problem.nparams, pp, py, pyp,
+                                                 tol_control.ida_rtol, self._atol.ctypes.data, self._mem, device,
+                                                 B.current_stream(self._mem, device)))
         self._h = h
 
     new = classmethod(lambda cls, *a, **k: cls(*a, **k))
+
+    def _call(self, name, *args):
+        """one C-ABI call on this ensemble's device; the caller's current CUDA device is restored afterwards"""
+        with B.on_device(self.device):
+            _lib.check(getattr(_lib.lib(), name)(*args))
 
     def close(self):
         if getattr(self, "_h", None):
@@ -106,7 +120,7 @@ class Ida:
 
     def set_kernel(self, kernel):
         """choose the kernel family ("auto", "thread", "warp", "cta"); results are bit-identical"""
-        _lib.check(_lib.lib().b200ida_set_kernel(self._h, self.KERNELS[kernel]))
+        self._call("b200ida_set_kernel", self._h, self.KERNELS[kernel])
 
     def reinit(self, yy0, yp0, params=None):
         """fresh Ida::new state for every instance (t = 0, counters 0), keeping the device allocation"""
@@ -114,7 +128,7 @@ class Ida:
         pyp, m2 = B.describe(yp0, np.float64, "yp0")
         pp, m3 = B.describe(params, np.float64, "params")
         mem = B.common_mem(m1, m2, m3)
-        _lib.check(_lib.lib().b200ida_reinit(self._h, pp, py, pyp, mem))
+        self._call("b200ida_reinit", self._h, pp, py, pyp, mem)
 
     # ---- stepping ---------------------------------------------------------------------------------------
     def solve(self, tout, itask=IdaTask.Normal):
@@ -124,10 +138,10 @@ class Ida:
             raise NotImplementedError("only IdaTask::Normal is on the device path")
         status = B.empty_like_space(self._ref, (self.batch,), np.int32)
         ps, _ = B.describe(status, np.int32, "status")
-        _lib.check(_lib.lib().b200ida_solve(self._h, float(tout), 0, ps, self._mem))
+        self._call("b200ida_solve", self._h, float(tout), 0, ps, self._mem)
         tret = B.empty_like_space(self._ref, (self.batch,), np.float64)
         pt, _ = B.describe(tret, np.float64, "tret")
-        _lib.check(_lib.lib().b200ida_get_state(self._h, None, None, pt, self._mem))
+        self._call("b200ida_get_state", self._h, None, None, pt, self._mem)
         return status, tret
 
     def solve_ladder(self, touts, itask=IdaTask.Normal, want_traj=True):
@@ -141,11 +155,11 @@ class Ida:
         traj = B.empty_like_space(self._ref, (nt, self.n, self.batch), np.float64) if want_traj else None
         ps, _ = B.describe(status, np.int32, "status")
         pj, _ = B.describe(traj, np.float64, "yy_traj")
-        _lib.check(_lib.lib().b200ida_solve_ladder(self._h, touts.ctypes.data, nt, 0, pj, ps, self._mem))
+        self._call("b200ida_solve_ladder", self._h, touts.ctypes.data, nt, 0, pj, ps, self._mem)
         return status, traj
 
     def sync(self):
-        _lib.check(_lib.lib().b200ida_sync(self._h))
+        self._call("b200ida_sync", self._h)
 
     # ---- rootfinding: src/impl_r_check.rs, Root returns of Ida::solve, get_root_info / get_num_g_evals ----------------
     def enable_roots(self, max_events=16):
@@ -154,7 +168,7 @@ class Ida:
         enable_roots(0) switches it off."""
         import torch
         if not max_events:
-            _lib.check(_lib.lib().b200ida_set_roots(self._h, 0, None, None, None, None))
+            self._call("b200ida_set_roots", self._h, 0, None, None, None, None)
             self._roots = None
             return None
         dev = torch.device("cuda", self.device)
@@ -162,8 +176,8 @@ class Ida:
                         torch.zeros((max_events, 2, self.batch), dtype=torch.float64, device=dev),
                         torch.zeros((self.batch,), dtype=torch.int32, device=dev),
                         torch.zeros((self.batch,), dtype=torch.int32, device=dev))
-        _lib.check(_lib.lib().b200ida_set_roots(self._h, int(max_events), ev.t.data_ptr(), ev.iroots.data_ptr(),
-                                                ev.count.data_ptr(), ev.nge.data_ptr()))
+        self._call("b200ida_set_roots", self._h, int(max_events), ev.t.data_ptr(), ev.iroots.data_ptr(),
+                                                ev.count.data_ptr(), ev.nge.data_ptr())
         self._roots = ev  # keeps the device buffers alive while the engine holds their addresses
         return ev
 
@@ -173,7 +187,7 @@ class Ida:
         (thread-per-instance kernels).  Returns an AttemptTrace; call .rows() after the solve; trace(None) stops."""
         import torch
         if instance is None:
-            _lib.check(_lib.lib().b200ida_set_trace(self._h, -1, None, None, None, 0))
+            self._call("b200ida_set_trace", self._h, -1, None, None, None, 0)
             self._trace = None
             return None
         dev = torch.device("cuda", self.device)
@@ -181,8 +195,8 @@ class Ida:
         t = AttemptTrace(self, torch.zeros((max_attempts, nd), dtype=torch.float64, device=dev),
                          torch.zeros((max_attempts, ni), dtype=torch.int32, device=dev),
                          torch.zeros((1,), dtype=torch.int32, device=dev))
-        _lib.check(_lib.lib().b200ida_set_trace(self._h, int(instance), t.d.data_ptr(), t.i.data_ptr(), t.count.data_ptr(),
-                                                int(max_attempts)))
+        self._call("b200ida_set_trace", self._h, int(instance), t.d.data_ptr(), t.i.data_ptr(), t.count.data_ptr(),
+                                                int(max_attempts))
         self._trace = t  # keeps the device buffers alive while the engine holds their addresses
         return t
 
@@ -192,7 +206,7 @@ class Ida:
         p, _ = B.describe(out, np.float64, "out")
         args = [None, None, None]
         args[which] = p
-        _lib.check(_lib.lib().b200ida_get_state(self._h, args[0], args[1], args[2], self._mem))
+        self._call("b200ida_get_state", self._h, args[0], args[1], args[2], self._mem)
         return out
 
     def get_yy(self):  # ida_io.rs:11
@@ -206,7 +220,7 @@ class Ida:
         p, _ = B.describe(out, np.int64, "out")
         args = [None] * 8
         args[idx] = p
-        _lib.check(_lib.lib().b200ida_get_counters(self._h, *args, self._mem))
+        self._call("b200ida_get_counters", self._h, *args, self._mem)
         return out
 
     def get_num_steps(self):  # :58
@@ -246,7 +260,7 @@ class Ida:
         st = B.empty_like_space(self._ref, (self.batch,), np.int32)
         po, _ = B.describe(out, np.float64, "out")
         ps, _ = B.describe(st, np.int32, "status")
-        _lib.check(_lib.lib().b200ida_get_dky(self._h, float(t), int(k), po, ps, self._mem))
+        self._call("b200ida_get_dky", self._h, float(t), int(k), po, ps, self._mem)
         return out, st
 
     def _stepinfo(self, idx):
@@ -255,7 +269,7 @@ class Ida:
         p, _ = B.describe(out, dt, "out")
         args = [None] * 6
         args[idx] = p
-        _lib.check(_lib.lib().b200ida_get_step_info(self._h, *args, self._mem))
+        self._call("b200ida_get_step_info", self._h, *args, self._mem)
         return out
 
     def get_last_order(self):  # :22

@@ -74,8 +74,10 @@ class Dense:
             self.info = B.empty_like_space(mat_a, (self.batch,), np.int32)
         pp, _ = B.describe(self.pivots, np.int64, "pivots")
         pi, _ = B.describe(self.info, np.int32, "info")
-        _lib.check(_lib.lib().b200ida_getrf_batched(pa, pp, pi, self.n, self.batch, _layout_code(self.layout), mem,
-                                                    B.current_stream(mem)))
+        ctx, dev = B.tensors_device(mat_a, self.pivots, self.info)
+        with ctx:
+            _lib.check(_lib.lib().b200ida_getrf_batched(pa, pp, pi, self.n, self.batch, _layout_code(self.layout), mem,
+                                                        B.current_stream(mem, dev)))
         if self.raise_on_singular:
             info = self.info.cpu().numpy() if B.is_torch(self.info) else self.info
             bad = np.nonzero(info)[0]
@@ -97,8 +99,10 @@ class Dense:
         px, m2 = B.describe(x, np.float64, "x")
         pp, m3 = B.describe(self.pivots, np.int64, "pivots")
         mem = B.common_mem(m1, m2, m3)
-        _lib.check(_lib.lib().b200ida_getrs_batched(pa, pp, px, self.n, self.batch, _layout_code(self.layout), mem,
-                                                    B.current_stream(mem)))
+        ctx, dev = B.tensors_device(mat_a, x, self.pivots)
+        with ctx:
+            _lib.check(_lib.lib().b200ida_getrs_batched(pa, pp, px, self.n, self.batch, _layout_code(self.layout), mem,
+                                                        B.current_stream(mem, dev)))
 
     def num_iters(self):  # traits.rs:83
         return 0
@@ -117,8 +121,10 @@ def norm_wrms(x, w, layout="soa"):
     mem = B.common_mem(m1, m2)
     out = B.empty_like_space(x, (batch,), np.float64)
     po, _ = B.describe(out, np.float64, "out")
-    _lib.check(_lib.lib().b200ida_wrms_batched(px, pw, po, int(n), int(batch), _layout_code(layout), mem,
-                                               B.current_stream(mem)))
+    ctx, dev = B.tensors_device(x, w)
+    with ctx:
+        _lib.check(_lib.lib().b200ida_wrms_batched(px, pw, po, int(n), int(batch), _layout_code(layout), mem,
+                                                   B.current_stream(mem, dev)))
     return out
 
 
@@ -142,6 +148,8 @@ def norm_wrms_masked(x, w, id_, layout="soa"):
         pm = mask.ctypes.data
     out = B.empty_like_space(x, (batch,), np.float64)
     po, _ = B.describe(out, np.float64, "out")
-    _lib.check(_lib.lib().b200ida_wrms_masked_batched(px, pw, pm, po, int(n), int(batch), _layout_code(layout), mem,
-                                                      B.current_stream(mem)))
+    ctx, dev = B.tensors_device(x, w)
+    with ctx:
+        _lib.check(_lib.lib().b200ida_wrms_masked_batched(px, pw, pm, po, int(n), int(batch), _layout_code(layout), mem,
+                                                          B.current_stream(mem, dev)))
     return out

@@ -35,51 +35,71 @@ def timed_solve(ida, yy0, yp0, touts, reps):
     return best, status
 
 
+def _to_dev(*a):
+    import torch
+    dev = torch.device("cuda", torch.cuda.current_device())
+    return [torch.from_numpy(np.ascontiguousarray(v)).to(dev) for v in a]
+
+
+def run_lorenz(batch=4 << 20, reps=2):
+    """config[2] on one GPU: Lorenz-63 DAE ensemble -> dict (instances/s, attempts, step-count statistics)"""
+    import rust_ida_b200 as r
+    from rust_ida_b200.problems import Lorenz63, lorenz_ensemble_params
+    p = lorenz_ensemble_params(batch, seed=1234)
+    yy0, yp0 = Lorenz63.consistent_ic(p)
+    pd, y0, yp = _to_dev(p, yy0, yp0)
+    ida = r.Ida(Lorenz63(pd), y0, yp, r.TolControlSV(1e-6, np.full(3, 1e-8)))
+    touts = 0.5 * np.arange(1, 11)
+    ms, st = timed_solve(ida, y0, yp, touts, reps)
+    nst = ida.get_num_steps()
+    natt = ida.get_num_step_attempts()
+    out = {"config": "lorenz63 DAE ensemble", "batch": batch, "n": 3, "kernel": "thread", "ms": ms,
+           "instances_per_s": batch / (ms * 1e-3), "all_success": bool((st == 0).all().item()),
+           "attempts": int(natt.sum().item()),
+           "nst_min_max_mean": [int(nst.min()), int(nst.max()), float(nst.double().mean())]}
+    ida.close()
+    return out
+
+
+def run_heat(batch=65536, reps=1, M=10):
+    """config[4] on one GPU: 2-D heat DAE (dense n = M*M), CTA-per-system kernel -> dict"""
+    import rust_ida_b200 as r
+    from rust_ida_b200.problems import Heat2D, heat_ensemble_params
+    p = heat_ensemble_params(batch, M=M, seed=1234)
+    yy0, yp0 = Heat2D.consistent_ic(p, M)
+    pd, y0, yp = _to_dev(p, yy0, yp0)
+    ida = r.Ida(Heat2D(pd, M=M), y0, yp, r.TolControlSV(1e-6, np.full(M * M, 1e-8)))
+    touts = 0.01 * 2.0 ** np.arange(11)
+    ms, st = timed_solve(ida, y0, yp, touts, reps)
+    nst, nje, nni = ida.get_num_steps(), ida.get_num_jac_evals(), ida.get_num_nonlin_solv_iters()
+    n = M * M
+    lu_flops = sum((n - k - 1) + 2 * (n - k - 1) ** 2 for k in range(n))
+    flops = float(nje.sum()) * lu_flops + float(nni.sum()) * (2 * n * n)
+    out = {"config": "heat2d %dx%d DAE ensemble" % (M, M), "batch": batch, "n": n, "kernel": "cta", "ms": ms,
+           "instances_per_s": batch / (ms * 1e-3), "all_success": bool((st == 0).all().item()),
+           "nst_mean": float(nst.double().mean()), "nje_mean": float(nje.double().mean()),
+           "lu_plus_solve_gflops": flops / (ms * 1e-3) * 1e-9}
+    ida.close()
+    return out
+
+
 def main():
     import torch
     import rust_ida_b200 as r
-    from rust_ida_b200.problems import (Heat2D, Lorenz63, Roberts, heat_ensemble_params, lorenz_ensemble_params,
-                                        roberts_ensemble_params)
+    from rust_ida_b200.problems import Roberts, roberts_ensemble_params
     ap = argparse.ArgumentParser()
     ap.add_argument("--which", default="lorenz,heat,kernels")
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--lorenz-batch", type=int, default=4 << 20)
     ap.add_argument("--heat-batch", type=int, default=65536)
     args = ap.parse_args()
-    dev = torch.device("cuda", 0)
-    to_dev = lambda *a: [torch.from_numpy(np.ascontiguousarray(v)).to(dev) for v in a]
+    to_dev = _to_dev
 
     if "lorenz" in args.which:
-        B = args.lorenz_batch
-        p = lorenz_ensemble_params(B, seed=1234)
-        yy0, yp0 = Lorenz63.consistent_ic(p)
-        pd, y0, yp = to_dev(p, yy0, yp0)
-        ida = r.Ida(Lorenz63(pd), y0, yp, r.TolControlSV(1e-6, np.full(3, 1e-8)))
-        touts = 0.5 * np.arange(1, 11)
-        ms, st = timed_solve(ida, y0, yp, touts, args.reps)
-        nst = ida.get_num_steps()
-        print(json.dumps({"config": "lorenz63 DAE ensemble", "batch": B, "n": 3, "kernel": "thread", "ms": ms,
-                          "instances_per_s": B / (ms * 1e-3), "all_success": bool((st == 0).all().item()),
-                          "nst_min_max_mean": [int(nst.min()), int(nst.max()), float(nst.double().mean())]}), flush=True)
-        ida.close()
+        print(json.dumps(run_lorenz(args.lorenz_batch, args.reps)), flush=True)
 
     if "heat" in args.which:
-        B, M = args.heat_batch, 10
-        p = heat_ensemble_params(B, M=M, seed=1234)
-        yy0, yp0 = Heat2D.consistent_ic(p, M)
-        pd, y0, yp = to_dev(p, yy0, yp0)
-        ida = r.Ida(Heat2D(pd, M=M), y0, yp, r.TolControlSV(1e-6, np.full(M * M, 1e-8)))
-        touts = 0.01 * 2.0 ** np.arange(11)
-        ms, st = timed_solve(ida, y0, yp, touts, max(1, args.reps - 1))
-        nst, nje, nni = ida.get_num_steps(), ida.get_num_jac_evals(), ida.get_num_nonlin_solv_iters()
-        n = M * M
-        lu_flops = sum((n - k - 1) + 2 * (n - k - 1) ** 2 for k in range(n))
-        flops = float(nje.sum()) * lu_flops + float(nni.sum()) * (2 * n * n)
-        print(json.dumps({"config": "heat2d 10x10 DAE ensemble", "batch": B, "n": n, "kernel": "cta", "ms": ms,
-                          "instances_per_s": B / (ms * 1e-3), "all_success": bool((st == 0).all().item()),
-                          "nst_mean": float(nst.double().mean()), "nje_mean": float(nje.double().mean()),
-                          "lu_plus_solve_gflops": flops / (ms * 1e-3) * 1e-9}), flush=True)
-        ida.close()
+        print(json.dumps(run_heat(args.heat_batch, max(1, args.reps - 1))), flush=True)
 
     if "kernels" in args.which:
         B = 1 << 17

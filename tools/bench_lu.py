@@ -24,17 +24,31 @@ def flops_getrf(n):
     return sum((n - k - 1) + 2 * (n - k - 1) ** 2 for k in range(n))
 
 
-def main():
+def pivots_match_oracle(a, piv_dev, n, layout, sample=24):
+    """pivot sequences of `sample` matrices of the batch against the CPU oracle's dense_get_rf (bit-exact integers)"""
+    from oracle import binding as ob
+    batch = a.shape[0]
+    ids = np.unique(np.linspace(0, batch - 1, min(sample, batch)).astype(np.int64))
+    piv = piv_dev.cpu().numpy()
+    piv = piv.reshape(n, batch).T if layout == "soa" else piv.reshape(batch, n)
+    for b in ids:
+        _, pref, info = ob.getrf(a[b].numpy())
+        if info != 0 or not np.array_equal(pref, piv[b]):
+            return False
+    return True
+
+
+def run_lu(sizes=(3, 4, 8, 16, 32, 64, 100, 128, 256), reps=3, min_mb=512.0, batch_scale=1, fp64_peak_gops=None, emit=None,
+           check_pivots=True, flags=0):
+    """the config-4 table as a list of dicts (one per (n, op)); `emit` (if given) is called with every row"""
     import torch
-    import rust_ida_b200 as r
     from rust_ida_b200 import _lib
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--sizes", default="3,4,8,16,32,64,100,128,256")
-    ap.add_argument("--reps", type=int, default=3)
-    ap.add_argument("--min-mb", type=float, default=512.0)
-    ap.add_argument("--batch-scale", type=int, default=1,
-                    help="multiply the config's batch (throughput regime: many systems per resident CTA / warp)")
-    args = ap.parse_args()
+
+    class A:
+        pass
+    args = A()
+    args.sizes, args.reps, args.min_mb, args.batch_scale = ",".join(str(x) for x in sizes), reps, min_mb, batch_scale
+    rows = []
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -91,13 +105,34 @@ def main():
         else:
             x = xs[-1].cpu()
         res = (torch.einsum("bij,bj->bi", a, x) - rhs).abs().max().item()
+        piv_ok = pivots_match_oracle(a, piv[-1], n, layout) if check_pivots else None
         for op, ms in best.items():
             fl = flops_getrf(n) if op == "getrf" else (2 * n * n - n + n)
             by = (16 * n * n + 8 * n) if op == "getrf" else (8 * n * n + 24 * n)
             rate = batch / (ms * 1e-3)
-            print(json.dumps({"op": op, "n": n, "batch": batch, "layout": layout, "copies": copies, "ms": ms,
-                              "matrices_per_s": rate, "gflops": rate * fl * 1e-9, "algorithmic_gbs": rate * by * 1e-9,
-                              "hbm_frac_of_measured": rate * by * 1e-9 / hbm, "max_abs_residual": res}), flush=True)
+            row = {"op": op, "n": n, "batch": batch, "layout": layout, "copies": copies, "ms": ms,
+                   "matrices_per_s": rate, "gflops": rate * fl * 1e-9, "algorithmic_gbs": rate * by * 1e-9,
+                   "hbm_frac_of_measured": rate * by * 1e-9 / hbm, "max_abs_residual": res}
+            if fp64_peak_gops:
+                row["fp64_frac"] = rate * fl * 1e-9 / fp64_peak_gops
+            if op == "getrf" and piv_ok is not None:
+                row["pivots_bit_exact_vs_oracle"] = piv_ok
+            rows.append(row)
+            if emit:
+                emit(row)
+    return rows
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--sizes", default="3,4,8,16,32,64,100,128,256")
+    ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--min-mb", type=float, default=512.0)
+    ap.add_argument("--batch-scale", type=int, default=1,
+                    help="multiply the config's batch (throughput regime: many systems per resident CTA / warp)")
+    args = ap.parse_args()
+    run_lu([int(x) for x in args.sizes.split(",")], args.reps, args.min_mb, args.batch_scale,
+           emit=lambda row: print(json.dumps(row), flush=True))
 
 
 if __name__ == "__main__":
