@@ -176,6 +176,14 @@ int b200ida_solve(b200ida_ensemble* e, double tout, int itask, int32_t* status, 
 int b200ida_solve_ladder(b200ida_ensemble* e, const double* touts /* host */, int ntout, int itask, double* yy_traj,
                          int32_t* status, int mem);
 
+/* ida_id and ida_suppressalg (src/lib.rs:102,122): id[i] != 0 marks component i as differential, 0 as algebraic.  With
+ * suppressalg != 0 every local-error norm -- wrms_norm(.., mask = suppressalg), src/lib.rs:1353-1370: the first step-size
+ * guess (src/impl_solve.rs:122-126), the tolsf check (:289-293), test_error (src/lib.rs:983-1004) and complete_step
+ * (src/impl_complete_step.rs:76) -- becomes norm_wrms_masked (src/norm_rms.rs:49-57); the Newton convergence norm stays
+ * unmasked.  The reference keeps both at their defaults (no setter exists, src/lib.rs:318-321); id == NULL restores
+ * them.  Applies to the solves that follow, in every kernel family; not combinable with rootfinding or the trace. */
+int b200ida_set_id(b200ida_ensemble* e, const unsigned char* id /* [n], host */, int suppressalg);
+
 /* Per-attempt state trace of ONE instance -- the device side of the reference's `data_trace` feature, which
  * serialises the whole solver at the top of every step attempt (src/lib.rs:297-301, 635-639; scripts/data_trace.ipynb).
  * Until switched off (instance < 0), every b200ida_solve / b200ida_solve_ladder of this handle records (thread

@@ -88,6 +88,17 @@ def set_pow(fn_ptr):
     lib().oracle_set_pow(fn_ptr)
 
 
+def set_id(id_, suppressalg=True):
+    """ida_id / ida_suppressalg for the ensemble entry points that follow (process-global); set_id(None) switches it off"""
+    L = lib()
+    L.oracle_set_id.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    if id_ is None:
+        L.oracle_set_id(None, 0, 0)
+        return
+    m = np.ascontiguousarray(np.asarray(id_).reshape(-1) != 0, dtype=np.uint8)
+    L.oracle_set_id(m.ctypes.data, m.size, 1 if suppressalg else 0)
+
+
 def getrf(a):
     """a: (n, n) mathematical matrix.  Returns (LU as (n,n) mathematical, pivots int64, info)."""
     a = np.asarray(a, dtype=np.float64)

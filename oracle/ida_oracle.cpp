@@ -268,6 +268,7 @@ double norm_wrms_masked(const double* x, const double* w, const unsigned char* i
         const double p = (x[i] * w[i]) * (id[i] ? 1.0 : 0.0);
         acc = acc + p * p;
     }
+    CNT(n, 3 * n, 1, 1, 0);
     return std::sqrt(acc / (double)n);
 }
 
@@ -338,6 +339,16 @@ struct Ida {
     std::vector<double> atol;  // TolControlSV src/tol_control.rs:51-83
 
     bool setup_done = false;
+    // ida_id (true = differential component) and ida_suppressalg, src/lib.rs:102,122: when suppressalg is set, the
+    // local-error norms leave the algebraic components out (wrms_norm, src/lib.rs:1353-1370).  The reference has no
+    // setter (both stay false, :318); the oracle and the engine expose one (b200ida_set_id).
+    std::vector<unsigned char> id;
+    bool suppressalg = false;
+    // wrms_norm -- src/lib.rs:1353-1370: mask = false from the nonlinear solver, = suppressalg everywhere else
+    double wrms_norm(const double* x, const double* w, bool mask) const {
+        if (mask) return norm_wrms_masked(x, w, id.data(), n);
+        return norm_wrms(x, w, n);
+    }
     std::vector<double> phi;  // [6][n]
     double psi[MXORDP1], alpha[MXORDP1], beta[MXORDP1], sigma[MXORDP1], gamma[MXORDP1];
     std::vector<double> delta, ee, ewt, yy, yp, yypredict, yppredict, savres, x, tmp;
@@ -399,6 +410,7 @@ struct Ida {
         n = p.n;
         rtol = rtol_;
         atol.assign(atol_, atol_ + n);
+        if ((int)id.size() != n) id.assign(n, 0);
         phi.assign((size_t)MXORDP1 * n, 0.0);
         std::copy(yy0, yy0 + n, PHI(0));
         std::copy(yp0, yp0 + n, PHI(1));
@@ -575,7 +587,7 @@ struct Ida {
     // test_error -- src/lib.rs:967-1039 ; returns converged
     bool test_error(double ck, double& err_k, double& err_km1) {
         const double scalar_kk = (double)kk;
-        const double enorm_k = norm_wrms(ee.data(), ewt.data(), n);
+        const double enorm_k = wrms_norm(ee.data(), ewt.data(), suppressalg);
         err_k = sigma[kk] * enorm_k;
         const double terr_k = err_k * (scalar_kk + 1.0);
         CNT(1, 3, 0, 0, 0);  // incl. ck * enorm_k of the acceptance test
@@ -585,14 +597,14 @@ struct Ida {
             CNT(n, 2, 0, 0, 0);
             const double* phk = PHI(kk);
             for (int i = 0; i < n; ++i) delta[i] = phk[i] + ee[i];
-            const double enorm_km1 = norm_wrms(delta.data(), ewt.data(), n);
+            const double enorm_km1 = wrms_norm(delta.data(), ewt.data(), suppressalg);
             err_km1 = sigma[kk - 1] * enorm_km1;
             const double terr_km1 = scalar_kk * err_km1;
             if (kk > 2) {
                 CNT(n + 1, 2, 0, 0, 0);
                 const double* phkm1 = PHI(kk - 1);
                 for (int i = 0; i < n; ++i) delta[i] += phkm1[i];
-                const double enorm_km2 = norm_wrms(delta.data(), ewt.data(), n);
+                const double enorm_km2 = wrms_norm(delta.data(), ewt.data(), suppressalg);
                 const double err_km2 = sigma[kk - 2] * enorm_km2;
                 const double terr_km2 = (scalar_kk - 1.0) * err_km2;
                 if (std::fmax(terr_km1, terr_km2) <= terr_k) knew_ = kk - 1;
@@ -696,7 +708,7 @@ struct Ida {
             } else {
                 const double* php1 = PHI(kk + 1);
                 for (int i = 0; i < n; ++i) tmp[i] = ee[i] - php1[i];
-                const double enorm = norm_wrms(tmp.data(), ewt.data(), n);
+                const double enorm = wrms_norm(tmp.data(), ewt.data(), suppressalg);
                 err_kp1 = enorm / (double)(kk + 2);
                 const double terr_k = (double)(kk + 1) * err_k;
                 const double terr_kp1 = (double)(kk + 2) * err_kp1;
@@ -1122,7 +1134,7 @@ struct Ida {
             if (hh != 0.0 && (tout - tn) * hh < 0.0) return ST_ILL_INPUT;
             if (hh == 0.0) {
                 hh = 0.001 * tdist;
-                const double ypnorm = norm_wrms(PHI(1), ewt.data(), n);
+                const double ypnorm = wrms_norm(PHI(1), ewt.data(), suppressalg);
                 CNT(2, 5 + n, 1, 0, 0);  // tdist, troundoff, 0.001 tdist, 2/hh, rh, phi[1] *= hh, toldel
                 if (ypnorm > 2.0 / hh) {
                     hh = 0.5 / ypnorm;
@@ -1196,7 +1208,7 @@ struct Ida {
                     return ST_BAD_EWT;
                 }
             }
-            const double nrm = norm_wrms(PHI(0), ewt.data(), n);
+            const double nrm = wrms_norm(PHI(0), ewt.data(), suppressalg);
             tolsf = DBL_EPS * nrm;
             CNT(1, 2, 0, 0, 0);  // tolsf and the stop test (tn - tout) * hh after the step
             if (tolsf > 1.0) {
@@ -1239,7 +1251,20 @@ struct Ida {
 // =================================================================================================
 // C interface for ctypes (tests, bench cpu_baseline).  Everything here is test infrastructure.
 // =================================================================================================
+// ida_id / ida_suppressalg applied by the ensemble entry points to every instance they integrate (process-global, like
+// oracle_set_pow; oracle_set_id(nullptr, 0, 0) switches it off again)
+static std::vector<unsigned char> g_id;
+static bool g_suppressalg = false;
+static void apply_id(Ida& ida) {
+    if (!g_id.empty()) ida.id = g_id;
+    ida.suppressalg = g_suppressalg;
+}
+
 extern "C" {
+void oracle_set_id(const unsigned char* id, int n, int suppressalg) {
+    g_id.assign(id ? id : nullptr, id ? id + n : nullptr);
+    g_suppressalg = suppressalg != 0;
+}
 
 void oracle_set_pow(pow_fn_t f) { g_pow = f ? f : static_cast<double (*)(double, double)>(std::pow); }
 double oracle_pow(double x, double y) { return g_pow(x, y); }
@@ -1410,6 +1435,7 @@ int oracle_ensemble_solve(int kind, int n, int64_t B, int nparams, const double*
                 }
                 Ida ida;
                 Problem p{kind, n, par.data()};
+                apply_id(ida);
                 ida.init(p, y0.data(), yp0v.data(), rtol, atol);
                 double tret = 0.0;
                 for (int it = 0; it < ntout; ++it) {
@@ -1469,6 +1495,7 @@ int oracle_ensemble_dky(int kind, int n, int64_t B, int nparams, const double* p
             }
             Ida ida;
             Problem p{kind, n, par.data()};
+            apply_id(ida);
             ida.init(p, y0.data(), yp0v.data(), rtol, atol);
             double tret = 0.0;
             for (int it = 0; it < ntout; ++it) ida.solve(touts[it], tret);
@@ -1505,6 +1532,7 @@ int oracle_ensemble_events(int kind, int n, int64_t B, int nparams, const double
             }
             Ida ida;
             Problem p{kind, n, par.data()};
+            apply_id(ida);
             ida.init(p, y0.data(), yp0v.data(), rtol, atol);
             ida.ev = ev + (size_t)b * max_att;
             ida.ev_h = ev_h + (size_t)b * max_att;
@@ -1541,6 +1569,7 @@ int oracle_ensemble_ops(int kind, int n, int64_t B, int nparams, const double* p
             g_ops = OpCount();
             Ida ida;
             Problem p{kind, n, par.data()};
+            apply_id(ida);
             ida.init(p, y0.data(), yp0v.data(), rtol, atol);
             double tret = 0.0;
             for (int it = 0; it < ntout; ++it) ida.solve(touts[it], tret);
@@ -1564,6 +1593,7 @@ int oracle_single_trace(int kind, int n, const double* params, const double* yy0
                         int64_t* counters /*[9]*/) {
     Ida ida;
     Problem p{kind, n, params};
+    apply_id(ida);
     ida.init(p, yy0, yp0, rtol, atol);
     double tret = 0.0;
     int last = 0;
@@ -1589,6 +1619,7 @@ long oracle_attempt_trace(int kind, int n, const double* params, const double* y
                           int32_t* status /*[ntout]*/) {
     Ida ida;
     Problem p{kind, n, params};
+    apply_id(ida);
     ida.init(p, yy0, yp0, rtol, atol);
     ida.trace_d = dtrace;
     ida.trace_i = itrace;
@@ -1610,6 +1641,7 @@ long oracle_roots_run(int kind, int n, const double* params, const double* yy0, 
                       int64_t* counters, int32_t* status) {
     Ida ida;
     Problem p{kind, n, params};
+    apply_id(ida);
     ida.init(p, yy0, yp0, rtol, atol);
     ida.enable_roots();
     const int nr = ida.nrtfn;

@@ -37,7 +37,7 @@ char* last_error_buf() {
 #ifndef IDA_DEFER
 #define IDA_DEFER 1  // deferred output interpolation (DeferParams, ida_common.cuh); 0: interpolate in the solve kernel
 #endif
-template <class P, bool TRACE = false, bool ROOTS = false>
+template <class P, bool TRACE = false, bool ROOTS = false, bool MASK = false>
 __global__ void __launch_bounds__(THREAD_BLOCK, IDA_MIN_BLOCKS)
 ida_solve_thread_kernel(double* __restrict__ ds, int* __restrict__ is, const double* __restrict__ params, int64_t B,
                         TolN<P::N> tol, LadderParams lad, double* __restrict__ yy_traj, int32_t* __restrict__ status,
@@ -47,14 +47,18 @@ ida_solve_thread_kernel(double* __restrict__ ds, int* __restrict__ is, const dou
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // slot
     if (b >= B) return;
     const int64_t ob = perm ? (int64_t)perm[b] : b;  // caller-visible instance id of this slot
-    IdaThread<P> s;
+    IdaThread<P, MASK> s;
     s.sm = smem + threadIdx.x;
+    if constexpr (MASK) {
+#pragma unroll
+        for (int i = 0; i < P::N; ++i) s.idm[i] = tol.idmask[i];
+    }
     s.prob.load(params, B, b);
     s.load(ds, is, B, b);
     if constexpr (ROOTS) s.load_roots(rp, B, b);
     // the production instantiation defers the output interpolation to ida_interp_kernel; the TRACE and ROOTS
     // instantiations read yy / yp right after get_solution (trace frames, g(t, y)) and keep it in line
-    s.template solve_ladder<TRACE, ROOTS, !TRACE && !ROOTS && IDA_DEFER>(lad, tol, yy_traj, status, B, ob, tr, rp, df, b);
+    s.template solve_ladder<TRACE, ROOTS, !TRACE && !ROOTS && !MASK && IDA_DEFER>(lad, tol, yy_traj, status, B, ob, tr, rp, df, b);
     s.store(ds, is, B, b);
     if constexpr (ROOTS) {
         s.store_roots(rp, B, b);
@@ -139,13 +143,15 @@ template <class Team>
 __global__ void ida_solve_team_kernel(double* __restrict__ ds, int* __restrict__ is, const double* __restrict__ params,
                                       int64_t B, int n, int kind, int nparams, double rtol, const double* __restrict__ atol,
                                       LadderParams lad, double* __restrict__ yy_traj, int32_t* __restrict__ status,
-                                      unsigned arena_bytes, const int* __restrict__ perm, TraceParams tr) {
+                                      unsigned arena_bytes, const int* __restrict__ perm, TraceParams tr,
+                                      const double* __restrict__ idmask) {
     extern __shared__ __align__(16) unsigned char team_smem[];
     const int tpc = Team::teams_per_cta();
     IdaTeam<Team> s;
     s.bind(team_smem + (size_t)Team::team_in_cta() * arena_bytes, n);
     s.rtol = rtol;
     s.atol = atol;
+    s.idmask = idmask;  // null unless ida_suppressalg is set
     s.tr = tr;
     s.prob.kind = kind;
     s.prob.n = n;
@@ -354,6 +360,11 @@ struct b200ida_ensemble {
     TraceParams trace = {nullptr, nullptr, nullptr, 0, -1};  // b200ida_set_trace; id < 0: off
     RootParams roots = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0};  // b200ida_set_roots; max_ev == 0: off
     DevBuf root_d, root_i;  // the per-instance root state (engine-owned)
+    // ida_id / ida_suppressalg (src/lib.rs:102,122; b200ida_set_id): host copy as 1.0 / 0.0 and a device copy for the
+    // team kernels
+    double idmask[MAX_ATOL];
+    double* d_idmask = nullptr;
+    int suppressalg = 0;
     DevBuf snap, snap_valid;  // deferred output interpolation (DeferParams), grown to the longest ladder seen
     size_t snap_cap = 0, valid_cap = 0;
     // persistent device scratch for the host-buffer (end-to-end) entry points and the order builder: a few blocks
@@ -622,6 +633,7 @@ int b200ida_create(b200ida_ensemble** out, int problem, int n, int64_t batch, in
     e->rtol = rtol;
     memset(e->atol, 0, sizeof(e->atol));
     memcpy(e->atol, atol, sizeof(double) * n);
+    for (int i = 0; i < MAX_ATOL; ++i) e->idmask[i] = 0.0;  // ida_id is all false in Ida::new (src/lib.rs:321)
     e->stream = static_cast<cudaStream_t>(stream);
     const Layout lay(n);
     const size_t nd = (size_t)lay.ndouble() * batch, ni = (size_t)lay.nint() * batch;
@@ -650,9 +662,22 @@ int b200ida_destroy(b200ida_ensemble* e) {
     if (e->istate) cudaFree(e->istate);
     if (e->params) cudaFree(e->params);
     if (e->d_atol) cudaFree(e->d_atol);
+    if (e->d_idmask) cudaFree(e->d_idmask);
     if (e->perm) cudaFree(e->perm);
     e->scratch_free();
     delete e;
+    return B200IDA_OK;
+}
+
+int b200ida_set_id(b200ida_ensemble* e, const unsigned char* id, int suppressalg) {
+    if (!e) return set_error(B200IDA_ERR_ARG, "b200ida_set_id: null handle");
+    if (suppressalg && !id) return set_error(B200IDA_ERR_ARG, "b200ida_set_id: suppressalg needs an id vector");
+    B200_CUDA_TRY(cudaSetDevice(e->device));
+    for (int i = 0; i < e->n; ++i) e->idmask[i] = (id && id[i]) ? 1.0 : 0.0;
+    e->suppressalg = suppressalg ? 1 : 0;
+    if (!e->d_idmask) B200_CUDA_TRY(cudaMalloc(&e->d_idmask, (size_t)e->n * sizeof(double)));
+    B200_CUDA_TRY(cudaMemcpyAsync(e->d_idmask, e->idmask, (size_t)e->n * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    B200_CUDA_TRY(cudaStreamSynchronize(e->stream));  // e->idmask may change again before the copy would have run
     return B200IDA_OK;
 }
 
@@ -738,7 +763,22 @@ int b200ida_solve_ladder(b200ida_ensemble* e, const double* touts, int ntout, in
         TolN<3> tol;
         tol.rtol = e->rtol;
         for (int i = 0; i < 3; ++i) tol.atol[i] = e->atol[i];
-        if (e->roots.max_ev > 0) {
+        for (int i = 0; i < 3; ++i) tol.idmask[i] = e->idmask[i];
+        if (e->suppressalg && (e->roots.max_ev > 0 || e->trace.id >= 0))
+            return set_error(B200IDA_ERR_UNSUPPORTED, "suppressalg cannot be combined with rootfinding or the attempt trace");
+        if (e->suppressalg) {
+            // masked local-error norms: the MASK instantiation (interpolates in line; it is not the benchmarked path)
+            if (e->problem == B200IDA_PROBLEM_ROBERTS) {
+                B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_thread_kernel<Roberts, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                ida_solve_thread_kernel<Roberts, false, false, true><<<grid, tb, smem, e->stream>>>(e->dstate, e->istate, e->params, e->B, tol, lad,
+                                                                                                   d_traj, d_stat, e->perm);
+            } else {
+                B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_thread_kernel<Lorenz63, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                ida_solve_thread_kernel<Lorenz63, false, false, true><<<grid, tb, smem, e->stream>>>(e->dstate, e->istate, e->params, e->B, tol, lad,
+                                                                                                    d_traj, d_stat, e->perm);
+            }
+            count_launch();
+        } else if (e->roots.max_ev > 0) {
             if (e->problem != B200IDA_PROBLEM_ROBERTS)
                 return set_error(B200IDA_ERR_UNSUPPORTED, "rootfinding: the Roberts problem is the only one with root functions");
             const size_t rsmem = (size_t)(IdaThread<Roberts>::SMEM_DOUBLES + IdaThread<Roberts>::ROOT_DOUBLES) * tb * sizeof(double);
@@ -814,10 +854,12 @@ int b200ida_solve_ladder(b200ida_ensemble* e, const double* touts, int ntout, in
         const unsigned grid = (unsigned)(want < (int64_t)sms * occ ? want : (int64_t)sms * occ);  // persistent teams
         if (warp)
             ida_solve_team_kernel<WarpTeam><<<grid, tb, smem, e->stream>>>(e->dstate, e->istate, e->params, e->B, e->n, e->problem,
-                                                                           e->nparams, e->rtol, e->d_atol, lad, d_traj, d_stat, arena, e->perm, e->trace);
+                                                                           e->nparams, e->rtol, e->d_atol, lad, d_traj, d_stat, arena, e->perm, e->trace,
+                                                                           e->suppressalg ? e->d_idmask : nullptr);
         else
             ida_solve_team_kernel<CtaTeam><<<grid, tb, smem, e->stream>>>(e->dstate, e->istate, e->params, e->B, e->n, e->problem,
-                                                                          e->nparams, e->rtol, e->d_atol, lad, d_traj, d_stat, arena, e->perm, e->trace);
+                                                                          e->nparams, e->rtol, e->d_atol, lad, d_traj, d_stat, arena, e->perm, e->trace,
+                                                                          e->suppressalg ? e->d_idmask : nullptr);
         count_launch();
     }
     B200_CUDA_TRY(cudaGetLastError());

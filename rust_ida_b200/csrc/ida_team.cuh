@@ -161,6 +161,7 @@ struct IdaTeam {
     TeamScalars* S;
     TeamProblem prob;
     const double* atol;  // global, [n]
+    const double* idmask = nullptr;  // global, [n]: ida_id as 1.0 / 0.0 when ida_suppressalg is set, else null
     double rtol;
     TraceParams tr = {nullptr, nullptr, nullptr, 0, -1};  // b200ida_set_trace
 
@@ -269,9 +270,13 @@ struct IdaTeam {
 
     // ---- WRMS norm (src/norm_rms.rs:31-38): products by the team, ordered fold by the leader -> S->nrm --------
     // Callers must have a barrier between writing x and calling this; it ends with a barrier.
-    __device__ void wrms_to(const double* x, double* out) {
+    // masked = the call is a local-error norm (wrms_norm with mask = suppressalg, src/lib.rs:1353-1370): with
+    // ida_suppressalg set the algebraic components are left out like norm_wrms_masked does (src/norm_rms.rs:49-57)
+    __device__ void wrms_to(const double* x, double* out, bool masked = true) {
+        const bool m = masked && idmask != nullptr;
         for (int i = t; i < n; i += T) {
-            const double p = x[i] * ewt[i];
+            double p = x[i] * ewt[i];
+            if (m) p = p * idmask[i];
             prod[i] = p * p;
         }
         Team::sync();
@@ -457,7 +462,7 @@ struct IdaTeam {
                 lsolve();
                 for (int i = t; i < n; i += T) ee[i] += nd[i];
                 Team::sync();
-                wrms_to(nd, &S->nrm);
+                wrms_to(nd, &S->nrm, false);  // the nonlinear solver's norm is never masked
                 if (leader()) {  // ctest: src/ida_nls.rs:218-266
                     TeamScalars& s = *S;
                     const double delnrm = s.nrm;

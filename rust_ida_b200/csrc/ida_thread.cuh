@@ -56,6 +56,7 @@ template <int N>
 struct TolN {
     double rtol;
     double atol[N];
+    double idmask[N];  // ida_id as 1.0 (differential) / 0.0 (algebraic); read by the MASK instantiations only
 };
 
 #ifndef IDA_DIV_NOINLINE
@@ -393,7 +394,11 @@ __device__ __noinline__ unsigned root_check3(double* sm, P prob, unsigned gmask,
     return ier | (gmask << 1) | (evals << 8);
 }
 
-template <class P>
+// MASK: ida_suppressalg is set -- the local-error norms (wrms_norm with mask = suppressalg, src/lib.rs:1353-1370: ypnorm of
+// the first call, the tolsf norm, test_error, complete_step) leave the algebraic components out, as norm_wrms_masked
+// (src/norm_rms.rs:49-57) does: ((x_i w_i) m_i)^2 folded in index order, divided by n.  A separate instantiation, so the
+// production kernel carries none of it.
+template <class P, bool MASK = false>
 struct IdaThread {
     static constexpr int N = P::N;
     static constexpr int SMEM_DOUBLES = 6 * N + 30;  // phi + psi, alpha, beta, sigma, gamma
@@ -419,6 +424,26 @@ struct IdaThread {
     // ---- scratch ------------------------------------------------------------------------------------
     double yypredict[N], yppredict[N], delta[N], oldnrm;
     P prob;
+    double idm[N];  // TolN::idmask (MASK instantiations)
+
+    // wrms_norm(x, ewt, suppressalg): src/lib.rs:1353-1370
+    __device__ __forceinline__ double err_acc(const double (&x)[N]) const {
+        if constexpr (MASK) {
+            double acc = 0.0;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const double p = (x[i] * ewt[i]) * idm[i];
+                acc = acc + p * p;
+            }
+            return acc;
+        } else {
+            return wrms_acc<N>(x, ewt);
+        }
+    }
+    __device__ __forceinline__ double err_norm(const double (&x)[N]) const {
+        if constexpr (IDA_WRMS_INLINE) return wrms_tail_inline<N>(err_acc(x));
+        else return wrms_tail<N>(err_acc(x));
+    }
 
     // ---- HBM <-> registers / shared memory -----------------------------------------------------------
     __device__ __forceinline__ void load(const double* __restrict__ ds, const int* __restrict__ is, int64_t B, int64_t b) {
@@ -824,11 +849,11 @@ struct IdaThread {
         for (int i = 0; i < N; ++i) d2[i] = delta[i] + phi(km1, i);
         double enorm_k, enorm_km1, enorm_km2;
         if constexpr (IDA_WRMS_INLINE) {
-            enorm_k = wrms_inline<N>(ee, ewt);
-            enorm_km1 = wrms_inline<N>(delta, ewt);
-            enorm_km2 = wrms_inline<N>(d2, ewt);
+            enorm_k = err_norm(ee);
+            enorm_km1 = err_norm(delta);
+            enorm_km2 = err_norm(d2);
         } else {
-            wrms_tail3<N>(wrms_acc<N>(ee, ewt), wrms_acc<N>(delta, ewt), wrms_acc<N>(d2, ewt), enorm_k, enorm_km1, enorm_km2);
+            wrms_tail3<N>(err_acc(ee), err_acc(delta), err_acc(d2), enorm_k, enorm_km1, enorm_km2);
         }
         err_k = sigma(kk) * enorm_k;
         const double terr_k = err_k * (scalar_kk + 1.0);
@@ -935,7 +960,7 @@ struct IdaThread {
                 double t[N];
 #pragma unroll
                 for (int i = 0; i < N; ++i) t[i] = ee[i] - phi(kk + 1, i);
-                const double enorm = wrms<N>(t, ewt);
+                const double enorm = err_norm(t);
                 err_kp1 = enorm / (double)(kk + 2);
                 const double terr_k = (double)(kk + 1) * err_k;
                 const double terr_kp1 = (double)(kk + 2) * err_kp1;
@@ -1228,7 +1253,7 @@ struct IdaThread {
         double p1[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) p1[i] = phi(1, i);
-        const double ypnorm = wrms<N>(p1, ewt);
+        const double ypnorm = err_norm(p1);
         if (ypnorm > 2.0 / hh) hh = 0.5 / ypnorm;
         if (tout < tn) hh = -hh;
         if constexpr (HMAX_INV != 0.0) {
@@ -1353,7 +1378,7 @@ struct IdaThread {
                         double p0[N];
 #pragma unroll
                         for (int i = 0; i < N; ++i) p0[i] = phi(0, i);
-                        const double nrm = wrms<N>(p0, ewt);
+                        const double nrm = err_norm(p0);
                         tolsf = DBL_EPS * nrm;
                         if (tolsf > 1.0) {
                             tolsf *= 10.0;

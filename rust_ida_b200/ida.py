@@ -38,7 +38,7 @@ class IdaSolveStatus(enum.IntEnum):
 def set_default_reorder(mode):
     """"off" | "on" | "auto": internal warp-coherence ordering of instances (include/b200ida.h); results and
     the caller-visible instance order are unaffected."""
-    self._call("b200ida_set_default_reorder", {"off": 0, "on": 1, "auto": 2}[mode])
+    _lib.check(_lib.lib().b200ida_set_default_reorder({"off": 0, "on": 1, "auto": 2}[mode]))
 
 
 class AttemptTrace:
@@ -121,6 +121,18 @@ class Ida:
     def set_kernel(self, kernel):
         """choose the kernel family ("auto", "thread", "warp", "cta"); results are bit-identical"""
         self._call("b200ida_set_kernel", self._h, self.KERNELS[kernel])
+
+    def set_id(self, id_, suppressalg=True):
+        """ida_id / ida_suppressalg (src/lib.rs:102,122): id_[i] truthy = differential component, falsy = algebraic.
+        With suppressalg the local-error norms leave the algebraic components out (norm_wrms_masked,
+        src/norm_rms.rs:49-57).  set_id(None) restores the reference's defaults."""
+        if id_ is None:
+            self._call("b200ida_set_id", self._h, None, 0)
+            return
+        m = np.ascontiguousarray(np.asarray(id_).reshape(-1) != 0, dtype=np.uint8)
+        if m.size != self.n:
+            raise ValueError("id has %d entries, the systems have %d components" % (m.size, self.n))
+        self._call("b200ida_set_id", self._h, m.ctypes.data, 1 if suppressalg else 0)
 
     def reinit(self, yy0, yp0, params=None):
         """fresh Ida::new state for every instance (t = 0, counters 0), keeping the device allocation"""

@@ -26,5 +26,6 @@ def _oracle_pow_is_libm_again():
         from oracle import binding as ob
         if ob._lib is not None:
             ob.set_pow(None)
+            ob.set_id(None)
     except Exception:
         pass

@@ -16,13 +16,15 @@ COUNTERS = ("nst", "nre", "nje", "nni", "netf", "ncfn", "nsetups", "nattempts")
 
 
 def run_engine(problem_cls, params, yy0, yp0, rtol, atol, touts, ladder, device_buffers=False, kernel="auto",
-               problem_kw=None):
+               problem_kw=None, id_mask=None):
     import torch
     import rust_ida_b200 as r
     if device_buffers:
         params, yy0, yp0 = (torch.from_numpy(np.ascontiguousarray(v)).cuda() for v in (params, yy0, yp0))
     ida = r.Ida(problem_cls(params, **(problem_kw or {})), yy0, yp0, r.TolControlSV(rtol, atol))
     ida.set_kernel(kernel)
+    if id_mask is not None:
+        ida.set_id(id_mask, suppressalg=True)
     if ladder:
         status, traj = ida.solve_ladder(touts)
     else:
@@ -484,4 +486,86 @@ def test_get_dky_matches_the_oracle(problem, device_buffers):
     if device_buffers:
         y_at, yy = y_at.cpu().numpy(), yy.cpu().numpy()
     np.testing.assert_allclose(y_at, yy, rtol=1e-9, atol=1e-14)
+    ida.close()
+
+
+# ---- ida_id / ida_suppressalg inside the stepper -------------------------------------------------
+@pytest.mark.parametrize("kernel", ["thread", "warp"])
+def test_suppressalg_roberts_matches_the_oracle(kernel):
+    """Roberts' third equation is algebraic (y1 + y2 + y3 = 1): with id = [1, 1, 0] and suppressalg the local-error
+    norms (src/lib.rs:1353-1370 -> norm_wrms_masked, src/norm_rms.rs:49-57) leave y3 out.  Same bits as the oracle, and
+    a different integration from the unmasked one (the option really reaches the step-size controller)."""
+    from rust_ida_b200 import Roberts
+    from rust_ida_b200.problems import roberts_ensemble_params
+    ob, _ = parity_oracle()
+    B = 777 if kernel == "thread" else 96
+    p = roberts_ensemble_params(B, seed=77)
+    yy0, yp0 = Roberts.consistent_ic(p)
+    ob.set_id([1, 1, 0], True)
+    ref = ob.ensemble_solve(ob.PK_ROBERTS, 3, p, yy0, yp0, ROBERTS_RTOL, ROBERTS_ATOL, ROBERTS_TOUTS, nthreads=8, want_traj=True)
+    ob.set_id(None)
+    plain = ob.ensemble_solve(ob.PK_ROBERTS, 3, p, yy0, yp0, ROBERTS_RTOL, ROBERTS_ATOL, ROBERTS_TOUTS, nthreads=8)
+    g = run_engine(Roberts, p, yy0, yp0, ROBERTS_RTOL, ROBERTS_ATOL, ROBERTS_TOUTS, ladder=True, device_buffers=True,
+                   kernel=kernel, id_mask=[1, 1, 0])
+    compare(g, ref)
+    assert (g["status"] == 0).all()
+    assert (ref["counters"]["nst"] != plain["counters"]["nst"]).mean() > 0.5
+
+
+def test_suppressalg_heat_boundary_rows_match_the_oracle():
+    """the heat problem's boundary rows are algebraic (u = 0): masked out of the error norms, CTA-per-system kernel"""
+    from rust_ida_b200 import Heat2D
+    from rust_ida_b200.problems import heat_ensemble_params
+    ob, _ = parity_oracle()
+    M, B = 10, 48
+    n = M * M
+    idm = np.zeros((M, M), dtype=np.uint8)
+    idm[1:-1, 1:-1] = 1
+    p = heat_ensemble_params(B, M=M, seed=3)
+    yy0, yp0 = Heat2D.consistent_ic(p, M)
+    touts = 0.01 * 2.0 ** np.arange(11)
+    rtol, atol = 1e-6, np.full(n, 1e-8)
+    ob.set_id(idm.ravel(), True)
+    ref = ob.ensemble_solve(ob.PK_HEAT2D, n, p, yy0, yp0, rtol, atol, touts, nthreads=8, want_traj=True)
+    ob.set_id(None)
+    plain = ob.ensemble_solve(ob.PK_HEAT2D, n, p, yy0, yp0, rtol, atol, touts, nthreads=8)
+    g = run_engine(Heat2D, p, yy0, yp0, rtol, atol, touts, ladder=True, kernel="cta", problem_kw={"M": M}, id_mask=idm.ravel())
+    compare(g, ref)
+    assert not np.array_equal(ref["counters"]["nst"], plain["counters"]["nst"])
+
+
+def test_suppressalg_cannot_be_combined_with_roots():
+    import torch
+    import rust_ida_b200 as r
+    from rust_ida_b200._lib import B200IdaError
+    p = np.array(r.Roberts.DEFAULT).reshape(3, 1).repeat(8, axis=1).copy()
+    yy0, yp0 = r.Roberts.consistent_ic(p)
+    ida = r.Ida(r.Roberts(torch.from_numpy(p).cuda()), torch.from_numpy(yy0).cuda(), torch.from_numpy(yp0).cuda(),
+                r.TolControlSV(ROBERTS_RTOL, ROBERTS_ATOL))
+    ida.enable_roots(8)
+    ida.set_id([1, 1, 0], True)
+    with pytest.raises(B200IdaError):
+        ida.solve_ladder(ROBERTS_TOUTS)
+    ida.close()
+
+
+# ---- row f4: the reference's data_trace JSON from a device trace --------------------------------------------------------------
+def test_device_trace_serialises_to_the_reference_json(tmp_path):
+    import json
+    import torch
+    import rust_ida_b200 as r
+    from rust_ida_b200 import trace_json
+    p = r.problems.roberts_ensemble_params(64, seed=1234)
+    p[:, 5] = r.Roberts.DEFAULT
+    yy0, yp0 = r.Roberts.consistent_ic(p)
+    ida = r.Ida(r.Roberts(torch.from_numpy(p).cuda()), torch.from_numpy(yy0).cuda(), torch.from_numpy(yp0).cuda(),
+                r.TolControlSV(ROBERTS_RTOL, ROBERTS_ATOL))
+    tr = ida.trace(5)
+    ida.solve_ladder(ROBERTS_TOUTS, want_traj=False)
+    d, q = tr.rows()
+    path = tmp_path / "roberts_b200.json"
+    assert trace_json.write(str(path), d, q, 3, ROBERTS_RTOL, ROBERTS_ATOL) == 377
+    data = json.load(open(path))["data"]
+    nst = [s["counters"]["ida_nst"] for s in data]
+    assert nst[0] == 0 and nst[-1] == 361 and data[-1]["nlp"]["lp"]["nje"] == 60
     ida.close()
