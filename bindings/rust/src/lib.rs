@@ -35,6 +35,12 @@ extern "C" {
                                 mem: c_int, stream: *mut c_void) -> c_int;
     pub fn b200ida_wrms_masked_batched(x: *const f64, w: *const f64, id: *const u8, out: *mut f64, n: c_int, batch: i64,
                                        layout: c_int, mem: c_int, stream: *mut c_void) -> c_int;
+    /// NLSolver level (crates/nonlinear/src/traits.rs:129-209): Newton::solve over a batch of device NLProblems
+    pub fn b200ida_newton_batched(nlp_kind: c_int, n: c_int, batch: i64, y0: *const f64, w: *const f64, tol: f64,
+                                  maxiters: c_int, call_lsetup: c_int, y: *mut f64, status: *mut i32, niters: *mut i32,
+                                  nconvfails: *mut i32, mem: c_int, stream: *mut c_void) -> c_int;
+    /// ida_id / ida_suppressalg (src/lib.rs:102,122)
+    pub fn b200ida_set_id(e: *mut RawEnsemble, id: *const u8, suppressalg: c_int) -> c_int;
     pub fn b200ida_create(out: *mut *mut RawEnsemble, problem: c_int, n: c_int, batch: i64, nparams: c_int,
                           params: *const f64, yy0: *const f64, yp0: *const f64, rtol: f64, atol: *const f64,
                           mem: c_int, device: c_int, stream: *mut c_void) -> c_int;
@@ -229,4 +235,59 @@ impl Drop for EnsembleIda {
     fn drop(&mut self) {
         unsafe { b200ida_destroy(self.h) };
     }
+}
+
+
+// ---- NLSolver level ------------------------------------------------------------------------------------------------
+/// Problem kinds with a device functor (include/b200ida.h B200IDA_NLP_*)
+pub const NLP_QUAD3: c_int = 0;
+
+/// `impl NLSolver<f64, D>`-shaped wrapper over a batch: `GpuNewton::new(maxiters)` then `solve(..)`, with the reference's
+/// getters.  `nonlinear::NLSolver::solve` takes the problem as `&mut NLP where NLP: NLProblem<T, D>`; a GPU kernel cannot
+/// call those closures per iteration, so the batched form takes the problem KIND instead and returns one
+/// `Result`-equivalent status per system: 0 = Ok(()), 1 = Err(Error::ConvergenceRecover {}), -col =
+/// Err(Error::LinearSetupFailed { source: LUFactFail { col } }) (crates/nonlinear/src/lib.rs:10-35).
+pub struct GpuNewton {
+    maxiters: usize,
+    niters: Vec<usize>,
+    nconvfails: Vec<usize>,
+    curiter: Vec<usize>,
+}
+
+impl GpuNewton {
+    /// NLSolver::new (traits.rs:136)
+    pub fn new(maxiters: usize) -> Self {
+        GpuNewton { maxiters, niters: Vec::new(), nconvfails: Vec::new(), curiter: Vec::new() }
+    }
+
+    /// NLSolver::solve (traits.rs:176-193) for `batch` systems; y0, y, w are SoA [n][batch]
+    pub fn solve(&mut self, nlp_kind: c_int, n: usize, batch: usize, y0: &[f64], y: &mut [f64], w: &[f64], tol: f64,
+                 call_lsetup: bool) -> Result<Vec<i32>, EngineError> {
+        assert_eq!(y0.len(), n * batch);
+        assert_eq!(y.len(), n * batch);
+        assert_eq!(w.len(), n * batch);
+        let mut st = vec![0i32; batch];
+        let mut ni = vec![0i32; batch];
+        let mut nc = vec![0i32; batch];
+        check(unsafe {
+            b200ida_newton_batched(nlp_kind, n as c_int, batch as i64, y0.as_ptr(), w.as_ptr(), tol, self.maxiters as c_int,
+                                   call_lsetup as c_int, y.as_mut_ptr(), st.as_mut_ptr(), ni.as_mut_ptr(), nc.as_mut_ptr(),
+                                   MEM_HOST, std::ptr::null_mut())
+        })?;
+        if self.niters.len() != batch {
+            self.niters = vec![0; batch];
+            self.nconvfails = vec![0; batch];
+        }
+        for b in 0..batch {
+            self.niters[b] += ni[b] as usize;
+            self.nconvfails[b] += nc[b] as usize;
+        }
+        self.curiter = ni.iter().map(|&v| v as usize).collect();
+        Ok(st)
+    }
+
+    /// NLSolver::get_num_iters / get_cur_iter / get_num_conv_fails (traits.rs:196-208), per system
+    pub fn get_num_iters(&self) -> &[usize] { &self.niters }
+    pub fn get_cur_iter(&self) -> &[usize] { &self.curiter }
+    pub fn get_num_conv_fails(&self) -> &[usize] { &self.nconvfails }
 }

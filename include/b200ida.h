@@ -91,6 +91,26 @@ int b200ida_wrms_masked_batched(const double* x, const double* w, const unsigned
                                 int64_t batch, int layout, int mem, void* stream);
 
 /* =====================================================================================================
+ * Level 1.5 -- batched nonlinear solver.  Mirrors `NLSolver<T, D>` (crates/nonlinear/src/traits.rs:129-209) as implemented
+ * by `Newton<T, D>` (crates/nonlinear/src/newton.rs:14-167): one `Newton::new(maxiters)` + `solve(problem, y0, y, w, tol,
+ * call_lsetup)` per system of the batch.  The `NLProblem` callbacks (traits.rs:5-127: sys / setup / solve / ctest) are
+ * device functors selected by `nlp_kind` (a kernel cannot call back into host generics once per Newton iteration):
+ *   B200IDA_NLP_QUAD3  the reference's known-answer problem, newton.rs:192-343 (n = 3, analytic Jacobian, Dense LU,
+ *                      ctest = wrms(del, w) <= tol).
+ * y0, w, y: [n][batch] SoA.  Per-system results (each pointer may be NULL):
+ *   status      0 = Ok(()), 1 = Err(Error::ConvergenceRecover), -col = Err(Error::LinearSetupFailed{LUFactFail{col}})
+ *               (crates/nonlinear/src/lib.rs:10-35, crates/linear/src/dense.rs:43,121; col is 1-based)
+ *   niters      NLSolver::get_num_iters     (newton.rs:169-171)
+ *   nconvfails  NLSolver::get_num_conv_fails (newton.rs:177-179)
+ * Deviation shared with the oracle: "ConvergenceRecover while the Jacobian is current" returns the recoverable error
+ * (SUNDIALS semantics) where the reference's loop does not terminate (newton.rs:146-153).
+ * ===================================================================================================== */
+#define B200IDA_NLP_QUAD3 0
+int b200ida_newton_batched(int nlp_kind, int n, int64_t batch, const double* y0, const double* w, double tol, int maxiters,
+                           int call_lsetup, double* y, int32_t* status, int32_t* niters, int32_t* nconvfails, int mem,
+                           void* stream);
+
+/* =====================================================================================================
  * Level 2 -- ensemble IDA.  One handle = `batch` independent instances of
  *   Ida<P, Dense, Newton, TolControlSV>   (src/lib.rs:89-95)
  * whose whole solve() loop -- ewt_set, set_coeffs, predict, Newton with res/jac/getrf/getrs, ctest,
@@ -102,6 +122,9 @@ int b200ida_wrms_masked_batched(const double* x, const double* w, const unsigned
 #define B200IDA_PROBLEM_ROBERTS 0  /* src/sample_problems/roberts.rs, params (k1,k2,k3) = (0.04,1e4,3e7), n=3 */
 #define B200IDA_PROBLEM_LORENZ63 1 /* tests/lorenz63.rs posed as F = y' - f(y), params (p,r,b), n=3 */
 #define B200IDA_PROBLEM_HEAT2D 2   /* SUNDIALS idaHeat2D-style M x M grid, params (coeff), n=M*M */
+#define B200IDA_PROBLEM_USER 3     /* a user-supplied Residual / Jacobian (/ Root) functor (src/traits.rs:28-89) compiled in
+                                      with `make -C rust_ida_b200/csrc user PROBLEM_HDR=my_problem.cuh` -- INTEGRATION.md,
+                                      "Adding a problem"; n, nparams and the number of root functions come from the functor */
 
 /* IdaTask (src/lib.rs:51-55).  Only Normal is on the hot path. */
 #define B200IDA_TASK_NORMAL 0

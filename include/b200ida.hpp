@@ -61,6 +61,39 @@ class Dense {
     std::vector<int32_t> info_;
 };
 
+// `impl NLSolver<f64, D> for Newton<f64, D>` over a batch (crates/nonlinear/src/traits.rs:129-209, newton.rs:14-167).
+// The NLProblem is a device functor selected by kind (B200IDA_NLP_*).  Vectors SoA [n][batch].
+class Newton {
+  public:
+    explicit Newton(int maxiters) : maxiters_(maxiters) {}
+    static Newton new_(int maxiters) { return Newton(maxiters); }  // NLSolver::new, traits.rs:136
+    // NLSolver::solve, traits.rs:176-193; returns the per-system status (0 Ok, 1 ConvergenceRecover, -col LinearSetupFailed)
+    std::vector<int32_t> solve(int nlp_kind, int n, int64_t batch, const double* y0, double* y, const double* w, double tol,
+                               bool call_lsetup) {
+        std::vector<int32_t> st((size_t)batch), ni((size_t)batch), nc((size_t)batch);
+        check(b200ida_newton_batched(nlp_kind, n, batch, y0, w, tol, maxiters_, call_lsetup ? 1 : 0, y, st.data(), ni.data(),
+                                     nc.data(), B200IDA_MEM_HOST, nullptr));
+        if (niters_.size() != (size_t)batch) {
+            niters_.assign((size_t)batch, 0);
+            nconvfails_.assign((size_t)batch, 0);
+        }
+        for (size_t b = 0; b < (size_t)batch; ++b) {
+            niters_[b] += ni[b];
+            nconvfails_[b] += nc[b];
+        }
+        curiter_ = ni;
+        return st;
+    }
+    const std::vector<int64_t>& get_num_iters() const { return niters_; }           // traits.rs:196
+    const std::vector<int32_t>& get_cur_iter() const { return curiter_; }           // traits.rs:202
+    const std::vector<int64_t>& get_num_conv_fails() const { return nconvfails_; }  // traits.rs:205
+
+  private:
+    int maxiters_;
+    std::vector<int64_t> niters_, nconvfails_;
+    std::vector<int32_t> curiter_;
+};
+
 enum class IdaTask { Normal = B200IDA_TASK_NORMAL };  // src/lib.rs:51-55
 
 // Ida<P, Dense, Newton, TolControlSV> for an ensemble.

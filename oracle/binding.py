@@ -72,7 +72,7 @@ def lib():
                                           _dp, np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")]
         L.oracle_newton_quad3.restype = C.c_int
         L.oracle_newton_quad3.argtypes = [_dp, _dp, C.c_double, C.c_int, _dp, C.POINTER(C.c_long),
-                                          C.POINTER(C.c_long)]
+                                          C.POINTER(C.c_long), C.c_int]
         L.oracle_ensemble_solve.restype = C.c_int
         L.oracle_ensemble_solve.argtypes = [
             C.c_int, C.c_int, C.c_int64, C.c_int, _dp, _dp, _dp, C.c_double, _dp, _dp, C.c_int, C.c_int,
@@ -207,11 +207,13 @@ class Unit:
         return r, out
 
 
-def newton_quad3(y0, w, tol, maxiters):
+def newton_quad3(y0, w, tol, maxiters, call_lsetup=True):
+    """Newton::solve on the reference's test problem; returns (status: 0 ok, 1 ConvergenceRecover, -col singular
+    Jacobian column, y, niters, nconvfails)"""
     y = np.zeros(3)
     ni, nc = C.c_long(), C.c_long()
     r = lib().oracle_newton_quad3(np.ascontiguousarray(y0, dtype=np.float64), np.ascontiguousarray(w, dtype=np.float64),
-                                  tol, maxiters, y, C.byref(ni), C.byref(nc))
+                                  tol, maxiters, y, C.byref(ni), C.byref(nc), 1 if call_lsetup else 0)
     return r, y, ni.value, nc.value
 
 
@@ -286,7 +288,7 @@ def roots_run(kind, params, yy0, yp0, rtol, atol, touts, max_ev=64):
     Returns dict: t (nev,), iroots (nev, nr), y (nev, n), yy (n,), counters {.., nge}, status (ntout,)."""
     yy0 = np.ascontiguousarray(yy0, dtype=np.float64)
     n = yy0.size
-    nr = 2 if kind == PK_ROBERTS else 0
+    nr = 2 if kind == PK_ROBERTS else (1 if kind == PK_LORENZ63 else 0)
     touts = np.ascontiguousarray(touts, dtype=np.float64)
     ev_t = np.zeros(max_ev)
     ev_r = np.zeros((max_ev, max(nr, 1)))

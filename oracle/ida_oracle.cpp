@@ -96,11 +96,15 @@ struct Problem {
     const double* p;  // per-instance parameters
 
     // Root::num_roots / Root::root -- src/traits.rs:72-89 ; Roberts: src/sample_problems/roberts.rs:99-113
-    int num_roots() const { return kind == PK_ROBERTS ? 2 : 0; }
+    // Lorenz: g0 = y0, the x = 0 crossings (not in the reference; the oracle side of the user-problem example,
+    // examples/user_problem_lorenz_root.cuh -- rootfinding is only active when a caller enables it)
+    int num_roots() const { return kind == PK_ROBERTS ? 2 : (kind == PK_LORENZ63 ? 1 : 0); }
     void root(double /*t*/, const double* y, const double* /*yp*/, double* gout) const {
         if (kind == PK_ROBERTS) {
             gout[0] = y[0] - 0.0001;
             gout[1] = y[2] - 0.01;
+        } else if (kind == PK_LORENZ63) {
+            gout[0] = y[0];
         }
     }
 
@@ -1388,7 +1392,7 @@ struct Quad3 {
         const double col0[3] = {2.0 * x, 4.0 * x, 6.0 * x}, col1[3] = {2.0 * y, 2.0 * y, -4.0},
                      col2[3] = {2.0 * z, -4.0, 2.0 * z};
         for (int i = 0; i < 3; ++i) { a[i] = col0[i]; a[3 + i] = col1[i]; a[6 + i] = col2[i]; }
-        return dense_get_rf(a, piv, 3);
+        return -dense_get_rf(a, piv, 3);  // 0, or -(1-based singular column): LinearSetupFailed { LUFactFail { col } }
     }
     void lsolve(const double*, double* b) { dense_get_rs(a, piv, b, 3); }
     int ctest(int, const double*, const double* del, double tol, const double* w) {
@@ -1396,12 +1400,14 @@ struct Quad3 {
     }
 };
 int oracle_newton_quad3(const double* y0, const double* w, double tol, int maxiters, double* y, long* niters,
-                        long* nconvfails) {
+                        long* nconvfails, int call_lsetup) {
     Newton nls;
     nls.maxiters = maxiters;
     nls.delta.assign(3, 0.0);
     Quad3 p;
-    const int r = nls.solve(p, 3, y0, y, w, tol, true);
+    for (int i = 0; i < 9; ++i) p.a[i] = 0.0;  // Matrix3::zeros() (newton.rs:316)
+    for (int i = 0; i < 3; ++i) p.piv[i] = 0;
+    const int r = nls.solve(p, 3, y0, y, w, tol, call_lsetup != 0);
     *niters = nls.niters;
     *nconvfails = nls.nconvfails;
     return r;

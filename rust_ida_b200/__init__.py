@@ -14,6 +14,7 @@ from . import _lib
 from ._lib import B200IdaError, build, device_count
 from .ida import Ida, IdaSolveStatus, IdaTask, set_default_reorder
 from .linear import Dense, LSolverType, LUFactFail, norm_wrms, norm_wrms_masked
+from .nonlinear import Newton, Quad3Problem
 from .problems import Heat2D, Lorenz63, Roberts
 from .tol_control import TolControlSS, TolControlSV
 

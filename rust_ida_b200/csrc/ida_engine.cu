@@ -13,7 +13,7 @@
 #include "host_util.h"
 #include "ida_common.cuh"
 #include "ida_team.cuh"
-#include "ida_thread.cuh"
+#include "ida_thread_launch.cuh"
 #include "problems.cuh"
 
 namespace b200ida {
@@ -23,120 +23,16 @@ long long& launch_counter() {
     return n;
 }
 
+static const UserProblemHooks* g_user_hooks = nullptr;
+void register_user_problem(const UserProblemHooks* h) { g_user_hooks = h; }
+const UserProblemHooks* user_problem_hooks() { return g_user_hooks; }
+
 char* last_error_buf() {
     static thread_local char buf[512] = "";
     return buf;
 }
 
 // ---- kernels -----------------------------------------------------------------------------------------
-
-// Thread-per-instance solve over a ladder of output times (ida_thread.cuh).
-#ifndef IDA_MIN_BLOCKS
-#define IDA_MIN_BLOCKS 3  // 168 regs, 12 warps/SM: measured faster than 4 (128 regs + spills) and 2
-#endif
-#ifndef IDA_DEFER
-#define IDA_DEFER 1  // deferred output interpolation (DeferParams, ida_common.cuh); 0: interpolate in the solve kernel
-#endif
-template <class P, bool TRACE = false, bool ROOTS = false, bool MASK = false>
-__global__ void __launch_bounds__(THREAD_BLOCK, IDA_MIN_BLOCKS)
-ida_solve_thread_kernel(double* __restrict__ ds, int* __restrict__ is, const double* __restrict__ params, int64_t B,
-                        TolN<P::N> tol, LadderParams lad, double* __restrict__ yy_traj, int32_t* __restrict__ status,
-                        const int* __restrict__ perm, TraceParams tr = TraceParams(), RootParams rp = RootParams(),
-                        DeferParams df = DeferParams()) {
-    extern __shared__ double smem[];
-    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // slot
-    if (b >= B) return;
-    const int64_t ob = perm ? (int64_t)perm[b] : b;  // caller-visible instance id of this slot
-    IdaThread<P, MASK> s;
-    s.sm = smem + threadIdx.x;
-    if constexpr (MASK) {
-#pragma unroll
-        for (int i = 0; i < P::N; ++i) s.idm[i] = tol.idmask[i];
-    }
-    s.prob.load(params, B, b);
-    s.load(ds, is, B, b);
-    if constexpr (ROOTS) s.load_roots(rp, B, b);
-    // the production instantiation defers the output interpolation to ida_interp_kernel; the TRACE and ROOTS
-    // instantiations read yy / yp right after get_solution (trace frames, g(t, y)) and keep it in line
-    s.template solve_ladder<TRACE, ROOTS, !TRACE && !ROOTS && !MASK && IDA_DEFER>(lad, tol, yy_traj, status, B, ob, tr, rp, df, b);
-    s.store(ds, is, B, b);
-    if constexpr (ROOTS) {
-        s.store_roots(rp, B, b);
-        if (rp.nge_out) rp.nge_out[ob] = s.nge;
-    }
-}
-
-// Second pass of the deferred output interpolation (DeferParams, ida_common.cuh): get_solution (src/lib.rs:1274-1343)
-// for every (instance, output time) whose call returned through stop_test2, from the snapshot the solve kernel took.
-// One thread per (slot, output time); the snapshot rows of consecutive threads are consecutive in HBM, each thread
-// pulls its 224-byte row with 16-byte loads issued back to back and interpolates from registers -- an HBM-streaming
-// kernel (algorithmic bytes: one row read, n doubles written).  y(tout) goes to yy_traj (caller order) when one was
-// asked for; y, y' of the LAST call go to the persistent state, where the reference's solve() leaves them.  The
-// arithmetic is get_solution_fn's (ida_thread.cuh) operation for operation, with the order loop unrolled and guarded.
-template <int N>
-__global__ void __launch_bounds__(256)
-ida_interp_kernel(double* __restrict__ ds, int64_t B, LadderParams lad, DeferParams df, double* __restrict__ yy_traj,
-                  const int* __restrict__ perm) {
-    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // slot * ntout + it
-    if (g >= B * lad.ntout) return;
-    if (!df.valid[g]) return;
-    const int64_t b = g / lad.ntout;
-    const int it = (int)(g - b * lad.ntout);
-    constexpr Layout lay(N);
-    constexpr int SD = snap_doubles(N);
-    static_assert(SD % 2 == 0, "rows are read as 16-byte pairs");
-    double v[SD];
-    const double2* row = reinterpret_cast<const double2*>(df.snap + (size_t)g * SD);
-#pragma unroll
-    for (int k = 0; k < SD / 2; ++k) {
-        const double2 t = row[k];
-        v[2 * k] = t.x;
-        v[2 * k + 1] = t.y;
-    }
-    const int kused = (int)v[6 * N + 6];
-    const double tn = v[6 * N + 7], hh = v[6 * N + 8], hused = v[6 * N + 9], t = lad.touts[it];
-    const double sgn = (hh > 0.0 || (hh == 0.0 && !signbit(hh))) ? 1.0 : -1.0;
-    const double tfuzz = 100.0 * DBL_EPS * (fabs(tn) + fabs(hh)) * sgn;
-    const double tp = tn - hused - tfuzz;
-    if ((t - tp) * hh < 0.0) return;  // unreachable after stop_test2 (tout lies inside the last step)
-    const int kord = (kused == 0) ? 1 : kused;
-    const double delt = t - tn;
-    double c = 1.0, d = 0.0, num = delt;
-    double y[N], yp[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-        y[i] = 0.0 + c * v[i];
-        yp[i] = 0.0;
-    }
-#pragma unroll
-    for (int j = 1; j <= MAXORD; ++j) {
-        if (j <= kord) {
-            const double psi_jm1 = v[6 * N + j - 1];
-            const double gam = num / psi_jm1;
-            d = d * gam + c / psi_jm1;
-            c = c * gam;
-            num = delt + psi_jm1;
-#pragma unroll
-            for (int i = 0; i < N; ++i) {
-                const double p = v[j * N + i];
-                y[i] += c * p;
-                yp[i] += d * p;
-            }
-        }
-    }
-    if (yy_traj) {
-        const int64_t ob = perm ? (int64_t)perm[b] : b;
-#pragma unroll
-        for (int i = 0; i < N; ++i) yy_traj[((int64_t)it * N + i) * B + ob] = y[i];
-    }
-    if (it == lad.ntout - 1) {
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            ds[(int64_t)lay.yy(i) * B + b] = y[i];
-            ds[(int64_t)lay.yp(i) * B + b] = yp[i];
-        }
-    }
-}
 
 // Team-per-instance solve (ida_team.cuh): persistent teams (warps or whole CTAs) stride over the ensemble.
 template <class Team>
@@ -346,6 +242,7 @@ using namespace b200ida;
 // ---- the opaque handle ---------------------------------------------------------------------------------
 struct b200ida_ensemble {
     int problem = 0, n = 0, nparams = 0, device = 0;
+    int nr = 0;  // Root::num_roots of the problem (Roberts 2; a user problem: its functor's NR)
     int64_t B = 0;
     double rtol = 0.0;
     double atol[MAX_ATOL];
@@ -556,8 +453,8 @@ int b200ida_reinit(b200ida_ensemble* e, const double* params, const double* yy0,
     B200_CUDA_TRY(cudaMemsetAsync(e->dstate, 0, nd * sizeof(double), st));
     B200_CUDA_TRY(cudaMemsetAsync(e->istate, 0, ni * sizeof(int), st));
     if (e->roots.max_ev > 0) {  // a re-initialised ensemble starts rootfinding afresh (Ida::new, src/lib.rs:360-375)
-        B200_CUDA_TRY(cudaMemsetAsync(e->root_d.p, 0, (size_t)(4 * Roberts::NR + 5) * batch * sizeof(double), st));
-        B200_CUDA_TRY(cudaMemsetAsync(e->root_i.p, 0, (size_t)(Roberts::NR + 2) * batch * sizeof(int), st));
+        B200_CUDA_TRY(cudaMemsetAsync(e->root_d.p, 0, (size_t)(4 * e->nr + 5) * batch * sizeof(double), st));
+        B200_CUDA_TRY(cudaMemsetAsync(e->root_i.p, 0, (size_t)(e->nr + 2) * batch * sizeof(int), st));
         B200_CUDA_TRY(cudaMemsetAsync(e->roots.ev_count, 0, (size_t)batch * sizeof(int), st));
     }
     if (params) {
@@ -613,6 +510,15 @@ int b200ida_create(b200ida_ensemble** out, int problem, int n, int64_t batch, in
         need_p = 1;
         break;
     }
+    case B200IDA_PROBLEM_USER: {
+        const UserProblemHooks* hk = user_problem_hooks();
+        if (!hk)
+            return set_error(B200IDA_ERR_UNSUPPORTED, "b200ida_create: this library was built without a user problem "
+                                                      "(make -C rust_ida_b200/csrc user PROBLEM_HDR=...)");
+        need_n = hk->n;
+        need_p = hk->nparams;
+        break;
+    }
     default: return set_error(B200IDA_ERR_UNSUPPORTED, "b200ida_create: problem %d has no kernel", problem);
     }
     if (n != need_n || nparams != need_p)
@@ -625,6 +531,7 @@ int b200ida_create(b200ida_ensemble** out, int problem, int n, int64_t batch, in
     b200ida_ensemble* e = new (std::nothrow) b200ida_ensemble();
     if (!e) return set_error(B200IDA_ERR_ARG, "out of host memory");
     e->problem = problem;
+    e->nr = problem == B200IDA_PROBLEM_ROBERTS ? Roberts::NR : (problem == B200IDA_PROBLEM_USER ? user_problem_hooks()->nroots : 0);
     e->reorder = g_reorder_mode.load();
     e->n = n;
     e->nparams = nparams;
@@ -702,11 +609,11 @@ int b200ida_set_roots(b200ida_ensemble* e, int max_events, double* ev_t, double*
         e->roots = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
         return B200IDA_OK;
     }
-    if (e->problem != B200IDA_PROBLEM_ROBERTS || e->n != 3)
-        return set_error(B200IDA_ERR_UNSUPPORTED, "b200ida_set_roots: the Roberts problem is the only one with root functions");
+    if (e->nr <= 0)
+        return set_error(B200IDA_ERR_UNSUPPORTED, "b200ida_set_roots: this problem has no root functions (Root::num_roots == 0)");
     if (!ev_t || !ev_iroots || !ev_count) return set_error(B200IDA_ERR_ARG, "b200ida_set_roots: null event buffer");
     B200_CUDA_TRY(cudaSetDevice(e->device));
-    constexpr int NR = Roberts::NR;
+    const int NR = e->nr;
     const size_t db = (size_t)(4 * NR + 5) * e->B * sizeof(double), ib = (size_t)(NR + 2) * e->B * sizeof(int);
     if (!e->root_d.p) B200_CUDA_TRY(e->root_d.alloc(db));  // the batch size of a handle is fixed
     if (!e->root_i.p) B200_CUDA_TRY(e->root_i.alloc(ib));
@@ -755,53 +662,29 @@ int b200ida_solve_ladder(b200ida_ensemble* e, const double* touts, int ntout, in
     if (e->roots.max_ev > 0 && e->trace.id >= 0)
         return set_error(B200IDA_ERR_UNSUPPORTED, "rootfinding and the per-attempt trace cannot be active in the same launch");
     if (kernel == B200IDA_KERNEL_THREAD) {
-        if (e->n != 3 || e->problem == B200IDA_PROBLEM_HEAT2D)
-            return set_error(B200IDA_ERR_UNSUPPORTED, "thread-per-instance kernels exist for the n = 3 problems only");
-        const int tb = THREAD_BLOCK;
-        const unsigned grid = (unsigned)((e->B + tb - 1) / tb);
-        const size_t smem = (size_t)IdaThread<Roberts>::SMEM_DOUBLES * tb * sizeof(double);
-        TolN<3> tol;
-        tol.rtol = e->rtol;
-        for (int i = 0; i < 3; ++i) tol.atol[i] = e->atol[i];
-        for (int i = 0; i < 3; ++i) tol.idmask[i] = e->idmask[i];
-        if (e->suppressalg && (e->roots.max_ev > 0 || e->trace.id >= 0))
-            return set_error(B200IDA_ERR_UNSUPPORTED, "suppressalg cannot be combined with rootfinding or the attempt trace");
-        if (e->suppressalg) {
-            // masked local-error norms: the MASK instantiation (interpolates in line; it is not the benchmarked path)
-            if (e->problem == B200IDA_PROBLEM_ROBERTS) {
-                B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_thread_kernel<Roberts, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                ida_solve_thread_kernel<Roberts, false, false, true><<<grid, tb, smem, e->stream>>>(e->dstate, e->istate, e->params, e->B, tol, lad,
-                                                                                                   d_traj, d_stat, e->perm);
-            } else {
-                B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_thread_kernel<Lorenz63, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                ida_solve_thread_kernel<Lorenz63, false, false, true><<<grid, tb, smem, e->stream>>>(e->dstate, e->istate, e->params, e->B, tol, lad,
-                                                                                                    d_traj, d_stat, e->perm);
-            }
-            count_launch();
-        } else if (e->roots.max_ev > 0) {
-            if (e->problem != B200IDA_PROBLEM_ROBERTS)
-                return set_error(B200IDA_ERR_UNSUPPORTED, "rootfinding: the Roberts problem is the only one with root functions");
-            const size_t rsmem = (size_t)(IdaThread<Roberts>::SMEM_DOUBLES + IdaThread<Roberts>::ROOT_DOUBLES) * tb * sizeof(double);
-            B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_thread_kernel<Roberts, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
-            ida_solve_thread_kernel<Roberts, false, true><<<grid, tb, rsmem, e->stream>>>(e->dstate, e->istate, e->params, e->B, tol, lad,
-                                                                                         d_traj, d_stat, e->perm, TraceParams(), e->roots);
-            count_launch();
-        } else if (e->trace.id >= 0) {
-            // traced run: the TRACE instantiation of the same kernel (the production instantiation carries no trace code)
-            if (e->problem == B200IDA_PROBLEM_ROBERTS) {
-                B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_thread_kernel<Roberts, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                ida_solve_thread_kernel<Roberts, true><<<grid, tb, smem, e->stream>>>(e->dstate, e->istate, e->params, e->B, tol, lad,
-                                                                                      d_traj, d_stat, e->perm, e->trace);
-                count_launch();
-            } else {
-                B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_thread_kernel<Lorenz63, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                ida_solve_thread_kernel<Lorenz63, true><<<grid, tb, smem, e->stream>>>(e->dstate, e->istate, e->params, e->B, tol, lad,
-                                                                                       d_traj, d_stat, e->perm, e->trace);
-                count_launch();
-            }
-        } else {
-            // production path: solve kernel (snapshots at the output times) + the coherent interpolation pass
-            const size_t need_snap = (size_t)e->B * ntout * snap_doubles(3) * sizeof(double), need_valid = (size_t)e->B * ntout;
+        const bool user = e->problem == B200IDA_PROBLEM_USER;
+        if (!user && (e->n != 3 || e->problem == B200IDA_PROBLEM_HEAT2D))
+            return set_error(B200IDA_ERR_UNSUPPORTED, "thread-per-instance kernels exist for the n = 3 problems and for user problems only");
+        ThreadLaunch a;
+        a.ds = e->dstate;
+        a.is = e->istate;
+        a.params = e->params;
+        a.B = e->B;
+        a.rtol = e->rtol;
+        a.atol = e->atol;
+        a.idmask = e->idmask;
+        a.suppressalg = e->suppressalg;
+        a.lad = lad;
+        a.traj = d_traj;
+        a.stat = d_stat;
+        a.perm = e->perm;
+        a.trace = e->trace;
+        a.roots = e->roots;
+        a.stream = e->stream;
+        a.df = DeferParams{nullptr, nullptr};
+        if (!e->suppressalg && e->roots.max_ev <= 0 && e->trace.id < 0) {
+            // production path: snapshot buffers of the deferred output interpolation, grown to the longest ladder seen
+            const size_t need_snap = (size_t)e->B * ntout * snap_doubles(e->n) * sizeof(double), need_valid = (size_t)e->B * ntout;
             if (need_snap > e->snap_cap) {
                 e->snap.release();
                 e->snap_cap = 0;
@@ -814,24 +697,19 @@ int b200ida_solve_ladder(b200ida_ensemble* e, const double* touts, int ntout, in
                 B200_CUDA_TRY(e->snap_valid.alloc(need_valid));
                 e->valid_cap = need_valid;
             }
-            const DeferParams df = {e->snap.as<double>(), e->snap_valid.as<unsigned char>()};
-            if (e->problem == B200IDA_PROBLEM_ROBERTS) {
-                B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_thread_kernel<Roberts>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                ida_solve_thread_kernel<Roberts><<<grid, tb, smem, e->stream>>>(e->dstate, e->istate, e->params, e->B, tol, lad,
-                                                                                d_traj, d_stat, e->perm, TraceParams(), RootParams(), df);
-                count_launch();
-            } else {
-                B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_thread_kernel<Lorenz63>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                ida_solve_thread_kernel<Lorenz63><<<grid, tb, smem, e->stream>>>(e->dstate, e->istate, e->params, e->B, tol, lad,
-                                                                                 d_traj, d_stat, e->perm, TraceParams(), RootParams(), df);
-                count_launch();
-            }
-            B200_CUDA_TRY(cudaGetLastError());
-            if (IDA_DEFER) {
-                ida_interp_kernel<3><<<(unsigned)((e->B * ntout + 255) / 256), 256, 0, e->stream>>>(e->dstate, e->B, lad, df, d_traj, e->perm);
-                count_launch();
-            }
+            a.df = DeferParams{e->snap.as<double>(), e->snap_valid.as<unsigned char>()};
         }
+        int rc;
+        if (user) {
+            const UserProblemHooks* hk = user_problem_hooks();
+            if (!hk) return set_error(B200IDA_ERR_UNSUPPORTED, "no user problem is linked into this library");
+            rc = hk->launch(a);
+        } else if (e->problem == B200IDA_PROBLEM_ROBERTS) {
+            rc = launch_thread_family<Roberts, CAP_TRACE | CAP_ROOTS | CAP_MASK>(a);
+        } else {
+            rc = launch_thread_family<Lorenz63, CAP_TRACE | CAP_MASK>(a);
+        }
+        if (rc != B200IDA_OK) return rc;
     } else {
         const bool warp = kernel == B200IDA_KERNEL_WARP;
         if (warp && e->n > 32) return set_error(B200IDA_ERR_UNSUPPORTED, "warp-per-system needs n <= 32 (n = %d)", e->n);

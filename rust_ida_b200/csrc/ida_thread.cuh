@@ -68,7 +68,7 @@ struct TolN {
 #define IDA_FASTDIV 1
 #endif
 #if IDA_DIV_NOINLINE
-__device__ __noinline__ double ddiv(double a, double b) { return a / b; }
+static __device__ __noinline__ double ddiv(double a, double b) { return a / b; }
 #elif IDA_FASTDIV
 __device__ __forceinline__ double ddiv(double a, double b) { return div1(a, b); }
 #else
@@ -80,9 +80,9 @@ __device__ __forceinline__ double drcp(double b) { return rcp1(b); }
 __device__ __forceinline__ double drcp(double b) { return 1.0 / b; }
 #endif
 #if IDA_POW_INLINE
-__device__ __forceinline__ double pow_noinline(double x, double y) { return detpow::det_pow(x, y); }
+static __device__ __forceinline__ double pow_noinline(double x, double y) { return detpow::det_pow(x, y); }
 #else
-__device__ __noinline__ double pow_noinline(double x, double y) { return detpow::det_pow(x, y); }
+static __device__ __noinline__ double pow_noinline(double x, double y) { return detpow::det_pow(x, y); }
 #endif
 
 // x / D for a small integer constant D, bit-identical to the IEEE division the reference performs.

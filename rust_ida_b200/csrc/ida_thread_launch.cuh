@@ -1,0 +1,216 @@
+// ida_thread_launch.cuh -- the thread-per-instance kernels and the one place that launches them, for ANY problem functor.
+//
+// Included by ida_engine.cu (built-in problems: Roberts, Lorenz63) and by user_problem.cu (a user-supplied functor,
+// `make user PROBLEM_HDR=...`, INTEGRATION.md "Adding a problem"): both get the same kernels, instantiated for their
+// problem type.  A problem functor P provides (see problems.cuh):
+//     static constexpr int N, NP, NR;  static constexpr bool ROOT_USES_YP;
+//     void load(const double* params, int64_t B, int64_t b);            // per-instance parameters, SoA [NP][B]
+//     void res(double t, const double (&yy)[N], const double (&yp)[N], double (&r)[N]) const;         // Residual::res
+//     void jac(double t, double cj, const double (&yy)[N], const double (&yp)[N], const double (&r)[N], double (&J)[N][N]) const;
+//     void root(double t, const double (&y)[N], const double (&yp)[N], double (&g)[NR]) const;        // Root::root (NR > 0)
+// i.e. the reference's Residual / Jacobian / Root traits (src/traits.rs:28-89) as device code.
+#pragma once
+#include "host_util.h"
+#include "ida_thread.cuh"
+
+namespace b200ida {
+
+// Thread-per-instance solve over a ladder of output times (ida_thread.cuh).
+#ifndef IDA_MIN_BLOCKS
+#define IDA_MIN_BLOCKS 3  // 168 regs, 12 warps/SM: measured faster than 4 (128 regs + spills) and 2
+#endif
+#ifndef IDA_DEFER
+#define IDA_DEFER 1  // deferred output interpolation (DeferParams, ida_common.cuh); 0: interpolate in the solve kernel
+#endif
+template <class P, bool TRACE = false, bool ROOTS = false, bool MASK = false>
+__global__ void __launch_bounds__(THREAD_BLOCK, IDA_MIN_BLOCKS)
+ida_solve_thread_kernel(double* __restrict__ ds, int* __restrict__ is, const double* __restrict__ params, int64_t B,
+                        TolN<P::N> tol, LadderParams lad, double* __restrict__ yy_traj, int32_t* __restrict__ status,
+                        const int* __restrict__ perm, TraceParams tr = TraceParams(), RootParams rp = RootParams(),
+                        DeferParams df = DeferParams()) {
+    extern __shared__ double smem[];
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // slot
+    if (b >= B) return;
+    const int64_t ob = perm ? (int64_t)perm[b] : b;  // caller-visible instance id of this slot
+    IdaThread<P, MASK> s;
+    s.sm = smem + threadIdx.x;
+    if constexpr (MASK) {
+#pragma unroll
+        for (int i = 0; i < P::N; ++i) s.idm[i] = tol.idmask[i];
+    }
+    s.prob.load(params, B, b);
+    s.load(ds, is, B, b);
+    if constexpr (ROOTS) s.load_roots(rp, B, b);
+    // the production instantiation defers the output interpolation to ida_interp_kernel; the TRACE and ROOTS
+    // instantiations read yy / yp right after get_solution (trace frames, g(t, y)) and keep it in line
+    s.template solve_ladder<TRACE, ROOTS, !TRACE && !ROOTS && !MASK && IDA_DEFER>(lad, tol, yy_traj, status, B, ob, tr, rp, df, b);
+    s.store(ds, is, B, b);
+    if constexpr (ROOTS) {
+        s.store_roots(rp, B, b);
+        if (rp.nge_out) rp.nge_out[ob] = s.nge;
+    }
+}
+
+// Second pass of the deferred output interpolation (DeferParams, ida_common.cuh): get_solution (src/lib.rs:1274-1343)
+// for every (instance, output time) whose call returned through stop_test2, from the snapshot the solve kernel took.
+// One thread per (slot, output time); the snapshot rows of consecutive threads are consecutive in HBM, each thread
+// pulls its 224-byte row with 16-byte loads issued back to back and interpolates from registers -- an HBM-streaming
+// kernel (algorithmic bytes: one row read, n doubles written).  y(tout) goes to yy_traj (caller order) when one was
+// asked for; y, y' of the LAST call go to the persistent state, where the reference's solve() leaves them.  The
+// arithmetic is get_solution_fn's (ida_thread.cuh) operation for operation, with the order loop unrolled and guarded.
+template <int N>
+__global__ void __launch_bounds__(256)
+ida_interp_kernel(double* __restrict__ ds, int64_t B, LadderParams lad, DeferParams df, double* __restrict__ yy_traj,
+                  const int* __restrict__ perm) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // slot * ntout + it
+    if (g >= B * lad.ntout) return;
+    if (!df.valid[g]) return;
+    const int64_t b = g / lad.ntout;
+    const int it = (int)(g - b * lad.ntout);
+    constexpr Layout lay(N);
+    constexpr int SD = snap_doubles(N);
+    static_assert(SD % 2 == 0, "rows are read as 16-byte pairs");
+    double v[SD];
+    const double2* row = reinterpret_cast<const double2*>(df.snap + (size_t)g * SD);
+#pragma unroll
+    for (int k = 0; k < SD / 2; ++k) {
+        const double2 t = row[k];
+        v[2 * k] = t.x;
+        v[2 * k + 1] = t.y;
+    }
+    const int kused = (int)v[6 * N + 6];
+    const double tn = v[6 * N + 7], hh = v[6 * N + 8], hused = v[6 * N + 9], t = lad.touts[it];
+    const double sgn = (hh > 0.0 || (hh == 0.0 && !signbit(hh))) ? 1.0 : -1.0;
+    const double tfuzz = 100.0 * DBL_EPS * (fabs(tn) + fabs(hh)) * sgn;
+    const double tp = tn - hused - tfuzz;
+    if ((t - tp) * hh < 0.0) return;  // unreachable after stop_test2 (tout lies inside the last step)
+    const int kord = (kused == 0) ? 1 : kused;
+    const double delt = t - tn;
+    double c = 1.0, d = 0.0, num = delt;
+    double y[N], yp[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        y[i] = 0.0 + c * v[i];
+        yp[i] = 0.0;
+    }
+#pragma unroll
+    for (int j = 1; j <= MAXORD; ++j) {
+        if (j <= kord) {
+            const double psi_jm1 = v[6 * N + j - 1];
+            const double gam = num / psi_jm1;
+            d = d * gam + c / psi_jm1;
+            c = c * gam;
+            num = delt + psi_jm1;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const double p = v[j * N + i];
+                y[i] += c * p;
+                yp[i] += d * p;
+            }
+        }
+    }
+    if (yy_traj) {
+        const int64_t ob = perm ? (int64_t)perm[b] : b;
+#pragma unroll
+        for (int i = 0; i < N; ++i) yy_traj[((int64_t)it * N + i) * B + ob] = y[i];
+    }
+    if (it == lad.ntout - 1) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            ds[(int64_t)lay.yy(i) * B + b] = y[i];
+            ds[(int64_t)lay.yp(i) * B + b] = yp[i];
+        }
+    }
+}
+
+
+// everything one launch of the thread-per-instance family needs (filled by b200ida_solve_ladder)
+struct ThreadLaunch {
+    double* ds;
+    int* is;
+    const double* params;
+    int64_t B;
+    double rtol;
+    const double* atol;    // host, [n]
+    const double* idmask;  // host, [n]: ida_id as 1.0 / 0.0
+    int suppressalg;
+    LadderParams lad;
+    double* traj;
+    int32_t* stat;
+    const int* perm;
+    TraceParams trace;  // id < 0: off
+    RootParams roots;   // max_ev == 0: off
+    DeferParams df;     // snapshot buffers sized for snap_doubles(n) (production instantiation)
+    cudaStream_t stream;
+};
+
+// which optional instantiations a problem is compiled with (each one is a full copy of the solver: ~1 minute of nvcc)
+enum { CAP_TRACE = 1, CAP_ROOTS = 2, CAP_MASK = 4 };
+
+template <class P, int CAPS>
+int launch_thread_family(const ThreadLaunch& a) {
+    constexpr int N = P::N;
+    const int tb = THREAD_BLOCK;
+    const unsigned grid = (unsigned)((a.B + tb - 1) / tb);
+    const size_t smem = (size_t)IdaThread<P>::SMEM_DOUBLES * tb * sizeof(double);
+    if (smem > 75 * 1024) return set_error(B200IDA_ERR_UNSUPPORTED, "thread-per-instance: n = %d needs %zu bytes of shared memory per CTA", N, smem);
+    TolN<N> tol;
+    tol.rtol = a.rtol;
+    for (int i = 0; i < N; ++i) tol.atol[i] = a.atol[i];
+    for (int i = 0; i < N; ++i) tol.idmask[i] = a.idmask ? a.idmask[i] : 0.0;
+    const int ntout = a.lad.ntout;
+    if (a.suppressalg && (a.roots.max_ev > 0 || a.trace.id >= 0))
+        return set_error(B200IDA_ERR_UNSUPPORTED, "suppressalg cannot be combined with rootfinding or the attempt trace");
+    if (a.suppressalg) {
+        // masked local-error norms: the MASK instantiation (interpolates in line; it is not the benchmarked path)
+        if constexpr ((CAPS & CAP_MASK) != 0) {
+            B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_thread_kernel<P, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ida_solve_thread_kernel<P, false, false, true><<<grid, tb, smem, a.stream>>>(a.ds, a.is, a.params, a.B, tol, a.lad, a.traj, a.stat, a.perm);
+            count_launch();
+        } else {
+            return set_error(B200IDA_ERR_UNSUPPORTED, "this problem was built without the suppressalg instantiation");
+        }
+    } else if (a.roots.max_ev > 0) {
+        if constexpr ((CAPS & CAP_ROOTS) != 0 && P::NR > 0) {
+            const size_t rsmem = (size_t)(IdaThread<P>::SMEM_DOUBLES + IdaThread<P>::ROOT_DOUBLES) * tb * sizeof(double);
+            B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_thread_kernel<P, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
+            ida_solve_thread_kernel<P, false, true><<<grid, tb, rsmem, a.stream>>>(a.ds, a.is, a.params, a.B, tol, a.lad, a.traj, a.stat, a.perm,
+                                                                                  TraceParams(), a.roots);
+            count_launch();
+        } else {
+            return set_error(B200IDA_ERR_UNSUPPORTED, "rootfinding: this problem has no root functions (Root::num_roots == 0)");
+        }
+    } else if (a.trace.id >= 0) {
+        // traced run: the TRACE instantiation of the same kernel (the production instantiation carries no trace code)
+        if constexpr ((CAPS & CAP_TRACE) != 0) {
+            B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_thread_kernel<P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ida_solve_thread_kernel<P, true><<<grid, tb, smem, a.stream>>>(a.ds, a.is, a.params, a.B, tol, a.lad, a.traj, a.stat, a.perm, a.trace);
+            count_launch();
+        } else {
+            return set_error(B200IDA_ERR_UNSUPPORTED, "this problem was built without the trace instantiation");
+        }
+    } else {
+        // production path: solve kernel (snapshots at the output times) + the coherent interpolation pass
+        B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_thread_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ida_solve_thread_kernel<P><<<grid, tb, smem, a.stream>>>(a.ds, a.is, a.params, a.B, tol, a.lad, a.traj, a.stat, a.perm, TraceParams(),
+                                                                 RootParams(), a.df);
+        count_launch();
+        B200_CUDA_TRY(cudaGetLastError());
+        if (IDA_DEFER) {
+            ida_interp_kernel<N><<<(unsigned)((a.B * ntout + 255) / 256), 256, 0, a.stream>>>(a.ds, a.B, a.lad, a.df, a.traj, a.perm);
+            count_launch();
+        }
+    }
+    B200_CUDA_TRY(cudaGetLastError());
+    return B200IDA_OK;
+}
+
+// ---- user-supplied problems (user_problem.cu registers itself through this at load time) -----------------------------
+struct UserProblemHooks {
+    int n, nparams, nroots;
+    int (*launch)(const ThreadLaunch&);
+};
+void register_user_problem(const UserProblemHooks* h);  // ida_engine.cu
+const UserProblemHooks* user_problem_hooks();
+
+}  // namespace b200ida

@@ -184,8 +184,11 @@ class Ida:
             self._roots = None
             return None
         dev = torch.device("cuda", self.device)
+        nr = int(getattr(self.problem, "nroots", 0))
+        if nr < 1:
+            raise NotImplementedError("%s has no root functions (Root::num_roots == 0)" % type(self.problem).__name__)
         ev = RootEvents(self, torch.zeros((max_events, self.batch), dtype=torch.float64, device=dev),
-                        torch.zeros((max_events, 2, self.batch), dtype=torch.float64, device=dev),
+                        torch.zeros((max_events, nr, self.batch), dtype=torch.float64, device=dev),
                         torch.zeros((self.batch,), dtype=torch.int32, device=dev),
                         torch.zeros((self.batch,), dtype=torch.int32, device=dev))
         self._call("b200ida_set_roots", self._h, int(max_events), ev.t.data_ptr(), ev.iroots.data_ptr(),

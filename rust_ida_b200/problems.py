@@ -24,10 +24,22 @@ class EnsembleProblem:
         return self.n
 
 
+class UserProblem(EnsembleProblem):
+    """A user-supplied Residual / Jacobian (/ Root) functor (src/traits.rs:28-89) that was compiled into the library with
+    `make -C rust_ida_b200/csrc user PROBLEM_HDR=...` ("Adding a problem"); load that library through the
+    B200IDA_LIB environment variable.  n, nparams and nroots must match the functor's N, NP, NR (the engine checks)."""
+    kind = 3  # B200IDA_PROBLEM_USER
+
+    def __init__(self, params, n, nroots=0):
+        self.n, self.nparams, self.nroots = int(n), int(params.shape[0]), int(nroots)
+        super().__init__(params)
+
+
 class Roberts(EnsembleProblem):
     """Robertson kinetics (src/sample_problems/roberts.rs); params rows (k1, k2, k3), reference values
     (0.04, 1e4, 3e7)."""
     kind, n, nparams = PROBLEM_ROBERTS, 3, 3
+    nroots = 2  # Root::num_roots, src/sample_problems/roberts.rs:99-113
     DEFAULT = (0.04, 1.0e4, 3.0e7)
 
     @classmethod

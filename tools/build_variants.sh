@@ -8,13 +8,14 @@ mkdir -p ../../variants
 ARCH="-gencode arch=compute_100a,code=sm_100a"
 NVFLAGS="$ARCH -O3 -lineinfo -fmad=false -std=c++17 -Xcompiler -fPIC -Xcompiler -O2"
 [ -f linalg_batched.o ] || nvcc $NVFLAGS -c linalg_batched.cu -o linalg_batched.o
+[ -f newton_batched.o ] || nvcc $NVFLAGS -c newton_batched.cu -o newton_batched.o
 pids=()
 for spec in "$@"; do
     name="${spec%%:*}"
     flags="${spec#*:}"
     (
         nvcc $NVFLAGS $flags -c ida_engine.cu -o ../../variants/ida_engine_$name.o
-        nvcc $ARCH -shared -o ../../variants/libb200ida_$name.so ../../variants/ida_engine_$name.o linalg_batched.o --cudart static
+        nvcc $ARCH -shared -o ../../variants/libb200ida_$name.so ../../variants/ida_engine_$name.o linalg_batched.o newton_batched.o --cudart static
         rm -f ../../variants/ida_engine_$name.o
         echo "built variants/libb200ida_$name.so ($flags)"
     ) &
