@@ -438,6 +438,9 @@ def run_extra(fp64_peak_gops):
     try:
         import bench_lu
         rows = bench_lu.run_lu(reps=2, fp64_peak_gops=fp64_peak_gops)
+        # the tolerance mode of the same table: FP64 tensor-core (DMMA) trailing update where it applies (even n >= 115)
+        rows += [r_ for r_ in bench_lu.run_lu(sizes=(128, 256), reps=2, fp64_peak_gops=fp64_peak_gops, flags=0x100)
+                 if r_["op"].startswith("getrf")]
         out["lu_config4"] = [{k: (round(v, 6) if isinstance(v, float) else v) for k, v in row.items()
                               if k in ("op", "n", "batch", "layout", "ms", "matrices_per_s", "gflops", "algorithmic_gbs",
                                        "hbm_frac_of_measured", "fp64_frac", "pivots_bit_exact_vs_oracle")} for row in rows]

@@ -45,6 +45,11 @@ extern "C" {
 #define B200IDA_MEM_HOST 1
 #define B200IDA_LAYOUT_SOA 0
 #define B200IDA_LAYOUT_AOS 1
+/* OR-ed into `layout` of b200ida_getrf_batched: TOLERANCE mode -- for AoS matrices with even n >= 115 the trailing-matrix
+ * update of the blocked LU runs on the FP64 tensor cores (mma.sync m8n8k4, SASS DMMA) instead of the bit-exact un-fused
+ * multiply / subtract.  Factors then agree with the reference's dense_get_rf to rounding (tests: rel 1e-12), pivot
+ * sequences are equal unless two pivot candidates tie to within rounding.  Ignored for other sizes / layouts. */
+#define B200IDA_LU_DMMA 0x100
 
 const char* b200ida_last_error(void); /* thread-local text of the last failure */
 int b200ida_version(void);

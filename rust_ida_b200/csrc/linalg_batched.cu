@@ -747,7 +747,7 @@ __host__ __device__ inline size_t lubg_smem_bytes(int n) {
 }
 template <int NT>
 __global__ void __launch_bounds__(NT, NT <= 128 ? 4 : (NT <= 256 ? 2 : 1))
-    getrf_blocked_global(double* __restrict__ A, int64_t* __restrict__ piv, int32_t* __restrict__ info, int n, int64_t B) {
+    getrf_blocked_global(double* __restrict__ A, int64_t* __restrict__ piv, int32_t* __restrict__ info, int n, int64_t B, int dmma) {
     extern __shared__ __align__(16) unsigned char lu_smem[];
     const int ldp = n | 1;
     double* Pb0 = reinterpret_cast<double*>(lu_smem);
@@ -760,14 +760,16 @@ __global__ void __launch_bounds__(NT, NT <= 128 ? 4 : (NT <= 256 ? 2 : 1))
     LubCtl* ctl = reinterpret_cast<LubCtl*>(lu_smem + off);
     const int tid = threadIdx.x, nt = blockDim.x;
     for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
-        lub_factor_global<8>(A + (size_t)b * n * n, n, ctl, pivs, Ub, Pb0, Pb1);
+        lub_factor_global<8>(A + (size_t)b * n * n, n, ctl, pivs, Ub, Pb0, Pb1, dmma != 0);
         const int inf = ctl->info;
         for (int k = tid; k < n; k += nt) piv[(size_t)b * n + k] = (inf == 0 || k < inf) ? pivs[k] : 0;
         if (tid == 0) info[b] = inf;
         __syncthreads();
     }
 }
-static int launch_getrf_blocked_global(double* A, int64_t* piv, int32_t* info, int n, int64_t B, cudaStream_t st) {
+static int launch_getrf_blocked_global(double* A, int64_t* piv, int32_t* info, int n, int64_t B, cudaStream_t st, int dmma = 0) {
+    // the tensor-core update stores 16-byte pairs: even n and a 16-byte aligned batch, else the exact path
+    if ((n & 1) || (reinterpret_cast<uintptr_t>(A) & 15)) dmma = 0;
     const size_t smem = lubg_smem_bytes(n);
     unsigned grid = 1;
     int rc;
@@ -775,21 +777,21 @@ static int launch_getrf_blocked_global(double* A, int64_t* piv, int32_t* info, i
     const char* force = experiment_env("B200IDA_LUBG_THREADS");
     if (force && atoi(force) == 128) {
         if ((rc = launch_cfg(getrf_blocked_global<128>, 128, smem, B, 1, &grid))) return rc;
-        getrf_blocked_global<128><<<grid, 128, smem, st>>>(A, piv, info, n, B);
+        getrf_blocked_global<128><<<grid, 128, smem, st>>>(A, piv, info, n, B, dmma);
     } else if (force && atoi(force) == 256) {
         if ((rc = launch_cfg(getrf_blocked_global<256>, 256, smem, B, 1, &grid))) return rc;
-        getrf_blocked_global<256><<<grid, 256, smem, st>>>(A, piv, info, n, B);
+        getrf_blocked_global<256><<<grid, 256, smem, st>>>(A, piv, info, n, B, dmma);
     } else if (n <= SMEM_MAX_N) {
         // 115..160: the shared-memory-resident kernel fits one CTA per SM only; four small CTAs per SM on L2-resident
         // matrices keep four pivot chains in flight instead (measured: n = 128 0.47 -> 0.37 ms)
         if ((rc = launch_cfg(getrf_blocked_global<128>, 128, smem, B, 1, &grid))) return rc;
-        getrf_blocked_global<128><<<grid, 128, smem, st>>>(A, piv, info, n, B);
+        getrf_blocked_global<128><<<grid, 128, smem, st>>>(A, piv, info, n, B, dmma);
     } else if (B <= (int64_t)sm_count() && n >= 224) {
         if ((rc = launch_cfg(getrf_blocked_global<512>, 512, smem, B, 1, &grid))) return rc;
-        getrf_blocked_global<512><<<grid, 512, smem, st>>>(A, piv, info, n, B);
+        getrf_blocked_global<512><<<grid, 512, smem, st>>>(A, piv, info, n, B, dmma);
     } else {
         if ((rc = launch_cfg(getrf_blocked_global<256>, 256, smem, B, 1, &grid))) return rc;
-        getrf_blocked_global<256><<<grid, 256, smem, st>>>(A, piv, info, n, B);
+        getrf_blocked_global<256><<<grid, 256, smem, st>>>(A, piv, info, n, B, dmma);
     }
     B200_CUDA_TRY(cudaGetLastError());
     return B200IDA_OK;
@@ -1108,6 +1110,8 @@ static int launch_group(double* A, int64_t* piv, int32_t* info, double* bx, int 
 
 // device-pointer implementations -------------------------------------------------------------------------
 static int getrf_dev(double* A, int64_t* piv, int32_t* info, int n, int64_t B, int layout, cudaStream_t st) {
+    const int dmma = (layout & B200IDA_LU_DMMA) ? 1 : 0;  // tolerance mode: honoured by the global-memory blocked LU (n >= 115, AoS)
+    layout &= ~B200IDA_LU_DMMA;
     const bool soa = layout == B200IDA_LAYOUT_SOA;
     if (soa && n <= 8) {
         switch (n) {
@@ -1123,7 +1127,7 @@ static int getrf_dev(double* A, int64_t* piv, int32_t* info, int n, int64_t B, i
         B200_CUDA_TRY(cudaGetLastError());
         return B200IDA_OK;
     }
-    if (!soa && n > 32 && (n >= 115 || experiment_env("B200IDA_LUBG_THREADS"))) return launch_getrf_blocked_global(A, piv, info, n, B, st);
+    if (!soa && n > 32 && (n >= 115 || experiment_env("B200IDA_LUBG_THREADS"))) return launch_getrf_blocked_global(A, piv, info, n, B, st, dmma);
     if (n > 32 && n <= SMEM_MAX_N)
         return soa ? launch_getrf_blocked_n<true>(A, piv, info, n, B, st) : launch_getrf_blocked_n<false>(A, piv, info, n, B, st);
     return launch_group<true>(A, piv, info, nullptr, n, B, soa, st);
@@ -1206,7 +1210,7 @@ int b200ida_debug_lub_prof(unsigned long long* out16, int reset) {
 
 int b200ida_getrf_batched(double* A, int64_t* piv, int32_t* info, int n, int64_t batch, int layout, int mem,
                           void* stream) {
-    int rc = check_common(A, piv, n, batch, layout, mem, "b200ida_getrf_batched");
+    int rc = check_common(A, piv, n, batch, layout & ~B200IDA_LU_DMMA, mem, "b200ida_getrf_batched");
     if (rc) return rc;
     if (!info) return set_error(B200IDA_ERR_ARG, "b200ida_getrf_batched: info is null");
     cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -465,6 +465,87 @@ __device__ __noinline__ void lub_update(double* M, int ld, int n, int kb, int K,
     }
 }
 
+// ---- [U] on the FP64 tensor cores: the TOLERANCE mode of the trailing update (B200IDA_LU_DMMA) ---------------------------
+// A block step's update  A22 -= L21 * U12  (K = 8) really is a dense contraction, and for n >= 128 it dominates the
+// flops.  mma.sync.m8n8k4.f64 (SASS: DMMA) does 8 x 8 x 4 fused multiply-adds per warp instruction, i.e. the work of 16
+// un-fused DMUL + DADD warp instructions of lub_tile.  It is NOT the reference's arithmetic -- products are fused into
+// the accumulation and the four k of one instruction are summed in hardware order -- so this path is an explicit mode:
+// pivots still compare equal to the oracle's on well-conditioned inputs, factors agree to ~1e-15 relative (the tests
+// bound them at 1e-12), and the default stays the bit-exact lub_update.
+//
+// The product is formed TRANSPOSED so that a thread's two accumulator elements are two consecutive ROWS of one column
+// of the column-major matrix (one 16-byte load / store):  D^T[j][i] = sum_k U[k][j] * (-L[i][k]) + C^T[j][i], with the mma
+// "m" dimension = 8 matrix columns, "n" = 8 matrix rows:
+//   A fragment (8 x 4, row):  a  = U[k = lane % 4 (+4)][j0 + lane / 4]                     from Ub
+//   B fragment (4 x 8, col):  b  = -L[i0 + lane / 4][k = lane % 4 (+4)]                    from the panel Lp
+//   C / D fragment (8 x 8):   c0, c1 = M[j0 + lane / 4][i0 + 2 (lane % 4) + {0, 1}]        one double2
+// A warp item is a block of 64 rows (its 16 negated L fragments stay in registers) times the column tiles of its chunk.
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+// rows >= kb + 8, columns [c0, c1) (c0 a multiple of 8), K == 8 fused k-steps; ld even and M 16-byte aligned.
+static __device__ __noinline__ void lub_update_dmma(double* M, int ld, int n, int kb, int c0, int c1, const double* Lp, int ldl,
+                                                    const double* Ub, int ldu, int w, int nw, int lane) {
+    constexpr int RB = 64;
+    const int r0 = kb + LUB_NB;
+    const int nrows = n - r0, ncols = c1 - c0;
+    if (nrows <= 0 || ncols <= 0) return;
+    const int nrb = (nrows + RB - 1) / RB, nct = (ncols + 7) / 8;
+    const int items = nrb * nct, chunk = (items + nw - 1) / nw;
+    int it = w * chunk;
+    if (it >= items) return;
+    const int itend = (it + chunk < items) ? it + chunk : items;
+    int rb = it / nct, ct = it - rb * nct;
+    int cur_rb = -1;
+    const int g = lane >> 2, q = lane & 3;
+    double bl[8][2];  // -L fragments of the 8 row tiles of this row block, k halves 0..3 / 4..7
+    for (; it < itend; ++it) {
+        const int ib = r0 + rb * RB;
+        if (rb != cur_rb) {
+            cur_rb = rb;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const int i = ib + 8 * t + g;
+                const bool ok = i < n;
+                const int ic = ok ? i : n - 1;
+                const double v0 = Lp[q * ldl + ic], v1 = Lp[(q + 4) * ldl + ic];
+                bl[t][0] = ok ? -v0 : 0.0;
+                bl[t][1] = ok ? -v1 : 0.0;
+            }
+        }
+        const int j = c0 + ct * 8 + g;  // this thread's matrix column
+        const bool jok = j < c1;
+        const int jc = jok ? j : c1 - 1;
+        const double a0 = jok ? Ub[q * ldu + jc] : 0.0, a1 = jok ? Ub[(q + 4) * ldu + jc] : 0.0;
+        double* col = M + (size_t)jc * ld;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const int i = ib + 8 * t + 2 * q;  // first of this thread's two rows (even: r0 and the tile offsets are even)
+            if (ib + 8 * t < n) {              // warp-uniform: the tile has at least one row
+                const bool ok0 = jok && i < n, ok1 = jok && i + 1 < n;
+                double d0 = 0.0, d1 = 0.0;
+                if (ok1) {
+                    const double2 c = *reinterpret_cast<const double2*>(col + i);
+                    d0 = c.x;
+                    d1 = c.y;
+                } else if (ok0) {
+                    d0 = col[i];
+                }
+                dmma_m8n8k4(d0, d1, a0, bl[t][0]);
+                dmma_m8n8k4(d0, d1, a1, bl[t][1]);
+                if (ok1) *reinterpret_cast<double2*>(col + i) = make_double2(d0, d1);
+                else if (ok0) col[i] = d0;
+            }
+        }
+        if (++ct == nct) {
+            ct = 0;
+            ++rb;
+        }
+    }
+}
+
 // In-place LU of the n x n column-major matrix M (leading dimension ld) in shared memory.  Every thread of the CTA
 // calls it (blockDim.x a multiple of 32, at least 64).  RP >= ceil(n / 32).  Ub: lub_ub_bytes(n) of shared scratch,
 // 16-byte aligned.  On return (after a barrier) ctl->info holds 0 or the 1-based singular column, pivs[0..n) the pivot
@@ -543,7 +624,7 @@ __device__ __forceinline__ void lub_panel_copy(double* dst, int ldd, const doubl
 
 template <int RP>
 __device__ __forceinline__ void lub_factor_global(double* Mg, int n, LubCtl* ctl, int* pivs, double* Ub, double* Pb0,
-                                                  double* Pb1) {
+                                                  double* Pb1, bool dmma = false) {
     const int tid = threadIdx.x, nt = blockDim.x, w = tid >> 5, nw = nt >> 5, lane = tid & 31;
     const int ld = n, ldp = n | 1, ldu = lub_ldu(n);
     unsigned char* zcol = reinterpret_cast<unsigned char*>(Ub + LUB_NB * ldu);
@@ -575,7 +656,8 @@ __device__ __forceinline__ void lub_factor_global(double* Mg, int n, LubCtl* ctl
                 if (info == 0) lub_panel_any<RP>(Pnxt - (size_t)c0 * ldp, ldp, n, c0, nb2, ctl, pivs);
             } else if ((w & 3) != 0 || nw <= 4) {
                 const int uw = nw <= 4 ? w - 1 : w - 1 - (w >> 2), unw = nw <= 4 ? nw - 1 : nw - (nw >> 2);
-                lub_update<64>(Mg, ld, n, kb, nbd, c0 + nb2, n, Pcur, ldp, Ub, zcol, ldu, uw, unw, lane);
+                if (dmma && nbd == LUB_NB) lub_update_dmma(Mg, ld, n, kb, c0 + nb2, n, Pcur, ldp, Ub, ldu, uw, unw, lane);
+                else lub_update<64>(Mg, ld, n, kb, nbd, c0 + nb2, n, Pcur, ldp, Ub, zcol, ldu, uw, unw, lane);
             }
             __syncthreads();
             if (info == 0) lub_panel_copy(Mg + (size_t)c0 * ld, ld, Pnxt, ldp, c0, n, nb2, w, nw, lane);

@@ -234,3 +234,47 @@ def test_wrms_masked_bit_exact(n, batch, layout, dev):
     m[-1] = False
     fac = np.sqrt(np.float64(31) / np.float64(32))
     assert r.norm_wrms_masked(np.full((32, 1), -0.5), np.full((32, 1), 0.5), m)[0] == fac * 0.5 * 0.5
+
+
+# ---- SURVEY.md row N3 / BASELINE config 4: FP64 tensor-core (DMMA) trailing update, the TOLERANCE mode ---------------------
+@pytest.mark.parametrize("n,batch", [(128, 7), (192, 4), (250, 3), (256, 5)])
+def test_getrf_tensor_core_update_within_tolerance(n, batch):
+    """B200IDA_LU_DMMA: pivots equal the oracle's, factors within rel 1e-12 (config 4's bar for the DMMA path), P A = L U,
+    and the mode really differs from the bit-exact default somewhere (it is a different rounding, not a no-op)."""
+    import torch
+    import rust_ida_b200 as r
+    a, b = gen_matrices(n, batch, seed=99)
+    lu_ref, piv_ref, x_ref, info_ref = oracle_lu(a, b)
+    A = torch.from_numpy(np.ascontiguousarray(a.transpose(0, 2, 1))).cuda()
+    ls = r.Dense.new(n, batch, layout="aos", raise_on_singular=False, tensor_core_update=True)
+    ls.setup(A)
+    X = torch.from_numpy(b.copy()).cuda()
+    ls.solve(A, X, torch.from_numpy(b.copy()).cuda(), 0.0)
+    lu = A.cpu().numpy().transpose(0, 2, 1)
+    piv, info = ls.pivots.cpu().numpy(), ls.info.cpu().numpy()
+    assert np.array_equal(info, info_ref) and (info == 0).all()
+    assert np.array_equal(piv, piv_ref), "pivot sequences differ"
+    scale = np.abs(lu_ref).max(axis=(1, 2), keepdims=True)
+    assert (np.abs(lu - lu_ref) / scale).max() < 1e-12
+    np.testing.assert_allclose(X.cpu().numpy(), x_ref, rtol=1e-9, atol=1e-12)
+    for k in range(batch):  # P A = L U
+        Lm = np.tril(lu[k], -1) + np.eye(n)
+        Um = np.triu(lu[k])
+        pa = a[k].copy()
+        for i in range(n):
+            pa[[i, piv[k, i]]] = pa[[piv[k, i], i]]
+        assert np.abs(Lm @ Um - pa).max() < 1e-12
+    assert not np.array_equal(lu.view(np.uint64), lu_ref.view(np.uint64))
+
+
+def test_tensor_core_flag_is_ignored_where_it_does_not_apply():
+    """odd n, small n and SoA keep the bit-exact path even with the flag set"""
+    import rust_ida_b200 as r
+    for n, layout in ((100, "aos"), (129, "aos"), (8, "soa")):
+        a, b = gen_matrices(n, 3, seed=5)
+        lu_ref, piv_ref, _, _ = oracle_lu(a, b)
+        A = np.ascontiguousarray(a.transpose(1, 2, 0)) if layout == "soa" else np.ascontiguousarray(a.transpose(0, 2, 1))
+        ls = r.Dense.new(n, 3, layout=layout, raise_on_singular=False, tensor_core_update=True)
+        ls.setup(A)
+        lu = A.transpose(2, 0, 1) if layout == "soa" else A.transpose(0, 2, 1)
+        assert_bit_equal(lu, lu_ref, "n=%d %s" % (n, layout))

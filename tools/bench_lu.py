@@ -87,7 +87,7 @@ def run_lu(sizes=(3, 4, 8, 16, 32, 64, 100, 128, 256), reps=3, min_mb=512.0, bat
             e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
             e0.record()
             for c in range(copies):
-                _lib.check(L.b200ida_getrf_batched(bufs[c].data_ptr(), piv[c].data_ptr(), info.data_ptr(), n, batch, lay,
+                _lib.check(L.b200ida_getrf_batched(bufs[c].data_ptr(), piv[c].data_ptr(), info.data_ptr(), n, batch, lay | flags,
                                                    _lib.MEM_DEVICE, st))
             e1.record()
             for c in range(copies):
@@ -110,7 +110,7 @@ def run_lu(sizes=(3, 4, 8, 16, 32, 64, 100, 128, 256), reps=3, min_mb=512.0, bat
             fl = flops_getrf(n) if op == "getrf" else (2 * n * n - n + n)
             by = (16 * n * n + 8 * n) if op == "getrf" else (8 * n * n + 24 * n)
             rate = batch / (ms * 1e-3)
-            row = {"op": op, "n": n, "batch": batch, "layout": layout, "copies": copies, "ms": ms,
+            row = {"op": op + ("+dmma" if (flags and op == "getrf") else ""), "n": n, "batch": batch, "layout": layout, "copies": copies, "ms": ms,
                    "matrices_per_s": rate, "gflops": rate * fl * 1e-9, "algorithmic_gbs": rate * by * 1e-9,
                    "hbm_frac_of_measured": rate * by * 1e-9 / hbm, "max_abs_residual": res}
             if fp64_peak_gops:
@@ -130,9 +130,10 @@ def main():
     ap.add_argument("--min-mb", type=float, default=512.0)
     ap.add_argument("--batch-scale", type=int, default=1,
                     help="multiply the config's batch (throughput regime: many systems per resident CTA / warp)")
+    ap.add_argument("--dmma", action="store_true", help="B200IDA_LU_DMMA: tensor-core trailing update (tolerance mode)")
     args = ap.parse_args()
     run_lu([int(x) for x in args.sizes.split(",")], args.reps, args.min_mb, args.batch_scale,
-           emit=lambda row: print(json.dumps(row), flush=True))
+           emit=lambda row: print(json.dumps(row), flush=True), flags=0x100 if args.dmma else 0)
 
 
 if __name__ == "__main__":
