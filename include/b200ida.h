@@ -283,6 +283,11 @@ int b200ida_fp64_issue_rate(int kind, int device, double* ginstr_per_s);
  * as `gpu_launches`. */
 long long b200ida_kernel_launches(void);
 
+/* Diagnostic: how many instances the last b200ida_solve / solve_ladder of this handle handed from the production
+ * (fast-path-only) pass to the exact pass -- a fast division / square root / pow left its range, or a rare control
+ * path was reached (csrc/ida_thread.cuh, "FAST").  Results do not depend on it; throughput does.  Synchronises. */
+int b200ida_get_fallback_count(b200ida_ensemble* e, int64_t* count);
+
 /* out[i] = det_pow(x[i], y[i]) on the device: the glibc-2.39-compatible pow the engine uses wherever the
  * reference calls f64::powf (src/impl_complete_step.rs:128-132, src/lib.rs:1163-1169, src/ida_nls.rs:249-253).
  * Exposed so tests can prove device pow == host libm pow bit-for-bit. */

@@ -22,7 +22,7 @@ SYMBOLS = (
     "b200ida_getrf_batched", "b200ida_getrs_batched", "b200ida_wrms_batched", "b200ida_wrms_masked_batched", "b200ida_newton_batched",
     "b200ida_create", "b200ida_destroy", "b200ida_reinit", "b200ida_set_kernel", "b200ida_set_default_reorder", "b200ida_solve", "b200ida_solve_ladder", "b200ida_set_trace", "b200ida_set_roots", "b200ida_set_id",
     "b200ida_get_state", "b200ida_get_counters", "b200ida_get_step_info", "b200ida_get_dky", "b200ida_sync",
-    "b200ida_fp64_issue_rate", "b200ida_detpow_batched", "b200ida_fastdiv_batched", "b200ida_kernel_launches",
+    "b200ida_fp64_issue_rate", "b200ida_detpow_batched", "b200ida_fastdiv_batched", "b200ida_kernel_launches", "b200ida_get_fallback_count",
 )
 
 
@@ -81,6 +81,7 @@ def lib():
     L.b200ida_set_id.argtypes = [vp, vp, i32]
     L.b200ida_newton_batched.argtypes = [i32, i32, i64, vp, vp, dbl, i32, i32, vp, vp, vp, vp, i32, vp]
     L.b200ida_kernel_launches.restype = C.c_longlong
+    L.b200ida_get_fallback_count.argtypes = [vp, vp]
     for name in SYMBOLS:
         getattr(L, name).restype = C.c_char_p if name == "b200ida_last_error" else i32
     _lib = L

@@ -202,13 +202,18 @@ __global__ void fastdiv_kernel(const double* __restrict__ a, const double* __res
         double qq[3], rr[3];
         div_batch<3>(aa, bb, qq);
         rcp_batch<3>(bb, rr);
+        bool okz;
+        const double qz = div_fast_z(aa[0], bb[0], okz);  // element 0 of every triple: the zero-numerator variant
+        if (okz) qq[0] = qz;
         for (int k = 0; k < 3; ++k) {
             q[i0 + k] = qq[k];
             r[i0 + k] = rr[k];
         }
     } else {
         for (int64_t i = i0; i < n; ++i) {
-            q[i] = div1(a[i], b[i]);
+            bool ok;
+            const double qz = div_fast_z(a[i], b[i], ok);  // the zero-numerator variant, with the cold fallback of div1
+            q[i] = ok ? qz : div_slow(a[i], b[i]);
             r[i] = rcp1(b[i]);
         }
     }
@@ -262,6 +267,12 @@ struct b200ida_ensemble {
     double idmask[MAX_ATOL];
     double* d_idmask = nullptr;
     int suppressalg = 0;
+    // production thread path: second state buffers (the FAST pass writes there; swapped with dstate / istate after the
+    // launch) and the per-slot flags of the instances it handed to the exact pass
+    double* dstate2 = nullptr;
+    int* istate2 = nullptr;
+    DevBuf poisoned;
+    bool fast_ran = false;  // the last solve went through the FAST pass (b200ida_get_fallback_count)
     DevBuf snap, snap_valid;  // deferred output interpolation (DeferParams), grown to the longest ladder seen
     size_t snap_cap = 0, valid_cap = 0;
     // persistent device scratch for the host-buffer (end-to-end) entry points and the order builder: a few blocks
@@ -567,6 +578,8 @@ int b200ida_destroy(b200ida_ensemble* e) {
     cudaSetDevice(e->device);
     if (e->dstate) cudaFree(e->dstate);
     if (e->istate) cudaFree(e->istate);
+    if (e->dstate2) cudaFree(e->dstate2);
+    if (e->istate2) cudaFree(e->istate2);
     if (e->params) cudaFree(e->params);
     if (e->d_atol) cudaFree(e->d_atol);
     if (e->d_idmask) cudaFree(e->d_idmask);
@@ -698,6 +711,15 @@ int b200ida_solve_ladder(b200ida_ensemble* e, const double* touts, int ntout, in
                 e->valid_cap = need_valid;
             }
             a.df = DeferParams{e->snap.as<double>(), e->snap_valid.as<unsigned char>()};
+            if (IDA_FAST) {
+                const Layout lay2(e->n);
+                if (!e->dstate2) B200_CUDA_TRY(cudaMalloc(&e->dstate2, (size_t)lay2.ndouble() * e->B * sizeof(double)));
+                if (!e->istate2) B200_CUDA_TRY(cudaMalloc(&e->istate2, (size_t)lay2.nint() * e->B * sizeof(int)));
+                if (!e->poisoned.p) B200_CUDA_TRY(e->poisoned.alloc((size_t)e->B));
+                a.ds2 = e->dstate2;
+                a.is2 = e->istate2;
+                a.poisoned = e->poisoned.as<unsigned char>();
+            }
         }
         int rc;
         if (user) {
@@ -710,6 +732,15 @@ int b200ida_solve_ladder(b200ida_ensemble* e, const double* touts, int ntout, in
             rc = launch_thread_family<Lorenz63, CAP_TRACE | CAP_MASK>(a);
         }
         if (rc != B200IDA_OK) return rc;
+        e->fast_ran = a.ds2 != nullptr;
+        if (a.ds2) {  // the FAST / exact passes wrote the new state to the second buffers: they are the state now
+            double* td = e->dstate;
+            e->dstate = e->dstate2;
+            e->dstate2 = td;
+            int* ti = e->istate;
+            e->istate = e->istate2;
+            e->istate2 = ti;
+        }
     } else {
         const bool warp = kernel == B200IDA_KERNEL_WARP;
         if (warp && e->n > 32) return set_error(B200IDA_ERR_UNSUPPORTED, "warp-per-system needs n <= 32 (n = %d)", e->n);
@@ -746,6 +777,24 @@ int b200ida_solve_ladder(b200ida_ensemble* e, const double* touts, int ntout, in
         if (status) B200_CUDA_TRY(cudaMemcpyAsync(status, d_stat, stat_bytes, cudaMemcpyDeviceToHost, e->stream));
         B200_CUDA_TRY(cudaStreamSynchronize(e->stream));
     }
+    return B200IDA_OK;
+}
+
+int b200ida_get_fallback_count(b200ida_ensemble* e, int64_t* count) {
+    if (!e || !count) return set_error(B200IDA_ERR_ARG, "b200ida_get_fallback_count: bad argument");
+    *count = 0;
+    if (!e->poisoned.p || !e->fast_ran) return B200IDA_OK;  // the last solve did not take the FAST path
+    B200_CUDA_TRY(cudaSetDevice(e->device));
+    unsigned char* h = static_cast<unsigned char*>(malloc((size_t)e->B));
+    if (!h) return set_error(B200IDA_ERR_ARG, "out of host memory");
+    cudaError_t err = cudaMemcpyAsync(h, e->poisoned.p, (size_t)e->B, cudaMemcpyDeviceToHost, e->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+    int64_t c = 0;
+    if (err == cudaSuccess)
+        for (int64_t i = 0; i < e->B; ++i) c += h[i] != 0;
+    free(h);
+    B200_CUDA_TRY(err);
+    *count = c;
     return B200IDA_OK;
 }
 

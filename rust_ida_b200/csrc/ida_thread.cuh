@@ -79,6 +79,13 @@ __device__ __forceinline__ double drcp(double b) { return rcp1(b); }
 #else
 __device__ __forceinline__ double drcp(double b) { return 1.0 / b; }
 #endif
+// det_pow's main path only (FAST kernels): NaN when the arguments leave it -- the caller poisons the lane, the generic
+// pow fallback (several hundred instructions) is not in the kernel
+static __device__ __noinline__ double pow_main_noinline(double x, double y) {
+    double r;
+    if (!detpow::pow_main(x, y, &r)) r = __longlong_as_double(0x7ff8000000000000LL);
+    return r;
+}
 #if IDA_POW_INLINE
 static __device__ __forceinline__ double pow_noinline(double x, double y) { return detpow::det_pow(x, y); }
 #else
@@ -94,7 +101,7 @@ template <int D>
 __device__ __forceinline__ double div_const(double x) {
     constexpr double y = 1.0 / (double)D;
     const unsigned hi = (unsigned)__double2hiint(x) & 0x7ff00000u;
-    if (hi - 0x07b00000u <= 0x70800000u) {  // biased exponent in [123, 1923]
+    if (IDA_UNSAFE_NOFALLBACK || hi - 0x07b00000u <= 0x70800000u) {  // biased exponent in [123, 1923]
         const double q = __dmul_rn(x, y);
         const double r = __fma_rn(-(double)D, q, x);
         return __fma_rn(r, y, q);
@@ -119,8 +126,13 @@ __device__ __forceinline__ double wrms_acc(const double (&x)[N], const double (&
 }
 template <int N>
 __device__ __forceinline__ double wrms_tail_inline(double acc) {
+#if IDA_UNSAFE_NOFALLBACK
+    bool ok;
+    return sqrt_fast(div_const<N>(acc), ok);
+#else
     if constexpr (N >= 2 && N <= 7) return sqrt(div_const<N>(acc));
     else return sqrt(acc / (double)N);
+#endif
 }
 template <int N>
 __device__ __noinline__ double wrms_tail(double acc) { return wrms_tail_inline<N>(acc); }
@@ -398,9 +410,98 @@ __device__ __noinline__ unsigned root_check3(double* sm, P prob, unsigned gmask,
 // the first call, the tolsf norm, test_error, complete_step) leave the algebraic components out, as norm_wrms_masked
 // (src/norm_rms.rs:49-57) does: ((x_i w_i) m_i)^2 folded in index order, divided by n.  A separate instantiation, so the
 // production kernel carries none of it.
-template <class P, bool MASK = false>
+//
+// FAST: the production instantiation.  Every division, reciprocal, square root and pow runs its fast path ONLY -- no
+// range test branches to a fallback, no slow-path code is in the kernel at all -- and a failed range test just sets the
+// lane's `poison` flag; so do the rare control paths (fatal statuses, mxstep, an output time already passed).  A
+// poisoned lane leaves the loop at once and its results are discarded: the launcher re-integrates exactly those
+// instances from the untouched input state with the exact (FAST = false) instantiation of the same code, which has
+// every fallback.  On a healthy ensemble nothing is poisoned and the results are, bit for bit, the exact kernel's --
+// a fast path that passes its range test returns the correctly rounded value by construction (fastdiv.cuh).  Why it
+// pays: the cold fallback blocks were interleaved with the hot code (19 % of the static instructions), pushing the
+// touched part of the step loop past the 32 KB instruction cache; without them the same loop runs 27 % faster.
+template <class P, bool MASK = false, bool FAST = false>
 struct IdaThread {
     static constexpr int N = P::N;
+    bool poison = false;  // FAST only: some fast path left its range or a rare path was reached -> redo exactly
+
+    // ---- arithmetic through one door, so that FAST can drop the fallbacks ----------------------------------------
+    __device__ __forceinline__ double D(double a, double b) {  // a / b
+        if constexpr (FAST) {
+            bool ok;
+            const double q = div_fast(a, b, ok);
+            poison = poison || !ok;
+            return q;
+        } else {
+            return ddiv(a, b);
+        }
+    }
+    __device__ __forceinline__ double R(double b) {  // 1.0 / b
+        if constexpr (FAST) {
+            bool ok;
+            const double r = rcp_fast(b, ok);
+            poison = poison || !ok;
+            return r;
+        } else {
+            return drcp(b);
+        }
+    }
+    template <int K>
+    __device__ __forceinline__ void DK(const double (&a)[K], const double (&b)[K], double (&q)[K]) {
+        if constexpr (FAST) {
+            bool all = true;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                bool ok;
+                q[k] = div_fast(a[k], b[k], ok);
+                all = all && ok;
+            }
+            poison = poison || !all;
+        } else {
+            div_batch<K>(a, b, q);
+        }
+    }
+    template <int K>
+    __device__ __forceinline__ void RK(const double (&b)[K], double (&r)[K]) {
+        if constexpr (FAST) {
+            bool all = true;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                bool ok;
+                r[k] = rcp_fast(b[k], ok);
+                all = all && ok;
+            }
+            poison = poison || !all;
+        } else {
+            rcp_batch<K>(b, r);
+        }
+    }
+    // sqrt(acc / N): the tail of every WRMS norm
+    __device__ __forceinline__ double norm_tail(double acc) {
+        if constexpr (FAST && N >= 2 && N <= 7) {
+            constexpr double y = 1.0 / (double)N;
+            const unsigned hi = (unsigned)__double2hiint(acc) & 0x7ff00000u;
+            const double q = __dmul_rn(acc, y);  // Markstein's exact x / N (div_const), its range test folded into poison
+            const double r = __fma_rn(-(double)N, q, acc);
+            bool ok;
+            const double v = sqrt_fast(__fma_rn(r, y, q), ok);
+            poison = poison || !ok || !(hi - 0x07b00000u <= 0x70800000u);
+            return v;
+        } else if constexpr (IDA_WRMS_INLINE) {
+            return wrms_tail_inline<N>(acc);
+        } else {
+            return wrms_tail<N>(acc);
+        }
+    }
+    __device__ __forceinline__ double PW(double x, double y) {  // pow(x, y)
+        if constexpr (FAST) {
+            const double r = pow_main_noinline(x, y);  // NaN when (x, y) is off det_pow's main path
+            poison = poison || (r != r);
+            return r;
+        } else {
+            return pow_noinline(x, y);
+        }
+    }
     static constexpr int SMEM_DOUBLES = 6 * N + 30;  // phi + psi, alpha, beta, sigma, gamma
     using L = Layout;
 
@@ -440,9 +541,8 @@ struct IdaThread {
             return wrms_acc<N>(x, ewt);
         }
     }
-    __device__ __forceinline__ double err_norm(const double (&x)[N]) const {
-        if constexpr (IDA_WRMS_INLINE) return wrms_tail_inline<N>(err_acc(x));
-        else return wrms_tail<N>(err_acc(x));
+    __device__ __forceinline__ double err_norm(const double (&x)[N]) {
+        return norm_tail(err_acc(x));
     }
 
     // ---- HBM <-> registers / shared memory -----------------------------------------------------------
@@ -504,10 +604,10 @@ struct IdaThread {
         double den[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) den[i] = tol.rtol * fabs(phi(0, i)) + tol.atol[i];
-        rcp_batch<N>(den, ewt);
+        RK<N>(den, ewt);
 #else
 #pragma unroll
-        for (int i = 0; i < N; ++i) ewt[i] = ddiv(1.0, tol.rtol * fabs(phi(0, i)) + tol.atol[i]);
+        for (int i = 0; i < N; ++i) ewt[i] = R(tol.rtol * fabs(phi(0, i)) + tol.atol[i]);
 #endif
     }
 
@@ -535,7 +635,7 @@ struct IdaThread {
                 temp1 = temp2 + hh;
                 const double den[3] = {temp2, temp1, hh};
                 double quo[3];
-                div_batch<3>(num, den, quo);
+                DK<3>(num, den, quo);
                 const double b_i = quo[0], a_i = quo[1];
                 const double s_i = (double)i * sigma_prev * a_i;
                 const double g_i = gamma_prev + quo[2];
@@ -564,7 +664,7 @@ struct IdaThread {
         // so it comes from a table built with the same sequential IEEE operations at compile time.
         const double alphas = alphas_of(kk);
         cjlast = cj;
-        cj = ddiv(-alphas, hh);
+        cj = D(-alphas, hh);
         const double akk = alpha(kk);
         double ck = fabs(akk + alphas - alpha0);
         ck = fmax(ck, akk);
@@ -623,7 +723,7 @@ struct IdaThread {
                     }
                 }
             }
-            const double mult = drcp(J[k][k]);
+            const double mult = R(J[k][k]);
 #pragma unroll
             for (int i = k + 1; i < N; ++i) J[i][k] *= mult;
 #pragma unroll
@@ -639,7 +739,7 @@ struct IdaThread {
     }
 
     // ---- dense_get_rs: crates/linear/src/dense.rs:165-206 ---------------------------------------------
-    __device__ __forceinline__ void getrs(double (&b)[N]) const {
+    __device__ __forceinline__ void getrs(double (&b)[N]) {
 #pragma unroll
         for (int k = 0; k < N; ++k) {
 #pragma unroll
@@ -668,7 +768,7 @@ struct IdaThread {
 #pragma unroll
         for (int k = N - 1; k >= 1; --k) {
             bool ok;
-            b[k] = div_fast(b[k], J[k][k], ok);
+            b[k] = div_fast_z(b[k], J[k][k], ok);
             all = all && ok;
             const double bk = b[k];
 #pragma unroll
@@ -676,10 +776,11 @@ struct IdaThread {
         }
         {
             bool ok;
-            b[0] = div_fast(b[0], J[0][0], ok);
+            b[0] = div_fast_z(b[0], J[0][0], ok);
             all = all && ok;
         }
-        if (__builtin_expect(!all, 0)) {
+        if constexpr (FAST) poison = poison || !all;
+        if (!FAST && !IDA_UNSAFE_NOFALLBACK && __builtin_expect(!all, 0)) {
 #pragma unroll
             for (int i = 0; i < N; ++i) b[i] = save[i];
 #pragma unroll
@@ -732,10 +833,10 @@ struct IdaThread {
     }
 
     // ---- IdaNLProblem::solve -> IdaLProblem::solve: src/ida_nls.rs:190-215, src/ida_ls.rs:298-455 --------
-    __device__ __forceinline__ void nls_lsolve(double (&b)[N]) const {
+    __device__ __forceinline__ void nls_lsolve(double (&b)[N]) {
         getrs(b);
         if (cjratio != 1.0) {
-            const double f = ddiv(2.0, 1.0 + cjratio);
+            const double f = D(2.0, 1.0 + cjratio);
 #pragma unroll
             for (int i = 0; i < N; ++i) b[i] *= f;
         }
@@ -743,19 +844,19 @@ struct IdaThread {
 
     // ---- IdaNLProblem::ctest: src/ida_nls.rs:218-266 ; 1 converged, 0 continue, -1 recover ----------------
     __device__ __forceinline__ int nls_ctest(int m, const double (&del)[N], double tol) {
-        const double delnrm = wrms<N>(del, ewt);
+        const double delnrm = norm_tail(wrms_acc<N>(del, ewt));
         if (m == 0) {
             oldnrm = delnrm;
             if (delnrm <= 0.0001 * toldel) return 1;
         } else {
-            const double base = ddiv(delnrm, oldnrm);
-            const double arg = 1.0 / (double)m;
+            const double base = D(delnrm, oldnrm);
+            const double arg = inv_small(m);  // 1.0 / m, m = 1..3 (MAXNLSIT = 4)
             // m == 1 (the second Newton iteration, by far the most frequent case): pow(x, 1.0) returns x bit-for-bit
             // in the reference's libm (tests/test_detpow.py::test_pow_with_exponent_one_is_the_identity), so the
             // ~60-instruction pow is skipped for the lanes that do not need it
-            const double rate = (m == 1) ? base : pow_noinline(base, arg);
+            const double rate = (m == 1) ? base : PW(base, arg);
             if (rate > RATEMAX) return -1;
-            ss = ddiv(rate, 1.0 - rate);
+            ss = D(rate, 1.0 - rate);
         }
         if (ss * delnrm <= tol) return 1;
         return 0;
@@ -771,7 +872,7 @@ struct IdaThread {
             ss = 20.0;
             call_lsetup = true;
         }
-        cjratio = ddiv(cj, cjold);
+        cjratio = D(cj, cjold);
         const double temp1 = (1.0 - XRATE) / (1.0 + XRATE);
         const double temp2 = 1.0 / temp1;
         if (cjratio < temp1 || cjratio > temp2) call_lsetup = true;
@@ -848,7 +949,7 @@ struct IdaThread {
 #pragma unroll
         for (int i = 0; i < N; ++i) d2[i] = delta[i] + phi(km1, i);
         double enorm_k, enorm_km1, enorm_km2;
-        if constexpr (IDA_WRMS_INLINE) {
+        if constexpr (IDA_WRMS_INLINE || FAST) {
             enorm_k = err_norm(ee);
             enorm_km1 = err_norm(delta);
             enorm_km2 = err_norm(d2);
@@ -881,7 +982,7 @@ struct IdaThread {
         for (int j = 1; j <= kk; ++j) psi(j - 1) = psi(j) - hh;
 #pragma unroll 1
         for (int j = ns; j <= kk; ++j) {
-            const double c = drcp(beta(j));
+            const double c = R(beta(j));
 #pragma unroll
             for (int i = 0; i < N; ++i) phi(j, i) *= c;
         }
@@ -898,7 +999,7 @@ struct IdaThread {
                 kk = knew;
                 const double base = 2.0 * err_knew + 0.0001;
                 const double arg = inv_small(kk + 1);
-                rr = 0.9 * pow_noinline(base, -arg);
+                rr = 0.9 * PW(base, -arg);
                 rr = fmax(0.25, fmin(0.9, rr));
                 hh *= rr;
                 return 0;
@@ -961,7 +1062,7 @@ struct IdaThread {
 #pragma unroll
                 for (int i = 0; i < N; ++i) t[i] = ee[i] - phi(kk + 1, i);
                 const double enorm = err_norm(t);
-                err_kp1 = enorm / (double)(kk + 2);
+                err_kp1 = D(enorm, (double)(kk + 2));
                 const double terr_k = (double)(kk + 1) * err_k;
                 const double terr_kp1 = (double)(kk + 2) * err_kp1;
                 if (kk == 1) {
@@ -987,7 +1088,7 @@ struct IdaThread {
             {
                 const double base = 2.0 * err_knew + 0.0001;
                 const double arg = -inv_small(kk + 1);
-                rr = pow_noinline(base, arg);
+                rr = PW(base, arg);
             }
             if (rr >= 2.0) {
                 hnew = 2.0 * hh;
@@ -1254,7 +1355,7 @@ struct IdaThread {
 #pragma unroll
         for (int i = 0; i < N; ++i) p1[i] = phi(1, i);
         const double ypnorm = err_norm(p1);
-        if (ypnorm > 2.0 / hh) hh = 0.5 / ypnorm;
+        if (ypnorm > D(2.0, hh)) hh = D(0.5, ypnorm);
         if (tout < tn) hh = -hh;
         if constexpr (HMAX_INV != 0.0) {
             const double rh = fabs(hh) * HMAX_INV;
@@ -1292,7 +1393,7 @@ struct IdaThread {
         int ncf = 0, nef = 0;
 
 #pragma unroll 1
-        while (it < lad.ntout) {
+        while (it < lad.ntout && !(FAST && poison)) {
             RP_T(ti0);
             if (need_prologue) {
                 need_prologue = false;
@@ -1306,6 +1407,7 @@ struct IdaThread {
                 if (nst == 0) {
                     const int r = first_call<ROOTS>(tout, tol);
                     if (r != 0) {
+                        if constexpr (FAST) poison = true;  // rare: the exact instantiation reports it
                         call_done = true;
                         call_status = r;
                     }
@@ -1343,19 +1445,25 @@ struct IdaThread {
                         tret = tout;
                         call_done = true;
                     } else if ((tn - tout) * hh >= 0.0) {
-                        const int ier = get_solution(tout);
-                        if (ier == 0) {
-                            tretlast = tout;
-                            tret = tout;
+                        if constexpr (FAST) {
+                            poison = true;  // output time already passed: interpolated in line by the exact instantiation
+                            call_done = true;
+                        } else {
+                            const int ier = get_solution(tout);
+                            if (ier == 0) {
+                                tretlast = tout;
+                                tret = tout;
+                            }
+                            call_status = ier;
+                            call_done = true;
                         }
-                        call_status = ier;
-                        call_done = true;
                     }
                 }
             }
             if (!call_done && !in_step) {
                 // top of the step loop: src/impl_solve.rs:246-311
                 if (nstloc >= MXSTEP) {
+                    if constexpr (FAST) poison = true;
                     if constexpr (ROOTS) get_solution(tn);  // what the reference's r_check3 left in yy / yp (see r_check3)
                     tret = tn;
                     tretlast = tn;
@@ -1369,7 +1477,8 @@ struct IdaThread {
                         for (int i = 0; i < N; ++i) bad = bad || (ewt[i] <= 0.0);
                     }
                     if (bad) {
-                        get_solution(tn);
+                        if constexpr (FAST) poison = true;
+                        else get_solution(tn);
                         tret = tn;
                         tretlast = tn;
                         call_status = B200IDA_ST_BAD_EWT;
@@ -1384,7 +1493,8 @@ struct IdaThread {
                             tolsf *= 10.0;
                             tret = tn;
                             tretlast = tn;
-                            if (nst > 0) get_solution(tn);
+                            if constexpr (FAST) poison = true;
+                            else if (nst > 0) get_solution(tn);
                             call_status = B200IDA_ST_TOO_MUCH_ACC;
                             call_done = true;
                         } else {
@@ -1395,7 +1505,7 @@ struct IdaThread {
                                 kused = 0;
                                 hused = 0.0;
                                 psi(0) = hh;
-                                cj = 1.0 / hh;
+                                cj = R(hh);
                                 phase = 0;
                                 ns = 0;
                             }
@@ -1468,6 +1578,7 @@ struct IdaThread {
                             sp[6 * N + 9] = hused;
                             deferred = true;
                         } else {
+                            static_assert(!FAST, "the FAST instantiation defers the output interpolation");
                             get_solution(tout);
                         }
                         call_status = B200IDA_ST_SUCCESS;
@@ -1484,7 +1595,9 @@ struct IdaThread {
                     }
                     if (kflag != 0) {
                         // failed step: src/impl_solve.rs:314-327
-                        if (get_solution(tn) == 0) {
+                        if constexpr (FAST) {
+                            poison = true;
+                        } else if (get_solution(tn) == 0) {
                             tret = tn;
                             tretlast = tn;
                         }

@@ -19,20 +19,33 @@ namespace b200ida {
 #ifndef IDA_MIN_BLOCKS
 #define IDA_MIN_BLOCKS 3  // 168 regs, 12 warps/SM: measured faster than 4 (128 regs + spills) and 2
 #endif
+#ifndef IDA_FAST
+#define IDA_FAST 1  // production path = FAST pass + exact pass over the flagged instances; 0: the exact kernel alone
+#endif
 #ifndef IDA_DEFER
 #define IDA_DEFER 1  // deferred output interpolation (DeferParams, ida_common.cuh); 0: interpolate in the solve kernel
 #endif
-template <class P, bool TRACE = false, bool ROOTS = false, bool MASK = false>
+// FAST (production): fast paths only, poisoned lanes flagged in xp.poisoned (IdaThread, ida_thread.cuh).  The state is
+// read from (ds, is) and written to (xp.ds_out, xp.is_out) -- a different buffer, so that the exact instantiation can
+// re-integrate the flagged instances from the untouched input: launched right after with xp.select = the flags.
+struct FastParams {
+    double* ds_out = nullptr;        // null: in place
+    int* is_out = nullptr;
+    unsigned char* poisoned = nullptr;     // [batch] by slot, written by the FAST kernel
+    const unsigned char* select = nullptr; // exact kernel: integrate only the slots whose flag is set (null: all)
+};
+template <class P, bool TRACE = false, bool ROOTS = false, bool MASK = false, bool FAST = false>
 __global__ void __launch_bounds__(THREAD_BLOCK, IDA_MIN_BLOCKS)
 ida_solve_thread_kernel(double* __restrict__ ds, int* __restrict__ is, const double* __restrict__ params, int64_t B,
                         TolN<P::N> tol, LadderParams lad, double* __restrict__ yy_traj, int32_t* __restrict__ status,
                         const int* __restrict__ perm, TraceParams tr = TraceParams(), RootParams rp = RootParams(),
-                        DeferParams df = DeferParams()) {
+                        DeferParams df = DeferParams(), FastParams xp = FastParams()) {
     extern __shared__ double smem[];
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // slot
     if (b >= B) return;
+    if (xp.select && !xp.select[b]) return;
     const int64_t ob = perm ? (int64_t)perm[b] : b;  // caller-visible instance id of this slot
-    IdaThread<P, MASK> s;
+    IdaThread<P, MASK, FAST> s;
     s.sm = smem + threadIdx.x;
     if constexpr (MASK) {
 #pragma unroll
@@ -44,7 +57,11 @@ ida_solve_thread_kernel(double* __restrict__ ds, int* __restrict__ is, const dou
     // the production instantiation defers the output interpolation to ida_interp_kernel; the TRACE and ROOTS
     // instantiations read yy / yp right after get_solution (trace frames, g(t, y)) and keep it in line
     s.template solve_ladder<TRACE, ROOTS, !TRACE && !ROOTS && !MASK && IDA_DEFER>(lad, tol, yy_traj, status, B, ob, tr, rp, df, b);
-    s.store(ds, is, B, b);
+    if constexpr (FAST) {
+        xp.poisoned[b] = s.poison ? 1 : 0;
+        if (s.poison) return;  // its outputs are rewritten by the exact pass
+    }
+    s.store(xp.ds_out ? xp.ds_out : ds, xp.is_out ? xp.is_out : is, B, b);
     if constexpr (ROOTS) {
         s.store_roots(rp, B, b);
         if (rp.nge_out) rp.nge_out[ob] = s.nge;
@@ -141,6 +158,9 @@ struct ThreadLaunch {
     TraceParams trace;  // id < 0: off
     RootParams roots;   // max_ev == 0: off
     DeferParams df;     // snapshot buffers sized for snap_doubles(n) (production instantiation)
+    double* ds2 = nullptr;  // production path: the output state buffers of the FAST pass (the caller swaps them in
+    int* is2 = nullptr;     // afterwards) and the per-slot poison flags
+    unsigned char* poisoned = nullptr;
     cudaStream_t stream;
 };
 
@@ -190,14 +210,36 @@ int launch_thread_family(const ThreadLaunch& a) {
             return set_error(B200IDA_ERR_UNSUPPORTED, "this problem was built without the trace instantiation");
         }
     } else {
-        // production path: solve kernel (snapshots at the output times) + the coherent interpolation pass
-        B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_thread_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ida_solve_thread_kernel<P><<<grid, tb, smem, a.stream>>>(a.ds, a.is, a.params, a.B, tol, a.lad, a.traj, a.stat, a.perm, TraceParams(),
-                                                                 RootParams(), a.df);
-        count_launch();
+        // production path: FAST pass (state a.ds -> a.ds2, snapshots at the output times), the exact pass over the
+        // instances the FAST pass flagged (normally none: its CTAs exit at once), the coherent interpolation pass
+        if (IDA_FAST && a.ds2 && a.is2 && a.poisoned) {
+            FastParams xf;
+            xf.ds_out = a.ds2;
+            xf.is_out = a.is2;
+            xf.poisoned = a.poisoned;
+            B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_thread_kernel<P, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ida_solve_thread_kernel<P, false, false, false, true><<<grid, tb, smem, a.stream>>>(a.ds, a.is, a.params, a.B, tol, a.lad, a.traj, a.stat,
+                                                                                               a.perm, TraceParams(), RootParams(), a.df, xf);
+            count_launch();
+            B200_CUDA_TRY(cudaGetLastError());
+            FastParams xe;
+            xe.ds_out = a.ds2;
+            xe.is_out = a.is2;
+            xe.select = a.poisoned;
+            B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_thread_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ida_solve_thread_kernel<P><<<grid, tb, smem, a.stream>>>(a.ds, a.is, a.params, a.B, tol, a.lad, a.traj, a.stat, a.perm, TraceParams(),
+                                                                     RootParams(), a.df, xe);
+            count_launch();
+        } else {
+            B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_thread_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ida_solve_thread_kernel<P><<<grid, tb, smem, a.stream>>>(a.ds, a.is, a.params, a.B, tol, a.lad, a.traj, a.stat, a.perm, TraceParams(),
+                                                                     RootParams(), a.df);
+            count_launch();
+        }
         B200_CUDA_TRY(cudaGetLastError());
         if (IDA_DEFER) {
-            ida_interp_kernel<N><<<(unsigned)((a.B * ntout + 255) / 256), 256, 0, a.stream>>>(a.ds, a.B, a.lad, a.df, a.traj, a.perm);
+            ida_interp_kernel<N><<<(unsigned)((a.B * ntout + 255) / 256), 256, 0, a.stream>>>((IDA_FAST && a.ds2 && a.is2 && a.poisoned) ? a.ds2 : a.ds,
+                                                                                              a.B, a.lad, a.df, a.traj, a.perm);
             count_launch();
         }
     }

@@ -483,28 +483,81 @@ static int launch_cfg(K kernel, int threads, size_t smem, int64_t groups_needed,
 }
 
 
+// ---- mbarrier / bulk-copy (TMA) helpers shared by the CTA LU below and getrs_tma ------------------------------------------
+__device__ __forceinline__ void gt_mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void gt_mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void gt_mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "GT_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra GT_DONE;\n"
+        "bra GT_WAIT;\n"
+        "GT_DONE:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void gt_bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+// shared -> global bulk store (the TMA unit again): writes by the generic proxy must be fenced before the async proxy
+// reads them; completion through the bulk async-group
+__device__ __forceinline__ void gt_bulk_s2g(void* dst, unsigned src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void gt_bulk_commit_wait() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 // ---- CTA-per-system blocked LU (lu_blocked.cuh), 33 <= n <= 160: matrix resident in shared memory ---------------------
+// TMA staging (AoS, even n, 16-byte aligned batch): every column goes in and out as ONE bulk copy, which needs 16-byte
+// aligned shared-memory columns, i.e. an EVEN leading dimension -- n + 2 when n is a multiple of 4 (so that ld / 2 stays
+// odd and row accesses across columns are at worst 2-way bank conflicts), else n.  Other shapes keep the odd ld.
+__host__ __device__ inline int lub_ld_tma(int n) { return (n & 3) ? n : n + 2; }
 __host__ __device__ inline size_t lub_smem_bytes(int n) {
-    size_t b = (size_t)lu_ld(n) * n * sizeof(double);
+    const int ldmax = lu_ld(n) > lub_ld_tma(n) ? lu_ld(n) : lub_ld_tma(n);
+    size_t b = (size_t)ldmax * n * sizeof(double);
     b = (b + 15) / 16 * 16 + (lub_ub_bytes(n) + 15) / 16 * 16 + ((size_t)n * sizeof(int) + 15) / 16 * 16 + sizeof(LubCtl);
-    return (b + 15) / 16 * 16;
+    return (b + 15) / 16 * 16 + 16;  // + the staging mbarrier
 }
 constexpr int lub_threads(int RP) { return RP <= 2 ? 128 : 256; }
 constexpr int lub_min_ctas(int RP) { return RP <= 2 ? 4 : (RP <= 4 ? 2 : 1); }
 
 template <bool SOA, int RP>
 __global__ void __launch_bounds__(lub_threads(RP), lub_min_ctas(RP))
-    getrf_blocked(double* __restrict__ A, int64_t* __restrict__ piv, int32_t* __restrict__ info, int n, int64_t B) {
+    getrf_blocked(double* __restrict__ A, int64_t* __restrict__ piv, int32_t* __restrict__ info, int n, int64_t B, int tma) {
     extern __shared__ __align__(16) unsigned char lu_smem[];
-    const int ld = lu_ld(n);
+    const bool use_tma = !SOA && tma != 0;
+    const int ld = use_tma ? lub_ld_tma(n) : lu_ld(n);
     double* Ms = reinterpret_cast<double*>(lu_smem);
-    size_t off = ((size_t)ld * n * sizeof(double) + 15) / 16 * 16;
+    const int ldmax = lu_ld(n) > lub_ld_tma(n) ? lu_ld(n) : lub_ld_tma(n);
+    size_t off = ((size_t)ldmax * n * sizeof(double) + 15) / 16 * 16;
     double* Ub = reinterpret_cast<double*>(lu_smem + off);
     off += (lub_ub_bytes(n) + 15) / 16 * 16;
     int* pivs = reinterpret_cast<int*>(lu_smem + off);
     off += ((size_t)n * sizeof(int) + 15) / 16 * 16;
     LubCtl* ctl = reinterpret_cast<LubCtl*>(lu_smem + off);
+    off += (sizeof(LubCtl) + 15) / 16 * 16;
+    const unsigned mbar = (unsigned)__cvta_generic_to_shared(lu_smem + off);
     const int tid = threadIdx.x, nt = blockDim.x;
+    if (use_tma) {
+        if (tid == 0) {
+            gt_mbar_init(mbar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
+    unsigned phase = 0;
     for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
         // stage: warp per column (4 columns in flight), lanes along the rows -> coalesced, no index divisions
         LUB_T(ts0);
@@ -521,6 +574,18 @@ __global__ void __launch_bounds__(lub_threads(RP), lub_min_ctas(RP))
                         if (j + u < n) Ms[(j + u) * ld + i] = v[u];
                 }
             }
+        } else if (use_tma) {
+            // AoS, TMA-staged: the whole matrix arrives as n bulk copies (cp.async.bulk, one per column, n * 8 bytes each)
+            // issued by the threads of warp 0 and counted in bytes on one mbarrier every thread then waits on -- no
+            // per-element copy instructions at all (the per-element LDGSTS staging below costs n^2 / threads of them)
+            const double* Ab = A + (size_t)b * n * n;
+            const unsigned sbase = (unsigned)__cvta_generic_to_shared(Ms);
+            if (tid == 0) gt_mbar_expect_tx(mbar, (unsigned)(n * n) * 8u);
+            __syncthreads();  // the expected byte count is in place before any copy can complete
+            if (tid < 32)
+                for (int j = tid; j < n; j += 32) gt_bulk_g2s(sbase + (unsigned)(j * ld) * 8u, Ab + (size_t)j * n, (unsigned)n * 8u, mbar);
+            gt_mbar_wait(mbar, phase);
+            phase ^= 1u;
         } else {
             // AoS: the matrix is n*n contiguous doubles; 8-byte asynchronous copies (LDGSTS) straight into the padded
             // shared-memory columns, all in flight at once, no registers and no per-load round trip
@@ -539,7 +604,17 @@ __global__ void __launch_bounds__(lub_threads(RP), lub_min_ctas(RP))
         LUB_T(ts1);
         LUB_ACC(7, ts0, ts1);
         lub_factor<RP>(Ms, ld, n, ctl, pivs, Ub);
-        {
+        if (use_tma) {
+            // factors back to global the same way: one bulk store per column (lub_factor ended with a CTA barrier)
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            double* Ab = A + (size_t)b * n * n;
+            const unsigned sbase = (unsigned)__cvta_generic_to_shared(Ms);
+            if (tid < 32) {
+                for (int j = tid; j < n; j += 32) gt_bulk_s2g(Ab + (size_t)j * n, sbase + (unsigned)(j * ld) * 8u, (unsigned)n * 8u);
+                gt_bulk_commit_wait();  // the shared-memory columns may be overwritten by the next system after this
+            }
+        } else {
             const int w = tid >> 5, nw = nt >> 5, lane = tid & 31;
             for (int j = 4 * w; j < n; j += 4 * nw) {
                 for (int i = lane; i < n; i += 32) {
@@ -561,8 +636,10 @@ static int launch_getrf_blocked(double* A, int64_t* piv, int32_t* info, int n, i
     const size_t smem = lub_smem_bytes(n);
     unsigned grid = 1;
     int rc;
+    // TMA-staged panels when every column segment is 16-byte aligned: AoS, even n, aligned batch
+    const int tma = (!SOA && (n & 1) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 && !experiment_env("B200IDA_GETRF_NO_TMA")) ? 1 : 0;
     if ((rc = launch_cfg(getrf_blocked<SOA, RP>, lub_threads(RP), smem, B, 1, &grid))) return rc;
-    getrf_blocked<SOA, RP><<<grid, lub_threads(RP), smem, st>>>(A, piv, info, n, B);
+    getrf_blocked<SOA, RP><<<grid, lub_threads(RP), smem, st>>>(A, piv, info, n, B, tma);
     B200_CUDA_TRY(cudaGetLastError());
     return B200IDA_OK;
 }
@@ -809,31 +886,6 @@ static int launch_getrf_blocked_global(double* A, int64_t* piv, int32_t* info, i
 constexpr int GT_CB = 8;
 constexpr int GT_STAGES = 4;
 constexpr int GT_WARPS = 2;
-
-__device__ __forceinline__ void gt_mbar_init(unsigned bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void gt_mbar_expect_tx(unsigned bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void gt_mbar_wait(unsigned bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "GT_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra GT_DONE;\n"
-        "bra GT_WAIT;\n"
-        "GT_DONE:\n"
-        "}\n" ::"r"(bar),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void gt_bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-                 "r"(bytes), "r"(bar)
-                 : "memory");
-}
 
 struct GtPlan {  // chunk schedule of one system: forward chunks 0..nf-1, then the backward chunks
     int n, nf, ntop, nc, rbb;

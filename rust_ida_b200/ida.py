@@ -170,6 +170,13 @@ class Ida:
         self._call("b200ida_solve_ladder", self._h, touts.ctypes.data, nt, 0, pj, ps, self._mem)
         return status, traj
 
+    def fallback_count(self):
+        """instances the last solve handed from the fast-path-only pass to the exact pass (diagnostic; results do not
+        depend on it)"""
+        c = C.c_int64(0)
+        self._call("b200ida_get_fallback_count", self._h, C.byref(c))
+        return int(c.value)
+
     def sync(self):
         self._call("b200ida_sync", self._h)
 

@@ -58,7 +58,7 @@ def child(batch, problem, reps):
     ms = float(np.mean(times))
     print(json.dumps({"lib": os.path.basename(os.environ.get("B200IDA_LIB", "default")), "problem": problem, "batch": batch,
                       "kernel_ms": round(ms, 3), "ms_min": round(min(times), 3), "inst_per_s": round(batch / ms * 1e3),
-                      "attempts": int(natt.sum()), "ok": bool((status_d == 0).all().item()), "sha": hsh}), flush=True)
+                      "attempts": int(natt.sum()), "fallbacks": ida.fallback_count(), "ok": bool((status_d == 0).all().item()), "sha": hsh}), flush=True)
 
 
 def main():
