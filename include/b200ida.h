@@ -285,8 +285,10 @@ long long b200ida_kernel_launches(void);
 
 /* Diagnostic: how many instances the last b200ida_solve / solve_ladder of this handle handed from the production
  * (fast-path-only) pass to the exact pass -- a fast division / square root / pow left its range, or a rare control
- * path was reached (csrc/ida_thread.cuh, "FAST").  Results do not depend on it; throughput does.  Synchronises. */
-int b200ida_get_fallback_count(b200ida_ensemble* e, int64_t* count);
+ * path was reached (csrc/ida_thread.cuh, "FAST").  Results do not depend on it; throughput does.  Synchronises.
+ * hist16 (may be NULL): histogram of the per-instance flag bytes -- 0 / 1 in production builds; in -DIDA_POISON_REASON=1
+ * diagnostic builds 1 + the index of the first range test that failed. */
+int b200ida_get_fallback_count(b200ida_ensemble* e, int64_t* count, int64_t* hist16);
 
 /* out[i] = det_pow(x[i], y[i]) on the device: the glibc-2.39-compatible pow the engine uses wherever the
  * reference calls f64::powf (src/impl_complete_step.rs:128-132, src/lib.rs:1163-1169, src/ida_nls.rs:249-253).

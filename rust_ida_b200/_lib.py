@@ -81,7 +81,7 @@ def lib():
     L.b200ida_set_id.argtypes = [vp, vp, i32]
     L.b200ida_newton_batched.argtypes = [i32, i32, i64, vp, vp, dbl, i32, i32, vp, vp, vp, vp, i32, vp]
     L.b200ida_kernel_launches.restype = C.c_longlong
-    L.b200ida_get_fallback_count.argtypes = [vp, vp]
+    L.b200ida_get_fallback_count.argtypes = [vp, vp, vp]
     for name in SYMBOLS:
         getattr(L, name).restype = C.c_char_p if name == "b200ida_last_error" else i32
     _lib = L

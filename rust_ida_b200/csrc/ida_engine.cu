@@ -271,7 +271,7 @@ struct b200ida_ensemble {
     // launch) and the per-slot flags of the instances it handed to the exact pass
     double* dstate2 = nullptr;
     int* istate2 = nullptr;
-    DevBuf poisoned;
+    DevBuf poisoned, todo;  // todo: [batch + 1] ints, the compacted slot list of the exact pass and its length
     bool fast_ran = false;  // the last solve went through the FAST pass (b200ida_get_fallback_count)
     DevBuf snap, snap_valid;  // deferred output interpolation (DeferParams), grown to the longest ladder seen
     size_t snap_cap = 0, valid_cap = 0;
@@ -716,6 +716,9 @@ int b200ida_solve_ladder(b200ida_ensemble* e, const double* touts, int ntout, in
                 if (!e->dstate2) B200_CUDA_TRY(cudaMalloc(&e->dstate2, (size_t)lay2.ndouble() * e->B * sizeof(double)));
                 if (!e->istate2) B200_CUDA_TRY(cudaMalloc(&e->istate2, (size_t)lay2.nint() * e->B * sizeof(int)));
                 if (!e->poisoned.p) B200_CUDA_TRY(e->poisoned.alloc((size_t)e->B));
+                if (!e->todo.p) B200_CUDA_TRY(e->todo.alloc(((size_t)e->B + 1) * sizeof(int)));
+                a.todo = e->todo.as<int>() + 1;
+                a.todo_count = e->todo.as<int>();
                 a.ds2 = e->dstate2;
                 a.is2 = e->istate2;
                 a.poisoned = e->poisoned.as<unsigned char>();
@@ -780,9 +783,11 @@ int b200ida_solve_ladder(b200ida_ensemble* e, const double* touts, int ntout, in
     return B200IDA_OK;
 }
 
-int b200ida_get_fallback_count(b200ida_ensemble* e, int64_t* count) {
+int b200ida_get_fallback_count(b200ida_ensemble* e, int64_t* count, int64_t* hist16) {
     if (!e || !count) return set_error(B200IDA_ERR_ARG, "b200ida_get_fallback_count: bad argument");
     *count = 0;
+    if (hist16)
+        for (int i = 0; i < 16; ++i) hist16[i] = 0;
     if (!e->poisoned.p || !e->fast_ran) return B200IDA_OK;  // the last solve did not take the FAST path
     B200_CUDA_TRY(cudaSetDevice(e->device));
     unsigned char* h = static_cast<unsigned char*>(malloc((size_t)e->B));
@@ -791,7 +796,10 @@ int b200ida_get_fallback_count(b200ida_ensemble* e, int64_t* count) {
     if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
     int64_t c = 0;
     if (err == cudaSuccess)
-        for (int64_t i = 0; i < e->B; ++i) c += h[i] != 0;
+        for (int64_t i = 0; i < e->B; ++i) {
+            c += h[i] != 0;
+            if (hist16) hist16[h[i] & 15] += 1;
+        }
     free(h);
     B200_CUDA_TRY(err);
     *count = c;

@@ -423,14 +423,34 @@ __device__ __noinline__ unsigned root_check3(double* sm, P prob, unsigned gmask,
 template <class P, bool MASK = false, bool FAST = false>
 struct IdaThread {
     static constexpr int N = P::N;
+#ifndef IDA_POISON_REASON
+#define IDA_POISON_REASON 0  // 1 (diagnostic builds): xp.poisoned[] holds a bit mask of WHICH test failed
+#endif
+#if IDA_POISON_REASON
+    unsigned poison = 0;
+#define IDA_POISON(bit, cond) poison |= ((cond) ? (bit) : 0u)
+#else
     bool poison = false;  // FAST only: some fast path left its range or a rare path was reached -> redo exactly
+#define IDA_POISON(bit, cond) poison = poison || (cond)
+#endif
 
     // ---- arithmetic through one door, so that FAST can drop the fallbacks ----------------------------------------
     __device__ __forceinline__ double D(double a, double b) {  // a / b
         if constexpr (FAST) {
             bool ok;
             const double q = div_fast(a, b, ok);
-            poison = poison || !ok;
+            IDA_POISON(1u, !ok);
+            return q;
+        } else {
+            return ddiv(a, b);
+        }
+    }
+    // a / b where a may be exactly zero (a norm that vanished): FAST handles that in line instead of poisoning the lane
+    __device__ __forceinline__ double DZ(double a, double b) {
+        if constexpr (FAST) {
+            bool ok;
+            const double q = div_fast_z(a, b, ok);
+            IDA_POISON(1u, !ok);
             return q;
         } else {
             return ddiv(a, b);
@@ -440,7 +460,7 @@ struct IdaThread {
         if constexpr (FAST) {
             bool ok;
             const double r = rcp_fast(b, ok);
-            poison = poison || !ok;
+            IDA_POISON(2u, !ok);
             return r;
         } else {
             return drcp(b);
@@ -456,7 +476,7 @@ struct IdaThread {
                 q[k] = div_fast(a[k], b[k], ok);
                 all = all && ok;
             }
-            poison = poison || !all;
+            IDA_POISON(4u, !all);
         } else {
             div_batch<K>(a, b, q);
         }
@@ -471,7 +491,7 @@ struct IdaThread {
                 r[k] = rcp_fast(b[k], ok);
                 all = all && ok;
             }
-            poison = poison || !all;
+            IDA_POISON(8u, !all);
         } else {
             rcp_batch<K>(b, r);
         }
@@ -485,8 +505,10 @@ struct IdaThread {
             const double r = __fma_rn(-(double)N, q, acc);
             bool ok;
             const double v = sqrt_fast(__fma_rn(r, y, q), ok);
-            poison = poison || !ok || !(hi - 0x07b00000u <= 0x70800000u);
-            return v;
+            const bool zero = acc == 0.0;  // an exactly vanishing vector: sqrt(0 / N) = 0 (acc is a sum of squares: +0)
+            IDA_POISON(16u, !zero && !(hi - 0x07b00000u <= 0x70800000u));
+            IDA_POISON(32u, !zero && !ok);
+            return zero ? 0.0 : v;
         } else if constexpr (IDA_WRMS_INLINE) {
             return wrms_tail_inline<N>(acc);
         } else {
@@ -496,7 +518,7 @@ struct IdaThread {
     __device__ __forceinline__ double PW(double x, double y) {  // pow(x, y)
         if constexpr (FAST) {
             const double r = pow_main_noinline(x, y);  // NaN when (x, y) is off det_pow's main path
-            poison = poison || (r != r);
+            IDA_POISON(64u, r != r);
             return r;
         } else {
             return pow_noinline(x, y);
@@ -779,7 +801,7 @@ struct IdaThread {
             b[0] = div_fast_z(b[0], J[0][0], ok);
             all = all && ok;
         }
-        if constexpr (FAST) poison = poison || !all;
+        if constexpr (FAST) IDA_POISON(256u, !all);
         if (!FAST && !IDA_UNSAFE_NOFALLBACK && __builtin_expect(!all, 0)) {
 #pragma unroll
             for (int i = 0; i < N; ++i) b[i] = save[i];
@@ -849,14 +871,14 @@ struct IdaThread {
             oldnrm = delnrm;
             if (delnrm <= 0.0001 * toldel) return 1;
         } else {
-            const double base = D(delnrm, oldnrm);
+            const double base = DZ(delnrm, oldnrm);
             const double arg = inv_small(m);  // 1.0 / m, m = 1..3 (MAXNLSIT = 4)
             // m == 1 (the second Newton iteration, by far the most frequent case): pow(x, 1.0) returns x bit-for-bit
             // in the reference's libm (tests/test_detpow.py::test_pow_with_exponent_one_is_the_identity), so the
             // ~60-instruction pow is skipped for the lanes that do not need it
             const double rate = (m == 1) ? base : PW(base, arg);
             if (rate > RATEMAX) return -1;
-            ss = D(rate, 1.0 - rate);
+            ss = DZ(rate, 1.0 - rate);
         }
         if (ss * delnrm <= tol) return 1;
         return 0;
@@ -1407,7 +1429,7 @@ struct IdaThread {
                 if (nst == 0) {
                     const int r = first_call<ROOTS>(tout, tol);
                     if (r != 0) {
-                        if constexpr (FAST) poison = true;  // rare: the exact instantiation reports it
+                        if constexpr (FAST) IDA_POISON(128u, true);  // rare: the exact instantiation reports it
                         call_done = true;
                         call_status = r;
                     }
@@ -1446,7 +1468,7 @@ struct IdaThread {
                         call_done = true;
                     } else if ((tn - tout) * hh >= 0.0) {
                         if constexpr (FAST) {
-                            poison = true;  // output time already passed: interpolated in line by the exact instantiation
+                            IDA_POISON(128u, true);  // output time already passed: interpolated in line by the exact instantiation
                             call_done = true;
                         } else {
                             const int ier = get_solution(tout);
@@ -1463,7 +1485,7 @@ struct IdaThread {
             if (!call_done && !in_step) {
                 // top of the step loop: src/impl_solve.rs:246-311
                 if (nstloc >= MXSTEP) {
-                    if constexpr (FAST) poison = true;
+                    if constexpr (FAST) IDA_POISON(128u, true);
                     if constexpr (ROOTS) get_solution(tn);  // what the reference's r_check3 left in yy / yp (see r_check3)
                     tret = tn;
                     tretlast = tn;
@@ -1477,7 +1499,7 @@ struct IdaThread {
                         for (int i = 0; i < N; ++i) bad = bad || (ewt[i] <= 0.0);
                     }
                     if (bad) {
-                        if constexpr (FAST) poison = true;
+                        if constexpr (FAST) IDA_POISON(128u, true);
                         else get_solution(tn);
                         tret = tn;
                         tretlast = tn;
@@ -1493,7 +1515,7 @@ struct IdaThread {
                             tolsf *= 10.0;
                             tret = tn;
                             tretlast = tn;
-                            if constexpr (FAST) poison = true;
+                            if constexpr (FAST) IDA_POISON(128u, true);
                             else if (nst > 0) get_solution(tn);
                             call_status = B200IDA_ST_TOO_MUCH_ACC;
                             call_done = true;
@@ -1596,7 +1618,7 @@ struct IdaThread {
                     if (kflag != 0) {
                         // failed step: src/impl_solve.rs:314-327
                         if constexpr (FAST) {
-                            poison = true;
+                            IDA_POISON(512u, true);
                         } else if (get_solution(tn) == 0) {
                             tret = tn;
                             tretlast = tn;

@@ -31,8 +31,11 @@ namespace b200ida {
 struct FastParams {
     double* ds_out = nullptr;        // null: in place
     int* is_out = nullptr;
-    unsigned char* poisoned = nullptr;     // [batch] by slot, written by the FAST kernel
-    const unsigned char* select = nullptr; // exact kernel: integrate only the slots whose flag is set (null: all)
+    unsigned char* poisoned = nullptr;  // [batch] by slot, written by the FAST kernel (diagnostics)
+    int* list = nullptr;                // FAST kernel: appends the slots it hands to the exact pass ...
+    int* count = nullptr;               // ... counting them here (zeroed before the launch)
+    const int* todo = nullptr;          // exact kernel: thread t integrates slot todo[t], t < *todo_count (null: slot = t)
+    const int* todo_count = nullptr;
 };
 template <class P, bool TRACE = false, bool ROOTS = false, bool MASK = false, bool FAST = false>
 __global__ void __launch_bounds__(THREAD_BLOCK, IDA_MIN_BLOCKS)
@@ -41,9 +44,12 @@ ida_solve_thread_kernel(double* __restrict__ ds, int* __restrict__ is, const dou
                         const int* __restrict__ perm, TraceParams tr = TraceParams(), RootParams rp = RootParams(),
                         DeferParams df = DeferParams(), FastParams xp = FastParams()) {
     extern __shared__ double smem[];
-    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // slot
+    int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // slot
     if (b >= B) return;
-    if (xp.select && !xp.select[b]) return;
+    if (xp.todo) {  // exact pass over the compacted list of flagged slots: full warps however the flags are scattered
+        if (b >= (int64_t)*xp.todo_count) return;
+        b = xp.todo[b];
+    }
     const int64_t ob = perm ? (int64_t)perm[b] : b;  // caller-visible instance id of this slot
     IdaThread<P, MASK, FAST> s;
     s.sm = smem + threadIdx.x;
@@ -58,8 +64,15 @@ ida_solve_thread_kernel(double* __restrict__ ds, int* __restrict__ is, const dou
     // instantiations read yy / yp right after get_solution (trace frames, g(t, y)) and keep it in line
     s.template solve_ladder<TRACE, ROOTS, !TRACE && !ROOTS && !MASK && IDA_DEFER>(lad, tol, yy_traj, status, B, ob, tr, rp, df, b);
     if constexpr (FAST) {
+#if IDA_POISON_REASON
+        xp.poisoned[b] = (unsigned char)__ffs((int)s.poison);  // 1 + index of the first failed test (ida_thread.cuh)
+#else
         xp.poisoned[b] = s.poison ? 1 : 0;
-        if (s.poison) return;  // its outputs are rewritten by the exact pass
+#endif
+        if (s.poison) {  // its outputs are rewritten by the exact pass
+            xp.list[atomicAdd(xp.count, 1)] = (int)b;
+            return;
+        }
     }
     s.store(xp.ds_out ? xp.ds_out : ds, xp.is_out ? xp.is_out : is, B, b);
     if constexpr (ROOTS) {
@@ -161,6 +174,8 @@ struct ThreadLaunch {
     double* ds2 = nullptr;  // production path: the output state buffers of the FAST pass (the caller swaps them in
     int* is2 = nullptr;     // afterwards) and the per-slot poison flags
     unsigned char* poisoned = nullptr;
+    int* todo = nullptr;        // [batch] compacted slots of the flagged instances
+    int* todo_count = nullptr;  // [1]
     cudaStream_t stream;
 };
 
@@ -217,6 +232,9 @@ int launch_thread_family(const ThreadLaunch& a) {
             xf.ds_out = a.ds2;
             xf.is_out = a.is2;
             xf.poisoned = a.poisoned;
+            xf.list = a.todo;
+            xf.count = a.todo_count;
+            B200_CUDA_TRY(cudaMemsetAsync(a.todo_count, 0, sizeof(int), a.stream));
             B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_thread_kernel<P, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             ida_solve_thread_kernel<P, false, false, false, true><<<grid, tb, smem, a.stream>>>(a.ds, a.is, a.params, a.B, tol, a.lad, a.traj, a.stat,
                                                                                                a.perm, TraceParams(), RootParams(), a.df, xf);
@@ -225,7 +243,8 @@ int launch_thread_family(const ThreadLaunch& a) {
             FastParams xe;
             xe.ds_out = a.ds2;
             xe.is_out = a.is2;
-            xe.select = a.poisoned;
+            xe.todo = a.todo;
+            xe.todo_count = a.todo_count;
             B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_thread_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             ida_solve_thread_kernel<P><<<grid, tb, smem, a.stream>>>(a.ds, a.is, a.params, a.B, tol, a.lad, a.traj, a.stat, a.perm, TraceParams(),
                                                                      RootParams(), a.df, xe);

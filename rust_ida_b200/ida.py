@@ -111,7 +111,10 @@ class Ida:
 
     def close(self):
         if getattr(self, "_h", None):
-            _lib.lib().b200ida_destroy(self._h)
+            try:
+                _lib.lib().b200ida_destroy(self._h)
+            except Exception:  # interpreter shutdown: the module globals may be gone already
+                pass
             self._h = None
 
     __del__ = close
@@ -174,8 +177,15 @@ class Ida:
         """instances the last solve handed from the fast-path-only pass to the exact pass (diagnostic; results do not
         depend on it)"""
         c = C.c_int64(0)
-        self._call("b200ida_get_fallback_count", self._h, C.byref(c))
+        self._call("b200ida_get_fallback_count", self._h, C.byref(c), None)
         return int(c.value)
+
+    def fallback_histogram(self):
+        """histogram (16 bins) of the per-instance fallback flags (reason codes in -DIDA_POISON_REASON=1 builds)"""
+        c = C.c_int64(0)
+        h = (C.c_int64 * 16)()
+        self._call("b200ida_get_fallback_count", self._h, C.byref(c), h)
+        return [int(v) for v in h]
 
     def sync(self):
         self._call("b200ida_sync", self._h)
