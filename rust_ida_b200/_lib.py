@@ -20,7 +20,7 @@ OK, ERR_ARG, ERR_CUDA, ERR_NO_DEVICE, ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 SYMBOLS = (
     "b200ida_last_error", "b200ida_version", "b200ida_device_count",
     "b200ida_getrf_batched", "b200ida_getrs_batched", "b200ida_wrms_batched", "b200ida_wrms_masked_batched", "b200ida_newton_batched",
-    "b200ida_create", "b200ida_destroy", "b200ida_reinit", "b200ida_set_kernel", "b200ida_set_default_reorder", "b200ida_solve", "b200ida_solve_ladder", "b200ida_set_trace", "b200ida_set_roots", "b200ida_set_id",
+    "b200ida_create", "b200ida_destroy", "b200ida_reinit", "b200ida_set_kernel", "b200ida_set_default_reorder", "b200ida_solve", "b200ida_solve_ladder", "b200ida_set_trace", "b200ida_set_roots", "b200ida_set_id", "b200ida_set_regroup",
     "b200ida_get_state", "b200ida_get_counters", "b200ida_get_step_info", "b200ida_get_dky", "b200ida_sync",
     "b200ida_fp64_issue_rate", "b200ida_detpow_batched", "b200ida_fastdiv_batched", "b200ida_kernel_launches", "b200ida_get_fallback_count",
 )
@@ -79,6 +79,7 @@ def lib():
     L.b200ida_detpow_batched.argtypes = [vp, vp, vp, i64, i32, vp]
     L.b200ida_fastdiv_batched.argtypes = [vp, vp, vp, vp, i64]
     L.b200ida_set_id.argtypes = [vp, vp, i32]
+    L.b200ida_set_regroup.argtypes = [vp, i32, i32]
     L.b200ida_newton_batched.argtypes = [i32, i32, i64, vp, vp, dbl, i32, i32, vp, vp, vp, vp, i32, vp]
     L.b200ida_kernel_launches.restype = C.c_longlong
     L.b200ida_get_fallback_count.argtypes = [vp, vp, vp]

@@ -89,8 +89,8 @@ struct RootParams {
 // lane-coherent kernel (ida_interp_kernel) evaluates y(tout), y'(tout) for every (instance, output time) afterwards:
 // same operations on the same operands, so the values are bit-identical, but the ~400-instruction interpolation is no
 // longer issued once per lane per output time by a warp whose lanes reach their output times on different attempts.
-// snap: [batch][ntout][snap_doubles(n)] by slot, AoS so that the lone lane writes whole sectors and the second pass
-// streams; fields 0..6n+5 are phi / psi at their Layout offsets, then kused, tn, hh, hused.  valid: [batch][ntout] bytes,
+// snap: [batch][ntout][snap_doubles(n)] by caller-visible instance id (slots are re-assigned when the ensemble is
+// re-grouped between segments; ids are not), AoS so that the lone lane writes whole sectors and the second pass streams; fields 0..6n+5 are phi / psi at their Layout offsets, then kused, tn, hh, hused.  valid: [batch][ntout] bytes,
 // written for every call of every instance (1 = snapshot taken, 0 = the call returned some other way and interpolated
 // in line).
 struct DeferParams {
@@ -98,6 +98,20 @@ struct DeferParams {
     unsigned char* valid;
 };
 __host__ __device__ constexpr int snap_doubles(int n) { return 6 * n + 6 + 4; }
+
+// segmented launches (re-grouping of the ensemble between segments, ida_engine.cu): a launch runs at most max_trips
+// trips of the flattened solve loop, then parks the loop's own state -- which output time the lane is on, whether a
+// step is in progress, the per-call / per-step counters -- next to the solver state, and the next launch resumes it.
+// li: [2][batch] ints (word 0: it | need_prologue << 8 | in_step << 9 | ncf << 10 | nef << 18 ; word 1: nstloc),
+// ld: [1][batch] doubles (saved_t).  max_trips < 0: one unsegmented launch (nothing is loaded or stored).
+struct SegParams {
+    int max_trips = -1;
+    int resume = 0;      // 0: the launch starts the API call (fresh loop state), 1: continue from li / ld
+    const int* li = nullptr;   // read when resume != 0
+    const double* ld = nullptr;
+    int* li_out = nullptr;     // written at the end of the launch: a DIFFERENT buffer, so that the exact pass of the same
+    double* ld_out = nullptr;  // segment still finds the loop state its flagged lanes started the segment with
+};
 
 // select a[k] from a 6-entry register array without dynamic indexing
 __device__ __forceinline__ double pick6(const double (&a)[MXORDP1], int k) {

@@ -186,6 +186,45 @@ __global__ void order_key_kernel(const double* __restrict__ params, const double
     ids[b] = (int)b;
 }
 
+// ---- re-grouping of the ensemble between the segments of a solve ------------------------------------
+// key: finished instances last; otherwise (order kk, phase, ns, quantised log2 |h|) -- lanes that agree on these walk the
+// same loop trip counts and take the same branches for a while.  The radix sort is stable, so equal keys keep their
+// previous (parameter-Morton) neighbourhood.
+__global__ void regroup_key_kernel(const double* __restrict__ ds, const int* __restrict__ is, const int* __restrict__ li, int n,
+                                   int64_t B, int ntout, unsigned* __restrict__ keys, int* __restrict__ ids) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= B) return;
+    const Layout lay(n);
+    const unsigned done = ((li[s] & 0xff) >= ntout) ? 1u : 0u;
+    const unsigned kk = (unsigned)is[(int64_t)Layout::KK * B + s] & 7u;
+    const unsigned ph = (unsigned)is[(int64_t)Layout::PHASE * B + s] & 1u;
+    const unsigned ns = (unsigned)min(is[(int64_t)Layout::NS * B + s], 7) & 7u;
+    const unsigned hq = ((unsigned)__double2hiint(fabs(ds[(int64_t)lay.scal(Layout::HH) * B + s])) >> 16) & 0x7fffu;  // exponent + 4 mantissa bits
+    keys[s] = done << 23 | kk << 20 | ph << 19 | ns << 16 | hq;
+    ids[s] = (int)s;
+}
+// new slot s takes what old slot order[s] held, for every per-slot row of the engine
+__global__ void regroup_gather_kernel(const int* __restrict__ order, int64_t B, const double* __restrict__ d_src, double* __restrict__ d_dst,
+                                      int nd, const int* __restrict__ i_src, int* __restrict__ i_dst, int ni,
+                                      const double* __restrict__ p_src, double* __restrict__ p_dst, int np,
+                                      const int* __restrict__ li_src, int* __restrict__ li_dst, const double* __restrict__ ld_src,
+                                      double* __restrict__ ld_dst, const int* __restrict__ perm_src, int* __restrict__ perm_dst) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= B) return;
+    const int64_t o = order[s];
+    for (int f = 0; f < nd; ++f) d_dst[(int64_t)f * B + s] = d_src[(int64_t)f * B + o];
+    for (int f = 0; f < ni; ++f) i_dst[(int64_t)f * B + s] = i_src[(int64_t)f * B + o];
+    for (int f = 0; f < np; ++f) p_dst[(int64_t)f * B + s] = p_src[(int64_t)f * B + o];
+    li_dst[s] = li_src[o];
+    li_dst[B + s] = li_src[B + o];
+    ld_dst[s] = ld_src[o];
+    perm_dst[s] = perm_src[o];
+}
+__global__ void invert_perm_kernel(const int* __restrict__ perm, int* __restrict__ inv, int64_t B) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < B) inv[perm[s]] = (int)s;
+}
+
 __global__ void detpow_kernel(const double* __restrict__ x, const double* __restrict__ y, double* __restrict__ out,
                               int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -271,6 +310,11 @@ struct b200ida_ensemble {
     // launch) and the per-slot flags of the instances it handed to the exact pass
     double* dstate2 = nullptr;
     int* istate2 = nullptr;
+    // re-grouping between segments (thread-per-instance production path, large re-ordered ensembles)
+    int regroup_trips = 128, regroup_segments = 4;  // b200ida_set_regroup; segments <= 1: off
+    DevBuf params2, perm2, inv_perm, perm0, params0, loop_i, loop_i2, loop_d, loop_d2, rg_keys, rg_keys2, rg_ids, rg_order, rg_tmp;
+    size_t rg_tmp_bytes = 0;
+    bool regrouped = false;  // perm / params differ from the parameter-Morton order built at (re)init
     DevBuf poisoned, todo;  // todo: [batch + 1] ints, the compacted slot list of the exact pass and its length
     bool fast_ran = false;  // the last solve went through the FAST pass (b200ida_get_fallback_count)
     DevBuf snap, snap_valid;  // deferred output interpolation (DeferParams), grown to the longest ladder seen
@@ -391,6 +435,16 @@ static int build_order(b200ida_ensemble* e, const double* d_params_caller_order)
     return B200IDA_OK;  // scratch is persistent and stream-ordered: no synchronisation needed
 }
 
+// e->perm changed: refresh its inverse (instance id -> slot), used by the interpolation pass
+static int refresh_inverse_perm(b200ida_ensemble* e) {
+    if (!e->perm) return B200IDA_OK;
+    if (!e->inv_perm.p) B200_CUDA_TRY(e->inv_perm.alloc((size_t)e->B * sizeof(int)));
+    invert_perm_kernel<<<(unsigned)((e->B + 255) / 256), 256, 0, e->stream>>>(e->perm, e->inv_perm.as<int>(), e->B);
+    count_launch();
+    B200_CUDA_TRY(cudaGetLastError());
+    return B200IDA_OK;
+}
+
 static int check_mem(int mem) { return (mem == B200IDA_MEM_DEVICE || mem == B200IDA_MEM_HOST) ? 0 : -1; }
 
 // slot-ordered state rows -> caller-ordered output (device or host), converting TS -> TD
@@ -483,6 +537,21 @@ int b200ida_reinit(b200ida_ensemble* e, const double* params, const double* yy0,
         permute_rows_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, st>>>(dp, e->params, e->nparams, batch, e->perm);
         count_launch();
         B200_CUDA_TRY(cudaGetLastError());
+        e->regrouped = false;
+        if (e->perm) {
+            // keep the parameter-Morton order: a solve may re-group the slots, the next re-initialisation starts from here
+            if (!e->perm0.p) B200_CUDA_TRY(e->perm0.alloc((size_t)batch * sizeof(int)));
+            if (!e->params0.p) B200_CUDA_TRY(e->params0.alloc(pbytes));
+            B200_CUDA_TRY(cudaMemcpyAsync(e->perm0.p, e->perm, (size_t)batch * sizeof(int), cudaMemcpyDeviceToDevice, st));
+            B200_CUDA_TRY(cudaMemcpyAsync(e->params0.p, e->params, pbytes, cudaMemcpyDeviceToDevice, st));
+            if ((rc = refresh_inverse_perm(e))) return rc;
+        }
+    } else if (e->regrouped && e->perm && e->perm0.p) {
+        B200_CUDA_TRY(cudaMemcpyAsync(e->perm, e->perm0.p, (size_t)batch * sizeof(int), cudaMemcpyDeviceToDevice, st));
+        B200_CUDA_TRY(cudaMemcpyAsync(e->params, e->params0.p, (size_t)e->nparams * batch * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        e->regrouped = false;
+        int rc2 = refresh_inverse_perm(e);
+        if (rc2) return rc2;
     }
     if (mem == B200IDA_MEM_HOST) {
         void *y0b, *yp0b;
@@ -724,17 +793,80 @@ int b200ida_solve_ladder(b200ida_ensemble* e, const double* touts, int ntout, in
                 a.poisoned = e->poisoned.as<unsigned char>();
             }
         }
+        auto launch = [&](const ThreadLaunch& la) -> int {
+            if (user) {
+                const UserProblemHooks* hk = user_problem_hooks();
+                if (!hk) return set_error(B200IDA_ERR_UNSUPPORTED, "no user problem is linked into this library");
+                return hk->launch(la);
+            }
+            if (e->problem == B200IDA_PROBLEM_ROBERTS) return launch_thread_family<Roberts, CAP_TRACE | CAP_ROOTS | CAP_MASK>(la);
+            return launch_thread_family<Lorenz63, CAP_TRACE | CAP_MASK>(la);
+        };
+        a.slot_of_id = e->perm ? e->inv_perm.as<int>() : nullptr;
+        // Segmented solve with re-grouping: production path, internally re-ordered ensembles that are
+        // large enough for a sort + gather of the state (~1 ms per 2^20 instances) to pay
+        const bool segmented = a.ds2 && e->perm && e->regroup_segments > 1 && e->regroup_trips > 0 && e->B >= ((int64_t)1 << 16);
         int rc;
-        if (user) {
-            const UserProblemHooks* hk = user_problem_hooks();
-            if (!hk) return set_error(B200IDA_ERR_UNSUPPORTED, "no user problem is linked into this library");
-            rc = hk->launch(a);
-        } else if (e->problem == B200IDA_PROBLEM_ROBERTS) {
-            rc = launch_thread_family<Roberts, CAP_TRACE | CAP_ROOTS | CAP_MASK>(a);
+        if (!segmented) {
+            rc = launch(a);
+            if (rc != B200IDA_OK) return rc;
         } else {
-            rc = launch_thread_family<Lorenz63, CAP_TRACE | CAP_MASK>(a);
+            const int64_t B = e->B;
+            const Layout lay(e->n);
+            const int nd = lay.ndouble(), ni = lay.nint(), np = e->nparams;
+            if (!e->loop_i.p) {
+                B200_CUDA_TRY(e->loop_i.alloc(2 * (size_t)B * sizeof(int)));
+                B200_CUDA_TRY(e->loop_i2.alloc(2 * (size_t)B * sizeof(int)));
+                B200_CUDA_TRY(e->loop_d.alloc((size_t)B * sizeof(double)));
+                B200_CUDA_TRY(e->loop_d2.alloc((size_t)B * sizeof(double)));
+                B200_CUDA_TRY(e->params2.alloc((size_t)np * B * sizeof(double)));
+                B200_CUDA_TRY(e->perm2.alloc((size_t)B * sizeof(int)));
+                B200_CUDA_TRY(e->rg_keys.alloc((size_t)B * sizeof(unsigned)));
+                B200_CUDA_TRY(e->rg_keys2.alloc((size_t)B * sizeof(unsigned)));
+                B200_CUDA_TRY(e->rg_ids.alloc((size_t)B * sizeof(int)));
+                B200_CUDA_TRY(e->rg_order.alloc((size_t)B * sizeof(int)));
+                size_t tb = 0;
+                cub::DeviceRadixSort::SortPairs(nullptr, tb, (unsigned*)nullptr, (unsigned*)nullptr, (int*)nullptr, (int*)nullptr, (int)B, 0, 24, e->stream);
+                B200_CUDA_TRY(e->rg_tmp.alloc(tb));
+                e->rg_tmp_bytes = tb;
+            }
+            const int nseg = e->regroup_segments;
+            const unsigned g256 = (unsigned)((B + 255) / 256);
+            for (int seg = 0; seg < nseg; ++seg) {
+                ThreadLaunch la = a;
+                la.ds = e->dstate;
+                la.is = e->istate;
+                la.params = e->params;
+                la.perm = e->perm;
+                la.run_interp = 0;
+                la.seg.max_trips = (seg == nseg - 1) ? 0x7fffffff : e->regroup_trips;
+                la.seg.resume = seg > 0;
+                la.seg.li = e->loop_i.as<int>();
+                la.seg.ld = e->loop_d.as<double>();
+                la.seg.li_out = e->loop_i2.as<int>();
+                la.seg.ld_out = e->loop_d2.as<double>();
+                rc = launch(la);  // state: dstate -> dstate2, loop state: loop_* -> loop_*2 (FAST pass + exact pass over its flagged slots)
+                if (rc != B200IDA_OK) return rc;
+                if (seg == nseg - 1) break;
+                // re-group: sort the slots by behaviour key, gather every per-slot row dstate2 -> dstate in that order
+                regroup_key_kernel<<<g256, 256, 0, e->stream>>>(e->dstate2, e->istate2, e->loop_i2.as<int>(), e->n, B, ntout,
+                                                                e->rg_keys.as<unsigned>(), e->rg_ids.as<int>());
+                count_launch();
+                size_t tb = e->rg_tmp_bytes;
+                B200_CUDA_TRY(cub::DeviceRadixSort::SortPairs(e->rg_tmp.p, tb, e->rg_keys.as<unsigned>(), e->rg_keys2.as<unsigned>(),
+                                                              e->rg_ids.as<int>(), e->rg_order.as<int>(), (int)B, 0, 24, e->stream));
+                regroup_gather_kernel<<<g256, 256, 0, e->stream>>>(e->rg_order.as<int>(), B, e->dstate2, e->dstate, nd, e->istate2, e->istate, ni,
+                                                                   e->params, e->params2.as<double>(), np, e->loop_i2.as<int>(),
+                                                                   e->loop_i.as<int>(), e->loop_d2.as<double>(), e->loop_d.as<double>(),
+                                                                   e->perm, e->perm2.as<int>());
+                count_launch();
+                B200_CUDA_TRY(cudaGetLastError());
+                { void* t = e->params; e->params = e->params2.as<double>(); e->params2.p = t; }
+                { void* t = e->perm; e->perm = e->perm2.as<int>(); e->perm2.p = t; }
+                e->regrouped = true;
+            }
+            if ((rc = refresh_inverse_perm(e))) return rc;
         }
-        if (rc != B200IDA_OK) return rc;
         e->fast_ran = a.ds2 != nullptr;
         if (a.ds2) {  // the FAST / exact passes wrote the new state to the second buffers: they are the state now
             double* td = e->dstate;
@@ -743,6 +875,16 @@ int b200ida_solve_ladder(b200ida_ensemble* e, const double* touts, int ntout, in
             int* ti = e->istate;
             e->istate = e->istate2;
             e->istate2 = ti;
+        }
+        if (segmented) {  // the interpolation pass over all segments' snapshots, on the final state and slot order
+            ThreadLaunch la = a;
+            la.run_solve = 0;
+            la.run_interp = 1;
+            la.ds = e->dstate;
+            la.ds2 = nullptr;
+            la.slot_of_id = e->inv_perm.as<int>();
+            rc = launch(la);
+            if (rc != B200IDA_OK) return rc;
         }
     } else {
         const bool warp = kernel == B200IDA_KERNEL_WARP;
@@ -803,6 +945,14 @@ int b200ida_get_fallback_count(b200ida_ensemble* e, int64_t* count, int64_t* his
     free(h);
     B200_CUDA_TRY(err);
     *count = c;
+    return B200IDA_OK;
+}
+
+int b200ida_set_regroup(b200ida_ensemble* e, int trips_per_segment, int max_segments) {
+    if (!e || trips_per_segment < 0 || max_segments < 0 || max_segments > 64)
+        return set_error(B200IDA_ERR_ARG, "b200ida_set_regroup: bad argument");
+    e->regroup_trips = trips_per_segment;
+    e->regroup_segments = max_segments;
     return B200IDA_OK;
 }
 

@@ -1403,7 +1403,8 @@ struct IdaThread {
     template <bool TRACE, bool ROOTS = false, bool DEFER = false>
     __device__ __forceinline__ void solve_ladder(const LadderParams& lad, const TolN<N>& tol, double* __restrict__ yy_traj,
                                                  int32_t* __restrict__ status, int64_t B, int64_t b, const TraceParams& tr,
-                                                 const RootParams& rp = RootParams(), const DeferParams& df = DeferParams(), int64_t slot = 0) {
+                                                 const RootParams& rp = RootParams(), const DeferParams& df = DeferParams(), int64_t slot = 0,
+                                                 const SegParams& sg = SegParams()) {
         int it = 0;
         bool deferred = false;
         bool need_prologue = true;
@@ -1413,9 +1414,22 @@ struct IdaThread {
         int nstloc = 0;
         double saved_t = 0.0, tout = 0.0;
         int ncf = 0, nef = 0;
+        int trips_left = sg.max_trips < 0 ? 0x7fffffff : sg.max_trips;
+        if (sg.max_trips >= 0 && sg.resume) {  // continue the API call where the previous segment's launch parked it
+            const int w0 = sg.li[slot];
+            it = w0 & 0xff;
+            need_prologue = (w0 >> 8) & 1;
+            in_step = (w0 >> 9) & 1;
+            ncf = (w0 >> 10) & 0xff;
+            nef = (w0 >> 18) & 0xff;
+            nstloc = sg.li[B + slot];
+            saved_t = sg.ld[slot];
+            if (it < lad.ntout) tout = lad.touts[it];
+        }
 
 #pragma unroll 1
-        while (it < lad.ntout && !(FAST && poison)) {
+        while (it < lad.ntout && !(FAST && poison) && trips_left > 0) {
+            trips_left -= 1;
             RP_T(ti0);
             if (need_prologue) {
                 need_prologue = false;
@@ -1584,8 +1598,8 @@ struct IdaThread {
                         tret = tout;
                         tretlast = tout;
                         if constexpr (DEFER) {
-                            // what get_solution(tout) reads, to row (slot, it) of the snapshot buffer
-                            double* sp = df.snap + ((size_t)slot * lad.ntout + it) * snap_doubles(N);
+                            // what get_solution(tout) reads, to row (instance id, it) of the snapshot buffer
+                            double* sp = df.snap + ((size_t)b * lad.ntout + it) * snap_doubles(N);
                             const int kord = (kused == 0) ? 1 : kused;
 #pragma unroll 1
                             for (int j = 0; j <= kord; ++j) {
@@ -1646,7 +1660,7 @@ struct IdaThread {
                 }
             }
             if (call_done) {
-                if constexpr (DEFER) df.valid[slot * lad.ntout + it] = deferred ? 1 : 0;
+                if constexpr (DEFER) df.valid[b * lad.ntout + it] = deferred ? 1 : 0;
                 if (yy_traj && !(DEFER && deferred)) {
 #pragma unroll
                     for (int i = 0; i < N; ++i) yy_traj[((int64_t)it * N + i) * B + b] = yy[i];
@@ -1657,6 +1671,11 @@ struct IdaThread {
             }
             RP_ACC(3, ti0);
             RP_COUNT(4);
+        }
+        if (sg.max_trips >= 0) {  // park the loop state for the next segment (call_done is always consumed by here)
+            sg.li_out[slot] = it | ((int)need_prologue << 8) | ((int)in_step << 9) | (ncf << 10) | (nef << 18);
+            sg.li_out[B + slot] = nstloc;
+            sg.ld_out[slot] = saved_t;
         }
     }
 };

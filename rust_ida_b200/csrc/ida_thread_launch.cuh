@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(THREAD_BLOCK, IDA_MIN_BLOCKS)
 ida_solve_thread_kernel(double* __restrict__ ds, int* __restrict__ is, const double* __restrict__ params, int64_t B,
                         TolN<P::N> tol, LadderParams lad, double* __restrict__ yy_traj, int32_t* __restrict__ status,
                         const int* __restrict__ perm, TraceParams tr = TraceParams(), RootParams rp = RootParams(),
-                        DeferParams df = DeferParams(), FastParams xp = FastParams()) {
+                        DeferParams df = DeferParams(), FastParams xp = FastParams(), SegParams sg = SegParams()) {
     extern __shared__ double smem[];
     int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // slot
     if (b >= B) return;
@@ -62,7 +62,7 @@ ida_solve_thread_kernel(double* __restrict__ ds, int* __restrict__ is, const dou
     if constexpr (ROOTS) s.load_roots(rp, B, b);
     // the production instantiation defers the output interpolation to ida_interp_kernel; the TRACE and ROOTS
     // instantiations read yy / yp right after get_solution (trace frames, g(t, y)) and keep it in line
-    s.template solve_ladder<TRACE, ROOTS, !TRACE && !ROOTS && !MASK && IDA_DEFER>(lad, tol, yy_traj, status, B, ob, tr, rp, df, b);
+    s.template solve_ladder<TRACE, ROOTS, !TRACE && !ROOTS && !MASK && IDA_DEFER>(lad, tol, yy_traj, status, B, ob, tr, rp, df, b, sg);
     if constexpr (FAST) {
 #if IDA_POISON_REASON
         xp.poisoned[b] = (unsigned char)__ffs((int)s.poison);  // 1 + index of the first failed test (ida_thread.cuh)
@@ -91,12 +91,12 @@ ida_solve_thread_kernel(double* __restrict__ ds, int* __restrict__ is, const dou
 template <int N>
 __global__ void __launch_bounds__(256)
 ida_interp_kernel(double* __restrict__ ds, int64_t B, LadderParams lad, DeferParams df, double* __restrict__ yy_traj,
-                  const int* __restrict__ perm) {
-    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // slot * ntout + it
+                  const int* __restrict__ slot_of_id) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // instance id * ntout + it
     if (g >= B * lad.ntout) return;
     if (!df.valid[g]) return;
-    const int64_t b = g / lad.ntout;
-    const int it = (int)(g - b * lad.ntout);
+    const int64_t ob = g / lad.ntout;  // caller-visible instance id
+    const int it = (int)(g - ob * lad.ntout);
     constexpr Layout lay(N);
     constexpr int SD = snap_doubles(N);
     static_assert(SD % 2 == 0, "rows are read as 16-byte pairs");
@@ -140,11 +140,11 @@ ida_interp_kernel(double* __restrict__ ds, int64_t B, LadderParams lad, DeferPar
         }
     }
     if (yy_traj) {
-        const int64_t ob = perm ? (int64_t)perm[b] : b;
 #pragma unroll
         for (int i = 0; i < N; ++i) yy_traj[((int64_t)it * N + i) * B + ob] = y[i];
     }
     if (it == lad.ntout - 1) {
+        const int64_t b = slot_of_id ? (int64_t)slot_of_id[ob] : ob;  // where this instance's state lives now
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             ds[(int64_t)lay.yy(i) * B + b] = y[i];
@@ -176,6 +176,10 @@ struct ThreadLaunch {
     unsigned char* poisoned = nullptr;
     int* todo = nullptr;        // [batch] compacted slots of the flagged instances
     int* todo_count = nullptr;  // [1]
+    SegParams seg;              // segmented launch (max_trips < 0: the whole ladder in one launch)
+    int run_solve = 1;          // 0: only the interpolation pass (after the last segment of a segmented solve)
+    int run_interp = 1;         // 0: this is not the last segment, the interpolation pass comes later
+    const int* slot_of_id = nullptr;  // inverse of perm for the interpolation pass's final-state write (null: identity)
     cudaStream_t stream;
 };
 
@@ -227,7 +231,8 @@ int launch_thread_family(const ThreadLaunch& a) {
     } else {
         // production path: FAST pass (state a.ds -> a.ds2, snapshots at the output times), the exact pass over the
         // instances the FAST pass flagged (normally none: its CTAs exit at once), the coherent interpolation pass
-        if (IDA_FAST && a.ds2 && a.is2 && a.poisoned) {
+        if (!a.run_solve) {
+        } else if (IDA_FAST && a.ds2 && a.is2 && a.poisoned) {
             FastParams xf;
             xf.ds_out = a.ds2;
             xf.is_out = a.is2;
@@ -237,7 +242,7 @@ int launch_thread_family(const ThreadLaunch& a) {
             B200_CUDA_TRY(cudaMemsetAsync(a.todo_count, 0, sizeof(int), a.stream));
             B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_thread_kernel<P, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             ida_solve_thread_kernel<P, false, false, false, true><<<grid, tb, smem, a.stream>>>(a.ds, a.is, a.params, a.B, tol, a.lad, a.traj, a.stat,
-                                                                                               a.perm, TraceParams(), RootParams(), a.df, xf);
+                                                                                               a.perm, TraceParams(), RootParams(), a.df, xf, a.seg);
             count_launch();
             B200_CUDA_TRY(cudaGetLastError());
             FastParams xe;
@@ -247,7 +252,7 @@ int launch_thread_family(const ThreadLaunch& a) {
             xe.todo_count = a.todo_count;
             B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_thread_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             ida_solve_thread_kernel<P><<<grid, tb, smem, a.stream>>>(a.ds, a.is, a.params, a.B, tol, a.lad, a.traj, a.stat, a.perm, TraceParams(),
-                                                                     RootParams(), a.df, xe);
+                                                                     RootParams(), a.df, xe, a.seg);
             count_launch();
         } else {
             B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_thread_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -256,9 +261,9 @@ int launch_thread_family(const ThreadLaunch& a) {
             count_launch();
         }
         B200_CUDA_TRY(cudaGetLastError());
-        if (IDA_DEFER) {
+        if (IDA_DEFER && a.run_interp) {
             ida_interp_kernel<N><<<(unsigned)((a.B * ntout + 255) / 256), 256, 0, a.stream>>>((IDA_FAST && a.ds2 && a.is2 && a.poisoned) ? a.ds2 : a.ds,
-                                                                                              a.B, a.lad, a.df, a.traj, a.perm);
+                                                                                              a.B, a.lad, a.df, a.traj, a.slot_of_id);
             count_launch();
         }
     }

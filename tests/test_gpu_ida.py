@@ -572,3 +572,38 @@ def test_device_trace_serialises_to_the_reference_json(tmp_path):
     nst = [s["counters"]["ida_nst"] for s in data]
     assert nst[0] == 0 and nst[-1] == 361 and data[-1]["nlp"]["lp"]["nje"] in (59, 60)  # frames precede their attempt
     ida.close()
+
+
+# ---- re-grouping between segments of a solve: pure engine tuning, results must not move -----------------------
+@pytest.mark.parametrize("trips,segments", [(16, 8), (128, 4), (0, 0)])
+def test_regrouped_solve_is_bit_identical(trips, segments):
+    """70,000 Roberts instances (enough for the segmented path), every output time's y and every counter against the
+    oracle, for an aggressive re-grouping schedule, the default one, and re-grouping switched off; then a second ladder
+    on the re-grouped slots and a re-initialisation (which must restore the parameter order) give the same again."""
+    import torch
+    import rust_ida_b200 as r
+    from rust_ida_b200.problems import roberts_ensemble_params
+    ob, _ = parity_oracle()
+    B = 70000
+    p = roberts_ensemble_params(B, seed=4321)
+    yy0, yp0 = r.Roberts.consistent_ic(p)
+    ref = ob.ensemble_solve(ob.PK_ROBERTS, 3, p, yy0, yp0, ROBERTS_RTOL, ROBERTS_ATOL, ROBERTS_TOUTS, nthreads=16, want_traj=True)
+    dp, dy, dyp = (torch.from_numpy(v).cuda() for v in (p, yy0, yp0))
+    ida = r.Ida(r.Roberts(dp), dy, dyp, r.TolControlSV(ROBERTS_RTOL, ROBERTS_ATOL))
+    ida.set_regroup(trips, segments)
+    for rep in range(2):
+        if rep:
+            ida.reinit(dy, dyp)
+        # first half of the ladder, then the rest in a second call on whatever slot order the first one left
+        st1, tr1 = ida.solve_ladder(ROBERTS_TOUTS[:5])
+        st2, tr2 = ida.solve_ladder(ROBERTS_TOUTS[5:])
+        traj = torch.cat([tr1, tr2]).cpu().numpy()
+        assert (st1 == 0).all() and (st2 == 0).all()
+        assert_bit_equal(traj, ref["yy_traj"], "yy_traj")
+        assert_bit_equal(ida.get_yy().cpu().numpy(), ref["yy"], "yy")
+        assert_bit_equal(ida.get_yp().cpu().numpy(), ref["yp"], "yp")
+        c = ida.counters()
+        for k in COUNTERS:
+            assert np.array_equal(c[k].cpu().numpy(), ref["counters"][k]), k
+        assert ida.fallback_count() == 0
+    ida.close()

@@ -83,6 +83,27 @@ def run_heat(batch=65536, reps=1, M=10):
     return out
 
 
+def run_small_heat(M, batch=65536, cpu_sample=2048):
+    """3 < n <= 32: the AUTO path is the warp-per-system kernel.  Heat 2-D on an M x M grid (n = M*M = 16 / 25) against
+    the CPU oracle on a sample of the same instances (one instance per host thread) -> dict"""
+    import time
+    from oracle import binding as ob
+    from rust_ida_b200.problems import Heat2D, heat_ensemble_params
+    out = run_heat(batch, reps=1, M=M)
+    out["kernel"] = "warp (AUTO for 3 < n <= 32)"
+    n = M * M
+    p = heat_ensemble_params(cpu_sample, M=M, seed=1234)
+    yy0, yp0 = Heat2D.consistent_ic(p, M)
+    cores = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    ob.ensemble_solve(ob.PK_HEAT2D, n, p, yy0, yp0, 1e-6, np.full(n, 1e-8), 0.01 * 2.0 ** np.arange(11), nthreads=cores)
+    dt = time.perf_counter() - t0
+    out["cpu_oracle_instances_per_s"] = cpu_sample / dt
+    out["cpu_cores"] = cores
+    out["gpu_over_cpu"] = out["instances_per_s"] / out["cpu_oracle_instances_per_s"]
+    return out
+
+
 def main():
     import torch
     import rust_ida_b200 as r
@@ -100,6 +121,10 @@ def main():
 
     if "heat" in args.which:
         print(json.dumps(run_heat(args.heat_batch, max(1, args.reps - 1))), flush=True)
+
+    if "small" in args.which:
+        for M in (4, 5):
+            print(json.dumps(run_small_heat(M)), flush=True)
 
     if "kernels" in args.which:
         B = 1 << 17
