@@ -311,7 +311,7 @@ struct b200ida_ensemble {
     double* dstate2 = nullptr;
     int* istate2 = nullptr;
     // re-grouping between segments (thread-per-instance production path, large re-ordered ensembles)
-    int regroup_trips = 128, regroup_segments = 4;  // b200ida_set_regroup; segments <= 1: off
+    int regroup_trips = 128, regroup_segments = 3;  // b200ida_set_regroup; segments <= 1: off
     DevBuf params2, perm2, inv_perm, perm0, params0, loop_i, loop_i2, loop_d, loop_d2, rg_keys, rg_keys2, rg_ids, rg_order, rg_tmp;
     size_t rg_tmp_bytes = 0;
     bool regrouped = false;  // perm / params differ from the parameter-Morton order built at (re)init

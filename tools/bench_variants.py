@@ -16,7 +16,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def child(batch, problem, reps):
+def child(batch, problem, reps, regroup=None):
     sys.path.insert(0, ROOT)
     import numpy as np
     import torch
@@ -36,6 +36,8 @@ def child(batch, problem, reps):
     ida = r.Ida(prob_cls(p_d), yy0_d, yp0_d, tol, device=0)
     L = _lib.lib()
     h = ida._h
+    if regroup:
+        ida.set_regroup(*regroup)
     touts = np.ascontiguousarray(touts)
     status_d = torch.empty((len(touts), batch), dtype=torch.int32, device=dev)
     times = []
@@ -57,7 +59,7 @@ def child(batch, problem, reps):
     hsh = hashlib.sha256(np.ascontiguousarray(yy).tobytes() + np.ascontiguousarray(nst).tobytes() + status_d.cpu().numpy().tobytes()).hexdigest()[:16]
     ms = float(np.mean(times))
     print(json.dumps({"lib": os.path.basename(os.environ.get("B200IDA_LIB", "default")), "problem": problem, "batch": batch,
-                      "kernel_ms": round(ms, 3), "ms_min": round(min(times), 3), "inst_per_s": round(batch / ms * 1e3),
+                      "regroup": regroup, "kernel_ms": round(ms, 3), "ms_min": round(min(times), 3), "inst_per_s": round(batch / ms * 1e3),
                       "attempts": int(natt.sum()), "fallbacks": ida.fallback_count(), "ok": bool((status_d == 0).all().item()), "sha": hsh}), flush=True)
 
 
@@ -67,17 +69,22 @@ def main():
     ap.add_argument("--problem", default="roberts")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--child", action="store_true")
+    ap.add_argument("--regroup", default="", help="trips,segments[;trips,segments...] -> b200ida_set_regroup, one run each")
     ap.add_argument("libs", nargs="*")
     a = ap.parse_args()
     if a.child:
-        child(a.batch, a.problem, a.reps)
+        if a.regroup:
+            for spec in a.regroup.split(";"):
+                child(a.batch, a.problem, a.reps, tuple(int(x) for x in spec.split(",")))
+        else:
+            child(a.batch, a.problem, a.reps)
         return
     for lib in a.libs or [""]:
         env = dict(os.environ)
         if lib:
             env["B200IDA_LIB"] = os.path.abspath(lib)
         subprocess.call([sys.executable, os.path.abspath(__file__), "--child", "--batch", str(a.batch), "--problem", a.problem,
-                         "--reps", str(a.reps)], env=env)
+                         "--reps", str(a.reps)] + (["--regroup", a.regroup] if a.regroup else []), env=env)
 
 
 if __name__ == "__main__":
