@@ -377,8 +377,9 @@ def run_ours(args, rank, world, local_rank):
                                   "note": "state read once + written once per launch; three orders of magnitude below the "
                                           "FP64 bound, which is why the roofline above is the FP64 issue rate"},
                      "quoted_from_profile": quoted,
-                     "kernel": "ida_solve_thread_kernel<Roberts> (+ ida_interp_kernel<3>, the deferred output interpolation, "
-                               "inside the same CUDA-event bracket)",
+                     "kernel": "ida_solve_thread_kernel<Roberts, FAST>: one solve = its segment launches (+ the slot re-grouping "
+                               "between them, the empty exact pass and ida_interp_kernel<3>), all inside the same CUDA-event "
+                               "bracket; `achieved` divides by that bracket",
                      "kernel_ms": kernel_ms, "ops_per_attempt": opa, "ops_per_attempt_source": opa_src,
                      "ops_per_launch": tot_attempts * opa, "attempts_per_launch": tot_attempts,
                      "peak_source": "measured on this GPU by b200ida_fp64_issue_rate (MEASURED_PEAKS.json has no FP64 entry): "
@@ -394,39 +395,43 @@ def run_ours(args, rank, world, local_rank):
 
 def quoted_profile():
     """ncu figures of the solve kernel, READ from the newest committed summary under profiles/ (never typed in here):
-    they describe the build that summary was taken from, which the entry names."""
+    they describe the build that summary was taken from, which the entry names.  A summary may hold several launches
+    (the segments of one solve): byte counts, durations and instruction counts are summed, percentages and ratios are
+    averaged with the launch durations as weights."""
     import csv
     import glob
     cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ida_solve_thread*_ncu_summary.csv")))
     if not cands:
         return {}
     path = cands[-1]
-    vals = {}
+    launches = []  # one dict per launch, in file order
     note = ""
+    want = ("dram__bytes_read.sum", "dram__bytes_write.sum", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+            "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__thread_inst_executed_per_inst_executed.ratio",
+            "gpu__time_duration.sum", "smsp__inst_executed.sum")
+    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3}
     try:
         for row in csv.reader(open(path)):
             if row and row[0].startswith("#"):
                 note = ",".join(row).lstrip("# ").strip()
-            if len(row) >= 4 and row[1] in ("dram__bytes_read.sum", "dram__bytes_write.sum",
-                                            "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
-                                            "smsp__issue_active.avg.pct_of_peak_sustained_active",
-                                            "smsp__thread_inst_executed_per_inst_executed.ratio", "gpu__time_duration.sum",
-                                            "smsp__inst_executed.sum"):
-                vals[row[1]] = (float(row[3]), row[2])
+            if len(row) >= 4 and row[1] in want:
+                if not launches or row[1] in launches[-1]:
+                    launches.append({})
+                launches[-1][row[1]] = float(row[3]) * scale.get(row[2], 1.0)
     except Exception:
         return {}
-    out = {"source": os.path.relpath(path, ROOT), "source_note": note,
-           "applies_to": "the build and batch (2^20) that file was captured from, not necessarily this run"}
-    if "dram__bytes_read.sum" in vals and "dram__bytes_write.sum" in vals:
-        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
-        out["traffic_bytes_per_launch"] = int(sum(vals[k][0] * scale.get(vals[k][1], 1.0)
-                                                  for k in ("dram__bytes_read.sum", "dram__bytes_write.sum")))
-    for k, name in (("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_fp64_cycles_active_pct"),
-                    ("smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__issue_active_pct"),
-                    ("smsp__thread_inst_executed_per_inst_executed.ratio", "active_lanes_per_instruction"),
-                    ("gpu__time_duration.sum", "kernel_ms_under_ncu"), ("smsp__inst_executed.sum", "warp_instructions")):
-        if k in vals:
-            out[name] = vals[k][0]
+    launches = [l for l in launches if "gpu__time_duration.sum" in l]
+    if not launches:
+        return {}
+    tsum = sum(l["gpu__time_duration.sum"] for l in launches)
+    wavg = lambda k: sum(l.get(k, 0.0) * l["gpu__time_duration.sum"] for l in launches) / tsum
+    out = {"source": os.path.relpath(path, ROOT), "source_note": note, "launches_in_summary": len(launches),
+           "applies_to": "the build and batch (2^20) that file was captured from, not necessarily this run",
+           "traffic_bytes_per_launch": int(sum(l.get("dram__bytes_read.sum", 0.0) + l.get("dram__bytes_write.sum", 0.0) for l in launches)),
+           "sm__pipe_fp64_cycles_active_pct": wavg("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+           "smsp__issue_active_pct": wavg("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+           "active_lanes_per_instruction": wavg("smsp__thread_inst_executed_per_inst_executed.ratio"),
+           "kernel_ms_under_ncu": tsum, "warp_instructions": sum(l.get("smsp__inst_executed.sum", 0.0) for l in launches)}
     return out
 
 

@@ -42,7 +42,7 @@ __device__ unsigned long long root_prof[8];
 #endif
 
 #ifndef IDA_THREAD_BLOCK
-#define IDA_THREAD_BLOCK 128
+#define IDA_THREAD_BLOCK 64  // 6 CTAs of 2 warps per SM: same 12 warps as 3 x 128, finer tail granularity (measured -1.5 %)
 #endif
 #ifndef IDA_WRMS_INLINE
 #define IDA_WRMS_INLINE 1

@@ -17,7 +17,7 @@ namespace b200ida {
 
 // Thread-per-instance solve over a ladder of output times (ida_thread.cuh).
 #ifndef IDA_MIN_BLOCKS
-#define IDA_MIN_BLOCKS 3  // 168 regs, 12 warps/SM: measured faster than 4 (128 regs + spills) and 2
+#define IDA_MIN_BLOCKS 6  // x 64 threads: 168 regs, 12 warps/SM; 128 regs (16 warps) is slower: the spills thrash the small L1
 #endif
 #ifndef IDA_FAST
 #define IDA_FAST 1  // production path = FAST pass + exact pass over the flagged instances; 0: the exact kernel alone
