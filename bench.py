@@ -414,10 +414,11 @@ def quoted_profile():
         for row in csv.reader(open(path)):
             if row and row[0].startswith("#"):
                 note = ",".join(row).lstrip("# ").strip()
-            if len(row) >= 4 and row[1] in want:
-                if not launches or row[1] in launches[-1]:
+            # kernel names hold commas ("<Roberts, 0, 0, 0, 1>"): the metric, unit and value are the LAST three fields
+            if len(row) >= 4 and row[-3] in want:
+                if not launches or row[-3] in launches[-1]:
                     launches.append({})
-                launches[-1][row[1]] = float(row[3]) * scale.get(row[2], 1.0)
+                launches[-1][row[-3]] = float(row[-1]) * scale.get(row[-2], 1.0)
     except Exception:
         return {}
     launches = [l for l in launches if "gpu__time_duration.sum" in l]
