@@ -208,7 +208,7 @@ int b200ida_solve_ladder(b200ida_ensemble* e, const double* touts /* host */, in
  * thread-per-instance production path are integrated in segments of `trips_per_segment` step attempts per instance;
  * between segments the engine re-sorts its slots by a behaviour key (finished, order, phase, ns, log2 |h|) so that the
  * lanes of a warp take the same branches again.  max_segments <= 1 or trips_per_segment == 0:
- * one launch for the whole ladder.  Default: 128 attempts, 3 segments. */
+ * one launch for the whole ladder.  Default: 96 attempts, 4 segments. */
 int b200ida_set_regroup(b200ida_ensemble* e, int trips_per_segment, int max_segments);
 
 /* ida_id and ida_suppressalg (src/lib.rs:102,122): id[i] != 0 marks component i as differential, 0 as algebraic.  With

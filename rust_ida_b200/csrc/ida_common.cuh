@@ -107,11 +107,30 @@ __host__ __device__ constexpr int snap_doubles(int n) { return 6 * n + 6 + 4; }
 struct SegParams {
     int max_trips = -1;
     int resume = 0;      // 0: the launch starts the API call (fresh loop state), 1: continue from li / ld
-    const int* li = nullptr;   // read when resume != 0
+    const int* li = nullptr;   // read when resume != 0: words at li[slot], li[stride + slot]
     const double* ld = nullptr;
     int* li_out = nullptr;     // written at the end of the launch: a DIFFERENT buffer, so that the exact pass of the same
     double* ld_out = nullptr;  // segment still finds the loop state its flagged lanes started the segment with
+    long long stride = 0;      // distance between the two loop-state words (batch for [2][batch] arrays, 1 inside a row)
 };
+
+// How a launch of the thread-per-instance kernel finds and leaves the per-instance state.  Default: the engine's
+// structure-of-arrays buffers, slot = thread.  Between the segments of a segmented solve the state travels through an
+// EXCHANGE buffer of one contiguous row per instance -- [ndouble state doubles | saved_t | params] and
+// [nint state ints | loop word | nstloc | instance id] -- which a lane writes at its slot and the next segment's lane
+// reads at order[slot]: the re-grouping of the slots costs no pass over the state at all, it is the load of the next
+// segment (each lane reads its own contiguous row; whole sectors either way).
+struct IoParams {
+    const double* xd_in = nullptr;  // exchange rows in (null: SoA in)
+    const int* xi_in = nullptr;
+    const int* order = nullptr;     // row of slot s = order[s] (null: s)
+    double* xd_out = nullptr;       // exchange rows out, row = slot (null: SoA out)
+    int* xi_out = nullptr;
+    double* params_out = nullptr;   // SoA out only: the instance's parameters and id follow it to its final slot
+    int* perm_out = nullptr;
+};
+__host__ __device__ constexpr int xrow_doubles(int n, int np) { return (10 * n + 45 + n * n + 1 + np + 1) & ~1; }
+__host__ __device__ constexpr int xrow_ints(int n) { return (16 + n + 3 + 3) & ~3; }
 
 // select a[k] from a 6-entry register array without dynamic indexing
 __device__ __forceinline__ double pick6(const double (&a)[MXORDP1], int k) {

@@ -190,35 +190,19 @@ __global__ void order_key_kernel(const double* __restrict__ params, const double
 // key: finished instances last; otherwise (order kk, phase, ns, quantised log2 |h|) -- lanes that agree on these walk the
 // same loop trip counts and take the same branches for a while.  The radix sort is stable, so equal keys keep their
 // previous (parameter-Morton) neighbourhood.
-__global__ void regroup_key_kernel(const double* __restrict__ ds, const int* __restrict__ is, const int* __restrict__ li, int n,
-                                   int64_t B, int ntout, unsigned* __restrict__ keys, int* __restrict__ ids) {
+__global__ void regroup_key_kernel(const double* __restrict__ xd, const int* __restrict__ xi, int n, int XD, int XI, int64_t B, int ntout,
+                                   unsigned* __restrict__ keys, int* __restrict__ ids) {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= B) return;
     const Layout lay(n);
-    const unsigned done = ((li[s] & 0xff) >= ntout) ? 1u : 0u;
-    const unsigned kk = (unsigned)is[(int64_t)Layout::KK * B + s] & 7u;
-    const unsigned ph = (unsigned)is[(int64_t)Layout::PHASE * B + s] & 1u;
-    const unsigned ns = (unsigned)min(is[(int64_t)Layout::NS * B + s], 7) & 7u;
-    const unsigned hq = ((unsigned)__double2hiint(fabs(ds[(int64_t)lay.scal(Layout::HH) * B + s])) >> 16) & 0x7fffu;  // exponent + 4 mantissa bits
+    const int* ir = xi + s * XI;
+    const unsigned done = ((ir[lay.nint()] & 0xff) >= ntout) ? 1u : 0u;  // loop word 0: output-time index
+    const unsigned kk = (unsigned)ir[Layout::KK] & 7u;
+    const unsigned ph = (unsigned)ir[Layout::PHASE] & 1u;
+    const unsigned ns = (unsigned)min(ir[Layout::NS], 7) & 7u;
+    const unsigned hq = ((unsigned)__double2hiint(fabs(xd[s * XD + lay.scal(Layout::HH)])) >> 16) & 0x7fffu;  // exponent + 4 mantissa bits
     keys[s] = done << 23 | kk << 20 | ph << 19 | ns << 16 | hq;
     ids[s] = (int)s;
-}
-// new slot s takes what old slot order[s] held, for every per-slot row of the engine
-__global__ void regroup_gather_kernel(const int* __restrict__ order, int64_t B, const double* __restrict__ d_src, double* __restrict__ d_dst,
-                                      int nd, const int* __restrict__ i_src, int* __restrict__ i_dst, int ni,
-                                      const double* __restrict__ p_src, double* __restrict__ p_dst, int np,
-                                      const int* __restrict__ li_src, int* __restrict__ li_dst, const double* __restrict__ ld_src,
-                                      double* __restrict__ ld_dst, const int* __restrict__ perm_src, int* __restrict__ perm_dst) {
-    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= B) return;
-    const int64_t o = order[s];
-    for (int f = 0; f < nd; ++f) d_dst[(int64_t)f * B + s] = d_src[(int64_t)f * B + o];
-    for (int f = 0; f < ni; ++f) i_dst[(int64_t)f * B + s] = i_src[(int64_t)f * B + o];
-    for (int f = 0; f < np; ++f) p_dst[(int64_t)f * B + s] = p_src[(int64_t)f * B + o];
-    li_dst[s] = li_src[o];
-    li_dst[B + s] = li_src[B + o];
-    ld_dst[s] = ld_src[o];
-    perm_dst[s] = perm_src[o];
 }
 __global__ void invert_perm_kernel(const int* __restrict__ perm, int* __restrict__ inv, int64_t B) {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -311,8 +295,9 @@ struct b200ida_ensemble {
     double* dstate2 = nullptr;
     int* istate2 = nullptr;
     // re-grouping between segments (thread-per-instance production path, large re-ordered ensembles)
-    int regroup_trips = 128, regroup_segments = 3;  // b200ida_set_regroup; segments <= 1: off
-    DevBuf params2, perm2, inv_perm, perm0, params0, loop_i, loop_i2, loop_d, loop_d2, rg_keys, rg_keys2, rg_ids, rg_order, rg_tmp;
+    int regroup_trips = 96, regroup_segments = 4;  // b200ida_set_regroup; segments <= 1: off
+    DevBuf params2, perm2, inv_perm, perm0, params0, rg_keys, rg_keys2, rg_ids, rg_order, rg_tmp;
+    DevBuf xd[2], xi[2];  // the exchange buffers the state travels through between segments (IoParams, ida_common.cuh)
     size_t rg_tmp_bytes = 0;
     bool regrouped = false;  // perm / params differ from the parameter-Morton order built at (re)init
     DevBuf poisoned, todo;  // todo: [batch + 1] ints, the compacted slot list of the exact pass and its length
@@ -812,13 +797,13 @@ int b200ida_solve_ladder(b200ida_ensemble* e, const double* touts, int ntout, in
             if (rc != B200IDA_OK) return rc;
         } else {
             const int64_t B = e->B;
-            const Layout lay(e->n);
-            const int nd = lay.ndouble(), ni = lay.nint(), np = e->nparams;
-            if (!e->loop_i.p) {
-                B200_CUDA_TRY(e->loop_i.alloc(2 * (size_t)B * sizeof(int)));
-                B200_CUDA_TRY(e->loop_i2.alloc(2 * (size_t)B * sizeof(int)));
-                B200_CUDA_TRY(e->loop_d.alloc((size_t)B * sizeof(double)));
-                B200_CUDA_TRY(e->loop_d2.alloc((size_t)B * sizeof(double)));
+            const int np = e->nparams;
+            const size_t XD = (size_t)xrow_doubles(e->n, np), XI = (size_t)xrow_ints(e->n);
+            if (!e->xd[0].p) {
+                for (int k = 0; k < 2; ++k) {
+                    B200_CUDA_TRY(e->xd[k].alloc(XD * B * sizeof(double)));
+                    B200_CUDA_TRY(e->xi[k].alloc(XI * B * sizeof(int)));
+                }
                 B200_CUDA_TRY(e->params2.alloc((size_t)np * B * sizeof(double)));
                 B200_CUDA_TRY(e->perm2.alloc((size_t)B * sizeof(int)));
                 B200_CUDA_TRY(e->rg_keys.alloc((size_t)B * sizeof(unsigned)));
@@ -832,39 +817,41 @@ int b200ida_solve_ladder(b200ida_ensemble* e, const double* touts, int ntout, in
             }
             const int nseg = e->regroup_segments;
             const unsigned g256 = (unsigned)((B + 255) / 256);
+            int cur = 0;  // exchange buffer the NEXT segment reads
             for (int seg = 0; seg < nseg; ++seg) {
+                const bool last = seg == nseg - 1;
                 ThreadLaunch la = a;
-                la.ds = e->dstate;
-                la.is = e->istate;
-                la.params = e->params;
-                la.perm = e->perm;
                 la.run_interp = 0;
-                la.seg.max_trips = (seg == nseg - 1) ? 0x7fffffff : e->regroup_trips;
+                la.seg.max_trips = last ? 0x7fffffff : e->regroup_trips;
                 la.seg.resume = seg > 0;
-                la.seg.li = e->loop_i.as<int>();
-                la.seg.ld = e->loop_d.as<double>();
-                la.seg.li_out = e->loop_i2.as<int>();
-                la.seg.ld_out = e->loop_d2.as<double>();
-                rc = launch(la);  // state: dstate -> dstate2, loop state: loop_* -> loop_*2 (FAST pass + exact pass over its flagged slots)
+                if (seg > 0) {  // state comes from the rows the previous segment wrote, in the re-grouped order
+                    la.io.xd_in = e->xd[cur].as<double>();
+                    la.io.xi_in = e->xi[cur].as<int>();
+                    la.io.order = e->rg_order.as<int>();
+                }
+                if (!last) {
+                    la.io.xd_out = e->xd[cur ^ 1].as<double>();
+                    la.io.xi_out = e->xi[cur ^ 1].as<int>();
+                } else {  // back to the structure-of-arrays buffers (dstate2 / istate2), with parameters and ids in the final slot order
+                    la.io.params_out = e->params2.as<double>();
+                    la.io.perm_out = e->perm2.as<int>();
+                }
+                rc = launch(la);  // FAST pass + exact pass over its flagged slots; inputs are never written
                 if (rc != B200IDA_OK) return rc;
-                if (seg == nseg - 1) break;
-                // re-group: sort the slots by behaviour key, gather every per-slot row dstate2 -> dstate in that order
-                regroup_key_kernel<<<g256, 256, 0, e->stream>>>(e->dstate2, e->istate2, e->loop_i2.as<int>(), e->n, B, ntout,
+                if (last) break;
+                cur ^= 1;
+                // re-group: sort the slots by behaviour key; the next segment's lane s loads row order[s]
+                regroup_key_kernel<<<g256, 256, 0, e->stream>>>(e->xd[cur].as<double>(), e->xi[cur].as<int>(), e->n, (int)XD, (int)XI, B, ntout,
                                                                 e->rg_keys.as<unsigned>(), e->rg_ids.as<int>());
                 count_launch();
                 size_t tb = e->rg_tmp_bytes;
                 B200_CUDA_TRY(cub::DeviceRadixSort::SortPairs(e->rg_tmp.p, tb, e->rg_keys.as<unsigned>(), e->rg_keys2.as<unsigned>(),
                                                               e->rg_ids.as<int>(), e->rg_order.as<int>(), (int)B, 0, 24, e->stream));
-                regroup_gather_kernel<<<g256, 256, 0, e->stream>>>(e->rg_order.as<int>(), B, e->dstate2, e->dstate, nd, e->istate2, e->istate, ni,
-                                                                   e->params, e->params2.as<double>(), np, e->loop_i2.as<int>(),
-                                                                   e->loop_i.as<int>(), e->loop_d2.as<double>(), e->loop_d.as<double>(),
-                                                                   e->perm, e->perm2.as<int>());
-                count_launch();
                 B200_CUDA_TRY(cudaGetLastError());
-                { void* t = e->params; e->params = e->params2.as<double>(); e->params2.p = t; }
-                { void* t = e->perm; e->perm = e->perm2.as<int>(); e->perm2.p = t; }
-                e->regrouped = true;
             }
+            { void* t = e->params; e->params = e->params2.as<double>(); e->params2.p = t; }
+            { void* t = e->perm; e->perm = e->perm2.as<int>(); e->perm2.p = t; }
+            e->regrouped = true;
             if ((rc = refresh_inverse_perm(e))) return rc;
         }
         e->fast_ran = a.ds2 != nullptr;

@@ -1415,14 +1415,14 @@ struct IdaThread {
         double saved_t = 0.0, tout = 0.0;
         int ncf = 0, nef = 0;
         int trips_left = sg.max_trips < 0 ? 0x7fffffff : sg.max_trips;
-        if (sg.max_trips >= 0 && sg.resume) {  // continue the API call where the previous segment's launch parked it
+        if (sg.max_trips >= 0 && sg.resume && sg.li) {  // continue the API call where the previous segment's launch parked it
             const int w0 = sg.li[slot];
             it = w0 & 0xff;
             need_prologue = (w0 >> 8) & 1;
             in_step = (w0 >> 9) & 1;
             ncf = (w0 >> 10) & 0xff;
             nef = (w0 >> 18) & 0xff;
-            nstloc = sg.li[B + slot];
+            nstloc = sg.li[sg.stride + slot];
             saved_t = sg.ld[slot];
             if (it < lad.ntout) tout = lad.touts[it];
         }
@@ -1672,9 +1672,9 @@ struct IdaThread {
             RP_ACC(3, ti0);
             RP_COUNT(4);
         }
-        if (sg.max_trips >= 0) {  // park the loop state for the next segment (call_done is always consumed by here)
+        if (sg.max_trips >= 0 && sg.li_out) {  // park the loop state for the next segment (call_done is always consumed by here)
             sg.li_out[slot] = it | ((int)need_prologue << 8) | ((int)in_step << 9) | (ncf << 10) | (nef << 18);
-            sg.li_out[B + slot] = nstloc;
+            sg.li_out[sg.stride + slot] = nstloc;
             sg.ld_out[slot] = saved_t;
         }
     }

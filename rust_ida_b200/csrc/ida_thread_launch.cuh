@@ -42,7 +42,8 @@ __global__ void __launch_bounds__(THREAD_BLOCK, IDA_MIN_BLOCKS)
 ida_solve_thread_kernel(double* __restrict__ ds, int* __restrict__ is, const double* __restrict__ params, int64_t B,
                         TolN<P::N> tol, LadderParams lad, double* __restrict__ yy_traj, int32_t* __restrict__ status,
                         const int* __restrict__ perm, TraceParams tr = TraceParams(), RootParams rp = RootParams(),
-                        DeferParams df = DeferParams(), FastParams xp = FastParams(), SegParams sg = SegParams()) {
+                        DeferParams df = DeferParams(), FastParams xp = FastParams(), SegParams sg = SegParams(),
+                        IoParams io = IoParams()) {
     extern __shared__ double smem[];
     int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // slot
     if (b >= B) return;
@@ -50,19 +51,42 @@ ida_solve_thread_kernel(double* __restrict__ ds, int* __restrict__ is, const dou
         if (b >= (int64_t)*xp.todo_count) return;
         b = xp.todo[b];
     }
-    const int64_t ob = perm ? (int64_t)perm[b] : b;  // caller-visible instance id of this slot
+    constexpr Layout xlay(P::N);
+    constexpr int ND = xlay.ndouble(), NI = xlay.nint(), XD = xrow_doubles(P::N, P::NP), XI = xrow_ints(P::N);
+    // where this lane's state comes from: its SoA column, or its row of the exchange buffer (IoParams)
+    const bool row_in = io.xd_in != nullptr;
+    const int64_t r_in = row_in ? (io.order ? (int64_t)io.order[b] : b) : 0;
+    const double* din = row_in ? io.xd_in + r_in * XD : ds;
+    const int* iin = row_in ? io.xi_in + r_in * XI : is;
+    const int64_t Bin = row_in ? 1 : B, bin = row_in ? 0 : b;
+    const int64_t ob = row_in ? (int64_t)iin[NI + 2] : (perm ? (int64_t)perm[b] : b);  // caller-visible instance id
     IdaThread<P, MASK, FAST> s;
     s.sm = smem + threadIdx.x;
     if constexpr (MASK) {
 #pragma unroll
         for (int i = 0; i < P::N; ++i) s.idm[i] = tol.idmask[i];
     }
-    s.prob.load(params, B, b);
-    s.load(ds, is, B, b);
+    double pr[P::NP];  // the instance's parameters travel with it
+#pragma unroll
+    for (int k = 0; k < P::NP; ++k) pr[k] = row_in ? din[ND + 1 + k] : params[(int64_t)k * B + b];
+    s.prob.load(pr, 1, 0);
+    s.load(din, iin, Bin, bin);
+    if (sg.max_trips >= 0) {  // loop state of a segmented solve lives in the exchange rows
+        sg.li = iin + NI;
+        sg.ld = din + ND;
+        sg.stride = 1;
+        if (io.xd_out) {
+            sg.li_out = io.xi_out + b * XI + NI;
+            sg.ld_out = io.xd_out + b * XD + ND;
+        } else {  // last segment: nothing resumes after it; park into the (discarded) tail of this lane's own scratch
+            sg.li_out = nullptr;
+            sg.ld_out = nullptr;
+        }
+    }
     if constexpr (ROOTS) s.load_roots(rp, B, b);
     // the production instantiation defers the output interpolation to ida_interp_kernel; the TRACE and ROOTS
     // instantiations read yy / yp right after get_solution (trace frames, g(t, y)) and keep it in line
-    s.template solve_ladder<TRACE, ROOTS, !TRACE && !ROOTS && !MASK && IDA_DEFER>(lad, tol, yy_traj, status, B, ob, tr, rp, df, b, sg);
+    s.template solve_ladder<TRACE, ROOTS, !TRACE && !ROOTS && !MASK && IDA_DEFER>(lad, tol, yy_traj, status, B, ob, tr, rp, df, 0, sg);
     if constexpr (FAST) {
 #if IDA_POISON_REASON
         xp.poisoned[b] = (unsigned char)__ffs((int)s.poison);  // 1 + index of the first failed test (ida_thread.cuh)
@@ -74,7 +98,21 @@ ida_solve_thread_kernel(double* __restrict__ ds, int* __restrict__ is, const dou
             return;
         }
     }
-    s.store(xp.ds_out ? xp.ds_out : ds, xp.is_out ? xp.is_out : is, B, b);
+    if (io.xd_out) {  // a segment that is not the last: the whole instance goes to row `slot` of the exchange buffer
+        double* dout = io.xd_out + b * XD;
+        int* iout = io.xi_out + b * XI;
+        s.store(dout, iout, 1, 0);
+#pragma unroll
+        for (int k = 0; k < P::NP; ++k) dout[ND + 1 + k] = pr[k];
+        iout[NI + 2] = (int)ob;
+    } else {
+        s.store(xp.ds_out ? xp.ds_out : ds, xp.is_out ? xp.is_out : is, B, b);
+        if (io.params_out) {
+#pragma unroll
+            for (int k = 0; k < P::NP; ++k) io.params_out[(int64_t)k * B + b] = pr[k];
+            io.perm_out[b] = (int)ob;
+        }
+    }
     if constexpr (ROOTS) {
         s.store_roots(rp, B, b);
         if (rp.nge_out) rp.nge_out[ob] = s.nge;
@@ -177,6 +215,7 @@ struct ThreadLaunch {
     int* todo = nullptr;        // [batch] compacted slots of the flagged instances
     int* todo_count = nullptr;  // [1]
     SegParams seg;              // segmented launch (max_trips < 0: the whole ladder in one launch)
+    IoParams io;                // where the state comes from / goes to (exchange rows between segments)
     int run_solve = 1;          // 0: only the interpolation pass (after the last segment of a segmented solve)
     int run_interp = 1;         // 0: this is not the last segment, the interpolation pass comes later
     const int* slot_of_id = nullptr;  // inverse of perm for the interpolation pass's final-state write (null: identity)
@@ -242,7 +281,7 @@ int launch_thread_family(const ThreadLaunch& a) {
             B200_CUDA_TRY(cudaMemsetAsync(a.todo_count, 0, sizeof(int), a.stream));
             B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_thread_kernel<P, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             ida_solve_thread_kernel<P, false, false, false, true><<<grid, tb, smem, a.stream>>>(a.ds, a.is, a.params, a.B, tol, a.lad, a.traj, a.stat,
-                                                                                               a.perm, TraceParams(), RootParams(), a.df, xf, a.seg);
+                                                                                               a.perm, TraceParams(), RootParams(), a.df, xf, a.seg, a.io);
             count_launch();
             B200_CUDA_TRY(cudaGetLastError());
             FastParams xe;
@@ -252,7 +291,7 @@ int launch_thread_family(const ThreadLaunch& a) {
             xe.todo_count = a.todo_count;
             B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_thread_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             ida_solve_thread_kernel<P><<<grid, tb, smem, a.stream>>>(a.ds, a.is, a.params, a.B, tol, a.lad, a.traj, a.stat, a.perm, TraceParams(),
-                                                                     RootParams(), a.df, xe, a.seg);
+                                                                     RootParams(), a.df, xe, a.seg, a.io);
             count_launch();
         } else {
             B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_thread_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -125,7 +125,7 @@ class Ida:
         """choose the kernel family ("auto", "thread", "warp", "cta"); results are bit-identical"""
         self._call("b200ida_set_kernel", self._h, self.KERNELS[kernel])
 
-    def set_regroup(self, trips_per_segment=128, max_segments=3):
+    def set_regroup(self, trips_per_segment=96, max_segments=4):
         """engine tuning (results are bit-identical): segment length and count of the re-grouped production solve;
         max_segments <= 1 switches re-grouping off"""
         self._call("b200ida_set_regroup", self._h, int(trips_per_segment), int(max_segments))
