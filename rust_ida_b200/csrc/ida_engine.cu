@@ -765,6 +765,8 @@ int b200ida_solve_ladder(b200ida_ensemble* e, const double* touts, int ntout, in
                 e->valid_cap = need_valid;
             }
             a.df = DeferParams{e->snap.as<double>(), e->snap_valid.as<unsigned char>()};
+        }
+        if (!e->suppressalg && e->trace.id < 0) {  // plain and rootfinding solves: FAST pass + exact pass
             if (IDA_FAST) {
                 const Layout lay2(e->n);
                 if (!e->dstate2) B200_CUDA_TRY(cudaMalloc(&e->dstate2, (size_t)lay2.ndouble() * e->B * sizeof(double)));
@@ -790,7 +792,8 @@ int b200ida_solve_ladder(b200ida_ensemble* e, const double* touts, int ntout, in
         a.slot_of_id = e->perm ? e->inv_perm.as<int>() : nullptr;
         // Segmented solve with re-grouping: production path, internally re-ordered ensembles that are
         // large enough for a sort + gather of the state (~1 ms per 2^20 instances) to pay
-        const bool segmented = a.ds2 && e->perm && e->regroup_segments > 1 && e->regroup_trips > 0 && e->B >= ((int64_t)1 << 16);
+        const bool segmented = a.ds2 && a.df.snap && e->roots.max_ev <= 0 && e->perm && e->regroup_segments > 1 && e->regroup_trips > 0 &&
+                               e->B >= ((int64_t)1 << 16);
         int rc;
         if (!segmented) {
             rc = launch(a);

@@ -1166,6 +1166,8 @@ struct IdaThread {
     bool gactive[NR];  // FALSE at start like the reference (src/lib.rs:373)
     bool irfnd;
     int nge;
+    int evc;  // events logged so far (rp.ev_count): kept in a register and written back with the root state, so that a
+              // lane the FAST pass abandons leaves no trace for the exact pass that redoes it
     __device__ __forceinline__ static double signum(double x) { return (x != x) ? x : (signbit(x) ? -1.0 : 1.0); }
     enum { GLO = 0, GHI = 1, GROUT = 2 };  // which array of the root state
     __device__ __forceinline__ void eval_root(double t, int which) {  // g(t, yy, yp) -> array `which`
@@ -1193,6 +1195,8 @@ struct IdaThread {
         irfnd = rp.ri[(int64_t)NR * B + b] != 0;
         nge = rp.ri[(int64_t)(NR + 1) * B + b];
     }
+    __device__ __forceinline__ void load_event_count(const RootParams& rp, int64_t ob) { evc = rp.ev_count[ob]; }
+    __device__ __forceinline__ void store_event_count(const RootParams& rp, int64_t ob) const { rp.ev_count[ob] = evc; }
     __device__ __forceinline__ void store_roots(const RootParams& rp, int64_t B, int64_t b) {
 #pragma unroll
         for (int i = 0; i < NR; ++i) {
@@ -1614,8 +1618,7 @@ struct IdaThread {
                             sp[6 * N + 9] = hused;
                             deferred = true;
                         } else {
-                            static_assert(!FAST, "the FAST instantiation defers the output interpolation");
-                            get_solution(tout);
+                            get_solution(tout);  // TRACE / ROOTS / MASK: in line (exact, out-of-line body)
                         }
                         call_status = B200IDA_ST_SUCCESS;
                         call_done = true;
@@ -1648,13 +1651,13 @@ struct IdaThread {
             if constexpr (ROOTS) {
                 if (call_done && call_status == B200IDA_ST_ROOT) {
                     // the caller of examples/roberts.rs:117-140: log (t, get_root_info) and call solve() again
-                    const int c = rp.ev_count[b];
+                    const int c = evc;
                     if (c < rp.max_ev) {
                         rp.ev_t[(int64_t)c * B + b] = tret;
 #pragma unroll
                         for (int i = 0; i < NR; ++i) rp.ev_iroots[((int64_t)c * NR + i) * B + b] = rsm(3 * NR + i);
                     }
-                    rp.ev_count[b] = c + 1;
+                    evc = c + 1;
                     call_done = false;  // falls through to the loop end (no `continue`: a second back edge splits the warp)
                     need_prologue = true;
                 }

@@ -83,7 +83,10 @@ ida_solve_thread_kernel(double* __restrict__ ds, int* __restrict__ is, const dou
             sg.ld_out = nullptr;
         }
     }
-    if constexpr (ROOTS) s.load_roots(rp, B, b);
+    if constexpr (ROOTS) {
+        s.load_roots(rp, B, b);
+        s.load_event_count(rp, ob);
+    }
     // the production instantiation defers the output interpolation to ida_interp_kernel; the TRACE and ROOTS
     // instantiations read yy / yp right after get_solution (trace frames, g(t, y)) and keep it in line
     s.template solve_ladder<TRACE, ROOTS, !TRACE && !ROOTS && !MASK && IDA_DEFER>(lad, tol, yy_traj, status, B, ob, tr, rp, df, 0, sg);
@@ -115,6 +118,7 @@ ida_solve_thread_kernel(double* __restrict__ ds, int* __restrict__ is, const dou
     }
     if constexpr (ROOTS) {
         s.store_roots(rp, B, b);
+        s.store_event_count(rp, ob);
         if (rp.nge_out) rp.nge_out[ob] = s.nge;
     }
 }
@@ -251,10 +255,37 @@ int launch_thread_family(const ThreadLaunch& a) {
     } else if (a.roots.max_ev > 0) {
         if constexpr ((CAPS & CAP_ROOTS) != 0 && P::NR > 0) {
             const size_t rsmem = (size_t)(IdaThread<P>::SMEM_DOUBLES + IdaThread<P>::ROOT_DOUBLES) * tb * sizeof(double);
-            B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_thread_kernel<P, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
-            ida_solve_thread_kernel<P, false, true><<<grid, tb, rsmem, a.stream>>>(a.ds, a.is, a.params, a.B, tol, a.lad, a.traj, a.stat, a.perm,
-                                                                                  TraceParams(), a.roots);
-            count_launch();
+            if (IDA_FAST && a.ds2 && a.is2 && a.poisoned) {
+                // FAST pass (root checks included; the rare Illinois iteration and the interpolation are exact out-of-line
+                // functions either way) + exact pass over the flagged instances; the root state is written at the very
+                // end of a lane's launch only, so an abandoned lane leaves it untouched
+                FastParams xf;
+                xf.ds_out = a.ds2;
+                xf.is_out = a.is2;
+                xf.poisoned = a.poisoned;
+                xf.list = a.todo;
+                xf.count = a.todo_count;
+                B200_CUDA_TRY(cudaMemsetAsync(a.todo_count, 0, sizeof(int), a.stream));
+                B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_thread_kernel<P, false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
+                ida_solve_thread_kernel<P, false, true, false, true><<<grid, tb, rsmem, a.stream>>>(a.ds, a.is, a.params, a.B, tol, a.lad, a.traj, a.stat,
+                                                                                                   a.perm, TraceParams(), a.roots, DeferParams(), xf);
+                count_launch();
+                B200_CUDA_TRY(cudaGetLastError());
+                FastParams xe;
+                xe.ds_out = a.ds2;
+                xe.is_out = a.is2;
+                xe.todo = a.todo;
+                xe.todo_count = a.todo_count;
+                B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_thread_kernel<P, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
+                ida_solve_thread_kernel<P, false, true><<<grid, tb, rsmem, a.stream>>>(a.ds, a.is, a.params, a.B, tol, a.lad, a.traj, a.stat, a.perm,
+                                                                                      TraceParams(), a.roots, DeferParams(), xe);
+                count_launch();
+            } else {
+                B200_CUDA_TRY(cudaFuncSetAttribute(ida_solve_thread_kernel<P, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
+                ida_solve_thread_kernel<P, false, true><<<grid, tb, rsmem, a.stream>>>(a.ds, a.is, a.params, a.B, tol, a.lad, a.traj, a.stat, a.perm,
+                                                                                      TraceParams(), a.roots);
+                count_launch();
+            }
         } else {
             return set_error(B200IDA_ERR_UNSUPPORTED, "rootfinding: this problem has no root functions (Root::num_roots == 0)");
         }

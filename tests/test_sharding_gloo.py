@@ -40,9 +40,14 @@ def _worker(rank, world, port, total, out_path):
     res = ob.ensemble_solve(ob.PK_ROBERTS, 3, p, yy0, yp0, ROBERTS_RTOL, ROBERTS_ATOL, touts, nthreads=2)
     nst = gather_per_instance(torch.from_numpy(res["counters"]["nst"]), total)
     yy = gather_per_instance(torch.from_numpy(res["yy"]), total)
+    # the per-instance statistics block of the final gather (bench.py): nst, nre, nje, nni, netf, ncfn, status, kused
+    c = res["counters"]
+    block = np.stack([c["nst"], c["nre"], c["nje"], c["nni"], c["netf"], c["ncfn"], res["status"][-1].astype(np.int64),
+                      res["kused"].astype(np.int64)])
+    stats = gather_per_instance(torch.from_numpy(block), total)
     dist.barrier()
     if rank == 0:
-        np.savez(out_path, nst=nst.numpy(), yy=yy.numpy())
+        np.savez(out_path, nst=nst.numpy(), yy=yy.numpy(), stats=stats.numpy())
     dist.destroy_process_group()
 
 
@@ -80,3 +85,7 @@ def test_two_rank_gloo_shard_and_gather(tmp_path):
     ref = ob.ensemble_solve(ob.PK_ROBERTS, 3, p, yy0, yp0, ROBERTS_RTOL, ROBERTS_ATOL, ROBERTS_TOUTS[:5], nthreads=4)
     assert np.array_equal(got["nst"], ref["counters"]["nst"])
     assert np.array_equal(got["yy"].view(np.uint64), ref["yy"].view(np.uint64))
+    c = ref["counters"]
+    want = np.stack([c["nst"], c["nre"], c["nje"], c["nni"], c["netf"], c["ncfn"], ref["status"][-1].astype(np.int64),
+                     ref["kused"].astype(np.int64)])
+    assert got["stats"].shape == (8, total) and np.array_equal(got["stats"], want)
