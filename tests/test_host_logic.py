@@ -91,3 +91,26 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1
     assert j["cpu_baseline"]["value"] == j["value"]
     assert j["e2e"] == {"value": j["value"], "unit": j["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_bench_reads_profile_summaries_with_commas_in_kernel_names(tmp_path, monkeypatch):
+    """bench.py quotes ncu figures from the newest summary under profiles/ at run time: kernel names hold commas
+    ("<Roberts, 0, 0, 0, 1>") and a summary may hold the several segment launches of one solve"""
+    import importlib
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    bench = importlib.import_module("bench")
+    prof = tmp_path / "profiles"
+    prof.mkdir()
+    rows = ["# note ; source x.ncu-rep", "kernel,metric,unit,value"]
+    for ms, rd, lanes in ((10.0, 1.0, 28.0), (30.0, 2.0, 20.0)):
+        k = "void ida_solve_thread_kernel<Roberts, 0, 0, 0, 1>"
+        rows += ["%s,gpu__time_duration.sum,ms,%f" % (k, ms), "%s,dram__bytes_read.sum,Gbyte,%f" % (k, rd),
+                 "%s,dram__bytes_write.sum,Gbyte,0.5" % k,
+                 "%s,smsp__thread_inst_executed_per_inst_executed.ratio,,%f" % (k, lanes)]
+    (prof / "r9_ida_solve_thread_x_ncu_summary.csv").write_text("\\n".join(rows) + "\\n")
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path))
+    q = bench.quoted_profile()
+    assert q["launches_in_summary"] == 2 and q["traffic_bytes_per_launch"] == 4_000_000_000
+    assert abs(q["kernel_ms_under_ncu"] - 40.0) < 1e-9 and abs(q["active_lanes_per_instruction"] - 22.0) < 1e-9
