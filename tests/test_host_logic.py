@@ -109,7 +109,7 @@ def test_bench_reads_profile_summaries_with_commas_in_kernel_names(tmp_path, mon
         rows += ["%s,gpu__time_duration.sum,ms,%f" % (k, ms), "%s,dram__bytes_read.sum,Gbyte,%f" % (k, rd),
                  "%s,dram__bytes_write.sum,Gbyte,0.5" % k,
                  "%s,smsp__thread_inst_executed_per_inst_executed.ratio,,%f" % (k, lanes)]
-    (prof / "r9_ida_solve_thread_x_ncu_summary.csv").write_text("\\n".join(rows) + "\\n")
+    (prof / "r9_ida_solve_thread_x_ncu_summary.csv").write_text("\n".join(rows) + "\n")
     monkeypatch.setattr(bench, "ROOT", str(tmp_path))
     q = bench.quoted_profile()
     assert q["launches_in_summary"] == 2 and q["traffic_bytes_per_launch"] == 4_000_000_000
