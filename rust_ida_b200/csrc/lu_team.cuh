@@ -360,14 +360,47 @@ __device__ __forceinline__ void lu_solve_cta_blocked(const double* M, int ld, in
             const int i = k0 + lane;
             const int ic = i < n ? i : n - 1;
             double x = b[ic];
+            bool done = false;
+            if (rdiag) {
+                // Straight-line chain: EVERY lane forms the exact-reciprocal quotient of its own (x, c) each step (three
+                // FP64 instructions, exact_div.cuh) and only the pivot lane keeps it -- the one-lane divergent region with
+                // its range tests and fallbacks was most of this chain's length (round-2 profile: the backward diagonal
+                // chains were a third of the heat kernel's run time, 4.4 x the forward ones).  The pivot lane's range test
+                // (and the exact +-0 numerator, which boundary rows produce all the time) is carried in a flag and voted
+                // on ONCE after the block; a block that fails is redone from its saved right-hand side by the guarded loop.
+                const double x_in = x;
+                bool ok = true;
 #pragma unroll 4
-            for (int k = ktop; k >= k0; --k) {
-                const double c = M[(size_t)k * ld + ic];  // lane == k - k0 reads u_kk
-                double xv = x;
-                if (i == k) xv = rdiag ? div_by_recip(x, c, rdiag[k]) : x / c;
-                const double bk = __shfl_sync(0xffffffffu, xv, k - k0);
-                const double t = x - c * bk;
-                x = (i == k) ? bk : ((i < k) ? t : x);
+                for (int k = ktop; k >= k0; --k) {
+                    const double c = M[(size_t)k * ld + ic];  // lane == k - k0 reads u_kk
+                    const double y = rdiag[k];
+                    const double q0 = __dmul_rn(x, y);
+                    const double rr = __fma_rn(-c, q0, x);
+                    const double q1 = __fma_rn(rr, y, q0);
+                    const bool piv = i == k;
+                    const unsigned ex = ((unsigned)__double2hiint(x) >> 20) & 0x7ffu, ed = ((unsigned)__double2hiint(c) >> 20) & 0x7ffu;
+                    const bool xz = x == 0.0;
+                    const bool okp = xz ? (ed - 1u < 0x7feu) : ((ex - 543u) <= 960u && (ed - 543u) <= 960u);
+                    ok = ok && (!piv || okp);
+                    const double qz = __hiloint2double((__double2hiint(x) ^ __double2hiint(c)) & (int)0x80000000, 0);
+                    const double xv = piv ? (xz ? qz : q1) : x;
+                    const double bk = __shfl_sync(0xffffffffu, xv, k - k0);
+                    const double t = x - c * bk;
+                    x = piv ? bk : ((i < k) ? t : x);
+                }
+                done = __all_sync(0xffffffffu, ok);
+                if (!done) x = x_in;
+            }
+            if (!done) {
+#pragma unroll 4
+                for (int k = ktop; k >= k0; --k) {
+                    const double c = M[(size_t)k * ld + ic];  // lane == k - k0 reads u_kk
+                    double xv = x;
+                    if (i == k) xv = rdiag ? div_by_recip(x, c, rdiag[k]) : x / c;
+                    const double bk = __shfl_sync(0xffffffffu, xv, k - k0);
+                    const double t = x - c * bk;
+                    x = (i == k) ? bk : ((i < k) ? t : x);
+                }
             }
             if (i < n) b[i] = x;
         }
