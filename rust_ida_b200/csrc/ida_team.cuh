@@ -25,6 +25,10 @@
 #include "lu_team.cuh"
 #include "lu_blocked.cuh"
 
+#ifndef IDA_TEAM_LUB_POL
+#define IDA_TEAM_LUB_POL 0  // lub_factor panel policy (lu_blocked.cuh), tools/build_variants.sh experiments
+#endif
+
 namespace b200ida {
 
 // ---- team policies ------------------------------------------------------------------------------------
@@ -372,7 +376,7 @@ struct IdaTeam {
     __device__ void getrf() {
         Team::sync();
         if (Team::T == 0 && n > 32) {
-            lub_factor<5>(J, ldj, n, lub, piv, Ub);
+            lub_factor<5>(J, ldj, n, lub, piv, Ub, IDA_TEAM_LUB_POL);
             if (leader()) S->info = lub->info;
         } else {
             lu_factor<Team::T == 32>(J, ldj, n, &S->lu, piv);

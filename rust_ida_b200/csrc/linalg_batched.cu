@@ -603,7 +603,7 @@ __global__ void __launch_bounds__(lub_threads(RP), lub_min_ctas(RP))
         __syncthreads();
         LUB_T(ts1);
         LUB_ACC(7, ts0, ts1);
-        lub_factor<RP>(Ms, ld, n, ctl, pivs, Ub);
+        lub_factor_1w<RP>(Ms, ld, n, ctl, pivs, Ub);
         if (use_tma) {
             // factors back to global the same way: one bulk store per column (lub_factor ended with a CTA barrier)
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
