@@ -369,7 +369,7 @@ __device__ __forceinline__ void lu_solve_cta_blocked(const double* M, int ld, in
                 // (and the exact +-0 numerator, which boundary rows produce all the time) is carried in a flag and voted
                 // on ONCE after the block; a block that fails is redone from its saved right-hand side by the guarded loop.
                 const double x_in = x;
-                bool ok = true;
+                double xp = 1.0;  // this lane's numerator at the step where it was the pivot lane (range-tested after the loop)
 #pragma unroll 4
                 for (int k = ktop; k >= k0; --k) {
                     const double c = M[(size_t)k * ld + ic];  // lane == k - k0 reads u_kk
@@ -378,16 +378,18 @@ __device__ __forceinline__ void lu_solve_cta_blocked(const double* M, int ld, in
                     const double rr = __fma_rn(-c, q0, x);
                     const double q1 = __fma_rn(rr, y, q0);
                     const bool piv = i == k;
-                    const unsigned ex = ((unsigned)__double2hiint(x) >> 20) & 0x7ffu, ed = ((unsigned)__double2hiint(c) >> 20) & 0x7ffu;
-                    const bool xz = x == 0.0;
-                    const bool okp = xz ? (ed - 1u < 0x7feu) : ((ex - 543u) <= 960u && (ed - 543u) <= 960u);
-                    ok = ok && (!piv || okp);
-                    const double qz = __hiloint2double((__double2hiint(x) ^ __double2hiint(c)) & (int)0x80000000, 0);
-                    const double xv = piv ? (xz ? qz : q1) : x;
-                    const double bk = __shfl_sync(0xffffffffu, xv, k - k0);
+                    // x = +-0: the quotient is the zero with the sign of x * y, which q0 already is (q1 can lose -0)
+                    const double q = (x == 0.0) ? q0 : q1;
+                    xp = piv ? x : xp;
+                    const double bk = __shfl_sync(0xffffffffu, piv ? q : x, k - k0);
                     const double t = x - c * bk;
                     x = piv ? bk : ((i < k) ? t : x);
                 }
+                // the pivot lanes' range tests, once per block: divisor u_ii and numerator within 2^-480 .. 2^480, or an
+                // exact zero numerator over a finite normal divisor (exact_div.cuh)
+                const double dg = M[(size_t)ic * ld + ic];
+                const unsigned ex = ((unsigned)__double2hiint(xp) >> 20) & 0x7ffu, ed = ((unsigned)__double2hiint(dg) >> 20) & 0x7ffu;
+                const bool ok = (xp == 0.0) ? (ed - 1u < 0x7feu) : ((ex - 543u) <= 960u && (ed - 543u) <= 960u);
                 done = __all_sync(0xffffffffu, ok);
                 if (!done) x = x_in;
             }
