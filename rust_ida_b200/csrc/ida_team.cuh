@@ -393,7 +393,7 @@ struct IdaTeam {
             Team::sync();
             lu_solve_cta_blocked(J, ldj, n, perm, nd, tmp, rdiag);
         } else {
-            lu_solve<Team::T == 32>(J, ldj, n, piv, nd, rdiag);
+            lu_solve<Team::T == 32>(J, ldj, n, piv, nd, rdiag, perm);
         }
         const double cjratio = S->cjratio;
         if (cjratio != 1.0) {

@@ -278,13 +278,63 @@ __device__ __forceinline__ void lu_solve_warp_r(const double* M, int ld, int n, 
     }
 }
 
+// n <= 32 with the row permutation (lu_build_perm) and the reciprocals of the diagonal at hand: one warp, lane = row, the
+// right-hand side gathered straight into registers (no serial interchange loop), the backward sweep's division done by
+// every lane in line (exact-reciprocal sequence) with the pivot lanes' range tests voted once at the end -- a failed
+// vote redoes the backward sweep with the guarded division.  Same operands and per-row order as dense_get_rs.
+__device__ __forceinline__ void lu_solve_warp32(const double* M, int ld, int n, const int* perm, double* b, const double* rdiag) {
+    const int lane = threadIdx.x & 31;
+    const int ic = lane < n ? lane : n - 1;  // lanes beyond the matrix mirror row n-1 and store nothing
+    double x = b[perm[ic]];
+    __syncwarp();
+#pragma unroll 4
+    for (int k = 0; k < n - 1; ++k) {
+        const double c = M[(size_t)k * ld + ic];
+        const double bk = __shfl_sync(0xffffffffu, x, k);
+        const double t = x - c * bk;
+        x = (lane > k) ? t : x;
+    }
+    const double x_in = x;
+    double xp = 1.0;
+#pragma unroll 4
+    for (int k = n - 1; k >= 0; --k) {
+        const double c = M[(size_t)k * ld + ic];
+        const double y = rdiag[k];
+        const double q0 = __dmul_rn(x, y);
+        const double rr = __fma_rn(-c, q0, x);
+        const double q1 = __fma_rn(rr, y, q0);
+        const bool piv = lane == k;
+        const double q = (x == 0.0) ? q0 : q1;  // +-0: the zero with the sign of x * y
+        xp = piv ? x : xp;
+        const double bk = __shfl_sync(0xffffffffu, piv ? q : x, k);
+        const double t = x - c * bk;
+        x = piv ? bk : ((lane < k) ? t : x);
+    }
+    const double dg = M[(size_t)ic * ld + ic];
+    const unsigned ex = ((unsigned)__double2hiint(xp) >> 20) & 0x7ffu, ed = ((unsigned)__double2hiint(dg) >> 20) & 0x7ffu;
+    const bool ok = (xp == 0.0) ? (ed - 1u < 0x7feu) : ((ex - 543u) <= 960u && (ed - 543u) <= 960u);
+    if (!__all_sync(0xffffffffu, ok)) {
+        x = x_in;
+        for (int k = n - 1; k >= 0; --k) {
+            const double c = M[(size_t)k * ld + ic];
+            double xv = x;
+            if (lane == k) xv = div_by_recip(x, c, rdiag[k]);
+            const double bk = __shfl_sync(0xffffffffu, xv, k);
+            const double t = x - c * bk;
+            x = (lane == k) ? bk : ((lane < k) ? t : x);
+        }
+    }
+    if (lane < n) b[lane] = x;
+}
+
 template <bool WARP, class PivT>
 __device__ __forceinline__ void lu_solve(const double* M, int ld, int n, const PivT* piv, double* b,
-                                         const double* rdiag = nullptr) {
+                                         const double* rdiag = nullptr, const int* perm = nullptr) {
     using G = LuGroup<WARP>;
     G::sync();
     if (G::warp() == 0) {
-        if (n <= 32) lu_solve_warp_r<1>(M, ld, n, piv, b, rdiag);
+        if (n <= 32 && perm != nullptr && rdiag != nullptr) lu_solve_warp32(M, ld, n, perm, b, rdiag);
+        else if (n <= 32) lu_solve_warp_r<1>(M, ld, n, piv, b, rdiag);
         else if (n <= 64) lu_solve_warp_r<2>(M, ld, n, piv, b, rdiag);
         else if (n <= 128) lu_solve_warp_r<4>(M, ld, n, piv, b, rdiag);
         else lu_solve_warp_r<8>(M, ld, n, piv, b, rdiag);
