@@ -384,6 +384,12 @@ struct Ida {
     // handle_n_flag, 17 err_kp1 norm formed, 18-20 kk after, 21 phase after, 22 output time reached by this step
     uint32_t* ev = nullptr;
     float* ev_h = nullptr;  // |hh| after the attempt (sort-key experiments)
+    float* ev_c = nullptr;  // cj the next attempt will use / cjold, i.e. the next attempt's cjratio (optional)
+    float ev_cjr() const {
+        double a = 0.0;
+        for (int j = 1; j <= kk; ++j) a += 1.0 / (double)j;
+        return (float)((a / hh) / cjold);
+    }
     long ev_max = 0, ev_count = 0;
     uint32_t ev_word = 0;
     void dump_frame() {
@@ -812,6 +818,7 @@ struct Ida {
                 if (ev_count < ev_max) {
                     ev[ev_count] = evw;
                     ev_h[ev_count] = (float)std::fabs(hh);
+                    if (ev_c) ev_c[ev_count] = ev_cjr();
                 }
                 ev_count += 1;
             }
@@ -830,6 +837,7 @@ struct Ida {
             if (ev_count < ev_max) {
                 ev[ev_count] = ev_word;
                 ev_h[ev_count] = (float)std::fabs(hh);
+                if (ev_c) ev_c[ev_count] = ev_cjr();
             }
             ev_count += 1;
         }
@@ -1521,9 +1529,19 @@ int oracle_ensemble_dky(int kind, int n, int64_t B, int nparams, const double* p
 }
 
 // per-attempt event words of every instance (see Ida::ev): ev [B][max_att] uint32, ev_h [B][max_att] float, natt [B].
+int oracle_ensemble_events2(int kind, int n, int64_t B, int nparams, const double* params, const double* yy0, const double* yp0,
+                            double rtol, const double* atol, const double* touts, int ntout, int nthreads, long max_att,
+                            uint32_t* ev, float* ev_h, int32_t* natt, float* ev_c);
 int oracle_ensemble_events(int kind, int n, int64_t B, int nparams, const double* params, const double* yy0, const double* yp0,
                            double rtol, const double* atol, const double* touts, int ntout, int nthreads, long max_att,
                            uint32_t* ev, float* ev_h, int32_t* natt) {
+    return oracle_ensemble_events2(kind, n, B, nparams, params, yy0, yp0, rtol, atol, touts, ntout, nthreads, max_att, ev, ev_h, natt,
+                                   nullptr);
+}
+// the same with ev_c [B][max_att]: the cjratio the NEXT attempt will see (optional, may be null)
+int oracle_ensemble_events2(int kind, int n, int64_t B, int nparams, const double* params, const double* yy0, const double* yp0,
+                            double rtol, const double* atol, const double* touts, int ntout, int nthreads, long max_att,
+                            uint32_t* ev, float* ev_h, int32_t* natt, float* ev_c) {
     if (nthreads < 1) nthreads = 1;
     std::atomic<int64_t> next(0);
     auto worker = [&]() {
@@ -1542,6 +1560,7 @@ int oracle_ensemble_events(int kind, int n, int64_t B, int nparams, const double
             ida.init(p, y0.data(), yp0v.data(), rtol, atol);
             ida.ev = ev + (size_t)b * max_att;
             ida.ev_h = ev_h + (size_t)b * max_att;
+            if (ev_c) ida.ev_c = ev_c + (size_t)b * max_att;
             ida.ev_max = max_att;
             double tret = 0.0;
             for (int it = 0; it < ntout; ++it) ida.solve(touts[it], tret);

@@ -36,7 +36,7 @@ char* last_error_buf() {
 
 // Team-per-instance solve (ida_team.cuh): persistent teams (warps or whole CTAs) stride over the ensemble.
 template <class Team>
-__global__ void ida_solve_team_kernel(double* __restrict__ ds, int* __restrict__ is, const double* __restrict__ params,
+__global__ void __launch_bounds__(Team::MAXT, Team::MINB) ida_solve_team_kernel(double* __restrict__ ds, int* __restrict__ is, const double* __restrict__ params,
                                       int64_t B, int n, int kind, int nparams, double rtol, const double* __restrict__ atol,
                                       LadderParams lad, double* __restrict__ yy_traj, int32_t* __restrict__ status,
                                       unsigned arena_bytes, const int* __restrict__ perm, TraceParams tr,

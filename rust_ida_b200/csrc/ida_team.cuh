@@ -32,8 +32,12 @@
 namespace b200ida {
 
 // ---- team policies ------------------------------------------------------------------------------------
+#ifndef IDA_WARP_MINB
+#define IDA_WARP_MINB 3  // the warp-team kernel is compiled for 3 resident CTAs (of 4 teams) per SM = 168 registers: 1-2 (232) lose a third of the warps, 4 (128) spills
+#endif
 struct WarpTeam {
     static constexpr int T = 32;
+    static constexpr int MAXT = 128, MINB = IDA_WARP_MINB;
     __device__ __forceinline__ static int tid() { return threadIdx.x & 31; }
     __device__ __forceinline__ static void sync() { __syncwarp(); }
     __device__ __forceinline__ static int teams_per_cta() { return blockDim.x >> 5; }
@@ -41,6 +45,7 @@ struct WarpTeam {
 };
 struct CtaTeam {
     static constexpr int T = 0;  // run-time: blockDim.x
+    static constexpr int MAXT = 256, MINB = 1;  // up to 255 registers
     __device__ __forceinline__ static int tid() { return threadIdx.x; }
     __device__ __forceinline__ static void sync() { __syncthreads(); }
     __device__ __forceinline__ static int teams_per_cta() { return 1; }

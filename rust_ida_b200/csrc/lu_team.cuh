@@ -183,10 +183,96 @@ __device__ __forceinline__ void lu_factor_r(double* M, int ld, int n, LuShared* 
     }
 }
 
+// ---- one warp, n <= N (N = 16 or 32), matrix in shared memory, factorisation in REGISTERS --------------------------------
+// Lane i loads row i of the matrix once and keeps it in registers for the whole factorisation; rows are never moved: each
+// lane tracks the LOGICAL position the reference's whole-row swaps would have given its row and writes the row there at
+// the end.  Per step: arg-max of |a_ik| by three integer redux.sync on the IEEE bit pattern (NaN below every candidate, ties
+// to the lowest logical position, the key carries the lane), exact reciprocal of the pivot in every lane, the pivot row
+// broadcast through the matrix's own storage (the owner lane writes u_kj to its final place M[j][k], everybody reads it
+// back as a broadcast), n-1-k independent mul / sub per lane.  Lanes >= n hold no row ("done" from the start).  The
+// shared-memory group LU above pays two warp barriers, a 10-shuffle butterfly and a shared-memory round trip of the whole
+// trailing matrix per step instead.  Same algorithm as the Level-1 getrf_warp_regs (linalg_batched.cu), any n <= N.
+template <int N, int K>
+__device__ __forceinline__ void lu_wregs_step(double (&row)[N], double* M, int ld, int n, int lane, int& pos, bool& done, int& inf,
+                                              int& mypiv) {
+    if (K < n && inf == 0) {  // uniform
+        const double x = row[K];
+        const bool isnan_ = x != x;
+        const int hi = done ? -2 : (isnan_ ? -1 : (__double2hiint(x) & 0x7fffffff));
+        const unsigned lo = (done || isnan_) ? 0u : (unsigned)__double2loint(x);
+        const unsigned pp = ((unsigned)pos << 8) | (unsigned)lane;
+        const int mhi = __reduce_max_sync(0xffffffffu, hi);
+        const unsigned mlo = __reduce_max_sync(0xffffffffu, (hi == mhi) ? lo : 0u);
+        unsigned mpp = __reduce_min_sync(0xffffffffu, (!done && hi == mhi && lo == mlo) ? pp : 0xffffffffu);
+        const bool atk = !done && pos == K;  // the lane that holds logical row K (positions < K are final pivot rows)
+        if (mhi < 0 || __any_sync(0xffffffffu, atk && isnan_)) {
+            // nothing comparable, or a NaN in row K: the reference keeps l = K
+            mpp = __reduce_min_sync(0xffffffffu, atk ? pp : 0xffffffffu);
+        }
+        const int l = (int)(mpp >> 8), lw = (int)(mpp & 0xffu);
+        const double pv = __shfl_sync(0xffffffffu, x, lw);
+        if (lane == K) mypiv = l;
+        if (pv == 0.0) {
+            inf = K + 1;
+        } else {
+            const double mult = 1.0 / pv;
+            const bool owner = lane == lw;
+            if (owner) {
+                pos = K;
+                done = true;
+            } else if (atk) {
+                pos = l;
+            }
+            const double lik = x * mult;
+            if (!done) row[K] = lik;
+            if (owner) {
+#pragma unroll
+                for (int j = K + 1; j < N; ++j)
+                    if (j < n) M[(size_t)j * ld + K] = row[j];
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j = K + 1; j < N; ++j) {
+                if (j < n) {  // uniform
+                    const double a = M[(size_t)j * ld + K];
+                    if (!done && a != 0.0) row[j] -= a * lik;
+                }
+            }
+        }
+    }
+    if constexpr (K + 1 < N) lu_wregs_step<N, K + 1>(row, M, ld, n, lane, pos, done, inf, mypiv);
+}
+
+template <int N, class PivT>
+__device__ __noinline__ void lu_factor_warp_regs(double* M, int ld, int n, LuShared* sh, PivT* piv) {
+    const int lane = threadIdx.x & 31;
+    const bool mine = lane < n;
+    const int lc = mine ? lane : n - 1;
+    double row[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) row[j] = (j < n) ? M[(size_t)j * ld + lc] : 0.0;
+    __syncwarp();
+    int pos = lane;
+    bool done = !mine;
+    int inf = 0, mypiv = 0;
+    lu_wregs_step<N, 0>(row, M, ld, n, lane, pos, done, inf, mypiv);
+    __syncwarp();
+    if (mine) {
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+            if (j < n) M[(size_t)j * ld + pos] = row[j];
+        if (inf == 0 || lane < inf) piv[lane] = (PivT)mypiv;
+    }
+    if (lane == 0) sh->info = inf;
+    __syncwarp();
+}
+
 // dispatch on ceil(n/32) so that small systems do not issue predicated-off row slots
 template <bool WARP, class PivT>
 __device__ __forceinline__ void lu_factor(double* M, int ld, int n, LuShared* sh, PivT* piv) {
-    if (n <= 32) lu_factor_r<WARP, 1>(M, ld, n, sh, piv);
+    if (WARP && n <= 16) lu_factor_warp_regs<16>(M, ld, n, sh, piv);
+    else if (WARP && n <= 32) lu_factor_warp_regs<32>(M, ld, n, sh, piv);
+    else if (n <= 32) lu_factor_r<WARP, 1>(M, ld, n, sh, piv);
     else if (n <= 64) lu_factor_r<WARP, 2>(M, ld, n, sh, piv);
     else if (n <= 128) lu_factor_r<WARP, 4>(M, ld, n, sh, piv);
     else lu_factor_r<WARP, 8>(M, ld, n, sh, piv);
