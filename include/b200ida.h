@@ -50,6 +50,12 @@ extern "C" {
  * multiply / subtract.  Factors then agree with the reference's dense_get_rf to rounding (tests: rel 1e-12), pivot
  * sequences are equal unless two pivot candidates tie to within rounding.  Ignored for other sizes / layouts. */
 #define B200IDA_LU_DMMA 0x100
+/* OR into `layout` of b200ida_getrf_batched: factor 33 <= n <= 160 (AoS) with the panel / update schedule of the
+ * CTA-per-system IDA kernel -- the panel shared by one warp per 32-row slot, the trailing update drawn from a work queue
+ * (lu_blocked.cuh, lub_factor) -- instead of the one-warp panel.  Results are bit-identical; at the benchmark batches it is
+ * 20-25 % slower than the default.  Exposed so that the team flavour can be tested and measured through
+ * the Level-1 entry point.  Ignored for other sizes / layouts. */
+#define B200IDA_LU_TEAM_PANEL 0x200
 
 const char* b200ida_last_error(void); /* thread-local text of the last failure */
 int b200ida_version(void);

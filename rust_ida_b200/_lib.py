@@ -14,6 +14,7 @@ SO_PATH = os.environ.get("B200IDA_LIB") or os.path.join(CSRC, "libb200ida.so")  
 MEM_DEVICE, MEM_HOST = 0, 1
 LAYOUT_SOA, LAYOUT_AOS = 0, 1
 LU_DMMA = 0x100  # OR into the layout of b200ida_getrf_batched: tensor-core trailing update (tolerance mode)
+LU_TEAM_PANEL = 0x200  # OR into the layout: the CTA-team kernel's shared panel + work-queue update (bit-identical)
 OK, ERR_ARG, ERR_CUDA, ERR_NO_DEVICE, ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 
 # every symbol include/b200ida.h declares (tests check that the .so exports exactly these)

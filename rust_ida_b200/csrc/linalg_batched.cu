@@ -533,7 +533,7 @@ __host__ __device__ inline size_t lub_smem_bytes(int n) {
 constexpr int lub_threads(int RP) { return RP <= 2 ? 128 : 256; }
 constexpr int lub_min_ctas(int RP) { return RP <= 2 ? 4 : (RP <= 4 ? 2 : 1); }
 
-template <bool SOA, int RP>
+template <bool SOA, int RP, bool TEAM = false>
 __global__ void __launch_bounds__(lub_threads(RP), lub_min_ctas(RP))
     getrf_blocked(double* __restrict__ A, int64_t* __restrict__ piv, int32_t* __restrict__ info, int n, int64_t B, int tma) {
     extern __shared__ __align__(16) unsigned char lu_smem[];
@@ -603,7 +603,8 @@ __global__ void __launch_bounds__(lub_threads(RP), lub_min_ctas(RP))
         __syncthreads();
         LUB_T(ts1);
         LUB_ACC(7, ts0, ts1);
-        lub_factor_1w<RP>(Ms, ld, n, ctl, pivs, Ub);
+        if (TEAM) lub_factor<RP>(Ms, ld, n, ctl, pivs, Ub);  // B200IDA_LU_TEAM_PANEL: the IDA team kernel's flavour
+        else lub_factor_1w<RP>(Ms, ld, n, ctl, pivs, Ub);
         if (use_tma) {
             // factors back to global the same way: one bulk store per column (lub_factor ended with a CTA barrier)
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -631,15 +632,15 @@ __global__ void __launch_bounds__(lub_threads(RP), lub_min_ctas(RP))
     }
 }
 
-template <bool SOA, int RP>
+template <bool SOA, int RP, bool TEAM = false>
 static int launch_getrf_blocked(double* A, int64_t* piv, int32_t* info, int n, int64_t B, cudaStream_t st) {
     const size_t smem = lub_smem_bytes(n);
     unsigned grid = 1;
     int rc;
     // TMA-staged panels when every column segment is 16-byte aligned: AoS, even n, aligned batch
     const int tma = (!SOA && (n & 1) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 && !experiment_env("B200IDA_GETRF_NO_TMA")) ? 1 : 0;
-    if ((rc = launch_cfg(getrf_blocked<SOA, RP>, lub_threads(RP), smem, B, 1, &grid))) return rc;
-    getrf_blocked<SOA, RP><<<grid, lub_threads(RP), smem, st>>>(A, piv, info, n, B, tma);
+    if ((rc = launch_cfg(getrf_blocked<SOA, RP, TEAM>, lub_threads(RP), smem, B, 1, &grid))) return rc;
+    getrf_blocked<SOA, RP, TEAM><<<grid, lub_threads(RP), smem, st>>>(A, piv, info, n, B, tma);
     B200_CUDA_TRY(cudaGetLastError());
     return B200IDA_OK;
 }
@@ -649,6 +650,13 @@ static int launch_getrf_blocked_n(double* A, int64_t* piv, int32_t* info, int n,
     if (n <= 96) return launch_getrf_blocked<SOA, 3>(A, piv, info, n, B, st);
     if (n <= 128) return launch_getrf_blocked<SOA, 4>(A, piv, info, n, B, st);
     return launch_getrf_blocked<SOA, 5>(A, piv, info, n, B, st);
+}
+// B200IDA_LU_TEAM_PANEL (AoS, 33 <= n <= SMEM_MAX_N): the same kernel with the CTA-team flavour of the factorisation
+static int launch_getrf_blocked_team(double* A, int64_t* piv, int32_t* info, int n, int64_t B, cudaStream_t st) {
+    if (n <= 64) return launch_getrf_blocked<false, 2, true>(A, piv, info, n, B, st);
+    if (n <= 96) return launch_getrf_blocked<false, 3, true>(A, piv, info, n, B, st);
+    if (n <= 128) return launch_getrf_blocked<false, 4, true>(A, piv, info, n, B, st);
+    return launch_getrf_blocked<false, 5, true>(A, piv, info, n, B, st);
 }
 
 // ---- warp-per-system streaming getrs (AoS, n > 32): every element of the factors is used exactly once, so the
@@ -1163,8 +1171,10 @@ static int launch_group(double* A, int64_t* piv, int32_t* info, double* bx, int 
 // device-pointer implementations -------------------------------------------------------------------------
 static int getrf_dev(double* A, int64_t* piv, int32_t* info, int n, int64_t B, int layout, cudaStream_t st) {
     const int dmma = (layout & B200IDA_LU_DMMA) ? 1 : 0;  // tolerance mode: honoured by the global-memory blocked LU (n >= 115, AoS)
-    layout &= ~B200IDA_LU_DMMA;
+    const bool team = (layout & B200IDA_LU_TEAM_PANEL) != 0;
+    layout &= ~(B200IDA_LU_DMMA | B200IDA_LU_TEAM_PANEL);
     const bool soa = layout == B200IDA_LAYOUT_SOA;
+    if (team && !soa && n > 32 && n <= SMEM_MAX_N) return launch_getrf_blocked_team(A, piv, info, n, B, st);
     if (soa && n <= 8) {
         switch (n) {
         case 1: launch_getrf_thread<1>(A, piv, info, B, st); break;
@@ -1262,7 +1272,7 @@ int b200ida_debug_lub_prof(unsigned long long* out16, int reset) {
 
 int b200ida_getrf_batched(double* A, int64_t* piv, int32_t* info, int n, int64_t batch, int layout, int mem,
                           void* stream) {
-    int rc = check_common(A, piv, n, batch, layout & ~B200IDA_LU_DMMA, mem, "b200ida_getrf_batched");
+    int rc = check_common(A, piv, n, batch, layout & ~(B200IDA_LU_DMMA | B200IDA_LU_TEAM_PANEL), mem, "b200ida_getrf_batched");
     if (rc) return rc;
     if (!info) return set_error(B200IDA_ERR_ARG, "b200ida_getrf_batched: info is null");
     cudaStream_t st = static_cast<cudaStream_t>(stream);

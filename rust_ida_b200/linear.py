@@ -40,12 +40,15 @@ def _layout_code(layout):
 class Dense:
     """`impl LSolver<f64, D> for Dense<D>` over a batch (crates/linear/src/dense.rs:22-63)."""
 
-    def __init__(self, n, batch, layout="soa", raise_on_singular=True, tensor_core_update=False):
+    def __init__(self, n, batch, layout="soa", raise_on_singular=True, tensor_core_update=False, team_panel=False):
         """tensor_core_update: TOLERANCE mode (B200IDA_LU_DMMA) -- the trailing update of the blocked LU on the FP64
-        tensor cores for AoS matrices with even n >= 115; factors agree with dense_get_rf to rounding, not bit for bit."""
+        tensor cores for AoS matrices with even n >= 115; factors agree with dense_get_rf to rounding, not bit for bit.
+        team_panel: B200IDA_LU_TEAM_PANEL -- the CTA-team IDA kernel's panel / update schedule for AoS, 33 <= n <= 160
+        (bit-identical results; for tests and measurements)."""
         self.n, self.batch, self.layout = int(n), int(batch), layout
         self.raise_on_singular = raise_on_singular
         self.tensor_core_update = bool(tensor_core_update)
+        self.team_panel = bool(team_panel)
         self.pivots = None  # int64, (n, batch) soa / (batch, n) aos -- `Dense { pivots }`
         self.info = None    # int32 (batch,): 0 or 1-based zero-pivot column
 
@@ -79,7 +82,8 @@ class Dense:
         pi, _ = B.describe(self.info, np.int32, "info")
         ctx, dev = B.tensors_device(mat_a, self.pivots, self.info)
         with ctx:
-            code = _layout_code(self.layout) | (_lib.LU_DMMA if self.tensor_core_update else 0)
+            code = (_layout_code(self.layout) | (_lib.LU_DMMA if self.tensor_core_update else 0) |
+                    (_lib.LU_TEAM_PANEL if self.team_panel else 0))
             _lib.check(_lib.lib().b200ida_getrf_batched(pa, pp, pi, self.n, self.batch, code, mem, B.current_stream(mem, dev)))
         if self.raise_on_singular:
             info = self.info.cpu().numpy() if B.is_torch(self.info) else self.info

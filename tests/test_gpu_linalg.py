@@ -32,7 +32,7 @@ def oracle_lu(a, b):
     return np.array(lus), np.array(pivs), np.array(xs), np.array(infos)
 
 
-def run_gpu(a, b, layout, device_buffers):
+def run_gpu(a, b, layout, device_buffers, **dense_kw):
     """a: (batch, n, n) mathematical matrices, b: (batch, n)"""
     import torch
     import rust_ida_b200 as r
@@ -44,7 +44,7 @@ def run_gpu(a, b, layout, device_buffers):
         A = np.ascontiguousarray(a.transpose(0, 2, 1))  # column-major per matrix: [b, j, i]
         X = b.copy()
     Bv = X.copy()
-    ls = r.Dense.new(n, batch, layout=layout, raise_on_singular=False)
+    ls = r.Dense.new(n, batch, layout=layout, raise_on_singular=False, **dense_kw)
     if device_buffers:
         A, X, Bv = (torch.from_numpy(v).cuda() for v in (A, X, Bv))
     ls.setup(A)
@@ -278,3 +278,56 @@ def test_tensor_core_flag_is_ignored_where_it_does_not_apply():
         ls.setup(A)
         lu = A.transpose(2, 0, 1) if layout == "soa" else A.transpose(0, 2, 1)
         assert_bit_equal(lu, lu_ref, "n=%d %s" % (n, layout))
+
+
+# ---- B200IDA_LU_TEAM_PANEL: the CTA-team IDA kernel's factorisation (panel shared by one warp per 32-row slot, work-queue
+#      update; lu_blocked.cuh lub_factor / lub_panel_mw) driven through the Level-1 entry point, so that its tie / NaN / inf
+#      exchange paths, its zero-pivot exits and every panel-warp count (1..4 warps, one or two row slots per lane) are
+#      checked against the oracle and not only on the well-behaved heat Jacobians -------------------------------------------
+@pytest.mark.parametrize("n,batch", [(33, 5), (40, 7), (64, 9), (65, 4), (96, 5), (100, 9), (128, 3), (129, 3), (160, 2)])
+def test_team_panel_flavour_is_bit_exact(n, batch):
+    a, b = gen_matrices(n, batch)
+    lu_ref, piv_ref, x_ref, info_ref = oracle_lu(a, b)
+    lu, piv, x, info = run_gpu(a, b, "aos", device_buffers=True, team_panel=True)
+    assert (info == 0).all() and (info_ref == 0).all()
+    assert np.array_equal(piv, piv_ref)
+    assert_bit_equal(lu, lu_ref, "LU (team panel) n=%d" % n)
+    assert_bit_equal(x, x_ref, "x (team panel) n=%d" % n)
+
+
+@pytest.mark.parametrize("n", [48, 64, 100, 130, 160])
+def test_team_panel_ties_nan_inf_follow_the_reference(n):
+    rng = np.random.default_rng(3)
+    a = rng.integers(-3, 4, size=(8, n, n)).astype(np.float64)  # many exact ties and zeros, across the panel's warps
+    a += np.eye(n)[None] * 0.5
+    a[1, 3, 0] = np.nan
+    a[2, 0, 0] = np.nan
+    a[3, n - 1, 2] = np.inf
+    a[4, n // 2, 1] = np.nan       # NaN in another warp's row slot
+    a[5, 40, 9] = -np.inf          # inf in the second panel
+    a[6, :, 5] = np.abs(a[6, :, 5]).max() + 1.0  # a whole column of equal maxima: the tie spans every warp of the panel
+    b = rng.normal(size=(8, n))
+    lu_ref, piv_ref, x_ref, info_ref = oracle_lu(a, b)
+    lu, piv, x, info = run_gpu(a, b, "aos", device_buffers=True, team_panel=True)
+    assert np.array_equal(info, info_ref)
+    ok = info_ref == 0
+    assert np.array_equal(piv[ok], piv_ref[ok])
+    assert_bit_equal(lu[ok], lu_ref[ok], "LU with ties/NaN (team panel)")
+    assert_bit_equal(x[ok], x_ref[ok], "x with ties/NaN (team panel)")
+
+
+@pytest.mark.parametrize("n", [40, 100, 130])
+def test_team_panel_singular_leaves_the_reference_partial_factors(n):
+    rng = np.random.default_rng(11)
+    a = rng.uniform(0.5, 1.5, size=(3, n, n)) + np.eye(n)[None] * n
+    a[0, :, n // 2 + 3] = 0.0
+    a[1, :, 8] = 0.0
+    a[2, :, n - 1] = a[2, :, n - 2]
+    b = np.ones((3, n))
+    lu_ref, piv_ref, _, info_ref = oracle_lu(a, b)
+    lu, piv, _, info = run_gpu(a, b, "aos", device_buffers=True, team_panel=True)
+    assert info.tolist() == info_ref.tolist() and info_ref[0] == n // 2 + 4 and info_ref[1] == 9
+    assert_bit_equal(lu, lu_ref, "partial factors (team panel) n=%d" % n)
+    for k in range(3):
+        m = info_ref[k] if info_ref[k] > 0 else n
+        assert np.array_equal(piv[k, :m], piv_ref[k, :m])
