@@ -477,6 +477,18 @@ def run_extra(fp64_peak_gops):
         out["heat_config5"] = he
     except Exception as exc:  # noqa: BLE001
         out["heat_config5"] = {"error": repr(exc)}
+    try:
+        # the warp-per-system kernel (the AUTO path for 3 < n <= 32) on ensembles of its own size class: heat 2-D on a
+        # 4 x 4 and a 5 x 5 grid (n = 16 / 25), 65,536 instances each
+        import bench_configs
+        rows = []
+        for M in (4, 5):
+            hs = bench_configs.run_heat(65536, reps=1, M=M)
+            hs["kernel"] = "warp"
+            rows.append({k: hs[k] for k in ("config", "batch", "n", "kernel", "ms", "instances_per_s", "all_success")})
+        out["heat_small_warp_team"] = rows
+    except Exception as exc:  # noqa: BLE001
+        out["heat_small_warp_team"] = {"error": repr(exc)}
     return out
 
 

@@ -21,6 +21,7 @@
 // Arithmetic: operation-for-operation like the reference, -fmad=false, pow = detpow.h.
 #pragma once
 #include "detpow.h"
+#include "fastdiv.cuh"
 #include "ida_common.cuh"
 #include "lu_team.cuh"
 #include "lu_blocked.cuh"
@@ -292,7 +293,8 @@ struct IdaTeam {
         if (leader()) {
             double acc = 0.0;
             for (int i = 0; i < n; ++i) acc = acc + prod[i];
-            *out = sqrt(acc / (double)n);
+            const double dn = (double)n;
+            *out = sqrt(div_by_recip(acc, dn, 1.0 / dn));  // == acc / n (exact_div.cuh); 1 / n folds out of the loop
         }
         Team::sync();
     }
@@ -316,26 +318,58 @@ struct IdaTeam {
             if (s.hh != s.hused || s.kk != s.kused) s.ns = 0;
             s.ns = min(s.ns + 1, s.kused + 2);
             if (s.kk + 1 >= s.ns) {
+                // The recurrence of src/lib.rs:738-755 with its three divisions per order taken out of the serial loop
+                // where the operands allow it: alpha_i = hh / (psi_old[i-1] + hh) and alpha_{i-1} / hh do not depend on the
+                // previous order's results, so the (at most 5 + 5) quotients run as two batches of interleaved chains
+                // (fastdiv.cuh: one leader lane, bound by dependent-issue latency); beta_i = beta_{i-1} psi_{i-1} / psi_old[i-1]
+                // stays a chain.  Every quotient has the operands it had in the loop.
                 s.beta[0] = 1.0;
                 s.alpha[0] = 1.0;
-                double temp1 = s.hh;
                 s.gamma[0] = 0.0;
                 s.sigma[0] = 1.0;
-                for (int i = 1; i <= s.kk; ++i) {
-                    const double temp2 = s.psi[i - 1];
-                    s.psi[i - 1] = temp1;
-                    s.beta[i] = s.beta[i - 1] * s.psi[i - 1] / temp2;
-                    temp1 = temp2 + s.hh;
-                    s.alpha[i] = s.hh / temp1;
-                    s.sigma[i] = (double)i * s.sigma[i - 1] * s.alpha[i];
-                    s.gamma[i] = s.gamma[i - 1] + s.alpha[i - 1] / s.hh;
+                const int kk = s.kk;
+                const double hh = s.hh;
+                double t2[MXORDP1], tp[MXORDP1];  // psi_old[i-1] ; temp1 after order i (tp[0] = hh)
+                tp[0] = hh;
+#pragma unroll
+                for (int i = 1; i < MXORDP1; ++i) {
+                    t2[i] = (i <= kk) ? s.psi[i - 1] : 1.0;
+                    tp[i] = t2[i] + hh;
                 }
-                s.psi[s.kk] = temp1;
+                double num[5], den[5], al[5], gq[5];
+#pragma unroll
+                for (int i = 1; i <= 5; ++i) {
+                    num[i - 1] = (i <= kk) ? hh : 1.0;
+                    den[i - 1] = (i <= kk) ? tp[i] : 1.0;
+                }
+                div_batch<5>(num, den, al);  // alpha[i] = hh / temp1
+#pragma unroll
+                for (int i = 1; i <= 5; ++i) {
+                    num[i - 1] = (i == 1) ? 1.0 : ((i <= kk) ? al[i - 2] : 1.0);  // alpha[i-1]
+                    den[i - 1] = (i <= kk) ? hh : 1.0;
+                }
+                div_batch<5>(num, den, gq);  // alpha[i-1] / hh
+#pragma unroll
+                for (int i = 1; i <= 5; ++i) {
+                    if (i <= kk) {
+                        s.psi[i - 1] = tp[i - 1];
+                        s.beta[i] = s.beta[i - 1] * tp[i - 1] / t2[i];
+                        s.alpha[i] = al[i - 1];
+                        s.sigma[i] = (double)i * s.sigma[i - 1] * al[i - 1];
+                        s.gamma[i] = s.gamma[i - 1] + gq[i - 1];
+                    }
+                }
+                s.psi[kk] = pick6(tp, kk);
             }
+            // alphas = -sum 1/(i+1): the quotients are compile-time constants (correctly rounded, as at run time)
+            constexpr double RCPI[5] = {1.0 / 1.0, 1.0 / 2.0, 1.0 / 3.0, 1.0 / 4.0, 1.0 / 5.0};
             double alphas = 0.0, alpha0 = 0.0;
-            for (int i = 0; i < s.kk; ++i) {
-                alphas -= 1.0 / (double)(i + 1);
-                alpha0 -= s.alpha[i];
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                if (i < s.kk) {
+                    alphas -= RCPI[i];
+                    alpha0 -= s.alpha[i];
+                }
             }
             s.cjlast = s.cj;
             s.cj = -alphas / s.hh;
