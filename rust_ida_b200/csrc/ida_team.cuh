@@ -293,8 +293,7 @@ struct IdaTeam {
         if (leader()) {
             double acc = 0.0;
             for (int i = 0; i < n; ++i) acc = acc + prod[i];
-            const double dn = (double)n;
-            *out = sqrt(div_by_recip(acc, dn, 1.0 / dn));  // == acc / n (exact_div.cuh); 1 / n folds out of the loop
+            *out = sqrt(acc / (double)n);
         }
         Team::sync();
     }
