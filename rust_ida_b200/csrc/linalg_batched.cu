@@ -980,9 +980,14 @@ __device__ __forceinline__ void gt_fwd_block(const GtPlan& P, const double* __re
     }
 }
 
-template <int RMAX, int R0>
+// SAFE = false: the division of the pivot lane is straight-line code -- EVERY lane forms the exact-reciprocal quotient of its
+// own (x, u, 1/u) each step (three FP64 instructions, exact_div.cuh) and only the pivot lane's is broadcast; a zero numerator
+// takes q0 = x * (1/u), the zero of the right sign; the range test that guards the sequence runs once per panel on the
+// numerator each lane recorded when it was the pivot lane, and a failure sets `bad`: the caller then redoes the whole
+// system with SAFE = true (the guarded division under a one-lane branch, which is what used to sit on every step's chain).
+template <int RMAX, int R0, bool SAFE>
 __device__ __forceinline__ void gt_bwd_block(const GtPlan& P, const double* __restrict__ Mg, unsigned ring, unsigned bars,
-                                             const double* ringp, int lane, double (&x)[RMAX], unsigned& phases, int& j) {
+                                             const double* ringp, int lane, double (&x)[RMAX], unsigned& phases, int& j, bool& bad) {
     constexpr int NS = R0 + 1;  // slots 0 .. R0 hold the rows above the pivots of this block
     const int n = P.n;
     const int klo = 32 * R0;
@@ -1001,6 +1006,7 @@ __device__ __forceinline__ void gt_bwd_block(const GtPlan& P, const double* __re
             double myud = 1.0;
             if (myq < qn) myud = st[(qn - 1 - myq) * n + (k0 - myq)];  // columns ascend in the stage: k0 - q at slot qn-1-q
             const double myrd = 1.0 / myud;
+            double xp = 1.0;  // SAFE = false: this lane's numerator at its pivot step of the panel
 #pragma unroll 4
             for (int q = 0; q < qn; ++q) {
                 const int kk = (k0 - q) & 31;
@@ -1008,21 +1014,81 @@ __device__ __forceinline__ void gt_bwd_block(const GtPlan& P, const double* __re
 #pragma unroll
                 for (int r = 0; r < NS; ++r) c[r] = st[(qn - 1 - q) * n + lane + 32 * r];  // r < R0: always < k; r == R0: used if < k
                 double xv = x[R0];
-                if (lane == kk) xv = div_by_recip(xv, myud, myrd);
+                if (SAFE) {
+                    if (lane == kk) xv = div_by_recip(xv, myud, myrd);
+                } else {
+                    const double q0 = __dmul_rn(xv, myrd);
+                    const double rr = __fma_rn(-myud, q0, xv);
+                    const double q1 = __fma_rn(rr, myrd, q0);
+                    const double qq = (xv == 0.0) ? q0 : q1;
+                    xp = (lane == kk) ? xv : xp;
+                    xv = (lane == kk) ? qq : xv;
+                }
                 const double bk = __shfl_sync(0xffffffffu, xv, kk);
                 const double t0 = x[R0] - c[R0] * bk;
                 x[R0] = (lane == kk) ? bk : ((lane < kk) ? t0 : x[R0]);
 #pragma unroll
                 for (int r = 0; r < R0; ++r) x[r] -= c[r] * bk;
             }
+            if (!SAFE) {  // the range tests of exact_div.cuh, once per panel and lane
+                const unsigned ex = ((unsigned)__double2hiint(xp) >> 20) & 0x7ffu, ed = ((unsigned)__double2hiint(myud) >> 20) & 0x7ffu;
+                const bool ok = (xp == 0.0) ? (ed - 1u < 0x7feu) : ((ex - 543u) <= 960u && (ed - 543u) <= 960u);
+                bad = bad || !ok;
+            }
             __syncwarp();
         }
     }
-    if constexpr (R0 > 0) gt_bwd_block<RMAX, R0 - 1>(P, Mg, ring, bars, ringp, lane, x, phases, j);
+    if constexpr (R0 > 0) gt_bwd_block<RMAX, R0 - 1, SAFE>(P, Mg, ring, bars, ringp, lane, x, phases, j, bad);
 }
 
 __host__ __device__ inline size_t gt_warp_smem(int n) {  // ring (16-byte aligned: n even) + rhs + pivots + barriers
     return ((size_t)GT_STAGES * GT_CB * n * sizeof(double) + (size_t)n * sizeof(double) + (size_t)n * sizeof(int) + 8 * GT_STAGES + 15) / 16 * 16;
+}
+
+// one system by one warp; returns true (warp-uniform) when SAFE = false met a quotient outside the straight-line sequence's
+// range -- nothing has been written then and the caller repeats the system with SAFE = true
+template <int RMAX, bool SAFE>
+__device__ __forceinline__ bool gt_solve_one(const GtPlan& P, const double* __restrict__ Mg, const int64_t* __restrict__ pivb,
+                                             double* __restrict__ bxb, unsigned ring, unsigned bars, const double* ringp, double* xs,
+                                             int* ps, int lane, unsigned& phases) {
+    const int n = P.n;
+    for (int j = 0; j < GT_STAGES - 1; ++j) gt_issue(P, Mg, ring, bars, j, lane);  // the factors start streaming first
+    for (int i = lane; i < n; i += 32) {
+        xs[i] = bxb[i];
+        ps[i] = (int)pivb[i];
+    }
+    __syncwarp();
+    if (lane == 0) {  // the row interchanges, in order (dense.rs:176-181)
+        for (int k = 0; k < n; ++k) {
+            const int pk = ps[k];
+            if (pk != k) {
+                const double t = xs[k];
+                xs[k] = xs[pk];
+                xs[pk] = t;
+            }
+        }
+    }
+    __syncwarp();
+    double x[RMAX];
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r) {
+        const int i = lane + 32 * r;
+        x[r] = (i < n) ? xs[i] : 0.0;
+    }
+    gt_fwd_block<RMAX, 0>(P, Mg, ring, bars, ringp, lane, x, phases);
+    int j = P.nf;
+    bool bad = false;
+    gt_bwd_block<RMAX, RMAX - 1, SAFE>(P, Mg, ring, bars, ringp, lane, x, phases, j, bad);
+    const bool redo = !SAFE && __any_sync(0xffffffffu, bad);
+    if (!redo) {
+#pragma unroll
+        for (int r = 0; r < RMAX; ++r) {
+            const int i = lane + 32 * r;
+            if (i < n) bxb[i] = x[r];
+        }
+    }
+    __syncwarp();
+    return redo;
 }
 
 template <int RMAX>
@@ -1046,38 +1112,8 @@ __global__ void __launch_bounds__(32 * GT_WARPS) getrs_tma(const double* __restr
     const GtPlan P(n);
     for (int64_t b = (int64_t)blockIdx.x * GT_WARPS + wi; b < B; b += (int64_t)gridDim.x * GT_WARPS) {
         const double* Mg = A + (size_t)b * n * n;
-        for (int j = 0; j < GT_STAGES - 1; ++j) gt_issue(P, Mg, ring, bars, j, lane);  // the factors start streaming first
-        for (int i = lane; i < n; i += 32) {
-            xs[i] = bx[(size_t)b * n + i];
-            ps[i] = (int)piv[(size_t)b * n + i];
-        }
-        __syncwarp();
-        if (lane == 0) {  // the row interchanges, in order (dense.rs:176-181)
-            for (int k = 0; k < n; ++k) {
-                const int pk = ps[k];
-                if (pk != k) {
-                    const double t = xs[k];
-                    xs[k] = xs[pk];
-                    xs[pk] = t;
-                }
-            }
-        }
-        __syncwarp();
-        double x[RMAX];
-#pragma unroll
-        for (int r = 0; r < RMAX; ++r) {
-            const int i = lane + 32 * r;
-            x[r] = (i < n) ? xs[i] : 0.0;
-        }
-        gt_fwd_block<RMAX, 0>(P, Mg, ring, bars, ringp, lane, x, phases);
-        int j = P.nf;
-        gt_bwd_block<RMAX, RMAX - 1>(P, Mg, ring, bars, ringp, lane, x, phases, j);
-#pragma unroll
-        for (int r = 0; r < RMAX; ++r) {
-            const int i = lane + 32 * r;
-            if (i < n) bx[(size_t)b * n + i] = x[r];
-        }
-        __syncwarp();
+        if (gt_solve_one<RMAX, false>(P, Mg, piv + (size_t)b * n, bx + (size_t)b * n, ring, bars, ringp, xs, ps, lane, phases))
+            gt_solve_one<RMAX, true>(P, Mg, piv + (size_t)b * n, bx + (size_t)b * n, ring, bars, ringp, xs, ps, lane, phases);
     }
 }
 
