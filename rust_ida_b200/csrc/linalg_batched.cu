@@ -277,13 +277,40 @@ __global__ void __launch_bounds__(128) getrs_warp_regs(const double* __restrict_
             const double bk = __shfl_sync(0xffffffffu, x, k);
             if (lane > k) x -= row[k] * bk;
         }
+        // backward sweep.  The division by u_kk is straight-line code: every lane forms the exact-reciprocal quotient of its
+        // own (x, u_ll, 1 / u_ll) each step (exact_div.cuh; 1 / u_ll computed up front, off the chain), only the pivot
+        // lane's is broadcast, a zero numerator takes q0 (the zero of the right sign).  The range tests run once, on the
+        // numerator each lane had at its pivot step; a failure redoes the sweep with real divisions.
+        const double dg = (lane < N) ? Ab[lane * N + lane] : 1.0;
+        const double rd = 1.0 / dg;
+        const double x_fwd = x;
+        double xp = 1.0;
 #pragma unroll
-        for (int k = N - 1; k >= 1; --k) {
-            if (lane == k) x /= row[k];
-            const double bk = __shfl_sync(0xffffffffu, x, k);
-            if (lane < k) x -= row[k] * bk;
+        for (int k = N - 1; k >= 0; --k) {
+            const double q0 = __dmul_rn(x, rd);
+            const double rr = __fma_rn(-dg, q0, x);
+            const double q1 = __fma_rn(rr, rd, q0);
+            const double qq = (x == 0.0) ? q0 : q1;
+            const bool pv = lane == k;
+            xp = pv ? x : xp;
+            const double bk = __shfl_sync(0xffffffffu, pv ? qq : x, k);
+            const double t = x - row[k] * bk;
+            x = pv ? bk : ((lane < k) ? t : x);
         }
-        if (lane == 0) x /= row[0];
+        {
+            const unsigned ex = ((unsigned)__double2hiint(xp) >> 20) & 0x7ffu, ed = ((unsigned)__double2hiint(dg) >> 20) & 0x7ffu;
+            const bool ok = (xp == 0.0) ? (ed - 1u < 0x7feu) : ((ex - 543u) <= 960u && (ed - 543u) <= 960u);
+            if (!__all_sync(0xffffffffu, ok)) {  // rare
+                x = x_fwd;
+                for (int k = N - 1; k >= 1; --k) {
+                    if (lane == k) x /= dg;
+                    const double bk = __shfl_sync(0xffffffffu, x, k);
+                    const double c = (lane < N) ? Ab[k * N + lane] : 0.0;
+                    if (lane < k) x -= c * bk;
+                }
+                if (lane == 0) x /= dg;
+            }
+        }
         if (lane < N) bx[(size_t)b * N + lane] = x;
     }
 }
