@@ -254,34 +254,39 @@ __global__ void __launch_bounds__(128) getrf_warp_regs(double* __restrict__ A, i
 template <int N>
 __global__ void __launch_bounds__(128) getrs_warp_regs(const double* __restrict__ A, const int64_t* __restrict__ piv,
                                                        double* __restrict__ bx, int64_t B) {
-    const int lane = threadIdx.x & 31;
+    // N = 16 packs TWO systems into a warp (lanes 0..15 and 16..31), like getrf_warp_regs: every shuffle has width N
+    constexpr int G = 32 / N;
+    const int lane = threadIdx.x & 31, gl = lane & (N - 1), g = lane / N;
     const int64_t wpg = (int64_t)gridDim.x * (blockDim.x >> 5);
-    for (int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); b < B; b += wpg) {
-        const double* Ab = A + (size_t)b * N * N;
+    const int64_t nwork = (B + G - 1) / G;
+    for (int64_t wk = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); wk < nwork; wk += wpg) {
+        const int64_t b = wk * G + g;
+        const bool live = b < B;  // a trailing odd system leaves the second half idle (it computes on system 0, stores nothing)
+        const double* Ab = A + (size_t)(live ? b : 0) * N * N;
         double row[N];
 #pragma unroll
-        for (int j = 0; j < N; ++j) row[j] = (lane < N) ? Ab[j * N + lane] : 1.0;
-        double x = (lane < N) ? bx[(size_t)b * N + lane] : 0.0;
-        const int pl = (lane < N) ? (int)piv[(size_t)b * N + lane] : 0;
+        for (int j = 0; j < N; ++j) row[j] = Ab[j * N + gl];
+        double x = bx[(size_t)(live ? b : 0) * N + gl];
+        const int pl = (int)piv[(size_t)(live ? b : 0) * N + gl];
 #pragma unroll
         for (int k = 0; k < N; ++k) {  // apply the pivots in order: swap x_k <-> x_{p_k}
-            const int pk = __shfl_sync(0xffffffffu, pl, k);
-            const double xk = __shfl_sync(0xffffffffu, x, k), xp = __shfl_sync(0xffffffffu, x, pk);
+            const int pk = __shfl_sync(0xffffffffu, pl, k, N);
+            const double xk = __shfl_sync(0xffffffffu, x, k, N), xq = __shfl_sync(0xffffffffu, x, pk, N);
             if (pk != k) {
-                if (lane == k) x = xp;
-                else if (lane == pk) x = xk;
+                if (gl == k) x = xq;
+                else if (gl == pk) x = xk;
             }
         }
 #pragma unroll
         for (int k = 0; k < N - 1; ++k) {
-            const double bk = __shfl_sync(0xffffffffu, x, k);
-            if (lane > k) x -= row[k] * bk;
+            const double bk = __shfl_sync(0xffffffffu, x, k, N);
+            if (gl > k) x -= row[k] * bk;
         }
         // backward sweep.  The division by u_kk is straight-line code: every lane forms the exact-reciprocal quotient of its
         // own (x, u_ll, 1 / u_ll) each step (exact_div.cuh; 1 / u_ll computed up front, off the chain), only the pivot
         // lane's is broadcast, a zero numerator takes q0 (the zero of the right sign).  The range tests run once, on the
         // numerator each lane had at its pivot step; a failure redoes the sweep with real divisions.
-        const double dg = (lane < N) ? Ab[lane * N + lane] : 1.0;
+        const double dg = Ab[gl * N + gl];
         const double rd = 1.0 / dg;
         const double x_fwd = x;
         double xp = 1.0;
@@ -291,27 +296,27 @@ __global__ void __launch_bounds__(128) getrs_warp_regs(const double* __restrict_
             const double rr = __fma_rn(-dg, q0, x);
             const double q1 = __fma_rn(rr, rd, q0);
             const double qq = (x == 0.0) ? q0 : q1;
-            const bool pv = lane == k;
+            const bool pv = gl == k;
             xp = pv ? x : xp;
-            const double bk = __shfl_sync(0xffffffffu, pv ? qq : x, k);
+            const double bk = __shfl_sync(0xffffffffu, pv ? qq : x, k, N);
             const double t = x - row[k] * bk;
-            x = pv ? bk : ((lane < k) ? t : x);
+            x = pv ? bk : ((gl < k) ? t : x);
         }
         {
             const unsigned ex = ((unsigned)__double2hiint(xp) >> 20) & 0x7ffu, ed = ((unsigned)__double2hiint(dg) >> 20) & 0x7ffu;
             const bool ok = (xp == 0.0) ? (ed - 1u < 0x7feu) : ((ex - 543u) <= 960u && (ed - 543u) <= 960u);
-            if (!__all_sync(0xffffffffu, ok)) {  // rare
+            if (!__all_sync(0xffffffffu, ok)) {  // rare; both halves redo (the real divisions give the same bits)
                 x = x_fwd;
                 for (int k = N - 1; k >= 1; --k) {
-                    if (lane == k) x /= dg;
-                    const double bk = __shfl_sync(0xffffffffu, x, k);
-                    const double c = (lane < N) ? Ab[k * N + lane] : 0.0;
-                    if (lane < k) x -= c * bk;
+                    if (gl == k) x /= dg;
+                    const double bk = __shfl_sync(0xffffffffu, x, k, N);
+                    const double c = Ab[k * N + gl];
+                    if (gl < k) x -= c * bk;
                 }
-                if (lane == 0) x /= dg;
+                if (gl == 0) x /= dg;
             }
         }
-        if (lane < N) bx[(size_t)b * N + lane] = x;
+        if (live) bx[(size_t)b * N + gl] = x;
     }
 }
 
@@ -1172,7 +1177,7 @@ static int launch_group(double* A, int64_t* piv, int32_t* info, double* bx, int 
     } while (0)
     if (!soa && (n == 16 || n == 32)) {
         const int threads = 128, wpc = 4;
-        const int64_t items = (FACTOR && n == 16) ? (B + 1) / 2 : B;  // getrf n = 16: two systems per warp
+        const int64_t items = (n == 16) ? (B + 1) / 2 : B;  // n = 16: two systems per warp
         const int64_t want = (items + wpc - 1) / wpc, cap = (int64_t)sm_count() * 16;
         const unsigned g = (unsigned)(want < cap ? want : cap);
         if (FACTOR) {

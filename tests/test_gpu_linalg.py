@@ -61,7 +61,7 @@ def run_gpu(a, b, layout, device_buffers, **dense_kw):
 
 
 @pytest.mark.parametrize("layout", ["soa", "aos"])
-@pytest.mark.parametrize("n,batch", [(3, 4099), (4, 1000), (8, 517), (16, 130), (32, 67), (64, 19), (100, 9),
+@pytest.mark.parametrize("n,batch", [(3, 4099), (4, 1000), (8, 517), (16, 130), (16, 131), (16, 1), (32, 67), (64, 19), (100, 9),
                                      (128, 5), (200, 3), (256, 2)])
 def test_getrf_getrs_bit_exact(n, batch, layout):
     a, b = gen_matrices(n, batch)
