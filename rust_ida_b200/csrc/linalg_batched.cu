@@ -171,17 +171,20 @@ __device__ __forceinline__ void lu_regs_step(double (&row)[N], double* prow, uns
                                              int& mypiv) {
     if (inf == 0) {  // uniform over the group
         const double x = row[K];
-        const bool isnan_ = x != x;
-        const int hi = done ? -2 : (isnan_ ? -1 : (__double2hiint(x) & 0x7fffffff));
-        const unsigned lo = (done || isnan_) ? 0u : (unsigned)__double2loint(x);
         const unsigned pp = ((unsigned)pos << 8) | (unsigned)gl;
-        const int mhi = __reduce_max_sync(gmask, hi);
-        const unsigned mlo = __reduce_max_sync(gmask, (hi == mhi) ? lo : 0u);
-        unsigned mpp = __reduce_min_sync(gmask, (!done && hi == mhi && lo == mlo) ? pp : 0xffffffffu);
         const bool atk = pos == K;  // the lane that holds logical row K (not yet a pivot row: positions < K are final)
-        if (mhi < 0 || __any_sync(gmask, atk && isnan_)) {
-            // nothing comparable, or a NaN in row K: the reference keeps l = K
-            mpp = __reduce_min_sync(gmask, atk ? pp : 0xffffffffu);
+        // Fast path (the common case): the high words of |x| alone -- sign stripped, they order like the values for finite
+        // x -- name a UNIQUE, finite maximum: one reduction and a ballot instead of three reductions.  A unique strictly
+        // largest high word is a strictly largest |x|, so the choice is the reference's; equal high words (possible ties)
+        // and any inf / NaN candidate (a NaN's high word is >= 0x7ff00000, so it is the maximum) take the full key below.
+        const int key = done ? -1 : (__double2hiint(x) & 0x7fffffff);
+        const int mkey = __reduce_max_sync(gmask, key);
+        const unsigned wm = __ballot_sync(gmask, key == mkey) & gmask;
+        unsigned mpp;
+        if (__popc(wm) == 1 && mkey >= 0 && mkey < 0x7ff00000) {  // uniform over the group
+            mpp = __shfl_sync(gmask, pp, __ffs(wm) - 1);
+        } else {
+            mpp = lu_argmax_full(gmask, x, done, pp, !done && atk);
         }
         const int l = (int)(mpp >> 8), lw = (int)(mpp & 0xffu);
         const double pv = __shfl_sync(gmask, x, lw, N);

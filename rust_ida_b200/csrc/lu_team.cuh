@@ -192,22 +192,37 @@ __device__ __forceinline__ void lu_factor_r(double* M, int ld, int n, LuShared* 
 // back as a broadcast), n-1-k independent mul / sub per lane.  Lanes >= n hold no row ("done" from the start).  The
 // shared-memory group LU above pays two warp barriers, a 10-shuffle butterfly and a shared-memory round trip of the whole
 // trailing matrix per step instead.  Same algorithm as the Level-1 getrf_warp_regs (linalg_batched.cu), any n <= N.
+// full arg-max key of one pivot column over the lanes of `mask` (out of line: ties, inf and NaN only): bits of |x| (NaN below
+// every candidate, lanes that are done below that), ties to the lowest logical position (pp = position << 8 | lane); nothing
+// comparable, or a NaN in the row at logical position K (atk), keeps l = K like the reference
+static __device__ __noinline__ unsigned lu_argmax_full(unsigned mask, double x, bool done, unsigned pp, bool atk) {
+    const bool isnan_ = x != x;
+    const int hi = done ? -2 : (isnan_ ? -1 : (__double2hiint(x) & 0x7fffffff));
+    const unsigned lo = (done || isnan_) ? 0u : (unsigned)__double2loint(x);
+    const int mhi = __reduce_max_sync(mask, hi);
+    const unsigned mlo = __reduce_max_sync(mask, (hi == mhi) ? lo : 0u);
+    unsigned mpp = __reduce_min_sync(mask, (!done && hi == mhi && lo == mlo) ? pp : 0xffffffffu);
+    if (mhi < 0 || __any_sync(mask, atk && isnan_)) mpp = __reduce_min_sync(mask, atk ? pp : 0xffffffffu);
+    return mpp;
+}
+
 template <int N, int K>
 __device__ __forceinline__ void lu_wregs_step(double (&row)[N], double* M, int ld, int n, int lane, int& pos, bool& done, int& inf,
                                               int& mypiv) {
     if (K < n && inf == 0) {  // uniform
         const double x = row[K];
-        const bool isnan_ = x != x;
-        const int hi = done ? -2 : (isnan_ ? -1 : (__double2hiint(x) & 0x7fffffff));
-        const unsigned lo = (done || isnan_) ? 0u : (unsigned)__double2loint(x);
         const unsigned pp = ((unsigned)pos << 8) | (unsigned)lane;
-        const int mhi = __reduce_max_sync(0xffffffffu, hi);
-        const unsigned mlo = __reduce_max_sync(0xffffffffu, (hi == mhi) ? lo : 0u);
-        unsigned mpp = __reduce_min_sync(0xffffffffu, (!done && hi == mhi && lo == mlo) ? pp : 0xffffffffu);
         const bool atk = !done && pos == K;  // the lane that holds logical row K (positions < K are final pivot rows)
-        if (mhi < 0 || __any_sync(0xffffffffu, atk && isnan_)) {
-            // nothing comparable, or a NaN in row K: the reference keeps l = K
-            mpp = __reduce_min_sync(0xffffffffu, atk ? pp : 0xffffffffu);
+        // fast path: a unique, finite maximum among the high words of |x| (one reduction + a ballot); ties, inf and NaN
+        // (whose high word is the maximum) take the full key -- see getrf_warp_regs
+        const int key = done ? -1 : (__double2hiint(x) & 0x7fffffff);
+        const int mkey = __reduce_max_sync(0xffffffffu, key);
+        const unsigned wm = __ballot_sync(0xffffffffu, key == mkey);
+        unsigned mpp;
+        if (__popc(wm) == 1 && mkey >= 0 && mkey < 0x7ff00000) {  // uniform
+            mpp = __shfl_sync(0xffffffffu, pp, __ffs(wm) - 1);
+        } else {
+            mpp = lu_argmax_full(0xffffffffu, x, done, pp, atk);
         }
         const int l = (int)(mpp >> 8), lw = (int)(mpp & 0xffu);
         const double pv = __shfl_sync(0xffffffffu, x, lw);
