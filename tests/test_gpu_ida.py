@@ -180,7 +180,8 @@ def test_team_kernels_match_oracle_on_roberts(kernel):
     compare(g, ref)
 
 
-@pytest.mark.parametrize("M,kernel,B", [(4, "warp", 300), (5, "warp", 130), (4, "cta", 64), (10, "cta", 700), (10, "auto", 41)])
+@pytest.mark.parametrize("M,kernel,B", [(4, "warp", 300), (5, "warp", 130), (4, "cta", 64), (10, "cta", 700), (10, "auto", 41),
+                                        (3, "warp", 64), (7, "cta", 30), (8, "cta", 40), (12, "cta", 12)])
 def test_heat2d_parity(M, kernel, B):
     """config 5 at test size: 2-D heat DAE (n = M*M; 10x10 -> dense n = 100, CTA-per-system with the LU factors
     resident in shared memory), coefficient perturbed +-10 % per instance."""
