@@ -872,9 +872,12 @@ static __device__ __noinline__ void lub_update_dmma(double* M, int ld, int n, in
 // 16-byte aligned.  On return (after a barrier) ctl->info holds 0 or the 1-based singular column, pivs[0..n) the pivot
 // rows; after a zero pivot in column k the matrix is the reference's partially factored state (steps < k applied).
 //
-// Look-ahead: in block step kb all warps first bring the NEXT panel (columns kb+nb .. kb+2nb) up to date; then warp 0
-// eliminates it while warps 1.. update the rest of the trailing matrix, so the serial pivot chain of one panel
-// overlaps the parallel update of the previous one; three CTA barriers per block step.
+// The TEAM flavour (CTA-per-system IDA kernel; B200IDA_LU_TEAM_PANEL in the Level-1 entry point): blockDim.x >= 128.
+// In block step kb all warps first bring the NEXT panel (columns kb+nb .. kb+2nb) up to date; then its first
+// P = lub_panel_warps() warps eliminate it together (lub_panel_mw) while the rest of the trailing update is a work queue
+// that the other warps start on at once and the panel's warps join; three CTA barriers per block step.
+// pol (experiments, tools/build_variants.sh -DIDA_TEAM_LUB_POL): low 4 bits = cap on P (0: the default rule), bit 4 =
+// warps that share a scheduler with a panel warp (w % 4 < P) stay out of the update.
 template <int RP>
 __device__ __forceinline__ void lub_factor(double* M, int ld, int n, LubCtl* ctl, int* pivs, double* Ub, int pol = 0) {
     const int tid = threadIdx.x, nt = blockDim.x, w = tid >> 5, nw = nt >> 5, lane = tid & 31;
