@@ -143,6 +143,7 @@ struct TeamScalars {
     double psi[MXORDP1], alpha[MXORDP1], beta[MXORDP1], sigma[MXORDP1], gamma[MXORDP1];
     double hh, hused, rr, cj, cjold, cjlast, cjratio, ss, toldel, eps_newt, tn, tretlast, h0u, tolsf, tret;
     double oldnrm, ck, err_k, err_km1, saved_t, tout, nrm, scale;
+    double en1, en2;  // test_error: the norms of the order k-1 / k-2 error estimates (summed next to enorm_k)
     int kk, kused, knew, phase, ns, setup_done, jcur;
     int nst, nre, nje, nni, netf, ncfn, nsetups, nlscf, natt;
     int flag, info, nstloc, ncf, nef, it, call_status, curiter;
@@ -570,22 +571,48 @@ struct IdaTeam {
     // ---- test_error (src/lib.rs:967-1039): S->flag = converged ? 0 : 2 ; S->err_k, S->err_km1, S->knew ----------
     __device__ void test_error() {
         const int kk = S->kk;
-        wrms_to(ee, &S->nrm);  // enorm_k
-        double enorm_km1 = 0.0, enorm_km2 = 0.0;
-        if (kk > 1) {
-            for (int i = t; i < n; i += T) delta[i] = phi[kk * n + i] + ee[i];
-            Team::sync();
-            wrms_to(delta, &S->scale);
-            enorm_km1 = S->scale;
-            if (kk > 2) {
-                Team::sync();
-                for (int i = t; i < n; i += T) delta[i] += phi[(kk - 1) * n + i];
-                Team::sync();
-                wrms_to(delta, &S->scale);
-                enorm_km2 = S->scale;
+        // The up to three norms (ee; ee + phi[kk]; ee + phi[kk] + phi[kk-1]) are independent: their weighted squares are formed
+        // in ONE pass (delta gets the operands and the order of the reference's two assignments) and the three index-ordered
+        // sums -- each a chain of n dependent adds run by one thread -- are taken by three different threads (three warps of a
+        // CTA team, three lanes of a warp team) at the same time: one chain's latency and three barriers instead of three
+        // and ten.  nd and tmp are free between two Newton solves and hold the second and third set of squares.
+        const bool m = idmask != nullptr;
+        const int nnorm = 1 + (kk > 1 ? 1 : 0) + (kk > 2 ? 1 : 0);
+        for (int i = t; i < n; i += T) {
+            const double w = ewt[i], e = ee[i];
+            double q = e * w;
+            if (m) q = q * idmask[i];
+            prod[i] = q * q;
+            if (kk > 1) {
+                double d = phi[kk * n + i] + e;
+                q = d * w;
+                if (m) q = q * idmask[i];
+                nd[i] = q * q;
+                if (kk > 2) {
+                    d += phi[(kk - 1) * n + i];
+                    q = d * w;
+                    if (m) q = q * idmask[i];
+                    tmp[i] = q * q;
+                }
+                delta[i] = d;
             }
         }
         Team::sync();
+        {
+            const int step = (T >= 96) ? 32 : 1;  // CTA teams: one summing thread per warp; warp teams: lanes 0, 1, 2
+            const int which = (t == 0) ? 0 : ((t == step) ? 1 : ((t == 2 * step) ? 2 : 3));
+            if (which < nnorm) {
+                const double* pp = (which == 0) ? prod : ((which == 1) ? nd : tmp);
+                double acc = 0.0;
+                for (int i = 0; i < n; ++i) acc = acc + pp[i];
+                const double nrm = sqrt(acc / (double)n);
+                if (which == 0) S->nrm = nrm;
+                else if (which == 1) S->en1 = nrm;
+                else S->en2 = nrm;
+            }
+        }
+        Team::sync();
+        const double enorm_km1 = (kk > 1) ? S->en1 : 0.0, enorm_km2 = (kk > 2) ? S->en2 : 0.0;
         if (leader()) {
             TeamScalars& s = *S;
             const double scalar_kk = (double)kk;
